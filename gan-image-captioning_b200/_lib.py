@@ -1,0 +1,120 @@
+"""ctypes binding of libgic_b200.so (C ABI in include/gic_b200.h).  No torch types cross this boundary:
+tensors are passed as raw device pointers + sizes, the stream as a cudaStream_t handle.
+
+There is deliberately no CPU fallback: if the library is missing, or a compute entry point is called
+without an sm_100 device, this raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libgic_b200.so")
+HEADER = os.path.join(os.path.dirname(HERE), "include", "gic_b200.h")
+
+GEMM_FP32, GEMM_TF32, GEMM_TF32X3 = 0, 1, 2
+LOSS_TYPES = {"standard": 0, "JS": 1, "KL": 2, "hinge": 3, "tv": 4, "rsgan": 5}
+
+_lib = None
+
+
+class GicError(RuntimeError):
+    pass
+
+
+def header_symbols():
+    """Names of all functions include/gic_b200.h declares."""
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gic_[a-z0-9_]+)\s*\(", src)))
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GicError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(the hot path is CUDA-only; there is no CPU fallback)")
+        _lib = C.CDLL(LIB_PATH)
+        _declare(_lib)
+    return _lib
+
+
+P = C.c_void_p
+I = C.c_int
+F = C.c_float
+Z = C.c_size_t
+
+
+def _declare(L):
+    L.gic_version.restype = I
+    L.gic_last_error.restype = C.c_char_p
+    L.gic_check_device.restype = I
+    L.gic_launch_count.restype = C.c_ulonglong
+    L.gic_gemm.argtypes = [I, I, I, I, I, I, F, P, I, P, I, F, P, I, P, P]
+    L.gic_encoder_fwd.argtypes = [I, P, I, I, I, P, P, P, P, F, P, P, P, P, P]
+    L.gic_encoder_bwd.argtypes = [I, P, P, P, P, P, P, P, I, I, I, P, P, P, P, P, I, P]
+    L.gic_sample_step.argtypes = [I, P, P, F, I, I, I, I, P, P, P, P, I, P, P]
+    for f in (L.gic_decode_saved_floats, L.gic_decode_fwd_workspace_floats, L.gic_decode_bwd_workspace_floats,
+              L.gic_disc_saved_floats, L.gic_disc_fwd_workspace_floats, L.gic_disc_bwd_workspace_floats):
+        f.restype = Z
+    L.gic_decode_saved_floats.argtypes = [I] * 5
+    L.gic_decode_fwd_workspace_floats.argtypes = [I] * 3
+    L.gic_decode_bwd_workspace_floats.argtypes = [I] * 6
+    L.gic_disc_saved_floats.argtypes = [I] * 5
+    L.gic_disc_fwd_workspace_floats.argtypes = [I]
+    L.gic_disc_bwd_workspace_floats.argtypes = [I] * 5
+    L.gic_decode_sample_fwd.argtypes = [I, P, P, P, P, P, P, P, P, P, F, I, P, I, I, I, I, I, I, P, P, P, P, P]
+    L.gic_decode_sample_bwd.argtypes = [I, P, P, P, P, P, P, P, F, I, I, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P,
+                                        I, P]
+    L.gic_disc_fwd.argtypes = [I, P, P, I, I, I, I, I, I, P, P, P, P, P, P, P, P, P, I, P, P, I, P, F, P, P, P, P]
+    L.gic_disc_bwd.argtypes = [I, P, P, F, P, P, I, I, I, I, I, I, P, P, P, P, P, P, P, P, I, P, P, P, P, P, P, P, P,
+                               P, P, P, P, P, P, I, I, P]
+    L.gic_gan_loss_fwd_bwd.argtypes = [I, P, P, P, I, P, P, P, P, P]
+    L.gic_grad_sqnorm.argtypes = [P, Z, P, P]
+    L.gic_clip_adam.argtypes = [P, P, P, P, Z, P, F, F, I, F, F, F, F, P]
+    for name in header_symbols():      # every declared entry point must be exported
+        getattr(L, name)
+
+
+def check(rc: int, what: str = ""):
+    if rc == 0:
+        return
+    msg = lib().gic_last_error().decode(errors="replace")
+    if rc == 6:
+        raise NotImplementedError(msg)
+    raise GicError(f"{what}: {msg} (status {rc})")
+
+
+def ptr(t):
+    """Device pointer of a contiguous torch tensor (None -> NULL)."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "libgic_b200 takes dense row-major tensors"
+    return t.data_ptr()
+
+
+def ptr_array(ts):
+    """C array of device pointers (for per-layer / per-filter-group weights)."""
+    arr = (C.c_void_p * len(ts))()
+    for i, t in enumerate(ts):
+        arr[i] = None if t is None else ptr(t)
+    return arr
+
+
+def int_array(xs):
+    return (C.c_int * len(xs))(*[int(x) for x in xs])
+
+
+def stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda():
+    """Fail loudly when the CUDA path cannot run (no silent fallback)."""
+    import torch
+    if not torch.cuda.is_available():
+        raise GicError("no CUDA device: the gic_b200 hot path is CUDA-only (sm_100a) and has no CPU fallback")
+    check(lib().gic_check_device(), "gic_check_device")

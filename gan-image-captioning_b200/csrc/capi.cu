@@ -1,0 +1,337 @@
+// extern "C" entry points of libgic_b200.so (declared in include/gic_b200.h) and the host-side
+// composition of the decode forward/backward passes.
+#include "../../include/gic_b200.h"
+#include "gic_internal.cuh"
+
+namespace gic {
+// decode.cu
+int gather_rows(const float*, const int64_t*, int, int, int, float*, cudaStream_t);
+int sample_step(bool, const float*, const float*, float, int, int, int, int, float*, int64_t*, const int64_t*,
+                const float*, int, float*, cudaStream_t);
+int softmax_bwd(const float*, const float*, float, int, int, float*, cudaStream_t);
+int embed_scatter(const float*, const int64_t*, int, int, int, int, float*, float*, cudaStream_t);
+int bn_fwd(const float*, int, int, const float*, const float*, float, float*, float*, float*, cudaStream_t);
+int bn_bwd(const float*, const float*, int, int, const float*, const float*, const float*, float*, float*, float*,
+           cudaStream_t);
+int lstm_cell_fwd(const float*, const float*, int, int, float*, float*, float*, float*, int, int, cudaStream_t);
+int lstm_cell_bwd(const float*, const float*, const float*, const float*, long long, const float*, float*, int, int,
+                  float*, cudaStream_t);
+// disc.cu
+size_t disc_saved_floats(int, int, int, int, int);
+size_t disc_fwd_workspace_floats(int);
+size_t disc_bwd_workspace_floats(int, int, int, int, int);
+int scale_inplace(float*, size_t, float, cudaStream_t);
+// loss_optim.cu
+int gan_loss(int, const float*, const float*, const float*, int, float*, float*, float*, float*, cudaStream_t);
+int grad_sqnorm(const float*, size_t, float*, cudaStream_t);
+int clip_adam(float*, const float*, float*, float*, size_t, const float*, float, float, int, float, float, float,
+              float, cudaStream_t);
+const char* last_error();
+unsigned long long launch_count();
+// disc_api.cu-style wrappers implemented in disc.cu
+int disc_fwd_entry(int mode, const float* inp_soft, const int64_t* ids, int N, int L, int V, int De, int R,
+                   int n_groups, const int* fs, const int* nf, const float* W_e, const float* const* cw,
+                   const float* const* cb, const float* W_h, const float* b_h, const float* W_f, const float* b_f,
+                   int Hd, const float* W_o, const float* b_o, int n_heads, const uint8_t* const* keep, float drop_p,
+                   float* const* logits, float* saved, float* ws, cudaStream_t s);
+int disc_bwd_entry(int mode, const float* dlogits, const uint8_t* keep, float drop_p, const float* inp_soft,
+                   const int64_t* ids, int N, int L, int V, int De, int R, int n_groups, const int* fs, const int* nf,
+                   const float* W_e, const float* const* cw, const float* const* cb, const float* W_h,
+                   const float* W_f, const float* b_f, int Hd, const float* W_o, const float* b_o, const float* saved,
+                   float* ws, float* dW_e, float* const* dcw, float* const* dcb, float* dW_h, float* db_h,
+                   float* dW_f, float* db_f, float* dW_o, float* db_o, float* dinp, int want_param, int accumulate,
+                   cudaStream_t s);
+
+static size_t a4(size_t x) { return (x + 3) & ~(size_t)3; }
+
+// saved-for-backward layout of the decode (floats):
+//   xs[L][B][E] | per layer l: hs[l][(L+1)][B][H], cs[l][(L+1)][B][H], acts[l][L][B][4H] | htop[B][L][H]
+struct DecodeSaved {
+  size_t xs, hs0, cs0, acts0, per_layer, htop, total;
+  DecodeSaved(int B, int L, int E, int H, int layers) {
+    const size_t BH = (size_t)B * H;
+    xs = 0;
+    size_t off = a4((size_t)L * B * E);
+    hs0 = off;
+    cs0 = hs0 + a4((size_t)(L + 1) * BH);
+    acts0 = cs0 + a4((size_t)(L + 1) * BH);
+    per_layer = 2 * a4((size_t)(L + 1) * BH) + a4((size_t)L * BH * 4);
+    htop = off + (size_t)layers * per_layer;
+    total = htop + a4((size_t)B * L * H);
+  }
+  size_t hs(int l) const { return hs0 + (size_t)l * per_layer; }
+  size_t cs(int l) const { return cs0 + (size_t)l * per_layer; }
+  size_t acts(int l) const { return acts0 + (size_t)l * per_layer; }
+};
+
+static int decode_fwd(int mode, const float* features, const float* W_emb, const float* const* W_ih,
+                      const float* const* W_hh, const float* const* b_ih, const float* const* b_hh,
+                      const float* W_out, const float* b_out, const float* u, float T, int pretrain,
+                      const int64_t* forced, int B, int L, int V, int E, int H, int layers, float* out, int64_t* ids,
+                      float* saved, float* ws, cudaStream_t s) {
+  GIC_REQUIRE(B >= 0 && L >= 1 && V >= 1 && E >= 1 && H >= 1 && layers >= 1 && layers <= 8, GIC_ERR_SHAPE,
+              "decode_sample_fwd: bad shape B=%d L=%d V=%d E=%d H=%d layers=%d", B, L, V, E, H, layers);
+  if (B == 0) return GIC_OK;
+  GIC_REQUIRE(features && W_emb && W_ih && W_hh && b_ih && b_hh && W_out && b_out && out && ids && saved && ws,
+              GIC_ERR_NULL, "decode_sample_fwd: NULL pointer");
+  GIC_REQUIRE(pretrain || u, GIC_ERR_NULL, "decode_sample_fwd: uniforms u[L,B,V] required in adversarial mode");
+  const DecodeSaved sv(B, L, E, H, layers);
+  const size_t BH = (size_t)B * H, BE = (size_t)B * E;
+  float* gates = ws;                         // [B,4H]
+  float* logits = ws + a4(4 * BH);           // [B,V]
+  cudaMemcpyAsync(saved + sv.xs, features, BE * sizeof(float), cudaMemcpyDeviceToDevice, s);
+  for (int l = 0; l < layers; ++l) {
+    cudaMemsetAsync(saved + sv.hs(l), 0, BH * sizeof(float), s);
+    cudaMemsetAsync(saved + sv.cs(l), 0, BH * sizeof(float), s);
+  }
+  for (int t = 0; t < L; ++t) {
+    for (int l = 0; l < layers; ++l) {
+      const float* xin = (l == 0) ? saved + sv.xs + (size_t)t * BE : saved + sv.hs(l - 1) + (size_t)(t + 1) * BH;
+      const int In = (l == 0) ? E : H;
+      const float* hprev = saved + sv.hs(l) + (size_t)t * BH;
+      // gates = x W_ih^T + b_ih + h W_hh^T + b_hh          (src/generator.py:61)
+      GIC_TRY(gemm(mode, false, true, B, 4 * H, In, 1.f, xin, In, W_ih[l], In, 0.f, gates, 4 * H, b_ih[l], s));
+      GIC_TRY(gemm(mode, false, true, B, 4 * H, H, 1.f, hprev, H, W_hh[l], H, 1.f, gates, 4 * H, b_hh[l], s));
+      GIC_TRY(lstm_cell_fwd(gates, saved + sv.cs(l) + (size_t)t * BH, B, H, saved + sv.acts(l) + (size_t)t * BH * 4,
+                            saved + sv.cs(l) + (size_t)(t + 1) * BH, saved + sv.hs(l) + (size_t)(t + 1) * BH,
+                            (l == layers - 1) ? saved + sv.htop : nullptr, L, t, s));
+    }
+    const float* htop_t = saved + sv.hs(layers - 1) + (size_t)(t + 1) * BH;
+    GIC_TRY(gemm(mode, false, true, B, V, H, 1.f, htop_t, H, W_out, H, 0.f, logits, V, b_out, s));   // :64,68
+    float* x_next = (t + 1 < L) ? saved + sv.xs + (size_t)(t + 1) * BE : nullptr;
+    GIC_TRY(sample_step(pretrain != 0, logits, pretrain ? nullptr : u + (size_t)t * B * V, T, B, V, L, t, out, ids,
+                        forced, W_emb, E, x_next, s));
+  }
+  return GIC_OK;
+}
+
+// backward workspace (floats):
+//   dlogits[B*L*V] | dHtop[B*L*H] | dG[layers][L][B][4H] | dh_rec[layers][B][H] | dc_rec[layers][B][H]
+//   | dxin[B][H] | dX[L][B][E]
+struct DecodeBwdWs {
+  size_t dlogits, dhtop, dG, dhrec, dcrec, dxin, dX, total;
+  DecodeBwdWs(int B, int L, int V, int E, int H, int layers) {
+    const size_t BH = (size_t)B * H;
+    dlogits = 0;
+    dhtop = a4((size_t)B * L * V);
+    dG = dhtop + a4((size_t)B * L * H);
+    dhrec = dG + (size_t)layers * a4((size_t)L * BH * 4);
+    dcrec = dhrec + (size_t)layers * a4(BH);
+    dxin = dcrec + (size_t)layers * a4(BH);
+    dX = dxin + a4(BH);
+    total = dX + a4((size_t)L * B * E);
+  }
+};
+
+static int decode_bwd(int mode, const float* dout, const float* out, const int64_t* fed, const float* W_emb,
+                      const float* const* W_ih, const float* const* W_hh, const float* W_out, float T, int pretrain,
+                      int B, int L, int V, int E, int H, int layers, const float* saved, float* ws, float* dW_emb,
+                      float* const* dW_ih, float* const* dW_hh, float* const* db_ih, float* const* db_hh,
+                      float* dW_out, float* db_out, float* dfeat, int accumulate, cudaStream_t s) {
+  GIC_REQUIRE(B >= 0 && L >= 1 && V >= 1 && E >= 1 && H >= 1 && layers >= 1 && layers <= 8, GIC_ERR_SHAPE,
+              "decode_sample_bwd: bad shape");
+  if (B == 0) return GIC_OK;
+  GIC_REQUIRE(dout && fed && W_emb && W_ih && W_hh && W_out && saved && ws && dW_emb && dW_ih && dW_hh && db_ih &&
+                  db_hh && dW_out && db_out, GIC_ERR_NULL, "decode_sample_bwd: NULL pointer");
+  GIC_REQUIRE(pretrain || out, GIC_ERR_NULL, "decode_sample_bwd: soft captions `out` required");
+  const DecodeSaved sv(B, L, E, H, layers);
+  const DecodeBwdWs w(B, L, V, E, H, layers);
+  const size_t BH = (size_t)B * H, BE = (size_t)B * E;
+  const float beta = accumulate ? 1.f : 0.f;
+  const int BL = B * L;
+  const size_t dG_stride = a4((size_t)L * BH * 4);
+
+  // 1. through the tempered softmax (the Gumbel add is a constant)
+  const float* dlogits = dout;
+  if (!pretrain) {
+    GIC_TRY(softmax_bwd(out, dout, T, BL, V, ws + w.dlogits, s));
+    dlogits = ws + w.dlogits;
+  }
+  // 2. vocab projection: db_out, dW_out[V,H] = dlogits^T htop, dHtop[B*L,H] = dlogits W_out
+  GIC_TRY(colsum_f32(dlogits, BL, V, V, 1.f, accumulate != 0, db_out, s));
+  GIC_TRY(gemm(mode, true, false, V, H, BL, 1.f, dlogits, V, saved + sv.htop, H, beta, dW_out, H, nullptr, s));
+  GIC_TRY(gemm(mode, false, false, BL, H, V, 1.f, dlogits, V, W_out, H, 0.f, ws + w.dhtop, H, nullptr, s));
+  // 3. BPTT through (h, c)
+  cudaMemsetAsync(ws + w.dhrec, 0, (size_t)2 * layers * a4(BH) * sizeof(float), s);   // dh_rec and dc_rec
+  for (int t = L - 1; t >= 0; --t) {
+    for (int l = layers - 1; l >= 0; --l) {
+      const bool top = (l == layers - 1);
+      const float* dh_in = top ? ws + w.dhtop + (size_t)t * H : ws + w.dxin;
+      const long long stride = top ? (long long)L * H : (long long)H;
+      float* dG_lt = ws + w.dG + (size_t)l * dG_stride + (size_t)t * BH * 4;
+      float* dhrec = ws + w.dhrec + (size_t)l * a4(BH);
+      float* dcrec = ws + w.dcrec + (size_t)l * a4(BH);
+      GIC_TRY(lstm_cell_bwd(saved + sv.acts(l) + (size_t)t * BH * 4, saved + sv.cs(l) + (size_t)t * BH,
+                            saved + sv.cs(l) + (size_t)(t + 1) * BH, dh_in, stride, dhrec, dcrec, B, H, dG_lt, s));
+      // recurrent gradient for step t-1: dh_rec = dgates W_hh    ([B,4H] x [4H,H])
+      if (t > 0)
+        GIC_TRY(gemm(mode, false, false, B, H, 4 * H, 1.f, dG_lt, 4 * H, W_hh[l], H, 0.f, dhrec, H, nullptr, s));
+      // gradient to the layer below at the same step
+      if (l > 0)
+        GIC_TRY(gemm(mode, false, false, B, H, 4 * H, 1.f, dG_lt, 4 * H, W_ih[l], H, 0.f, ws + w.dxin, H, nullptr, s));
+    }
+  }
+  // 4. weight gradients, batched over all (t, b)
+  for (int l = 0; l < layers; ++l) {
+    const float* dG_l = ws + w.dG + (size_t)l * dG_stride;           // [L*B, 4H]
+    const int In = (l == 0) ? E : H;
+    const float* xin = (l == 0) ? saved + sv.xs : saved + sv.hs(l - 1) + BH;   // inputs of step t, t-major
+    GIC_TRY(gemm(mode, true, false, 4 * H, In, L * B, 1.f, dG_l, 4 * H, xin, In, beta, dW_ih[l], In, nullptr, s));
+    GIC_TRY(gemm(mode, true, false, 4 * H, H, L * B, 1.f, dG_l, 4 * H, saved + sv.hs(l), H, beta, dW_hh[l], H, nullptr, s));
+    GIC_TRY(colsum_f32(dG_l, L * B, 4 * H, 4 * H, 1.f, accumulate != 0, db_ih[l], s));
+    GIC_TRY(colsum_f32(dG_l, L * B, 4 * H, 4 * H, 1.f, accumulate != 0, db_hh[l], s));
+  }
+  // 5. input gradients: dX[L*B,E] = dG[0] W_ih[0]; t = 0 -> dfeatures, t >= 1 -> embedding rows
+  GIC_TRY(gemm(mode, false, false, L * B, E, 4 * H, 1.f, ws + w.dG, 4 * H, W_ih[0], E, 0.f, ws + w.dX, E, nullptr, s));
+  if (!accumulate) cudaMemsetAsync(dW_emb, 0, (size_t)V * E * sizeof(float), s);
+  GIC_TRY(embed_scatter(ws + w.dX, fed, B, L, E, V, dW_emb, dfeat, s));
+  (void)BE;
+  return GIC_OK;
+}
+
+static int require_device() {
+  static int cached = -1;
+  if (cached == GIC_OK) return GIC_OK;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { set_error("no CUDA device: %s (libgic_b200 has no CPU fallback)", cudaGetErrorString(e)); return GIC_ERR_CUDA; }
+  int major = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) { set_error("cudaDeviceGetAttribute: %s", cudaGetErrorString(e)); return GIC_ERR_CUDA; }
+  if (major != 10) { set_error("device compute capability %d.x is not sm_100 (B200)", major); return GIC_ERR_ARCH; }
+  cached = GIC_OK;
+  return GIC_OK;
+}
+
+}  // namespace gic
+
+using namespace gic;
+#define S(x) reinterpret_cast<cudaStream_t>(x)
+
+extern "C" {
+
+int gic_version(void) { return 100; }
+const char* gic_last_error(void) { return last_error(); }
+int gic_check_device(void) { return require_device(); }
+unsigned long long gic_launch_count(void) { return launch_count(); }
+
+int gic_gemm(int mode, int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
+             const float* B, int ldb, float beta, float* C, int ldc, const float* bias, gic_stream_t stream) {
+  GIC_TRY(require_device());
+  return gemm(mode, transA != 0, transB != 0, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, S(stream));
+}
+
+int gic_encoder_fwd(int mode, const float* pooled, int B, int Fin, int E, const float* W, const float* b,
+                    const float* gamma, const float* beta, float eps, float* lin_out, float* save_mean,
+                    float* save_rstd, float* features, gic_stream_t stream) {
+  GIC_TRY(require_device());
+  GIC_REQUIRE(B >= 1 && Fin >= 1 && E >= 1, GIC_ERR_SHAPE, "encoder_fwd: bad shape");
+  GIC_REQUIRE(pooled && W && b && gamma && beta && lin_out && save_mean && save_rstd && features, GIC_ERR_NULL,
+              "encoder_fwd: NULL pointer");
+  GIC_TRY(gemm(mode, false, true, B, E, Fin, 1.f, pooled, Fin, W, Fin, 0.f, lin_out, E, b, S(stream)));
+  return bn_fwd(lin_out, B, E, gamma, beta, eps, features, save_mean, save_rstd, S(stream));
+}
+
+int gic_encoder_bwd(int mode, const float* dfeatures, const float* pooled, const float* lin_out,
+                    const float* save_mean, const float* save_rstd, const float* W, const float* gamma, int B,
+                    int Fin, int E, float* dlin_ws, float* dW, float* db, float* dgamma, float* dbeta, int accumulate,
+                    gic_stream_t stream) {
+  GIC_TRY(require_device());
+  GIC_REQUIRE(B >= 1 && Fin >= 1 && E >= 1, GIC_ERR_SHAPE, "encoder_bwd: bad shape");
+  GIC_REQUIRE(dfeatures && pooled && lin_out && save_mean && save_rstd && gamma && dlin_ws && dW && db && dgamma && dbeta,
+              GIC_ERR_NULL, "encoder_bwd: NULL pointer");
+  GIC_REQUIRE(!accumulate, GIC_ERR_UNSUPPORTED, "encoder_bwd: accumulate is not supported");
+  (void)W;
+  GIC_TRY(bn_bwd(lin_out, dfeatures, B, E, gamma, save_mean, save_rstd, dlin_ws, dgamma, dbeta, S(stream)));
+  GIC_TRY(gemm(mode, true, false, E, Fin, B, 1.f, dlin_ws, E, pooled, Fin, 0.f, dW, Fin, nullptr, S(stream)));
+  return colsum_f32(dlin_ws, B, E, E, 1.f, false, db, S(stream));
+}
+
+int gic_sample_step(int pretrain, const float* logits, const float* u, float temperature, int B, int V, int L, int t,
+                    float* out, int64_t* ids, const int64_t* forced_ids, const float* embed, int E, float* x_next,
+                    gic_stream_t stream) {
+  GIC_TRY(require_device());
+  GIC_REQUIRE(B >= 0 && V >= 1 && L >= 1 && t >= 0 && t < L, GIC_ERR_SHAPE, "sample_step: bad shape");
+  if (B == 0) return GIC_OK;
+  GIC_REQUIRE(logits && out && ids && (pretrain || u), GIC_ERR_NULL, "sample_step: NULL pointer");
+  GIC_REQUIRE(!x_next || embed, GIC_ERR_NULL, "sample_step: embed table required for x_next");
+  return sample_step(pretrain != 0, logits, u, temperature, B, V, L, t, out, ids, forced_ids, embed, E, x_next,
+                     S(stream));
+}
+
+size_t gic_decode_saved_floats(int B, int L, int E, int H, int layers) { return DecodeSaved(B, L, E, H, layers).total; }
+size_t gic_decode_fwd_workspace_floats(int B, int V, int H) { return a4((size_t)4 * B * H) + a4((size_t)B * V); }
+size_t gic_decode_bwd_workspace_floats(int B, int L, int V, int E, int H, int layers) {
+  return DecodeBwdWs(B, L, V, E, H, layers).total;
+}
+
+int gic_decode_sample_fwd(int mode, const float* features, const float* W_emb, const float* const* W_ih,
+                          const float* const* W_hh, const float* const* b_ih, const float* const* b_hh,
+                          const float* W_out, const float* b_out, const float* u, float temperature, int pretrain,
+                          const int64_t* forced_ids, int B, int L, int V, int E, int H, int layers, float* out,
+                          int64_t* ids, float* saved, float* workspace, gic_stream_t stream) {
+  GIC_TRY(require_device());
+  return decode_fwd(mode, features, W_emb, W_ih, W_hh, b_ih, b_hh, W_out, b_out, u, temperature, pretrain, forced_ids,
+                    B, L, V, E, H, layers, out, ids, saved, workspace, S(stream));
+}
+
+int gic_decode_sample_bwd(int mode, const float* dout, const float* out, const int64_t* fed_ids, const float* W_emb,
+                          const float* const* W_ih, const float* const* W_hh, const float* W_out, float temperature,
+                          int pretrain, int B, int L, int V, int E, int H, int layers, const float* saved,
+                          float* workspace, float* dW_emb, float* const* dW_ih, float* const* dW_hh,
+                          float* const* db_ih, float* const* db_hh, float* dW_out, float* db_out, float* dfeatures,
+                          int accumulate, gic_stream_t stream) {
+  GIC_TRY(require_device());
+  return decode_bwd(mode, dout, out, fed_ids, W_emb, W_ih, W_hh, W_out, temperature, pretrain, B, L, V, E, H, layers,
+                    saved, workspace, dW_emb, dW_ih, dW_hh, db_ih, db_hh, dW_out, db_out, dfeatures, accumulate,
+                    S(stream));
+}
+
+size_t gic_disc_saved_floats(int N, int L, int De, int R, int F) { return disc_saved_floats(N, L, De, R, F); }
+size_t gic_disc_fwd_workspace_floats(int F) { return disc_fwd_workspace_floats(F); }
+size_t gic_disc_bwd_workspace_floats(int N, int L, int De, int R, int F) {
+  return disc_bwd_workspace_floats(N, L, De, R, F);
+}
+
+int gic_disc_fwd(int mode, const float* inp_soft, const int64_t* ids, int N, int L, int V, int De, int R,
+                 int n_groups, const int* filter_sizes, const int* num_filters, const float* W_e,
+                 const float* const* conv_w, const float* const* conv_b, const float* W_h, const float* b_h,
+                 const float* W_f, const float* b_f, int Hd, const float* W_o, const float* b_o, int n_heads,
+                 const uint8_t* const* keep, float drop_p, float* const* logits, float* saved, float* workspace,
+                 gic_stream_t stream) {
+  GIC_TRY(require_device());
+  return disc_fwd_entry(mode, inp_soft, ids, N, L, V, De, R, n_groups, filter_sizes, num_filters, W_e, conv_w, conv_b,
+                        W_h, b_h, W_f, b_f, Hd, W_o, b_o, n_heads, keep, drop_p, logits, saved, workspace, S(stream));
+}
+
+int gic_disc_bwd(int mode, const float* dlogits, const uint8_t* keep, float drop_p, const float* inp_soft,
+                 const int64_t* ids, int N, int L, int V, int De, int R, int n_groups, const int* filter_sizes,
+                 const int* num_filters, const float* W_e, const float* const* conv_w, const float* const* conv_b,
+                 const float* W_h, const float* W_f, const float* b_f, int Hd, const float* W_o, const float* b_o,
+                 const float* saved, float* workspace, float* dW_e, float* const* dconv_w, float* const* dconv_b,
+                 float* dW_h, float* db_h, float* dW_f, float* db_f, float* dW_o, float* db_o, float* dinp,
+                 int want_param, int accumulate, gic_stream_t stream) {
+  GIC_TRY(require_device());
+  return disc_bwd_entry(mode, dlogits, keep, drop_p, inp_soft, ids, N, L, V, De, R, n_groups, filter_sizes,
+                        num_filters, W_e, conv_w, conv_b, W_h, W_f, b_f, Hd, W_o, b_o, saved, workspace, dW_e, dconv_w,
+                        dconv_b, dW_h, db_h, dW_f, db_f, dW_o, db_o, dinp, want_param, accumulate, S(stream));
+}
+
+int gic_gan_loss_fwd_bwd(int loss_type, const float* d_out_real, const float* d_out_fake, const float* g_out, int n,
+                         float* losses, float* dd_real, float* dd_fake, float* dg_out, gic_stream_t stream) {
+  GIC_TRY(require_device());
+  return gan_loss(loss_type, d_out_real, d_out_fake, g_out, n, losses, dd_real, dd_fake, dg_out, S(stream));
+}
+
+int gic_grad_sqnorm(const float* g, size_t n, float* sqnorm, gic_stream_t stream) {
+  GIC_TRY(require_device());
+  return grad_sqnorm(g, n, sqnorm, S(stream));
+}
+
+int gic_clip_adam(float* p, const float* g, float* m, float* v, size_t n, const float* sqnorm, float max_norm,
+                  float grad_scale, int step, float lr, float beta1, float beta2, float eps, gic_stream_t stream) {
+  GIC_TRY(require_device());
+  return clip_adam(p, g, m, v, n, sqnorm, max_norm, grad_scale, step, lr, beta1, beta2, eps, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,315 @@
+// Caption generator hot path: LSTM decode step, Gumbel-softmax sampling, and their backward.
+// Replaces Decoder.sample / Decoder.add_gumbel (src/generator.py:55-96) and the autograd
+// backward of that graph.  Encoder.linear + Encoder.bn
+// (src/generator.py:15-16,23-24) is here too because it feeds step 0 of the decode.
+#include "gic_internal.cuh"
+
+namespace gic {
+
+// ---------------------------------------------------------------------------------------
+// row gather: out[i, :] = table[ids[i], :]     (nn.Embedding lookup, src/generator.py:75)
+// ---------------------------------------------------------------------------------------
+__global__ void gather_rows_kernel(const float* __restrict__ table, const int64_t* __restrict__ ids,
+                                   int n, int E, int V, float* __restrict__ out) {
+  const int i = blockIdx.x;
+  if (i >= n) return;
+  int64_t id = ids[i];
+  if (id < 0 || id >= V) id = 0;   // out-of-range ids never occur on the path; stay in bounds
+  const float* src = table + (size_t)id * E;
+  float* dst = out + (size_t)i * E;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) dst[e] = src[e];
+}
+
+int gather_rows(const float* table, const int64_t* ids, int n, int E, int V, float* out,
+                cudaStream_t s) {
+  if (n == 0) return GIC_OK;
+  gather_rows_kernel<<<n, 128, 0, s>>>(table, ids, n, E, V, out);
+  return check_launch("gather_rows_kernel");
+}
+
+// ---------------------------------------------------------------------------------------
+// LSTM cell, forward.  gates[B,4H] pre-activation (i,f,g,o chunks) -> acts (post-activation,
+// saved for backward), c_new, h_new; the top layer also writes h into htop[B,L,H] at step t.
+// ---------------------------------------------------------------------------------------
+__global__ void lstm_cell_fwd_kernel(const float* __restrict__ gates, const float* __restrict__ c_prev,
+                                     int B, int H, float* __restrict__ acts, float* __restrict__ c_new,
+                                     float* __restrict__ h_new, float* __restrict__ htop, int L, int t) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * H) return;
+  const int b = idx / H, j = idx % H;
+  const float* g = gates + (size_t)b * 4 * H;
+  const float i_ = sigmoidf_acc(g[j]);
+  const float f_ = sigmoidf_acc(g[H + j]);
+  const float g_ = tanhf(g[2 * H + j]);
+  const float o_ = sigmoidf_acc(g[3 * H + j]);
+  const float c = f_ * c_prev[idx] + i_ * g_;
+  const float h = o_ * tanhf(c);
+  float* a = acts + (size_t)b * 4 * H;
+  a[j] = i_; a[H + j] = f_; a[2 * H + j] = g_; a[3 * H + j] = o_;
+  c_new[idx] = c;
+  h_new[idx] = h;
+  if (htop) htop[((size_t)b * L + t) * H + j] = h;
+}
+
+// LSTM cell, backward for one (layer, step).  dh_in = gradient arriving at h_t from above
+// (vocab projection or the next layer) with row stride dh_stride; dh_rec / dc_rec are the
+// recurrent gradients from step t+1 (dc_rec is updated in place to dc_{t-1}).
+__global__ void lstm_cell_bwd_kernel(const float* __restrict__ acts, const float* __restrict__ c_prev,
+                                     const float* __restrict__ c_cur, const float* __restrict__ dh_in,
+                                     long long dh_stride, const float* __restrict__ dh_rec,
+                                     float* __restrict__ dc_rec, int B, int H, float* __restrict__ dgates) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * H) return;
+  const int b = idx / H, j = idx % H;
+  const float* a = acts + (size_t)b * 4 * H;
+  const float i_ = a[j], f_ = a[H + j], g_ = a[2 * H + j], o_ = a[3 * H + j];
+  float dh = dh_rec ? dh_rec[idx] : 0.f;
+  if (dh_in) dh += dh_in[(size_t)b * dh_stride + j];
+  const float tc = tanhf(c_cur[idx]);
+  const float dc = dh * o_ * (1.f - tc * tc) + dc_rec[idx];
+  float* dg = dgates + (size_t)b * 4 * H;
+  dg[j] = dc * g_ * i_ * (1.f - i_);
+  dg[H + j] = dc * c_prev[idx] * f_ * (1.f - f_);
+  dg[2 * H + j] = dc * i_ * (1.f - g_ * g_);
+  dg[3 * H + j] = dh * tc * o_ * (1.f - o_);
+  dc_rec[idx] = dc * f_;
+}
+
+// ---------------------------------------------------------------------------------------
+// Fused Gumbel perturbation + temperature + vocab softmax + first-max sample + next-input
+// embedding gather.  One CTA per caption row; the perturbed logits are staged in shared
+// memory (or, for huge vocabularies, in the output row itself) so u and the logits are read
+// from HBM exactly once and the probabilities are written exactly once: 8*V bytes per row.
+//   adversarial mode: out = softmax((logits + g(u)) * T)              (src/generator.py:68-70)
+//   pretrain mode   : out = logits, choice = argmax softmax(logits)   (src/generator.py:63-66)
+// Tie rule: lowest index among equal probabilities (torch.max first-max, :73).
+// ---------------------------------------------------------------------------------------
+template <bool PRETRAIN>
+__global__ void __launch_bounds__(256)
+sample_step_kernel(const float* __restrict__ logits, const float* __restrict__ u, float temperature,
+                   int V, int L, int t, float* __restrict__ out /*[B,L,V]*/, int64_t* __restrict__ ids,
+                   const int64_t* __restrict__ forced, const float* __restrict__ embed, int E,
+                   float* __restrict__ x_next, int stage_in_smem) {
+  extern __shared__ float zbuf[];
+  __shared__ float red[32];
+  __shared__ int red_i[32];
+  __shared__ int s_tok;
+  const int b = blockIdx.x;
+  const float* lrow = logits + (size_t)b * V;
+  float* orow = out + ((size_t)b * L + t) * V;
+  float* z = stage_in_smem ? zbuf : orow;
+  const float eps = 1e-10f;
+
+  // pass 1: z = (logit + gumbel(u)) * T, row max
+  float mx = -INFINITY;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    float x = lrow[v];
+    if (!PRETRAIN) {
+      const float uu = u[(size_t)b * V + v];
+      const float g = -logf(-logf(uu + eps) + eps);
+      x = (x + g) * temperature;
+    }
+    z[v] = x;
+    mx = fmaxf(mx, x);
+  }
+  mx = block_max(mx, red);
+  // pass 2: sum of exp
+  float sum = 0.f;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    const float e = expf(z[v] - mx);
+    z[v] = e;
+    sum += e;
+  }
+  sum = block_sum(sum, red);
+  // pass 3: probabilities, first-max index
+  float best = -1.f;
+  int best_i = 0x7fffffff;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    const float p = z[v] / sum;
+    if (PRETRAIN) orow[v] = lrow[v]; else orow[v] = p;
+    if (p > best) { best = p; best_i = v; }
+  }
+  // (value, index) arg-max across the block; ties -> lowest index
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) { red[w] = best; red_i[w] = best_i; }
+  __syncthreads();
+  if (w == 0) {
+    best = lane < nw ? red[lane] : -2.f;
+    best_i = lane < nw ? red_i[lane] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+      if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
+    }
+    if (lane == 0) {
+      ids[(size_t)b * L + t] = best_i;
+      int fed = best_i;
+      if (forced) {
+        const int64_t f = forced[(size_t)b * L + t];
+        fed = (f >= 0 && f < V) ? (int)f : 0;
+      }
+      s_tok = fed;
+    }
+  }
+  __syncthreads();
+  if (x_next) {
+    const float* src = embed + (size_t)s_tok * E;
+    float* dst = x_next + (size_t)b * E;
+    for (int e = threadIdx.x; e < E; e += blockDim.x) dst[e] = src[e];
+  }
+}
+
+int sample_step(bool pretrain, const float* logits, const float* u, float temperature, int B, int V,
+                int L, int t, float* out, int64_t* ids, const int64_t* forced, const float* embed,
+                int E, float* x_next, cudaStream_t s) {
+  const size_t smem = (size_t)V * sizeof(float);
+  const int in_smem = smem <= 200 * 1024 ? 1 : 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(sample_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(sample_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  const size_t dyn = in_smem ? smem : 0;
+  if (pretrain)
+    sample_step_kernel<true><<<B, 256, dyn, s>>>(logits, u, temperature, V, L, t, out, ids, forced, embed, E,
+                                               x_next, in_smem);
+  else
+    sample_step_kernel<false><<<B, 256, dyn, s>>>(logits, u, temperature, V, L, t, out, ids, forced, embed, E,
+                                                x_next, in_smem);
+  return check_launch("sample_step_kernel");
+}
+
+// ---------------------------------------------------------------------------------------
+// softmax backward with temperature: dz = T * p * (dp - sum_v p*dp), one CTA per (b,t) row.
+// (autograd of F.softmax(gumbel_t * T), src/generator.py:69; the Gumbel add is a constant.)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+softmax_bwd_kernel(const float* __restrict__ p, const float* __restrict__ dp, float temperature, int V,
+                   float* __restrict__ dz) {
+  __shared__ float red[32];
+  const size_t row = blockIdx.x;
+  const float* pr = p + row * V;
+  const float* dr = dp + row * V;
+  float* zr = dz + row * V;
+  float dot = 0.f;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) dot = fmaf(pr[v], dr[v], dot);
+  dot = block_sum(dot, red);
+  for (int v = threadIdx.x; v < V; v += blockDim.x) zr[v] = temperature * pr[v] * (dr[v] - dot);
+}
+
+int softmax_bwd(const float* p, const float* dp, float temperature, int rows, int V, float* dz,
+                cudaStream_t s) {
+  if (rows == 0) return GIC_OK;
+  softmax_bwd_kernel<<<rows, 256, 0, s>>>(p, dp, temperature, V, dz);
+  return check_launch("softmax_bwd_kernel");
+}
+
+// ---------------------------------------------------------------------------------------
+// embedding gradient: dW_emb[tok[b,t-1], :] += dX[t, b, :] for t >= 1 (the token fed back at
+// step t-1 is the input of step t); dfeatures[b,:] = dX[0,b,:].  fp32 atomics: the order of
+// duplicate-token accumulation differs from the reference (within rtol, not bitwise).
+// ---------------------------------------------------------------------------------------
+__global__ void embed_scatter_kernel(const float* __restrict__ dX /*[L,B,E]*/, const int64_t* __restrict__ fed /*[B,L]*/,
+                                     int B, int L, int E, int V, float* __restrict__ dW_emb,
+                                     float* __restrict__ dfeat) {
+  const int tb = blockIdx.x;      // t * B + b
+  const int t = tb / B, b = tb % B;
+  const float* src = dX + (size_t)tb * E;
+  if (t == 0) {
+    if (dfeat)
+      for (int e = threadIdx.x; e < E; e += blockDim.x) dfeat[(size_t)b * E + e] = src[e];
+    return;
+  }
+  int64_t tok = fed[(size_t)b * L + (t - 1)];
+  if (tok < 0 || tok >= V) tok = 0;
+  float* dst = dW_emb + (size_t)tok * E;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) atomicAdd(dst + e, src[e]);
+}
+
+int embed_scatter(const float* dX, const int64_t* fed, int B, int L, int E, int V, float* dW_emb,
+                  float* dfeat, cudaStream_t s) {
+  embed_scatter_kernel<<<L * B, 128, 0, s>>>(dX, fed, B, L, E, V, dW_emb, dfeat);
+  return check_launch("embed_scatter_kernel");
+}
+
+// ---------------------------------------------------------------------------------------
+// BatchNorm1d (train mode, batch statistics, biased variance) forward / backward over [B,E].
+// One warp per feature column.  (Encoder.bn, src/generator.py:16,24)
+// ---------------------------------------------------------------------------------------
+__global__ void bn_fwd_kernel(const float* __restrict__ y, int B, int E, const float* __restrict__ gamma,
+                              const float* __restrict__ beta, float eps, float* __restrict__ out,
+                              float* __restrict__ save_mean, float* __restrict__ save_rstd) {
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= E) return;
+  float s = 0.f;
+  for (int b = lane; b < B; b += 32) s += y[(size_t)b * E + j];
+  const float mu = warp_sum(s) / B;
+  float q = 0.f;
+  for (int b = lane; b < B; b += 32) { const float d = y[(size_t)b * E + j] - mu; q += d * d; }
+  const float var = warp_sum(q) / B;
+  const float rstd = 1.0f / sqrtf(var + eps);
+  for (int b = lane; b < B; b += 32)
+    out[(size_t)b * E + j] = (y[(size_t)b * E + j] - mu) * rstd * gamma[j] + beta[j];
+  if (lane == 0) { save_mean[j] = mu; save_rstd[j] = rstd; }
+}
+
+__global__ void bn_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dout, int B, int E,
+                              const float* __restrict__ gamma, const float* __restrict__ save_mean,
+                              const float* __restrict__ save_rstd, float* __restrict__ dy,
+                              float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= E) return;
+  const float mu = save_mean[j], rstd = save_rstd[j];
+  float sd = 0.f, sdx = 0.f;
+  for (int b = lane; b < B; b += 32) {
+    const float d = dout[(size_t)b * E + j];
+    const float xh = (y[(size_t)b * E + j] - mu) * rstd;
+    sd += d; sdx += d * xh;
+  }
+  sd = warp_sum(sd); sdx = warp_sum(sdx);
+  const float g = gamma[j];
+  for (int b = lane; b < B; b += 32) {
+    const float d = dout[(size_t)b * E + j];
+    const float xh = (y[(size_t)b * E + j] - mu) * rstd;
+    dy[(size_t)b * E + j] = g * rstd * (d - sd / B - xh * sdx / B);
+  }
+  if (lane == 0) { dgamma[j] = sdx; dbeta[j] = sd; }
+}
+
+int bn_fwd(const float* y, int B, int E, const float* gamma, const float* beta, float eps, float* out,
+           float* save_mean, float* save_rstd, cudaStream_t s) {
+  bn_fwd_kernel<<<cdiv(E, 4), 128, 0, s>>>(y, B, E, gamma, beta, eps, out, save_mean, save_rstd);
+  return check_launch("bn_fwd_kernel");
+}
+int bn_bwd(const float* y, const float* dout, int B, int E, const float* gamma, const float* save_mean,
+           const float* save_rstd, float* dy, float* dgamma, float* dbeta, cudaStream_t s) {
+  bn_bwd_kernel<<<cdiv(E, 4), 128, 0, s>>>(y, dout, B, E, gamma, save_mean, save_rstd, dy, dgamma, dbeta);
+  return check_launch("bn_bwd_kernel");
+}
+
+int lstm_cell_fwd(const float* gates, const float* c_prev, int B, int H, float* acts, float* c_new,
+                  float* h_new, float* htop, int L, int t, cudaStream_t s) {
+  lstm_cell_fwd_kernel<<<cdiv((long long)B * H, 256), 256, 0, s>>>(gates, c_prev, B, H, acts, c_new, h_new,
+                                                                  htop, L, t);
+  return check_launch("lstm_cell_fwd_kernel");
+}
+int lstm_cell_bwd(const float* acts, const float* c_prev, const float* c_cur, const float* dh_in,
+                  long long dh_stride, const float* dh_rec, float* dc_rec, int B, int H, float* dgates,
+                  cudaStream_t s) {
+  lstm_cell_bwd_kernel<<<cdiv((long long)B * H, 256), 256, 0, s>>>(acts, c_prev, c_cur, dh_in, dh_stride,
+                                                                  dh_rec, dc_rec, B, H, dgates);
+  return check_launch("lstm_cell_bwd_kernel");
+}
+
+}  // namespace gic

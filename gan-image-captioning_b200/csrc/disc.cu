@@ -1,0 +1,594 @@
+// Discriminator hot path (RelGAN multi-representation CNN): embedding (soft GEMM or hard
+// column gather), fused conv + bias + ReLU + max-over-time emitting [N*R, F] directly, highway
+// mix, dropout and the collapsed 900->100->1 score head, plus the backward of all of it.
+// Replaces Discriminator.forward (src/discriminator.py:34-62) and its autograd backward.
+#include "gic_internal.cuh"
+
+namespace gic {
+
+constexpr int MAX_GROUPS = 8;
+
+struct ConvGroups {
+  const float* w[MAX_GROUPS];   // [n, 1, f, es] contiguous == [n][f*es]
+  const float* b[MAX_GROUPS];   // [n]
+  float* dw[MAX_GROUPS];
+  float* db[MAX_GROUPS];
+  int f[MAX_GROUPS];
+  int n[MAX_GROUPS];
+  int col0[MAX_GROUPS];
+  int ngroups;
+  int F;                        // sum n
+  int kmax;                     // max f*es
+};
+
+// ---------------------------------------------------------------------------------------
+// hard-token embedding: Linear(one_hot(id)) == column `id` of embeddings.weight[De, V]
+// (src/training.py:158 + src/discriminator.py:40).  Bit-identical to the dense product.
+// ---------------------------------------------------------------------------------------
+__global__ void disc_embed_ids_kernel(const int64_t* __restrict__ ids, int n_tok, int V, int De,
+                                      const float* __restrict__ W_e, float* __restrict__ emb) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_tok * De) return;
+  const int i = idx / De, r = idx % De;
+  int64_t id = ids[i];
+  if (id < 0 || id >= V) id = 0;
+  emb[idx] = W_e[(size_t)r * V + id];
+}
+
+// dW_e[r, id] += demb[i, r]
+__global__ void disc_embed_ids_bwd_kernel(const int64_t* __restrict__ ids, int n_tok, int V, int De,
+                                          const float* __restrict__ demb, float* __restrict__ dW_e) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_tok * De) return;
+  const int i = idx / De, r = idx % De;
+  int64_t id = ids[i];
+  if (id < 0 || id >= V) id = 0;
+  atomicAdd(dW_e + (size_t)r * V + id, demb[idx]);
+}
+
+// ---------------------------------------------------------------------------------------
+// fused conv(f, es) + bias + ReLU + max over time, all filter groups, all R representations.
+// One CTA per caption.  smem: emb[L*De] | wk[kmax][F] | bias[F] | fsz[F].
+// Lanes run along the feature column c, so the [N*R, F] output rows are written coalesced and
+// the embedding reads are warp broadcasts.  ES1 fast path: float4 over 4 representations.
+// out: pooled[(n*R + r)*F + c] = max_t relu(conv), arg = first t attaining it (uint8).
+// ---------------------------------------------------------------------------------------
+// one (feature column, 4 representations) work item of the ES1 fast path, filter size FK
+template <int FK>
+__device__ __forceinline__ void conv_item_es1(const float* emb_s, const float* wk_s, int F, int c, float bias,
+                                              int L, int R, int rb, float4& best, int (&a)[4]) {
+  float w[FK];
+#pragma unroll
+  for (int k = 0; k < FK; ++k) w[k] = wk_s[k * F + c];
+  best = make_float4(-1.f, -1.f, -1.f, -1.f);
+  a[0] = a[1] = a[2] = a[3] = 0;
+  const int T = L - FK + 1;
+  for (int t = 0; t < T; ++t) {
+    float4 acc = make_float4(bias, bias, bias, bias);
+#pragma unroll
+    for (int k = 0; k < FK; ++k) {
+      const float4 e = *reinterpret_cast<const float4*>(&emb_s[(t + k) * R + rb * 4]);
+      acc.x = fmaf(w[k], e.x, acc.x);
+      acc.y = fmaf(w[k], e.y, acc.y);
+      acc.z = fmaf(w[k], e.z, acc.z);
+      acc.w = fmaf(w[k], e.w, acc.w);
+    }
+    acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f);
+    acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
+    if (acc.x > best.x) { best.x = acc.x; a[0] = t; }
+    if (acc.y > best.y) { best.y = acc.y; a[1] = t; }
+    if (acc.z > best.z) { best.z = acc.z; a[2] = t; }
+    if (acc.w > best.w) { best.w = acc.w; a[3] = t; }
+  }
+}
+
+template <bool ES1>
+__global__ void __launch_bounds__(256)
+conv_pool_fwd_kernel(const float* __restrict__ emb, int L, int De, int R, int es, ConvGroups g,
+                     float* __restrict__ pooled, uint8_t* __restrict__ arg) {
+  extern __shared__ __align__(16) float sm[];
+  const int F = g.F, kmax = g.kmax;
+  float* emb_s = sm;                                // L*De (De % 4 == 0 on the ES1 path)
+  float* wk_s = emb_s + ((L * De + 3) & ~3);        // [kmax][F]
+  float* bias_s = wk_s + kmax * F;                  // [F]
+  int* fk_s = reinterpret_cast<int*>(bias_s + F);   // [F]  f*es per column
+  const int n = blockIdx.x;
+  for (int i = threadIdx.x; i < L * De; i += blockDim.x) emb_s[i] = emb[(size_t)n * L * De + i];
+  for (int gi = 0; gi < g.ngroups; ++gi) {
+    const int fk = g.f[gi] * es;
+    for (int i = threadIdx.x; i < g.n[gi] * kmax; i += blockDim.x) {
+      const int c = i / kmax, k = i % kmax;
+      wk_s[k * F + g.col0[gi] + c] = (k < fk) ? g.w[gi][c * fk + k] : 0.f;
+    }
+    for (int c = threadIdx.x; c < g.n[gi]; c += blockDim.x) {
+      bias_s[g.col0[gi] + c] = g.b[gi][c];
+      fk_s[g.col0[gi] + c] = fk;
+    }
+  }
+  __syncthreads();
+
+  if (ES1) {
+    const int RB = R / 4;
+    for (int item = threadIdx.x; item < F * RB; item += blockDim.x) {
+      const int c = item % F, rb = item / F;
+      const float bias = bias_s[c];
+      float4 best;
+      int a[4];
+      switch (fk_s[c]) {   // lanes of a warp share a filter group except at group boundaries
+        case 1: conv_item_es1<1>(emb_s, wk_s, F, c, bias, L, R, rb, best, a); break;
+        case 2: conv_item_es1<2>(emb_s, wk_s, F, c, bias, L, R, rb, best, a); break;
+        case 3: conv_item_es1<3>(emb_s, wk_s, F, c, bias, L, R, rb, best, a); break;
+        case 4: conv_item_es1<4>(emb_s, wk_s, F, c, bias, L, R, rb, best, a); break;
+        case 5: conv_item_es1<5>(emb_s, wk_s, F, c, bias, L, R, rb, best, a); break;
+        case 6: conv_item_es1<6>(emb_s, wk_s, F, c, bias, L, R, rb, best, a); break;
+        case 7: conv_item_es1<7>(emb_s, wk_s, F, c, bias, L, R, rb, best, a); break;
+        default: conv_item_es1<8>(emb_s, wk_s, F, c, bias, L, R, rb, best, a); break;
+      }
+      const size_t row = (size_t)n * R + rb * 4;
+      pooled[(row + 0) * F + c] = best.x; arg[(row + 0) * F + c] = (uint8_t)a[0];
+      pooled[(row + 1) * F + c] = best.y; arg[(row + 1) * F + c] = (uint8_t)a[1];
+      pooled[(row + 2) * F + c] = best.z; arg[(row + 2) * F + c] = (uint8_t)a[2];
+      pooled[(row + 3) * F + c] = best.w; arg[(row + 3) * F + c] = (uint8_t)a[3];
+    }
+  } else {
+    for (int item = threadIdx.x; item < F * R; item += blockDim.x) {
+      const int c = item % F, r = item / F;
+      const int fk = fk_s[c], f = fk / es;
+      const float bias = bias_s[c];
+      float best = -1.f;
+      int a = 0;
+      const int T = L - f + 1;
+      for (int t = 0; t < T; ++t) {
+        float acc = bias;
+        for (int kk = 0; kk < fk; ++kk)
+          acc = fmaf(wk_s[kk * F + c], emb_s[(t + kk / es) * De + r * es + kk % es], acc);
+        acc = fmaxf(acc, 0.f);
+        if (acc > best) { best = acc; a = t; }
+      }
+      pooled[((size_t)n * R + r) * F + c] = best;
+      arg[((size_t)n * R + r) * F + c] = (uint8_t)a;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// backward of conv + ReLU + max-pool.  Persistent CTAs loop over captions; each thread owns
+// whole feature columns (weights and their gradient accumulators stay in registers across all
+// captions of the CTA, one global atomic per weight at the end); demb is accumulated in shared
+// memory and written once per caption.
+// ---------------------------------------------------------------------------------------
+constexpr int BWD_SLOTS = 4;     // columns per thread: F <= 256 * BWD_SLOTS
+constexpr int BWD_KMAX = 8;      // f * es <= 8 on the register path
+
+__global__ void __launch_bounds__(256)
+conv_pool_bwd_kernel(const float* __restrict__ emb, const float* __restrict__ pooled,
+                     const uint8_t* __restrict__ arg, const float* __restrict__ dx, int N, int L, int De,
+                     int R, int es, ConvGroups g, int want_param, float* __restrict__ demb) {
+  extern __shared__ __align__(16) float sm[];
+  const int F = g.F;
+  float* emb_s = sm;
+  float* demb_s = sm + L * De;
+  // per-thread column slots
+  float w[BWD_SLOTS][BWD_KMAX], dw[BWD_SLOTS][BWD_KMAX], dbias[BWD_SLOTS];
+  int fk[BWD_SLOTS], grp[BWD_SLOTS], cin[BWD_SLOTS];
+#pragma unroll
+  for (int s = 0; s < BWD_SLOTS; ++s) {
+    const int c = threadIdx.x + s * 256;
+    fk[s] = 0; grp[s] = 0; cin[s] = 0; dbias[s] = 0.f;
+#pragma unroll
+    for (int k = 0; k < BWD_KMAX; ++k) { w[s][k] = 0.f; dw[s][k] = 0.f; }
+    if (c < F) {
+      int gi = 0;
+      while (gi + 1 < g.ngroups && c >= g.col0[gi + 1]) ++gi;
+      grp[s] = gi; cin[s] = c - g.col0[gi]; fk[s] = g.f[gi] * es;
+#pragma unroll
+      for (int k = 0; k < BWD_KMAX; ++k)
+        if (k < fk[s]) w[s][k] = g.w[gi][cin[s] * fk[s] + k];
+    }
+  }
+
+  for (int n = blockIdx.x; n < N; n += gridDim.x) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < L * De; i += blockDim.x) {
+      emb_s[i] = emb[(size_t)n * L * De + i];
+      demb_s[i] = 0.f;
+    }
+    __syncthreads();
+    for (int r = 0; r < R; ++r) {
+      const size_t base = ((size_t)n * R + r) * F;
+#pragma unroll
+      for (int s = 0; s < BWD_SLOTS; ++s) {
+        const int c = threadIdx.x + s * 256;
+        if (c < F) {
+          const float gsd = dx[base + c];
+          const float pv = pooled[base + c];
+          if (pv > 0.f && gsd != 0.f) {
+            const int a = arg[base + c];
+#pragma unroll
+            for (int k = 0; k < BWD_KMAX; ++k) {
+              if (k < fk[s]) {
+                const int ei = (a + k / es) * De + r * es + k % es;
+                dw[s][k] = fmaf(gsd, emb_s[ei], dw[s][k]);
+                atomicAdd(&demb_s[ei], w[s][k] * gsd);
+              }
+            }
+            dbias[s] += gsd;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < L * De; i += blockDim.x) demb[(size_t)n * L * De + i] = demb_s[i];
+  }
+  if (want_param) {
+#pragma unroll
+    for (int s = 0; s < BWD_SLOTS; ++s) {
+      const int c = threadIdx.x + s * 256;
+      if (c < F) {
+#pragma unroll
+        for (int k = 0; k < BWD_KMAX; ++k)
+          if (k < fk[s]) atomicAdd(g.dw[grp[s]] + cin[s] * fk[s] + k, dw[s][k]);
+        atomicAdd(g.db[grp[s]] + cin[s], dbias[s]);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// score head.  feature2out (F->100) and out2logits (100->1) have no nonlinearity between them
+// (src/discriminator.py:58-60), so logits = yd . w_eff + b_eff with
+//   w_eff[j] = sum_k w_o[k] W_f[k, j],  b_eff = sum_k w_o[k] b_f[k] + b_o.
+// ---------------------------------------------------------------------------------------
+__global__ void head_collapse_kernel(const float* __restrict__ W_f, const float* __restrict__ b_f,
+                                     const float* __restrict__ w_o, const float* __restrict__ b_o, int F,
+                                     int Hd, float* __restrict__ weff /*[F+1]*/) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < F) {
+    float s = 0.f;
+    for (int k = 0; k < Hd; ++k) s = fmaf(w_o[k], W_f[(size_t)k * F + j], s);
+    weff[j] = s;
+  } else if (j == F) {
+    float s = b_o[0];
+    for (int k = 0; k < Hd; ++k) s = fmaf(w_o[k], b_f[k], s);
+    weff[F] = s;
+  }
+}
+
+constexpr int MAX_HEADS = 4;
+struct HeadPtrs {
+  const uint8_t* keep[MAX_HEADS];
+  float* logits[MAX_HEADS];
+  int n;
+};
+
+// highway mix + dropout + collapsed head; one warp per row (row = n*R + r).
+//   y = sig(h) relu(h) + (1 - sig(h)) x          (src/discriminator.py:55)
+__global__ void __launch_bounds__(256)
+head_fwd_kernel(const float* __restrict__ hpre, const float* __restrict__ pooled, int rows, int F,
+                const float* __restrict__ weff, float drop_scale, HeadPtrs hp) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float acc[MAX_HEADS] = {0.f, 0.f, 0.f, 0.f};
+  const size_t base = (size_t)row * F;
+  for (int j = lane; j < F; j += 32) {
+    const float h = hpre[base + j], x = pooled[base + j];
+    const float sg = sigmoidf_acc(h);
+    const float y = sg * fmaxf(h, 0.f) + (1.f - sg) * x;
+    const float yw = y * weff[j];
+#pragma unroll
+    for (int m = 0; m < MAX_HEADS; ++m)
+      if (m < hp.n) acc[m] += hp.keep[m] ? (hp.keep[m][base + j] ? yw : 0.f) : yw;
+  }
+#pragma unroll
+  for (int m = 0; m < MAX_HEADS; ++m) {
+    if (m < hp.n) {
+      const float s = warp_sum(acc[m]);
+      if (lane == 0) hp.logits[m][row] = s * (hp.keep[m] ? drop_scale : 1.f) + weff[F];
+    }
+  }
+}
+
+// backward of head + dropout + highway for one head.  Thread = feature column, CTA = row chunk.
+// Writes dh (gradient at the highway pre-activation) and the direct part of dx; accumulates
+// s[j] = sum_r dlogit_r * yd[r,j] and dbh[j] = sum_r dh[r,j] with one atomic per thread.
+__global__ void __launch_bounds__(256)
+head_bwd_kernel(const float* __restrict__ dlogit, const uint8_t* __restrict__ keep, float drop_scale,
+                const float* __restrict__ hpre, const float* __restrict__ pooled, int rows, int F,
+                const float* __restrict__ weff, int rows_per_cta, float* __restrict__ dh,
+                float* __restrict__ dx, float* __restrict__ s_acc, float* __restrict__ dbh_acc) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= F) return;
+  const int r0 = blockIdx.y * rows_per_cta;
+  const int r1 = min(rows, r0 + rows_per_cta);
+  const float wj = weff[j];
+  const float sc = keep ? drop_scale : 1.f;
+  float s = 0.f, sb = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    const size_t i = (size_t)r * F + j;
+    const float dl = dlogit[r] * sc;
+    const float kp = keep ? (keep[i] ? 1.f : 0.f) : 1.f;
+    const float h = hpre[i], x = pooled[i];
+    const float sg = sigmoidf_acc(h);
+    const float rl = fmaxf(h, 0.f);
+    const float y = sg * rl + (1.f - sg) * x;
+    const float dy = dl * kp * wj;
+    s = fmaf(dl * kp, y, s);
+    const float dhv = dy * (sg * (1.f - sg) * (rl - x) + (h > 0.f ? sg : 0.f));
+    dh[i] = dhv;
+    dx[i] = dy * (1.f - sg);
+    sb += dhv;
+  }
+  atomicAdd(s_acc + j, s);
+  atomicAdd(dbh_acc + j, sb);
+}
+
+// parameter gradients of the collapsed head, expanded back to the reference's tensors:
+//   dW_f[k,j] = w_o[k] s[j];  db_f[k] = w_o[k] S;  dw_o[k] = sum_j W_f[k,j] s[j] + b_f[k] S;
+//   db_o = S;  db_h[j] = dbh[j]          with S = sum_r dlogit_r.
+// grid = Hd CTAs (one per hidden unit k of feature2out).
+__global__ void __launch_bounds__(256)
+head_param_grads_kernel(const float* __restrict__ dlogit, int rows, const float* __restrict__ s_acc,
+                        const float* __restrict__ dbh_acc, const float* __restrict__ W_f,
+                        const float* __restrict__ b_f, const float* __restrict__ w_o, int F, int Hd,
+                        float beta, float* __restrict__ dW_f, float* __restrict__ db_f,
+                        float* __restrict__ dw_o, float* __restrict__ db_o, float* __restrict__ db_h) {
+  __shared__ float red[32];
+  const int k = blockIdx.x;
+  float S = 0.f;
+  for (int r = threadIdx.x; r < rows; r += blockDim.x) S += dlogit[r];
+  S = block_sum(S, red);
+  const float wo = w_o[k];
+  float dot = 0.f;
+  for (int j = threadIdx.x; j < F; j += blockDim.x) {
+    const float sj = s_acc[j];
+    const size_t i = (size_t)k * F + j;
+    dW_f[i] = (beta != 0.f ? beta * dW_f[i] : 0.f) + wo * sj;
+    dot = fmaf(W_f[i], sj, dot);
+    if (k == 0) db_h[j] = (beta != 0.f ? beta * db_h[j] : 0.f) + dbh_acc[j];
+  }
+  dot = block_sum(dot, red);
+  if (threadIdx.x == 0) {
+    db_f[k] = (beta != 0.f ? beta * db_f[k] : 0.f) + wo * S;
+    dw_o[k] = (beta != 0.f ? beta * dw_o[k] : 0.f) + dot + b_f[k] * S;
+    if (k == 0) db_o[0] = (beta != 0.f ? beta * db_o[0] : 0.f) + S;
+  }
+}
+
+__global__ void scale_kernel(float* __restrict__ p, size_t n, float a) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    p[i] = (a == 0.f) ? 0.f : p[i] * a;
+}
+int scale_inplace(float* p, size_t n, float a, cudaStream_t s) {
+  if (n == 0 || a == 1.f) return GIC_OK;
+  if (a == 0.f) {
+    cudaError_t e = cudaMemsetAsync(p, 0, n * sizeof(float), s);
+    if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); return GIC_ERR_CUDA; }
+    return GIC_OK;
+  }
+  scale_kernel<<<min(cdiv((long long)n, 256), 4 * num_sms()), 256, 0, s>>>(p, n, a);
+  return check_launch("scale_kernel");
+}
+
+// ---------------------------------------------------------------------------------------
+// host-side composition
+// ---------------------------------------------------------------------------------------
+struct DiscDims {
+  int N, L, V, De, R, es, F, Hd, ngroups, kmax;
+  size_t rows() const { return (size_t)N * R; }
+};
+
+static size_t align4(size_t x) { return (x + 3) & ~(size_t)3; }
+
+// saved-for-backward layout (floats): emb[N*L*De] | pooled[N*R*F] | hpre[N*R*F] | arg(u8)[N*R*F]
+size_t disc_saved_floats(int N, int L, int De, int R, int F) {
+  const size_t rows = (size_t)N * R;
+  return align4((size_t)N * L * De) + 2 * align4(rows * F) + align4((rows * F + 3) / 4);
+}
+// forward workspace: weff[F+1]
+size_t disc_fwd_workspace_floats(int F) { return align4((size_t)F + 1); }
+// backward workspace: weff[F+1] | dh[rows*F] | dx[rows*F] | s[F] | dbh[F] | demb[N*L*De]
+size_t disc_bwd_workspace_floats(int N, int L, int De, int R, int F) {
+  const size_t rows = (size_t)N * R;
+  return align4((size_t)F + 1) + 2 * align4(rows * F) + 2 * align4(F) + align4((size_t)N * L * De);
+}
+
+int disc_fill_groups(ConvGroups& g, int ngroups, const int* fs, const int* nf, const float* const* cw,
+                     const float* const* cb, float* const* dcw, float* const* dcb, int es) {
+  GIC_REQUIRE(ngroups >= 1 && ngroups <= MAX_GROUPS, GIC_ERR_SHAPE, "disc: 1..%d filter groups supported", MAX_GROUPS);
+  g.ngroups = ngroups; g.F = 0; g.kmax = 0;
+  for (int i = 0; i < MAX_GROUPS; ++i) { g.w[i] = g.b[i] = nullptr; g.dw[i] = g.db[i] = nullptr; g.f[i] = g.n[i] = g.col0[i] = 0; }
+  for (int i = 0; i < ngroups; ++i) {
+    GIC_REQUIRE(fs[i] >= 1 && nf[i] >= 1, GIC_ERR_SHAPE, "disc: bad filter group %d", i);
+    GIC_REQUIRE(cw[i] && cb[i], GIC_ERR_NULL, "disc: NULL conv weights for group %d", i);
+    g.w[i] = cw[i]; g.b[i] = cb[i];
+    g.dw[i] = dcw ? dcw[i] : nullptr; g.db[i] = dcb ? dcb[i] : nullptr;
+    g.f[i] = fs[i]; g.n[i] = nf[i]; g.col0[i] = g.F; g.F += nf[i];
+    if (fs[i] * es > g.kmax) g.kmax = fs[i] * es;
+  }
+  return GIC_OK;
+}
+
+int disc_forward(int mode, const float* inp_soft, const int64_t* ids, const DiscDims& d, const ConvGroups& g,
+                 const float* W_e, const float* W_h, const float* b_h, const float* W_f, const float* b_f,
+                 const float* W_o, const float* b_o, int n_heads, const uint8_t* const* keep, float drop_p,
+                 float* const* logits, float* saved, float* ws, cudaStream_t s) {
+  const size_t rows = d.rows();
+  float* emb = saved;
+  float* pooled = emb + align4((size_t)d.N * d.L * d.De);
+  float* hpre = pooled + align4(rows * d.F);
+  uint8_t* arg = reinterpret_cast<uint8_t*>(hpre + align4(rows * d.F));
+  float* weff = ws;
+  if (d.N == 0) return GIC_OK;
+  // 1. embedding
+  if (inp_soft) {
+    GIC_TRY(gemm(mode, false, true, d.N * d.L, d.De, d.V, 1.f, inp_soft, d.V, W_e, d.V, 0.f, emb, d.De, nullptr, s));
+  } else {
+    const int tot = d.N * d.L * d.De;
+    disc_embed_ids_kernel<<<cdiv(tot, 256), 256, 0, s>>>(ids, d.N * d.L, d.V, d.De, W_e, emb);
+    GIC_TRY(check_launch("disc_embed_ids_kernel"));
+  }
+  // 2. conv + relu + max-pool
+  {
+    const size_t smem = (((size_t)d.L * d.De + 3) & ~(size_t)3) * 4 + ((size_t)g.kmax + 2) * d.F * 4;
+    GIC_REQUIRE(smem <= 200 * 1024, GIC_ERR_SHAPE, "disc: conv tile needs %zu B of shared memory", smem);
+    GIC_REQUIRE(g.kmax <= 16, GIC_ERR_SHAPE, "disc: filter_size*emb_dim_single <= 16 supported");
+    const bool es1 = (d.es == 1) && (d.R % 4 == 0) && g.kmax <= 8;
+    GIC_REQUIRE(d.L <= 255, GIC_ERR_SHAPE, "disc: caption length <= 255 supported");
+    if (es1) {
+      cudaFuncSetAttribute(conv_pool_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      conv_pool_fwd_kernel<true><<<d.N, 256, smem, s>>>(emb, d.L, d.De, d.R, d.es, g, pooled, arg);
+    } else {
+      cudaFuncSetAttribute(conv_pool_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      conv_pool_fwd_kernel<false><<<d.N, 256, smem, s>>>(emb, d.L, d.De, d.R, d.es, g, pooled, arg);
+    }
+    GIC_TRY(check_launch("conv_pool_fwd_kernel"));
+  }
+  // 3. highway pre-activation
+  GIC_TRY(gemm(mode, false, true, (int)rows, d.F, d.F, 1.f, pooled, d.F, W_h, d.F, 0.f, hpre, d.F, b_h, s));
+  // 4. collapsed head
+  head_collapse_kernel<<<cdiv(d.F + 1, 256), 256, 0, s>>>(W_f, b_f, W_o, b_o, d.F, d.Hd, weff);
+  GIC_TRY(check_launch("head_collapse_kernel"));
+  HeadPtrs hp;
+  hp.n = n_heads;
+  for (int m = 0; m < MAX_HEADS; ++m) {
+    hp.keep[m] = (m < n_heads && keep) ? keep[m] : nullptr;
+    hp.logits[m] = (m < n_heads) ? logits[m] : nullptr;
+  }
+  head_fwd_kernel<<<cdiv((long long)rows, 8), 256, 0, s>>>(hpre, pooled, (int)rows, d.F, weff, 1.f / (1.f - drop_p), hp);
+  return check_launch("head_fwd_kernel");
+}
+
+int disc_backward(int mode, const float* dlogit, const uint8_t* keep, float drop_p, const float* inp_soft,
+                  const int64_t* ids, const DiscDims& d, ConvGroups& g, const float* W_e, const float* W_h,
+                  const float* W_f, const float* b_f, const float* W_o, const float* b_o, const float* saved,
+                  float* ws, float* dW_e, float* dW_h, float* db_h, float* dW_f, float* db_f, float* dW_o,
+                  float* db_o, float* dinp, int want_param, int accumulate, cudaStream_t s) {
+  const size_t rows = d.rows();
+  if (d.N == 0) return GIC_OK;
+  const float* emb = saved;
+  const float* pooled = emb + align4((size_t)d.N * d.L * d.De);
+  const float* hpre = pooled + align4(rows * d.F);
+  const uint8_t* arg = reinterpret_cast<const uint8_t*>(hpre + align4(rows * d.F));
+  float* weff = ws;
+  float* dh = weff + align4((size_t)d.F + 1);
+  float* dx = dh + align4(rows * d.F);
+  float* sacc = dx + align4(rows * d.F);
+  float* dbh = sacc + align4(d.F);
+  float* demb = dbh + align4(d.F);
+  const float beta = accumulate ? 1.f : 0.f;
+
+  head_collapse_kernel<<<cdiv(d.F + 1, 256), 256, 0, s>>>(W_f, b_f, W_o, b_o, d.F, d.Hd, weff);
+  GIC_TRY(check_launch("head_collapse_kernel"));
+  cudaMemsetAsync(sacc, 0, 2 * align4(d.F) * sizeof(float), s);
+  {
+    const int colb = cdiv(d.F, 256);
+    int chunks = max(1, (4 * num_sms()) / colb);
+    int rpc = cdiv((long long)rows, chunks);
+    chunks = cdiv((long long)rows, rpc);
+    head_bwd_kernel<<<dim3(colb, chunks), 256, 0, s>>>(dlogit, keep, 1.f / (1.f - drop_p), hpre, pooled, (int)rows,
+                                                      d.F, weff, rpc, dh, dx, sacc, dbh);
+    GIC_TRY(check_launch("head_bwd_kernel"));
+  }
+  if (want_param) {
+    head_param_grads_kernel<<<d.Hd, 256, 0, s>>>(dlogit, (int)rows, sacc, dbh, W_f, b_f, W_o, d.F, d.Hd, beta, dW_f,
+                                                db_f, dW_o, db_o, db_h);
+    GIC_TRY(check_launch("head_param_grads_kernel"));
+    // dW_h[F,F] (+)= dh^T [F, rows] * pooled [rows, F]
+    GIC_TRY(gemm(mode, true, false, d.F, d.F, (int)rows, 1.f, dh, d.F, pooled, d.F, beta, dW_h, d.F, nullptr, s));
+  }
+  // dx += dh * W_h        ([rows,F] x [F,F], W_h is [out,in] so this is the non-transposed product)
+  GIC_TRY(gemm(mode, false, false, (int)rows, d.F, d.F, 1.f, dh, d.F, W_h, d.F, 1.f, dx, d.F, nullptr, s));
+  // conv / pool backward
+  {
+    GIC_REQUIRE(d.F <= 256 * BWD_SLOTS, GIC_ERR_SHAPE, "disc bwd: at most %d feature columns supported", 256 * BWD_SLOTS);
+    GIC_REQUIRE(g.kmax <= BWD_KMAX, GIC_ERR_SHAPE, "disc bwd: filter_size*emb_dim_single <= %d supported", BWD_KMAX);
+    if (want_param && !accumulate) {
+      for (int i = 0; i < g.ngroups; ++i) {
+        cudaMemsetAsync(g.dw[i], 0, (size_t)g.n[i] * g.f[i] * d.es * sizeof(float), s);
+        cudaMemsetAsync(g.db[i], 0, (size_t)g.n[i] * sizeof(float), s);
+      }
+    }
+    const size_t smem = (size_t)2 * d.L * d.De * sizeof(float);
+    GIC_REQUIRE(smem <= 200 * 1024, GIC_ERR_SHAPE, "disc bwd: L*De too large for shared memory");
+    cudaFuncSetAttribute(conv_pool_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    const int grid = min(d.N, 2 * num_sms());
+    conv_pool_bwd_kernel<<<grid, 256, smem, s>>>(emb, pooled, arg, dx, d.N, d.L, d.De, d.R, d.es, g, want_param, demb);
+    GIC_TRY(check_launch("conv_pool_bwd_kernel"));
+  }
+  // embedding backward
+  if (want_param) {
+    if (inp_soft) {
+      // dW_e[De,V] (+)= demb^T [De, N*L] * inp [N*L, V]
+      GIC_TRY(gemm(mode, true, false, d.De, d.V, d.N * d.L, 1.f, demb, d.De, inp_soft, d.V, beta, dW_e, d.V, nullptr, s));
+    } else {
+      if (!accumulate) cudaMemsetAsync(dW_e, 0, (size_t)d.De * d.V * sizeof(float), s);
+      const int tot = d.N * d.L * d.De;
+      disc_embed_ids_bwd_kernel<<<cdiv(tot, 256), 256, 0, s>>>(ids, d.N * d.L, d.V, d.De, demb, dW_e);
+      GIC_TRY(check_launch("disc_embed_ids_bwd_kernel"));
+    }
+  }
+  if (dinp) {
+    // dinp[N*L, V] = demb [N*L, De] * W_e [De, V]
+    GIC_TRY(gemm(mode, false, false, d.N * d.L, d.V, d.De, 1.f, demb, d.De, W_e, d.V, 0.f, dinp, d.V, nullptr, s));
+  }
+  return GIC_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// C-ABI facing wrappers (argument validation + descriptor set-up)
+// ---------------------------------------------------------------------------------------
+static int disc_dims(DiscDims& d, int N, int L, int V, int De, int R, int Hd, const ConvGroups& g) {
+  GIC_REQUIRE(N >= 0 && L >= 1 && V >= 1 && De >= 1 && R >= 1 && Hd >= 1, GIC_ERR_SHAPE, "disc: bad shape");
+  GIC_REQUIRE(De % R == 0, GIC_ERR_SHAPE, "disc: disc_embed_dim %d not divisible by disc_num_rep %d", De, R);
+  d.N = N; d.L = L; d.V = V; d.De = De; d.R = R; d.es = De / R; d.F = g.F; d.Hd = Hd; d.ngroups = g.ngroups;
+  d.kmax = g.kmax;
+  for (int i = 0; i < g.ngroups; ++i)
+    GIC_REQUIRE(L >= g.f[i], GIC_ERR_SHAPE, "disc: caption length %d shorter than filter size %d", L, g.f[i]);
+  GIC_REQUIRE(L <= 255, GIC_ERR_SHAPE, "disc: caption length <= 255 supported");
+  return GIC_OK;
+}
+
+int disc_fwd_entry(int mode, const float* inp_soft, const int64_t* ids, int N, int L, int V, int De, int R,
+                   int n_groups, const int* fs, const int* nf, const float* W_e, const float* const* cw,
+                   const float* const* cb, const float* W_h, const float* b_h, const float* W_f, const float* b_f,
+                   int Hd, const float* W_o, const float* b_o, int n_heads, const uint8_t* const* keep, float drop_p,
+                   float* const* logits, float* saved, float* ws, cudaStream_t s) {
+  GIC_REQUIRE((inp_soft != nullptr) != (ids != nullptr), GIC_ERR_NULL, "disc_fwd: exactly one of inp_soft / ids");
+  GIC_REQUIRE(fs && nf && cw && cb && W_e && W_h && b_h && W_f && b_f && W_o && b_o && logits && saved && ws,
+              GIC_ERR_NULL, "disc_fwd: NULL pointer");
+  GIC_REQUIRE(n_heads >= 1 && n_heads <= MAX_HEADS, GIC_ERR_SHAPE, "disc_fwd: 1..%d heads", MAX_HEADS);
+  GIC_REQUIRE(drop_p >= 0.f && drop_p < 1.f, GIC_ERR_SHAPE, "disc_fwd: dropout p in [0,1)");
+  const int es = (R > 0 && De % R == 0) ? De / R : 1;
+  ConvGroups g;
+  GIC_TRY(disc_fill_groups(g, n_groups, fs, nf, cw, cb, nullptr, nullptr, es));
+  DiscDims d;
+  GIC_TRY(disc_dims(d, N, L, V, De, R, Hd, g));
+  for (int m = 0; m < n_heads; ++m) GIC_REQUIRE(logits[m], GIC_ERR_NULL, "disc_fwd: NULL logits[%d]", m);
+  return disc_forward(mode, inp_soft, ids, d, g, W_e, W_h, b_h, W_f, b_f, W_o, b_o, n_heads, keep, drop_p, logits,
+                      saved, ws, s);
+}
+
+int disc_bwd_entry(int mode, const float* dlogits, const uint8_t* keep, float drop_p, const float* inp_soft,
+                   const int64_t* ids, int N, int L, int V, int De, int R, int n_groups, const int* fs, const int* nf,
+                   const float* W_e, const float* const* cw, const float* const* cb, const float* W_h,
+                   const float* W_f, const float* b_f, int Hd, const float* W_o, const float* b_o, const float* saved,
+                   float* ws, float* dW_e, float* const* dcw, float* const* dcb, float* dW_h, float* db_h,
+                   float* dW_f, float* db_f, float* dW_o, float* db_o, float* dinp, int want_param, int accumulate,
+                   cudaStream_t s) {
+  GIC_REQUIRE((inp_soft != nullptr) != (ids != nullptr), GIC_ERR_NULL, "disc_bwd: exactly one of inp_soft / ids");
+  GIC_REQUIRE(dlogits && fs && nf && cw && cb && W_e && W_h && W_f && b_f && W_o && b_o && saved && ws, GIC_ERR_NULL,
+              "disc_bwd: NULL pointer");
+  GIC_REQUIRE(!want_param || (dW_e && dcw && dcb && dW_h && db_h && dW_f && db_f && dW_o && db_o), GIC_ERR_NULL,
+              "disc_bwd: NULL gradient buffer");
+  GIC_REQUIRE(!(dinp && ids), GIC_ERR_UNSUPPORTED, "disc_bwd: hard-token input has no gradient");
+  const int es = (R > 0 && De % R == 0) ? De / R : 1;
+  ConvGroups g;
+  GIC_TRY(disc_fill_groups(g, n_groups, fs, nf, cw, cb, want_param ? dcw : nullptr, want_param ? dcb : nullptr, es));
+  DiscDims d;
+  GIC_TRY(disc_dims(d, N, L, V, De, R, Hd, g));
+  return disc_backward(mode, dlogits, keep, drop_p, inp_soft, ids, d, g, W_e, W_h, W_f, b_f, W_o, b_o, saved, ws, dW_e,
+                       dW_h, db_h, dW_f, db_f, dW_o, db_o, dinp, want_param, accumulate, s);
+}
+
+}  // namespace gic

@@ -1,0 +1,94 @@
+// Internal helpers shared by the sm_100a kernels of libgic_b200.  Not part of the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/gic_b200.h"
+
+namespace gic {
+
+// status codes: GIC_OK / GIC_ERR_* macros from the public header
+
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+#define GIC_REQUIRE(cond, code, ...)            \
+  do {                                          \
+    if (!(cond)) {                              \
+      gic::set_error(__VA_ARGS__);              \
+      return (code);                            \
+    }                                           \
+  } while (0)
+
+#define GIC_TRY(expr)                           \
+  do {                                          \
+    int _rc = (expr);                           \
+    if (_rc != GIC_OK) return _rc;         \
+  } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int num_sms();
+
+// ---- fp32 GEMM (CUDA cores, exact-fp32 path) -------------------------------------------
+// C[M,N] = alpha * op(A)[M,K] * op(B)[K,N] + beta * C + bias[N]   (row-major everywhere)
+//   transA == 0: A is [M,K] with leading dim lda;  transA == 1: A is [K,M]
+//   transB == 0: B is [K,N] with leading dim ldb;  transB == 1: B is [N,K]  (nn.Linear weight)
+int gemm_f32(bool transA, bool transB, int M, int N, int K, float alpha, const float* A, int lda,
+             const float* B, int ldb, float beta, float* C, int ldc, const float* bias,
+             cudaStream_t stream);
+
+// Precision selector for the dense contractions of the hot path.
+enum GemmMode : int {
+  GEMM_FP32 = 0,     // CUDA-core FFMA, exact fp32 (parity mode)
+  GEMM_TF32 = 1,     // tcgen05 kind::tf32, single pass (throughput mode)
+  GEMM_TF32X3 = 2    // tcgen05 kind::tf32, 3-pass split (fp32-equivalent on tensor cores)
+};
+
+// Dispatching GEMM used by the path: routes to tcgen05 when the mode/shape allow, else FFMA.
+int gemm(int mode, bool transA, bool transB, int M, int N, int K, float alpha, const float* A,
+         int lda, const float* B, int ldb, float beta, float* C, int ldc, const float* bias,
+         cudaStream_t stream);
+
+// out[N] (+)= scale * sum_rows A[M,N]
+int colsum_f32(const float* A, int M, int N, int lda, float scale, bool accumulate, float* out,
+               cudaStream_t stream);
+
+// ---- device helpers ---------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// Block-wide sum; `red` is >= 32 floats of shared memory.  All threads get the result.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float r = (lane < nw) ? red[lane] : 0.0f;
+  r = warp_sum(r);
+  return r;
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float r = (lane < nw) ? red[lane] : -INFINITY;
+  r = warp_max(r);
+  return r;
+}
+
+}  // namespace gic

@@ -1,0 +1,153 @@
+// GAN losses with their backward seeds (src/utils.py:10-53) and the optimizer step
+// (clip_grad_norm_ + Adam, src/training.py:194-199 with the Adam ctor at :24-26).
+#include "gic_internal.cuh"
+
+namespace gic {
+
+enum LossType : int { LOSS_STANDARD = 0, LOSS_JS = 1, LOSS_KL = 2, LOSS_HINGE = 3, LOSS_TV = 4, LOSS_RSGAN = 5 };
+
+// BCEWithLogits(x, y) = max(x,0) - x*y + log1p(exp(-|x|))
+__device__ __forceinline__ float bce(float x, float y) { return fmaxf(x, 0.f) - x * y + log1pf(expf(-fabsf(x))); }
+
+// One CTA.  losses[0] = g_loss, losses[1] = d_loss (get_losses returns g first, utils.py:53).
+// Seeds: dd_real = d d_loss / d d_out_real, dd_fake = d d_loss / d d_out_fake,
+//        dg_out = d g_loss / d g_out.  (rsgan: g_loss only sees detached D outputs -> dg_out = 0.)
+__global__ void __launch_bounds__(1024)
+gan_loss_kernel(int type, const float* __restrict__ d_real, const float* __restrict__ d_fake,
+                const float* __restrict__ g_out, int n, float* __restrict__ losses,
+                float* __restrict__ dd_real, float* __restrict__ dd_fake, float* __restrict__ dg_out) {
+  __shared__ float red[32];
+  const float inv = 1.0f / (float)n;
+  float sd = 0.f, sg = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float r = d_real[i], f = d_fake[i], g = g_out[i];
+    float gr = 0.f, gf = 0.f, gg = 0.f;
+    switch (type) {
+      case LOSS_STANDARD:
+      case LOSS_JS:
+      case LOSS_KL:
+        sd += bce(r, 1.f) + bce(f, 0.f);
+        gr = (sigmoidf_acc(r) - 1.f) * inv;
+        gf = sigmoidf_acc(f) * inv;
+        if (type == LOSS_STANDARD) { sg += bce(g, 1.f); gg = (sigmoidf_acc(g) - 1.f) * inv; }
+        else if (type == LOSS_JS) { sg -= bce(g, 0.f); gg = -sigmoidf_acc(g) * inv; }
+        else { sg -= g; gg = -inv; }
+        break;
+      case LOSS_HINGE:   // Q4: F.relu intent
+        sd += fmaxf(1.f - r, 0.f) + fmaxf(1.f + f, 0.f);
+        gr = (1.f - r > 0.f) ? -inv : 0.f;
+        gf = (1.f + f > 0.f) ? inv : 0.f;
+        sg -= g; gg = -inv;
+        break;
+      case LOSS_TV: {    // Q4: torch.tanh intent
+        const float tr = tanhf(r), tf = tanhf(f), tg = tanhf(g);
+        sd += tf - tr;
+        gr = -(1.f - tr * tr) * inv;
+        gf = (1.f - tf * tf) * inv;
+        sg -= tg; gg = -(1.f - tg * tg) * inv;
+        break;
+      }
+      case LOSS_RSGAN: {
+        const float x = r - f;
+        sd += bce(x, 1.f);
+        gr = (sigmoidf_acc(x) - 1.f) * inv;
+        gf = -gr;
+        sg += bce(-x, 1.f);
+        gg = 0.f;
+        break;
+      }
+    }
+    if (dd_real) dd_real[i] = gr;
+    if (dd_fake) dd_fake[i] = gf;
+    if (dg_out) dg_out[i] = gg;
+  }
+  sd = block_sum(sd, red);
+  sg = block_sum(sg, red);
+  if (threadIdx.x == 0) { losses[0] = sg * inv; losses[1] = sd * inv; }
+}
+
+int gan_loss(int type, const float* d_real, const float* d_fake, const float* g_out, int n, float* losses,
+             float* dd_real, float* dd_fake, float* dg_out, cudaStream_t s) {
+  GIC_REQUIRE(type >= 0 && type <= LOSS_RSGAN, GIC_ERR_UNSUPPORTED, "Divergence type %d is not implemented", type);
+  GIC_REQUIRE(n > 0, GIC_ERR_SHAPE, "gan_loss: empty batch");
+  GIC_REQUIRE(d_real && d_fake && g_out && losses, GIC_ERR_NULL, "gan_loss: NULL operand");
+  gan_loss_kernel<<<1, 1024, 0, s>>>(type, d_real, d_fake, g_out, n, losses, dd_real, dd_fake, dg_out);
+  return check_launch("gan_loss_kernel");
+}
+
+// ---------------------------------------------------------------------------------------
+// global L2 norm (squared, accumulated into *out which the caller zeroes) over a flat buffer
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sqnorm_kernel(const float* __restrict__ g, size_t n, float* __restrict__ out) {
+  __shared__ float red[32];
+  float s = 0.f;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t n4 = n / 4;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = g4[i];
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  for (size_t i = n4 * 4 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += stride) s += g[i] * g[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(out, s);
+}
+
+__global__ void sqnorm_scalar_kernel(const float* __restrict__ g, size_t n, float* __restrict__ out) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) s += g[i] * g[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(out, s);
+}
+
+int grad_sqnorm(const float* g, size_t n, float* out, cudaStream_t s) {
+  if (n == 0) return GIC_OK;
+  GIC_REQUIRE(g && out, GIC_ERR_NULL, "grad_sqnorm: NULL operand");
+  const int grid = min(cdiv((long long)n, 1024), 2 * num_sms());
+  if (aligned16(g)) sqnorm_kernel<<<grid, 256, 0, s>>>(g, n, out);
+  else sqnorm_scalar_kernel<<<grid, 256, 0, s>>>(g, n, out);
+  return check_launch("sqnorm_kernel");
+}
+
+// ---------------------------------------------------------------------------------------
+// fused clip + Adam over a flat parameter buffer.
+//   coef = min(1, max_norm / (sqrt(*sqnorm) + 1e-6))          (clip_grad_norm_)
+//   g' = coef*g; m = b1 m + (1-b1) g'; v = b2 v + (1-b2) g'^2
+//   p -= (lr / (1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps)    (torch.optim.Adam)
+// sqnorm is read from device memory so the step needs no host sync; max_norm <= 0 disables
+// clipping.  grad_scale pre-multiplies g (1/world for a summed data-parallel all-reduce).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                 float* __restrict__ v, size_t n, const float* __restrict__ sqnorm, float max_norm,
+                 float grad_scale, float lr_over_bc1, float inv_sqrt_bc2, float b1, float b2, float eps) {
+  float coef = grad_scale;
+  if (max_norm > 0.f && sqnorm) {
+    const float nrm = sqrtf(*sqnorm) * grad_scale;
+    coef *= fminf(1.f, max_norm / (nrm + 1e-6f));
+  }
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float gi = g[i] * coef;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= lr_over_bc1 * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+  }
+}
+
+int clip_adam(float* p, const float* g, float* m, float* v, size_t n, const float* sqnorm, float max_norm,
+              float grad_scale, int step, float lr, float b1, float b2, float eps, cudaStream_t s) {
+  if (n == 0) return GIC_OK;
+  GIC_REQUIRE(p && g && m && v, GIC_ERR_NULL, "clip_adam: NULL operand");
+  GIC_REQUIRE(step >= 1, GIC_ERR_SHAPE, "clip_adam: step must be >= 1");
+  const double bc1 = 1.0 - pow((double)b1, step), bc2 = 1.0 - pow((double)b2, step);
+  const int grid = min(cdiv((long long)n, 256), 8 * num_sms());
+  clip_adam_kernel<<<grid, 256, 0, s>>>(p, g, m, v, n, sqnorm, max_norm, grad_scale, (float)(lr / bc1),
+                                        (float)(1.0 / sqrt(bc2)), b1, b2, eps);
+  return check_launch("clip_adam_kernel");
+}
+
+}  // namespace gic

@@ -1,0 +1,280 @@
+"""Adversarial training driver with the reference's ``GANInstructor`` surface (src/training.py:15-235)
+for the hot path: ``adv_loop`` body (:136-183), ``optimize`` (:194-199), ``update_temperature`` (:190-191).
+
+``adv_step`` is the fused B200 path: it calls the C ABI directly (no autograd graph), shares the
+discriminator trunk between ``disc(fake)`` and ``disc(gen_captions)`` (same values, different dropout
+masks, src/training.py:163-164), never materialises ``F.one_hot(real)`` (:158), writes gradients
+straight into flat buffers, and finishes with fused clip + Adam.  Ordering follows the Q1 fix
+(SURVEY.md section 0.1): both gradients are taken on the pre-update weights, then D and G step.
+
+Data parallel: one process per GPU, each rank owns B/world rows; the only exchange is an all-reduce
+(sum) of the flat G and D gradient buffers before the clip."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+import gic_b200
+from . import _lib
+from .discriminator import Discriminator, disc_fwd_raw
+from .generator import Generator
+from .utils import get_fixed_temperature, get_losses
+
+
+class FlatParams:
+    """Re-homes a list of parameters into one contiguous fp32 buffer (params become views), with matching
+    flat grad / Adam-moment buffers.  state_dict keys and nn.Parameter identities are unchanged."""
+
+    def __init__(self, params, device):
+        self.params = [p for p in params]
+        self.sizes = [p.numel() for p in self.params]
+        self.offsets = []
+        off = 0
+        for n in self.sizes:
+            self.offsets.append(off)
+            off += (n + 3) & ~3          # keep every tensor 16-byte aligned inside the flat buffer
+        self.n = off
+        self.flat = torch.zeros(self.n, device=device)
+        self.grad = torch.zeros(self.n, device=device)
+        self.m = torch.zeros(self.n, device=device)
+        self.v = torch.zeros(self.n, device=device)
+        self.step = 0
+        for p, o, n in zip(self.params, self.offsets, self.sizes):
+            view = self.flat[o:o + n].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+        self._index = {id(p): i for i, p in enumerate(self.params)}
+
+    def g(self, p):
+        i = self._index[id(p)]
+        return self.grad[self.offsets[i]:self.offsets[i] + self.sizes[i]].view(p.shape)
+
+    def homed(self):
+        return all(p.data_ptr() == self.flat.data_ptr() + 4 * o for p, o in zip(self.params, self.offsets))
+
+
+class GANInstructor:
+    def __init__(self, args, train_dataset=None, dev_dataset=None, device=None):
+        _lib.lib()        # fail loudly at construction if the CUDA library is missing
+        self.args = args
+        self.device = torch.device(device if device is not None else args.device)
+        self.gen = Generator(args).to(self.device)
+        self.disc = Discriminator(args).to(self.device)
+        self.train_dataset, self.dev_dataset = train_dataset, dev_dataset
+        self.cgan = (args.conditional_gan == 1)
+        self.adv_epoch = -1
+        self.pretrain_steps = self.gen_steps = self.disc_steps = 0
+        self._flat_g: Optional[FlatParams] = None
+        self._flat_d: Optional[FlatParams] = None
+        self._cache = {}
+        self.world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size()
+
+    # ---- reference-compatible pieces -------------------------------------------------------------
+    def update_temperature(self, i, N):
+        self.gen.decoder.temperature = get_fixed_temperature(self.args.temperature, i, N, self.args.temp_adpt)
+
+    def optimize(self, opt, loss, model=None, retain_graph=False):
+        """Autograd-driven variant kept for drop-in use with torch optimizers (src/training.py:194-199)."""
+        opt.zero_grad()
+        loss.backward(retain_graph=retain_graph)
+        if model is not None:
+            torch.nn.utils.clip_grad_norm_(model.parameters(), self.args.clip_norm)
+        opt.step()
+
+    # ---- flat buffers ---------------------------------------------------------------------------
+    def _gen_params(self):
+        dec = self.gen.decoder
+        ps = [dec.embed.weight, *dec.lstm_params(), dec.linear.weight, dec.linear.bias]
+        if self.cgan:
+            enc = self.gen.encoder
+            ps += [enc.linear.weight, enc.linear.bias, enc.bn.weight, enc.bn.bias]
+        return ps
+
+    def _disc_params(self):
+        d = self.disc
+        ps = [d.embeddings.weight]
+        for c in d.convs:
+            ps += [c.weight, c.bias]
+        ps += [d.highway.weight, d.highway.bias, d.feature2out.weight, d.feature2out.bias, d.out2logits.weight,
+               d.out2logits.bias]
+        return ps
+
+    def _ensure_flat(self):
+        if self._flat_g is None or not self._flat_g.homed():
+            self._flat_g = FlatParams(self._gen_params(), self.device)
+        if self._flat_d is None or not self._flat_d.homed():
+            self._flat_d = FlatParams(self._disc_params(), self.device)
+
+    def _buf(self, key, numel, dtype=torch.float32):
+        t = self._cache.get(key)
+        if t is None or t.numel() < numel or t.dtype != dtype:
+            t = torch.empty(int(numel), dtype=dtype, device=self.device)
+            self._cache[key] = t
+        return t
+
+    # ---- the fused adversarial step ---------------------------------------------------------------
+    @torch.no_grad()
+    def adv_step(self, captions, pooled=None, u=None, keep=None, train=True, forced_ids=None, loss_type=None,
+                 update=True):
+        """One adversarial step on a batch (src/training.py:136-169).
+
+        captions [B,L] int64 (collate contract); pooled [B,feature_dim] CNN features when conditional;
+        u [L,B,V] uniforms and keep [3,B*R,F] dropout keep-masks are drawn on-device when omitted.
+        Returns a dict with g_loss/d_loss (device scalars), ids, probs and the D logits."""
+        _lib.require_cuda()
+        lib = _lib.lib()
+        a, dev = self.args, self.device
+        mode = gic_b200.get_gemm_mode()
+        loss_type = loss_type or a.adv_loss_type
+        if loss_type not in _lib.LOSS_TYPES:
+            raise NotImplementedError("Divergence '%s' is not implemented" % loss_type)
+        self._ensure_flat()
+        fg, fd = self._flat_g, self._flat_d
+        dec, disc = self.gen.decoder, self.disc
+        captions = captions.to(dev).long().contiguous()
+        B, L = captions.shape
+        V, E, H, layers = a.vocab_size, a.gen_embed_dim, a.gen_hidden_dim, a.gen_num_layers
+        De, R, Fd = a.disc_embed_dim, a.disc_num_rep, sum(a.disc_num_filters)
+        fsz, nfl = list(a.disc_filter_sizes), list(a.disc_num_filters)
+        T = float(dec.temperature)
+        stream = _lib.stream()
+        P = _lib.ptr
+
+        # -- step-0 input (:144-147)
+        if self.cgan:
+            enc = self.gen.encoder
+            pooled = pooled.to(dev).float().contiguous()
+            Fin = pooled.shape[1]
+            lin, mean, rstd = self._buf("enc_lin", B * E).view(B, E), self._buf("enc_mean", E), self._buf("enc_rstd", E)
+            feats = self._buf("feats", B * E).view(B, E)
+            _lib.check(lib.gic_encoder_fwd(mode, P(pooled), B, Fin, E, P(enc.linear.weight), P(enc.linear.bias),
+                                           P(enc.bn.weight), P(enc.bn.bias), enc.bn.eps, P(lin), P(mean), P(rstd),
+                                           P(feats), stream), "gic_encoder_fwd")
+        else:
+            feats = dec.embed.weight[1].expand(B, E).contiguous()
+        # -- Decoder.sample (:150)
+        if u is None:
+            u = torch.rand(L, B, V, device=dev)
+        u = u.to(dev).float().contiguous()
+        probs = self._buf("probs", B * L * V).view(B, L, V)
+        ids = torch.empty(B, L, dtype=torch.int64, device=dev)
+        dsaved = self._buf("dec_saved", lib.gic_decode_saved_floats(B, L, E, H, layers))
+        dws = self._buf("dec_ws", lib.gic_decode_fwd_workspace_floats(B, V, H))
+        lp = dec.lstm_params()
+        W_ih, W_hh, b_ih, b_hh = lp[0::4], lp[1::4], lp[2::4], lp[3::4]
+        if forced_ids is not None:
+            forced_ids = forced_ids.to(dev).long().contiguous()
+        _lib.check(lib.gic_decode_sample_fwd(mode, P(feats), P(dec.embed.weight), _lib.ptr_array(W_ih),
+                                             _lib.ptr_array(W_hh), _lib.ptr_array(b_ih), _lib.ptr_array(b_hh),
+                                             P(dec.linear.weight), P(dec.linear.bias), P(u), T, 0, P(forced_ids), B, L,
+                                             V, E, H, layers, P(probs), P(ids), P(dsaved), P(dws), stream),
+                   "gic_decode_sample_fwd")
+        # -- discriminator: real (hard tokens) and fake/gen (shared trunk, two dropout masks) (:158-164)
+        if train:
+            if keep is None:
+                keep = torch.rand(3, B * R, Fd, device=dev) >= disc.dropout.p
+            keep = keep.to(dev).to(torch.uint8).contiguous()
+            k0, k1, k2 = keep[0], keep[1], keep[2]
+        else:
+            k0 = k1 = k2 = None
+        cw = [c.weight for c in disc.convs]
+        cb = [c.bias for c in disc.convs]
+        dW = (disc.embeddings.weight, cw, cb, disc.highway.weight, disc.highway.bias, disc.feature2out.weight,
+              disc.feature2out.bias, disc.out2logits.weight, disc.out2logits.bias)
+        drop_p = disc.dropout.p
+        (d_real,), saved_r = disc_fwd_raw(lib, mode, None, captions, B, L, V, De, R, fsz, nfl, *dW, [k0], drop_p, dev)
+        (d_fake, g_out), saved_f = disc_fwd_raw(lib, mode, probs, None, B, L, V, De, R, fsz, nfl, *dW, [k1, k2],
+                                                drop_p, dev)
+        # -- losses + seeds (:165)
+        n = B * R
+        losses = torch.empty(2, device=dev)
+        seeds = self._buf("seeds", 3 * n).view(3, n)
+        _lib.check(lib.gic_gan_loss_fwd_bwd(_lib.LOSS_TYPES[loss_type], P(d_real), P(d_fake), P(g_out), n, P(losses),
+                                            P(seeds[0]), P(seeds[1]), P(seeds[2]), stream), "gic_gan_loss_fwd_bwd")
+        out = dict(g_loss=losses[0], d_loss=losses[1], ids=ids, probs=probs, d_real=d_real, d_fake=d_fake,
+                   g_out=g_out, features=feats)
+        if not train:
+            return out
+
+        # -- backward: D parameter gradients from (real, fake); generator gradients through D(gen) (:168-169, Q1)
+        bws = self._buf("disc_bws", lib.gic_disc_bwd_workspace_floats(B, L, De, R, Fd))
+        g = fd.g
+        dcw, dcb = [g(c.weight) for c in disc.convs], [g(c.bias) for c in disc.convs]
+
+        def disc_bwd(seed, kp, inp, idz, saved, want_param, acc, dinp):
+            _lib.check(lib.gic_disc_bwd(mode, P(seed), P(kp), drop_p, P(inp), P(idz), B, L, V, De, R, len(fsz),
+                                        _lib.int_array(fsz), _lib.int_array(nfl), P(disc.embeddings.weight),
+                                        _lib.ptr_array(cw), _lib.ptr_array(cb), P(disc.highway.weight),
+                                        P(disc.feature2out.weight), P(disc.feature2out.bias),
+                                        disc.feature2out.weight.shape[0], P(disc.out2logits.weight),
+                                        P(disc.out2logits.bias), P(saved), P(bws), P(g(disc.embeddings.weight)),
+                                        _lib.ptr_array(dcw), _lib.ptr_array(dcb), P(g(disc.highway.weight)),
+                                        P(g(disc.highway.bias)), P(g(disc.feature2out.weight)),
+                                        P(g(disc.feature2out.bias)), P(g(disc.out2logits.weight)),
+                                        P(g(disc.out2logits.bias)), P(dinp), want_param, acc, stream), "gic_disc_bwd")
+
+        disc_bwd(seeds[0], k0, None, captions, saved_r, 1, 0, None)
+        disc_bwd(seeds[1], k1, probs, None, saved_f, 1, 1, None)
+        g_has_grad = loss_type != "rsgan"          # A14: rsgan's g_loss only sees detached D outputs
+        if g_has_grad:
+            dprobs = self._buf("dprobs", B * L * V).view(B, L, V)
+            disc_bwd(seeds[2], k2, probs, None, saved_f, 0, 0, dprobs)
+            gg = fg.g
+            gws = self._buf("dec_bws", lib.gic_decode_bwd_workspace_floats(B, L, V, E, H, layers))
+            dfeat = self._buf("dfeat", B * E).view(B, E)
+            fed = ids if forced_ids is None else forced_ids
+            _lib.check(lib.gic_decode_sample_bwd(
+                mode, P(dprobs), P(probs), P(fed), P(dec.embed.weight), _lib.ptr_array(W_ih), _lib.ptr_array(W_hh),
+                P(dec.linear.weight), T, 0, B, L, V, E, H, layers, P(dsaved), P(gws), P(gg(dec.embed.weight)),
+                _lib.ptr_array([gg(w) for w in W_ih]), _lib.ptr_array([gg(w) for w in W_hh]),
+                _lib.ptr_array([gg(w) for w in b_ih]), _lib.ptr_array([gg(w) for w in b_hh]),
+                P(gg(dec.linear.weight)), P(gg(dec.linear.bias)), P(dfeat), 0, stream), "gic_decode_sample_bwd")
+            if self.cgan:
+                enc = self.gen.encoder
+                _lib.check(lib.gic_encoder_bwd(mode, P(dfeat), P(pooled), P(lin), P(mean), P(rstd),
+                                               P(enc.linear.weight), P(enc.bn.weight), B, pooled.shape[1], E,
+                                               P(self._buf("enc_dlin", B * E)), P(gg(enc.linear.weight)),
+                                               P(gg(enc.linear.bias)), P(gg(enc.bn.weight)), P(gg(enc.bn.bias)), 0,
+                                               stream), "gic_encoder_bwd")
+            else:
+                gg(dec.embed.weight)[1] += dfeat.sum(0)      # features = embed(<S>) for every row (:147)
+        # -- data-parallel exchange: summed gradients, averaged inside the optimizer kernel
+        if self.world > 1:
+            torch.distributed.all_reduce(fd.grad)
+            if g_has_grad:
+                torch.distributed.all_reduce(fg.grad)
+        out["d_sqnorm"] = self._clip_adam(fd, a.disc_lr, update)
+        if g_has_grad:
+            out["g_sqnorm"] = self._clip_adam(fg, a.gen_lr, update)
+        return out
+
+    def _clip_adam(self, fp: FlatParams, lr: float, update: bool):
+        lib = _lib.lib()
+        sq = torch.zeros(1, device=self.device)
+        stream = _lib.stream()
+        _lib.check(lib.gic_grad_sqnorm(_lib.ptr(fp.grad), fp.n, _lib.ptr(sq), stream), "gic_grad_sqnorm")
+        if update:
+            fp.step += 1
+            _lib.check(lib.gic_clip_adam(_lib.ptr(fp.flat), _lib.ptr(fp.grad), _lib.ptr(fp.m), _lib.ptr(fp.v), fp.n,
+                                         _lib.ptr(sq), float(self.args.clip_norm), 1.0 / self.world, fp.step,
+                                         float(lr), 0.9, 0.999, 1e-8, stream), "gic_clip_adam")
+        return sq
+
+    def adv_loop(self, what, batches, total_batches=None):
+        """Body of the reference's adv_loop over an iterable of (pooled_or_None, captions) batches."""
+        gen_loss, disc_loss = [], []
+        nb = total_batches or (len(batches) if hasattr(batches, "__len__") else 1)
+        for i, (pooled, captions) in enumerate(batches, start=1):
+            r = self.adv_step(captions, pooled=pooled, train=(what == "train"))
+            gen_loss.append(r["g_loss"])
+            disc_loss.append(r["d_loss"])
+            self.gen_steps += 1
+            self.disc_steps += 1
+            self.update_temperature(self.adv_epoch + i / nb, self.args.adv_epochs)      # :183
+        g = torch.stack(gen_loss).mean().item() if gen_loss else float("nan")
+        d = torch.stack(disc_loss).mean().item() if disc_loss else float("nan")
+        return g, d

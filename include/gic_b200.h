@@ -1,0 +1,158 @@
+/*
+ * gic_b200.h -- C ABI of libgic_b200.so: the B200 (sm_100a) adversarial-captioning hot path.
+ *
+ * Drop-in boundary for kawshik8/GAN-Image-Captioning.  The reference is pure Python/PyTorch
+ * and has no FFI of its own; every entry point below replaces the body of one reference
+ * function (cited per function, paths relative to the reference checkout) and is what a
+ * ctypes binding inside that function would call (see INTEGRATION.md for the stubs).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all tensors are dense row-major fp32 unless stated;
+ *    token ids are int64 (torch.long); dropout keep-masks are uint8 (0 = dropped, 1 = kept).
+ *  - every pointer is a DEVICE pointer owned by the caller (PyTorch's caching allocator);
+ *    the library never allocates, frees or synchronises; outputs, "saved" (for backward) and
+ *    "workspace" buffers are caller-allocated with the *_floats() sizes below.
+ *  - kernels are enqueued on `stream` (a cudaStream_t); no hidden host syncs.
+ *  - return value: 0 = ok, non-zero = error (gic_last_error() gives the message); the Python
+ *    shim raises RuntimeError / NotImplementedError like the reference's own error paths
+ *    (src/utils.py:51).
+ *  - all randomness is an input: Gumbel uniforms u[L,B,V], dropout keep-masks.
+ *  - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef GIC_B200_H_
+#define GIC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* gic_stream_t; /* cudaStream_t */
+
+/* status codes */
+#define GIC_OK 0
+#define GIC_ERR_SHAPE 1
+#define GIC_ERR_NULL 2
+#define GIC_ERR_CUDA 3
+#define GIC_ERR_WORKSPACE 4
+#define GIC_ERR_ARCH 5
+#define GIC_ERR_UNSUPPORTED 6
+
+/* precision of the dense contractions (see DESIGN.md "GEMM modes") */
+#define GIC_GEMM_FP32 0   /* CUDA-core FFMA, exact fp32                                   */
+#define GIC_GEMM_TF32 1   /* tcgen05 kind::tf32, one pass, fp32 accumulate in TMEM         */
+#define GIC_GEMM_TF32X3 2 /* tcgen05 kind::tf32, 3-pass hi/lo split: fp32-equivalent       */
+
+/* adversarial loss types, src/utils.py:14-50 */
+#define GIC_LOSS_STANDARD 0
+#define GIC_LOSS_JS 1
+#define GIC_LOSS_KL 2
+#define GIC_LOSS_HINGE 3
+#define GIC_LOSS_TV 4
+#define GIC_LOSS_RSGAN 5
+
+int gic_version(void);
+const char* gic_last_error(void);
+/* 0 if the current device is an sm_100 part, GIC_ERR_ARCH / GIC_ERR_CUDA otherwise. */
+int gic_check_device(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches). */
+unsigned long long gic_launch_count(void);
+
+/* ---- dense contraction (nn.Linear / its autograd; src/generator.py:64,68, src/discriminator.py:40,53) ----
+ * C[M,N] = alpha * op(A) * op(B) + beta * C + bias[N];  transA: A stored [K,M]; transB: B stored [N,K]. */
+int gic_gemm(int mode, int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
+             const float* B, int ldb, float beta, float* C, int ldc, const float* bias, gic_stream_t stream);
+
+/* ---- Encoder.linear + Encoder.bn, train-mode batch statistics (src/generator.py:15-16,23-24) ---- */
+int gic_encoder_fwd(int mode, const float* pooled /*[B,Fin]*/, int B, int Fin, int E, const float* W /*[E,Fin]*/,
+                    const float* b, const float* gamma, const float* beta, float eps,
+                    float* lin_out /*[B,E] saved*/, float* save_mean /*[E]*/, float* save_rstd /*[E]*/,
+                    float* features /*[B,E]*/, gic_stream_t stream);
+int gic_encoder_bwd(int mode, const float* dfeatures /*[B,E]*/, const float* pooled, const float* lin_out,
+                    const float* save_mean, const float* save_rstd, const float* W, const float* gamma, int B,
+                    int Fin, int E, float* dlin_ws /*[B,E] workspace*/, float* dW, float* db, float* dgamma,
+                    float* dbeta, int accumulate, gic_stream_t stream);
+
+/* ---- one fused sampling step (K4): Gumbel + temperature + vocab softmax + first-max + embedding gather.
+ * Decoder.add_gumbel + F.softmax + pred.max(1) + self.embed (src/generator.py:68-76, 84-96).
+ * pretrain != 0: out row = raw logits, choice = argmax softmax(logits) (src/generator.py:63-66); u unused. */
+int gic_sample_step(int pretrain, const float* logits /*[B,V]*/, const float* u /*[B,V]*/, float temperature,
+                    int B, int V, int L, int t, float* out /*[B,L,V], row (b,t) written*/,
+                    int64_t* ids /*[B,L], (b,t) written*/, const int64_t* forced_ids /*[B,L] or NULL*/,
+                    const float* embed /*[V,E]*/, int E, float* x_next /*[B,E] or NULL*/, gic_stream_t stream);
+
+/* ---- Decoder.sample (src/generator.py:55-81) ----
+ * features[B,E] is the step-0 LSTM input; per-layer weight pointers follow nn.LSTM's state_dict
+ * (weight_ih_l{k}[4H,In], weight_hh_l{k}[4H,H], bias_ih_l{k}[4H], bias_hh_l{k}[4H], gate order i,f,g,o).
+ * u[L,B,V]: uniforms in [0,1) (ignored when pretrain).  forced_ids: teacher forcing for parity runs
+ * (token fed back at step t is forced_ids[b,t]; ids still receives this run's own choices).
+ * out[B,L,V]: soft captions (or logits when pretrain); ids[B,L]. */
+size_t gic_decode_saved_floats(int B, int L, int E, int H, int layers);
+size_t gic_decode_fwd_workspace_floats(int B, int V, int H);
+int gic_decode_sample_fwd(int mode, const float* features, const float* W_emb /*[V,E]*/,
+                          const float* const* W_ih, const float* const* W_hh, const float* const* b_ih,
+                          const float* const* b_hh, const float* W_out /*[V,H]*/, const float* b_out /*[V]*/,
+                          const float* u, float temperature, int pretrain, const int64_t* forced_ids, int B, int L,
+                          int V, int E, int H, int layers, float* out, int64_t* ids, float* saved,
+                          float* workspace, gic_stream_t stream);
+
+/* Backward of Decoder.sample: given dout[B,L,V] (gradient w.r.t. the soft captions, or w.r.t. the logits when
+ * pretrain) produce the gradients of every decoder parameter and of `features`.
+ * fed_ids[B,L]: the tokens that were fed back (ids, or forced_ids when teacher forcing was used).
+ * accumulate != 0 adds into the gradient buffers, else overwrites.  dfeatures may be NULL. */
+size_t gic_decode_bwd_workspace_floats(int B, int L, int V, int E, int H, int layers);
+int gic_decode_sample_bwd(int mode, const float* dout, const float* out, const int64_t* fed_ids,
+                          const float* W_emb, const float* const* W_ih, const float* const* W_hh,
+                          const float* W_out, float temperature, int pretrain, int B, int L, int V, int E, int H,
+                          int layers, const float* saved, float* workspace, float* dW_emb, float* const* dW_ih,
+                          float* const* dW_hh, float* const* db_ih, float* const* db_hh, float* dW_out,
+                          float* db_out, float* dfeatures, int accumulate, gic_stream_t stream);
+
+/* ---- Discriminator.forward (src/discriminator.py:34-62) ----
+ * Exactly one of inp_soft[N,L,V] (soft / dense one-hot captions) and ids[N,L] (hard tokens: Linear of a one-hot is
+ * a column pick, replacing F.one_hot at src/training.py:158) is non-NULL.  De = disc_embed_dim, R = disc_num_rep,
+ * emb_dim_single = De/R.  conv_w[g] is convs.g.weight [n_g,1,f_g,De/R], conv_b[g] its bias.  The trunk
+ * (embedding, conv+ReLU+max-pool, highway) is evaluated once and n_heads (<= 4) dropout masks are applied to it:
+ * logits[h][N*R] = head(dropout_h(trunk)), keep[h] == NULL meaning eval mode for that head.  The reference's three
+ * calls per step (real, fake, gen; src/training.py:162-164) are 2 trunks: real (1 head) and fake (2 heads). */
+size_t gic_disc_saved_floats(int N, int L, int De, int R, int F);
+size_t gic_disc_fwd_workspace_floats(int F);
+int gic_disc_fwd(int mode, const float* inp_soft, const int64_t* ids, int N, int L, int V, int De, int R,
+                 int n_groups, const int* filter_sizes, const int* num_filters, const float* W_e /*[De,V]*/,
+                 const float* const* conv_w, const float* const* conv_b, const float* W_h /*[F,F]*/,
+                 const float* b_h, const float* W_f /*[Hd,F]*/, const float* b_f, int Hd, const float* W_o /*[1,Hd]*/,
+                 const float* b_o, int n_heads, const uint8_t* const* keep, float drop_p, float* const* logits,
+                 float* saved, float* workspace, gic_stream_t stream);
+
+/* Backward of one head of Discriminator.forward.  dlogits[N*R] is the loss seed for that head, keep its mask
+ * (NULL = eval).  want_param: produce parameter gradients (accumulate != 0 adds).  dinp != NULL: also produce the
+ * gradient w.r.t. the soft input [N,L,V] (the generator's path). */
+size_t gic_disc_bwd_workspace_floats(int N, int L, int De, int R, int F);
+int gic_disc_bwd(int mode, const float* dlogits, const uint8_t* keep, float drop_p, const float* inp_soft,
+                 const int64_t* ids, int N, int L, int V, int De, int R, int n_groups, const int* filter_sizes,
+                 const int* num_filters, const float* W_e, const float* const* conv_w, const float* const* conv_b,
+                 const float* W_h, const float* W_f, const float* b_f, int Hd, const float* W_o, const float* b_o,
+                 const float* saved, float* workspace, float* dW_e, float* const* dconv_w, float* const* dconv_b,
+                 float* dW_h, float* db_h, float* dW_f, float* db_f, float* dW_o, float* db_o, float* dinp,
+                 int want_param, int accumulate, gic_stream_t stream);
+
+/* ---- get_losses (src/utils.py:10-53) with the backward seeds ----
+ * losses[0] = g_loss, losses[1] = d_loss (the reference returns g first).  dd_real/dd_fake = d d_loss / d logits,
+ * dg_out = d g_loss / d g_out; any of the three may be NULL. */
+int gic_gan_loss_fwd_bwd(int loss_type, const float* d_out_real, const float* d_out_fake, const float* g_out, int n,
+                         float* losses, float* dd_real, float* dd_fake, float* dg_out, gic_stream_t stream);
+
+/* ---- GANInstructor.optimize (src/training.py:194-199): clip_grad_norm_ + Adam over a flat buffer ----
+ * gic_grad_sqnorm accumulates sum(g^2) into *sqnorm (caller zeroes it; several buffers may share it).
+ * gic_clip_adam reads *sqnorm on the device (no host sync): coef = min(1, max_norm/(sqrt(sqnorm)*grad_scale+1e-6)),
+ * then torch.optim.Adam's update (weight_decay 0).  grad_scale = 1/world_size after a summed all-reduce. */
+int gic_grad_sqnorm(const float* g, size_t n, float* sqnorm, gic_stream_t stream);
+int gic_clip_adam(float* p, const float* g, float* m, float* v, size_t n, const float* sqnorm, float max_norm,
+                  float grad_scale, int step, float lr, float beta1, float beta2, float eps, gic_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GIC_B200_H_ */
