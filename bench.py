@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""Benchmark of the adversarial-captioning hot path (BASELINE.json: adversarial train steps/s and sampled
+caption tokens/s at 1/2/4/8 B200).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on host cores
+
+A "step" is one full adversarial train step (src/training.py:136-169) on the COCO-shaped workload
+(BASELINE.json configs[1], Tier-A shape): per GPU batch 256, caption length 20, vocab 10 000, E = H = 512,
+2048-d pooled CNN features through Encoder.linear+bn, discriminator with 64 representations and 3x300
+filters, loss 'standard', clip 5.0, Adam.  Data parallel = weak scaling: every rank owns 256 rows and the
+flat G/D gradients are all-reduced before the clip.
+
+Prints ONE JSON line (rank 0).  `value` = steps/s with every input already resident in HBM (two input sets
+of 250 MB alternate, each larger than L2); `e2e` = the same step through GANInstructor.adv_step with the
+user-facing inputs (captions, pooled features) copied from pinned host memory every step, the uniforms and
+dropout masks drawn on-device as the reference does (src/generator.py:90, nn.Dropout), and the two losses
+read back to the host.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1] (Tier-A: mean-pooled 7x7x2048 grid -> 2048-d feature)
+    "c2": dict(B=256, L=20, V=10000, E=512, H=512, layers=1, feat=2048, filters=[300, 300, 300]),
+    # BASELINE.json configs[0] (args.py defaults; CPU-runnable)
+    "c1": dict(B=8, L=16, V=1000, E=32, H=512, layers=1, feat=2048, filters=[300, 300, 300]),
+}
+MODES = {"fp32": 0, "tf32": 1, "tf32x3": 2}
+DTYPE_NAME = {"fp32": "f32", "tf32": "tf32 (fp32 accumulate)", "tf32x3": "f32 (3xTF32 tensor-core split, fp32 accumulate)"}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d.get("hbm_gbs", 6650.0), tf=d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0)),
+                    tf_burst=d.get("bf16_tflops", 1590.0), src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf=1400.0, tf_burst=1590.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU implementation (oracle port with the same torch library ops)
+# ------------------------------------------------------------------------------------------------------
+def cpu_reference_step_time(cfg, sample_B, steps, warmup, threads):
+    """Seconds per step of the library-op CPU port on `sample_B` rows of the workload."""
+    import torch
+    from oracle import ref_modules as rm
+    from oracle import ref_port as rp
+    torch.set_num_threads(threads)
+    small = dict(cfg, B=sample_B, feat=0)
+    inp = rp.make_inputs(small)
+    a = inp["args"]
+    a.temperature = 1.0
+    dec, disc = rm.load_port(a, inp["gen"], inp["disc"])
+    g_opt = torch.optim.Adam(dec.parameters(), lr=a.gen_lr)
+    d_opt = torch.optim.Adam(disc.parameters(), lr=a.disc_lr)
+    # features: the Encoder projection is a [B,2048]x[2048,E] GEMM, negligible on the CPU; start from embed(<S>)
+    times = []
+    for i in range(warmup + steps):
+        feats = dec.embed(torch.ones(sample_B, dtype=torch.long))
+        t0 = time.perf_counter()
+        rm.port_adv_step(a, dec, disc, g_opt, d_opt, inp["captions"], feats)      # draws u / dropout itself
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return statistics.median(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = WORKLOADS[args.workload]
+    threads = os.cpu_count() or 1
+    sample_B = min(cfg["B"], args.cpu_sample_rows)
+    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    t = cpu_reference_step_time(cfg, sample_B, steps, warmup, threads)
+    scale = cfg["B"] / sample_B
+    step_s = t * scale
+    val = 1.0 / step_s
+    sample = f"{sample_B} of {cfg['B']} rows per step, time scaled x{scale:g}; {steps} timed + {warmup} warm-up steps"
+    line = {
+        "impl": "reference", "metric": "adversarial_train_steps_per_sec", "value": val, "unit": "steps/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": step_s * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, cfg, 1),
+        "tokens_per_sec": None,
+        "cpu_baseline": {"value": val, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, cfg, world):
+    return {"workload": f"{args.workload}: COCO-shaped adversarial step, per-GPU batch {cfg['B']}, len {cfg['L']}, "
+                        f"vocab {cfg['V']}, E {cfg['E']}, H {cfg['H']}, feat {cfg['feat']} (pooled 7x7x2048 grid), "
+                        f"D 64 reps x {sum(cfg['filters'])} filters, loss standard",
+            "global_batch": cfg["B"] * world, "seq_len": cfg["L"], "vocab": cfg["V"], "parallelism": f"dp{world}",
+            "gemm_mode": args.mode, "cache": "two 250 MB input sets alternate (each > 126 MB L2)"}
+
+
+# ------------------------------------------------------------------------------------------------------
+# this repo's arm
+# ------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import gic_b200
+    from gic_b200 import _lib
+    from gic_b200.args import default_args
+    from gic_b200.training import GANInstructor
+    _lib.require_cuda()
+    lib = _lib.lib()
+    gic_b200.set_gemm_mode(MODES[args.mode])
+
+    cfg = WORKLOADS[args.workload]
+    B, L, V = cfg["B"], cfg["L"], cfg["V"]
+    a = default_args(vocab_size=V, gen_embed_dim=cfg["E"], gen_hidden_dim=cfg["H"], gen_num_layers=cfg["layers"],
+                     disc_num_filters=list(cfg["filters"]), conditional_gan=1, feature_dim=cfg["feat"], device="cuda")
+    torch.manual_seed(1008)                      # identical weights on every rank (src/main.py:14-17)
+    inst = GANInstructor(a, device=dev)
+    inst.gen.train(); inst.disc.train()
+    inst.gen.decoder.temperature = 1.0           # exp schedule start (reported config); T is a kernel argument
+    R, Fd = a.disc_num_rep, sum(a.disc_num_filters)
+
+    # synthetic inputs, sharded by batch row: rank r owns rows [r*B, (r+1)*B) of the global batch
+    def make_set(seed):
+        g = torch.Generator(device=dev).manual_seed(seed * 1000 + rank)
+        caps = torch.randint(4, V, (B, L), generator=g, device=dev)
+        caps[:, 0] = 1; caps[:, L - 1] = 2
+        return dict(caps=caps, pooled=torch.randn(B, cfg["feat"], generator=g, device=dev),
+                    u=torch.rand(L, B, V, generator=g, device=dev),
+                    keep=(torch.rand(3, B * R, Fd, generator=g, device=dev) >= 0.2).to(torch.uint8))
+    sets = [make_set(1008 + i) for i in range(2)]
+    h_caps = [s["caps"].cpu().pin_memory() for s in sets]
+    h_pool = [s["pooled"].cpu().pin_memory() for s in sets]
+
+    def step_resident(i):
+        s = sets[i % 2]
+        return inst.adv_step(s["caps"], pooled=s["pooled"], u=s["u"], keep=s["keep"])
+
+    def step_e2e(i):
+        caps = h_caps[i % 2].to(dev, non_blocking=True)
+        pooled = h_pool[i % 2].to(dev, non_blocking=True)
+        r = inst.adv_step(caps, pooled=pooled)                     # uniforms / masks drawn on-device
+        return torch.stack([r["g_loss"], r["d_loss"]]).cpu()      # D2H read of the step's result (syncs)
+
+    def timed(fn, steps, warmup, sample_clocks=False):
+        for i in range(warmup):
+            fn(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local) if (sample_clocks and rank == 0) else None
+        if sampler:
+            sampler.start()
+        n0 = lib.gic_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        launches = lib.gic_launch_count() - n0
+        clocks = sampler.stop() if sampler else None
+        if world > 1:
+            dist.barrier()
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches, clocks
+
+    ms, launches, clocks = timed(step_resident, args.steps, args.warmup, sample_clocks=True)
+    ms_step = ms / args.steps
+    value = world / (ms_step * 1e-3)             # global steps/s: every rank completes one 256-row step per iteration
+
+    # sampled-caption tokens/s: decode only (Decoder.sample), device resident
+    dec = inst.gen.decoder
+
+    def decode_only(i):
+        s = sets[i % 2]
+        feats = inst.gen.encoder(s["pooled"])
+        with torch.no_grad():
+            return dec.sample(feats, max_caption_len=L, u=s["u"])
+    with torch.no_grad():
+        dms, _, _ = timed(decode_only, args.steps, args.warmup)
+    tokens_per_sec = world * B * L / (dms / args.steps * 1e-3)
+
+    e2e_ms, _, _ = timed(step_e2e, args.steps, args.warmup)
+    e2e_val = world / (e2e_ms / args.steps * 1e-3)
+    h2d = h_caps[0].numel() * 8 + h_pool[0].numel() * 4
+
+    # roofline of the dominant kernel class: instrumented steps (events around every launch of the class)
+    peaks = load_peaks()
+    K = C.c_double * 6
+    ms_k, work_k, calls_k = K(), K(), (C.c_ulonglong * 6)()
+    step_resident(0); torch.cuda.synchronize()
+    psteps = min(args.steps, 3)
+    lib.gic_prof_begin()
+    for i in range(psteps):
+        step_resident(i)
+    torch.cuda.synchronize()
+    lib.gic_prof_end(ms_k, work_k, calls_k)
+    names = ["gemm", "sample_step", "conv_pool_fwd", "softmax_bwd", "clip_adam", "head_fwd"]
+    classes = {}
+    for k, nm in enumerate(names):
+        if calls_k[k]:
+            classes[nm] = dict(ms_per_step=ms_k[k] / psteps, calls_per_step=calls_k[k] / psteps,
+                               work_per_step=work_k[k] / psteps)
+    g = classes.get("gemm")
+    roofline = None
+    if g:
+        ach = g["work_per_step"] / (g["ms_per_step"] * 1e-3) / 1e12
+        roofline = {"kernel": "gemm (tcgen05)" if args.mode != "fp32" else "sgemm_kernel (fp32 FFMA)", "bound": "tensor",
+                    "achieved": ach, "peak": peaks["tf"], "unit": "TFLOP/s", "frac": ach / peaks["tf"],
+                    "traffic": None, "peak_source": peaks["src"] + ", sustained bf16 dense",
+                    "share_of_step": g["ms_per_step"] / ms_step, "launches_per_step": g["calls_per_step"],
+                    "algorithmic_flops_per_step": g["work_per_step"]}
+    hbm = {}
+    for nm in ("sample_step", "conv_pool_fwd", "softmax_bwd", "clip_adam", "head_fwd"):
+        c = classes.get(nm)
+        if c:
+            gbs = c["work_per_step"] / (c["ms_per_step"] * 1e-3) / 1e9
+            hbm[nm] = {"achieved_GBps": gbs, "frac_of_hbm_peak": gbs / peaks["hbm"], "ms_per_step": c["ms_per_step"],
+                       "launches_per_step": c["calls_per_step"]}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload on the host cores
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sb = min(B, args.cpu_sample_rows)
+        t = cpu_reference_step_time(cfg, sb, 2, 1, threads)
+        cpu = {"value": 1.0 / (t * B / sb), "unit": "steps/s", "cores": threads, "kind": "port",
+               "sample": f"{sb} of {B} rows per step, time scaled x{B / sb:g}; 2 timed + 1 warm-up steps "
+                         f"(oracle/ref_modules.py: nn.LSTM / nn.Conv2d port of the reference path)"}
+
+    line = {
+        "metric": "adversarial_train_steps_per_sec", "value": value, "unit": "steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": DTYPE_NAME[args.mode], "data": "synthetic",
+        "config": workload_config(args, cfg, world),
+        "tokens_per_sec": tokens_per_sec, "decode_ms": dms / args.steps,
+        "e2e": {"value": e2e_val, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "hbm_kernels": hbm,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--mode", default=os.environ.get("GIC_GEMM_MODE", "fp32"), choices=sorted(MODES))
+    ap.add_argument("--cpu-sample-rows", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

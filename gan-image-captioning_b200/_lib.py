@@ -52,6 +52,9 @@ def _declare(L):
     L.gic_last_error.restype = C.c_char_p
     L.gic_check_device.restype = I
     L.gic_launch_count.restype = C.c_ulonglong
+    L.gic_prof_begin.restype = None
+    L.gic_prof_end.restype = None
+    L.gic_prof_end.argtypes = [P, P, P]
     L.gic_gemm.argtypes = [I, I, I, I, I, I, F, P, I, P, I, F, P, I, P, P]
     L.gic_encoder_fwd.argtypes = [I, P, I, I, I, P, P, P, P, F, P, P, P, P, P]
     L.gic_encoder_bwd.argtypes = [I, P, P, P, P, P, P, P, I, I, I, P, P, P, P, P, I, P]

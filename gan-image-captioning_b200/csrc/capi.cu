@@ -28,6 +28,8 @@ int clip_adam(float*, const float*, float*, float*, size_t, const float*, float,
               float, cudaStream_t);
 const char* last_error();
 unsigned long long launch_count();
+void prof_begin();
+void prof_end(double*, double*, unsigned long long*);
 // disc_api.cu-style wrappers implemented in disc.cu
 int disc_fwd_entry(int mode, const float* inp_soft, const int64_t* ids, int N, int L, int V, int De, int R,
                    int n_groups, const int* fs, const int* nf, const float* W_e, const float* const* cw,
@@ -214,6 +216,8 @@ int gic_version(void) { return 100; }
 const char* gic_last_error(void) { return last_error(); }
 int gic_check_device(void) { return require_device(); }
 unsigned long long gic_launch_count(void) { return launch_count(); }
+void gic_prof_begin(void) { prof_begin(); }
+void gic_prof_end(double* ms, double* work, unsigned long long* calls) { prof_end(ms, work, calls); }
 
 int gic_gemm(int mode, int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
              const float* B, int ldb, float beta, float* C, int ldc, const float* bias, gic_stream_t stream) {

@@ -179,6 +179,7 @@ int sample_step(bool pretrain, const float* logits, const float* u, float temper
     attr_set = true;
   }
   const size_t dyn = in_smem ? smem : 0;
+  ProfScope prof(PROF_SAMPLE, 8.0 * B * V, s);     // algorithmic HBM bytes: read u, write probs
   if (pretrain)
     sample_step_kernel<true><<<B, 256, dyn, s>>>(logits, u, temperature, V, L, t, out, ids, forced, embed, E,
                                                x_next, in_smem);
@@ -209,6 +210,7 @@ softmax_bwd_kernel(const float* __restrict__ p, const float* __restrict__ dp, fl
 int softmax_bwd(const float* p, const float* dp, float temperature, int rows, int V, float* dz,
                 cudaStream_t s) {
   if (rows == 0) return GIC_OK;
+  ProfScope prof(PROF_SOFTMAX_BWD, 12.0 * rows * V, s);               // read p, dp; write dz
   softmax_bwd_kernel<<<rows, 256, 0, s>>>(p, dp, temperature, V, dz);
   return check_launch("softmax_bwd_kernel");
 }

@@ -433,6 +433,7 @@ int disc_forward(int mode, const float* inp_soft, const int64_t* ids, const Disc
     const size_t smem = (((size_t)d.L * d.De + 3) & ~(size_t)3) * 4 + ((size_t)g.kmax + 2) * d.F * 4;
     GIC_REQUIRE(smem <= 200 * 1024, GIC_ERR_SHAPE, "disc: conv tile needs %zu B of shared memory", smem);
     GIC_REQUIRE(g.kmax <= 16, GIC_ERR_SHAPE, "disc: filter_size*emb_dim_single <= 16 supported");
+    ProfScope prof(PROF_CONVPOOL, 5.0 * rows * d.F + 4.0 * d.N * d.L * d.De, s);   // write pooled f32 + arg u8, read emb
     const bool es1 = (d.es == 1) && (d.R % 4 == 0) && g.kmax <= 8;
     GIC_REQUIRE(d.L <= 255, GIC_ERR_SHAPE, "disc: caption length <= 255 supported");
     if (es1) {
@@ -455,6 +456,7 @@ int disc_forward(int mode, const float* inp_soft, const int64_t* ids, const Disc
     hp.keep[m] = (m < n_heads && keep) ? keep[m] : nullptr;
     hp.logits[m] = (m < n_heads) ? logits[m] : nullptr;
   }
+  ProfScope prof(PROF_HEAD, (8.0 + n_heads) * rows * d.F, s);      // read hpre, pooled (f32) + one u8 mask per head
   head_fwd_kernel<<<cdiv((long long)rows, 8), 256, 0, s>>>(hpre, pooled, (int)rows, d.F, weff, 1.f / (1.f - drop_p), hp);
   return check_launch("head_fwd_kernel");
 }

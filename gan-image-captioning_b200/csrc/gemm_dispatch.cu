@@ -1,9 +1,35 @@
 // GEMM dispatch: tcgen05 tensor-core kernels when the mode and the operand layout allow it,
 // the exact-fp32 CUDA-core kernel otherwise.  Both are this library's own kernels; nothing here
 // falls back to a CPU or to a vendor library.
+#include <vector>
+
 #include "gic_internal.cuh"
 
 namespace gic {
+
+struct ProfRec { int kind; double work; cudaEvent_t a, b; };
+static bool g_prof = false;
+static std::vector<ProfRec> g_recs;
+bool prof_enabled() { return g_prof; }
+void prof_open(int kind, double work, cudaStream_t s) {
+  ProfRec r; r.kind = kind; r.work = work;
+  cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, s);
+  g_recs.push_back(r);
+}
+void prof_close(cudaStream_t s) { if (!g_recs.empty()) cudaEventRecord(g_recs.back().b, s); }
+void prof_begin() { g_prof = true; }
+// call after the stream has been synchronised
+void prof_end(double* ms, double* work, unsigned long long* calls) {
+  g_prof = false;
+  for (int k = 0; k < PROF_KINDS; ++k) { ms[k] = 0; work[k] = 0; calls[k] = 0; }
+  for (auto& r : g_recs) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms[r.kind] += t; work[r.kind] += r.work; calls[r.kind] += 1; }
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  g_recs.clear();
+}
 
 int gemm_tc(int mode, bool transA, bool transB, int M, int N, int K, float alpha, const float* A, int lda,
             const float* B, int ldb, float beta, float* C, int ldc, const float* bias, cudaStream_t stream,
@@ -11,6 +37,7 @@ int gemm_tc(int mode, bool transA, bool transB, int M, int N, int K, float alpha
 
 int gemm(int mode, bool transA, bool transB, int M, int N, int K, float alpha, const float* A, int lda,
          const float* B, int ldb, float beta, float* C, int ldc, const float* bias, cudaStream_t stream) {
+  ProfScope prof(PROF_GEMM, 2.0 * M * N * K, stream);
   if (mode != GEMM_FP32) {
     bool handled = false;
     int rc = gemm_tc(mode, transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, stream, &handled);

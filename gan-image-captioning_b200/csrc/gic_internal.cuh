@@ -32,6 +32,18 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 
 int num_sms();
 
+// ---- optional per-kernel-class device timing (bench.py roofline): CUDA events on the launching stream ----
+enum ProfKind : int { PROF_GEMM = 0, PROF_SAMPLE = 1, PROF_CONVPOOL = 2, PROF_SOFTMAX_BWD = 3, PROF_ADAM = 4,
+                      PROF_HEAD = 5, PROF_KINDS = 6 };
+bool prof_enabled();
+void prof_open(int kind, double work, cudaStream_t s);    // work = algorithmic flops (GEMM) or bytes
+void prof_close(cudaStream_t s);
+struct ProfScope {
+  cudaStream_t s; bool on;
+  ProfScope(int kind, double work, cudaStream_t st) : s(st), on(prof_enabled()) { if (on) prof_open(kind, work, s); }
+  ~ProfScope() { if (on) prof_close(s); }
+};
+
 // ---- fp32 GEMM (CUDA cores, exact-fp32 path) -------------------------------------------
 // C[M,N] = alpha * op(A)[M,K] * op(B)[K,N] + beta * C + bias[N]   (row-major everywhere)
 //   transA == 0: A is [M,K] with leading dim lda;  transA == 1: A is [K,M]

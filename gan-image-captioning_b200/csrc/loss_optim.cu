@@ -145,6 +145,7 @@ int clip_adam(float* p, const float* g, float* m, float* v, size_t n, const floa
   GIC_REQUIRE(step >= 1, GIC_ERR_SHAPE, "clip_adam: step must be >= 1");
   const double bc1 = 1.0 - pow((double)b1, step), bc2 = 1.0 - pow((double)b2, step);
   const int grid = min(cdiv((long long)n, 256), 8 * num_sms());
+  ProfScope prof(PROF_ADAM, 28.0 * n, s);                              // read p,g,m,v; write p,m,v
   clip_adam_kernel<<<grid, 256, 0, s>>>(p, g, m, v, n, sqnorm, max_norm, grad_scale, (float)(lr / bc1),
                                         (float)(1.0 / sqrt(bc2)), b1, b2, eps);
   return check_launch("clip_adam_kernel");

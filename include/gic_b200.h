@@ -59,6 +59,13 @@ const char* gic_last_error(void);
 int gic_check_device(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches). */
 unsigned long long gic_launch_count(void);
+/* Optional per-kernel-class device timing for bench.py's roofline: between gic_prof_begin() and gic_prof_end()
+ * every launch of a profiled class is bracketed by CUDA events on its own stream.  gic_prof_end (call after the
+ * stream is synchronised) fills ms[k], work[k] (algorithmic flops for k=0 GEMM, bytes otherwise) and calls[k] for
+ * the GIC_PROF_KINDS classes: 0 GEMM, 1 sample step, 2 conv+pool fwd, 3 softmax bwd, 4 clip+Adam, 5 head fwd. */
+#define GIC_PROF_KINDS 6
+void gic_prof_begin(void);
+void gic_prof_end(double* ms, double* work, unsigned long long* calls);
 
 /* ---- dense contraction (nn.Linear / its autograd; src/generator.py:64,68, src/discriminator.py:40,53) ----
  * C[M,N] = alpha * op(A) * op(B) + beta * C + bias[N];  transA: A stored [K,M]; transB: B stored [N,K]. */
