@@ -150,6 +150,7 @@ sample_step_kernel(const float* __restrict__ logits, const float* __restrict__ u
       if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
     }
     if (lane == 0) {
+      if (best_i < 0 || best_i >= V) best_i = 0;      // all-NaN row: stay in bounds
       ids[(size_t)b * L + t] = best_i;
       int fed = best_i;
       if (forced) {

@@ -24,13 +24,21 @@ class _GanLoss(torch.autograd.Function):
                                                    _lib.ptr(seeds[2]), _lib.stream()), "gic_gan_loss_fwd_bwd")
         ctx.save_for_backward(seeds)
         ctx.shapes = (d_real.shape, d_fake.shape, g_out.shape)
+        ctx.rsgan = (loss_type == _lib.LOSS_TYPES["rsgan"])
         return losses[0], losses[1]
 
     @staticmethod
     def backward(ctx, dg_loss, dd_loss):
         (seeds,) = ctx.saved_tensors
         s0, s1, s2 = ctx.shapes
-        return (seeds[0].view(s0) * dd_loss, seeds[1].view(s1) * dd_loss, seeds[2].view(s2) * dg_loss, None)
+        g_real, g_fake = seeds[0] * dd_loss, seeds[1] * dd_loss
+        if ctx.rsgan:
+            # g_loss = BCE(d_fake - d_real, 1) also depends on the D outputs (src/utils.py:48); with
+            # x = d_real - d_fake and seeds[0] = (sig(x) - 1)/n:  d g_loss / d d_real = sig(x)/n = seeds[0] + 1/n
+            n = seeds.shape[1]
+            g_real = g_real + (seeds[0] + 1.0 / n) * dg_loss
+            g_fake = g_fake - (seeds[0] + 1.0 / n) * dg_loss
+        return (g_real.view(s0), g_fake.view(s1), (seeds[2] * dg_loss).view(s2), None)
 
 
 def get_losses(d_out_real, d_out_fake, g_out, loss_type="JS"):

@@ -1,0 +1,72 @@
+"""tcgen05 / TMA GEMM (kind::tf32, fp32 accumulate in TMEM) against an fp64 product of the same operands.
+
+TF32 keeps 10 mantissa bits: per-product relative error <= 2^-11 with round-to-nearest staging, so a
+K-term dot product of O(1) operands is expected within ~1e-3 * sqrt(K) absolute; the bound used here is
+rtol 2e-3 against max |C| (the fp32-exact path is tested in test_gpu_parity.py)."""
+import json
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+REPORT = {}
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _report():
+    yield
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "tcgen05_report.json"), "w") as f:
+        json.dump(REPORT, f, indent=1, sort_keys=True)
+
+
+def run_gemm(mode, tA, tB, M, N, K, alpha=1.0, beta=0.0, use_bias=False, seed=0):
+    import gic_b200
+    from gic_b200 import _lib as L
+    L.require_cuda()
+    g = torch.Generator().manual_seed(seed + M * 7 + N * 3 + K + tA * 2 + tB)
+    A = torch.randn((K, M) if tA else (M, K), generator=g)
+    B = torch.randn((N, K) if tB else (K, N), generator=g)
+    C0 = torch.randn(M, N, generator=g)
+    bias = torch.randn(N, generator=g) if use_bias else None
+    Ad, Bd, Cd = A.to(dev()), B.to(dev()), C0.clone().to(dev())
+    bd = bias.to(dev()) if use_bias else None
+    want = alpha * ((Ad.t() if tA else Ad).double() @ (Bd.t() if tB else Bd).double()) + beta * Cd.double()
+    if use_bias:
+        want = want + bd.double()
+    L.check(L.lib().gic_gemm(mode, tA, tB, M, N, K, alpha, L.ptr(Ad), A.shape[1], L.ptr(Bd), B.shape[1], beta,
+                             L.ptr(Cd), N, L.ptr(bd), L.stream()), "gic_gemm")
+    torch.cuda.synchronize()
+    scale = float(want.abs().max())
+    err = float((Cd.double() - want).abs().max())
+    return err, scale
+
+
+SHAPES = [(128, 128, 32), (128, 128, 64), (256, 2048, 1024), (256, 10000, 512), (300, 900, 900), (16384, 900, 900),
+          (5120, 64, 10000), (900, 900, 2048), (130, 100, 36), (5120, 512, 10000)]
+
+
+@pytest.mark.parametrize("tA,tB", [(0, 1), (0, 0), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_gemm_tf32_vs_fp64(tA, tB, M, N, K):
+    err, scale = run_gemm(1, tA, tB, M, N, K, seed=1)
+    REPORT[f"tf32/{M}x{N}x{K}/tA{tA}tB{tB}"] = dict(err=err, scale=scale, rel=err / scale)
+    assert err <= 2e-3 * scale, f"rel err {err / scale:.3e}"
+
+
+def test_gemm_tf32_alpha_beta_bias():
+    err, scale = run_gemm(1, 0, 1, 384, 900, 900, alpha=0.75, beta=0.5, use_bias=True, seed=2)
+    REPORT["tf32/alpha_beta_bias"] = dict(err=err, scale=scale, rel=err / scale)
+    assert err <= 2e-3 * scale
+
+
+def test_gemm_tf32_unaligned_falls_back_to_exact_kernel():
+    # lda = 37 is not TMA-addressable: the dispatcher must use the exact-fp32 kernel (still CUDA, still ours)
+    err, scale = run_gemm(1, 0, 1, 70, 90, 37, seed=3)
+    assert err <= 1e-5 * scale
