@@ -168,9 +168,136 @@ sample_step_kernel(const float* __restrict__ logits, const float* __restrict__ u
   }
 }
 
+// Register-resident variant for V % 4 == 0 and V <= 256 * 4 * NV4: every thread issues all of its float4 loads of
+// the logits row and the uniform row up front (2 * NV4 outstanding 16-byte loads), keeps its NV4 * 4 perturbed
+// logits in registers through the max / sum / normalise passes, and writes the probabilities with float4 stores.
+// Same arithmetic (accurate logf / expf, true division) and tie rule as sample_step_kernel.
+template <bool PRETRAIN, int NV4>
+__global__ void __launch_bounds__(256)
+sample_step_reg_kernel(const float* __restrict__ logits, const float* __restrict__ u, float temperature,
+                       int V, int L, int t, float* __restrict__ out, int64_t* __restrict__ ids,
+                       const int64_t* __restrict__ forced, const float* __restrict__ embed, int E,
+                       float* __restrict__ x_next) {
+  __shared__ float red[32];
+  __shared__ int red_i[32];
+  __shared__ int s_tok;
+  const int b = blockIdx.x;
+  const int nv4 = V >> 2;
+  const float4* lrow = reinterpret_cast<const float4*>(logits + (size_t)b * V);
+  const float4* urow = PRETRAIN ? nullptr : reinterpret_cast<const float4*>(u + (size_t)b * V);
+  float4* orow = reinterpret_cast<float4*>(out + ((size_t)b * L + t) * V);
+  const float eps = 1e-10f;
+  float4 z[NV4];
+  float4 uu[NV4];
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) {
+    const int v = threadIdx.x + i * 256;
+    z[i] = (v < nv4) ? lrow[v] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    if (!PRETRAIN) uu[i] = (v < nv4) ? urow[v] : make_float4(0.5f, 0.5f, 0.5f, 0.5f);
+  }
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) {
+    if (PRETRAIN) {
+      if (threadIdx.x + i * 256 < nv4) orow[threadIdx.x + i * 256] = z[i];       // out = raw logits
+    } else {
+      z[i].x = (z[i].x - logf(-logf(uu[i].x + eps) + eps)) * temperature;
+      z[i].y = (z[i].y - logf(-logf(uu[i].y + eps) + eps)) * temperature;
+      z[i].z = (z[i].z - logf(-logf(uu[i].z + eps) + eps)) * temperature;
+      z[i].w = (z[i].w - logf(-logf(uu[i].w + eps) + eps)) * temperature;
+    }
+    mx = fmaxf(mx, fmaxf(fmaxf(z[i].x, z[i].y), fmaxf(z[i].z, z[i].w)));
+  }
+  mx = block_max(mx, red);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) {
+    z[i].x = expf(z[i].x - mx); z[i].y = expf(z[i].y - mx);
+    z[i].z = expf(z[i].z - mx); z[i].w = expf(z[i].w - mx);
+    sum += (z[i].x + z[i].y) + (z[i].z + z[i].w);
+  }
+  sum = block_sum(sum, red);
+  float best = -1.f;
+  int best_i = 0x7fffffff;
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) {
+    const int v = threadIdx.x + i * 256;
+    if (v < nv4) {
+      float4 p;
+      p.x = z[i].x / sum; p.y = z[i].y / sum; p.z = z[i].z / sum; p.w = z[i].w / sum;
+      if (!PRETRAIN) orow[v] = p;
+      if (p.x > best) { best = p.x; best_i = 4 * v; }
+      if (p.y > best) { best = p.y; best_i = 4 * v + 1; }
+      if (p.z > best) { best = p.z; best_i = 4 * v + 2; }
+      if (p.w > best) { best = p.w; best_i = 4 * v + 3; }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) { red[w] = best; red_i[w] = best_i; }
+  __syncthreads();
+  if (w == 0) {
+    best = lane < 8 ? red[lane] : -2.f;
+    best_i = lane < 8 ? red_i[lane] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+      if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
+    }
+    if (lane == 0) {
+      if (best_i < 0 || best_i >= V) best_i = 0;
+      ids[(size_t)b * L + t] = best_i;
+      int fed = best_i;
+      if (forced) {
+        const int64_t f = forced[(size_t)b * L + t];
+        fed = (f >= 0 && f < V) ? (int)f : 0;
+      }
+      s_tok = fed;
+    }
+  }
+  __syncthreads();
+  if (x_next) {
+    const float* src = embed + (size_t)s_tok * E;
+    float* dst = x_next + (size_t)b * E;
+    for (int e = threadIdx.x; e < E; e += blockDim.x) dst[e] = src[e];
+  }
+}
+
+template <bool PRETRAIN>
+static bool launch_sample_reg(const float* logits, const float* u, float temperature, int B, int V, int L, int t,
+                              float* out, int64_t* ids, const int64_t* forced, const float* embed, int E,
+                              float* x_next, cudaStream_t s) {
+  const int nv4 = V >> 2;
+#define GIC_SAMPLE(NV4_)                                                                                         \
+  sample_step_reg_kernel<PRETRAIN, NV4_><<<B, 256, 0, s>>>(logits, u, temperature, V, L, t, out, ids, forced, embed, \
+                                                           E, x_next)
+  if (nv4 <= 256 * 1) GIC_SAMPLE(1);
+  else if (nv4 <= 256 * 2) GIC_SAMPLE(2);
+  else if (nv4 <= 256 * 4) GIC_SAMPLE(4);
+  else if (nv4 <= 256 * 8) GIC_SAMPLE(8);
+  else if (nv4 <= 256 * 10) GIC_SAMPLE(10);
+  else if (nv4 <= 256 * 16) GIC_SAMPLE(16);
+  else return false;
+#undef GIC_SAMPLE
+  return true;
+}
+
 int sample_step(bool pretrain, const float* logits, const float* u, float temperature, int B, int V,
                 int L, int t, float* out, int64_t* ids, const int64_t* forced, const float* embed,
                 int E, float* x_next, cudaStream_t s) {
+  ProfScope prof(PROF_SAMPLE, 8.0 * B * V, s);     // algorithmic HBM bytes: read u, write probs (SURVEY 8d)
+  if ((V % 4 == 0) && aligned16(logits) && aligned16(out) && (pretrain || aligned16(u))) {
+    const bool done = pretrain ? launch_sample_reg<true>(logits, u, temperature, B, V, L, t, out, ids, forced, embed, E, x_next, s)
+                               : launch_sample_reg<false>(logits, u, temperature, B, V, L, t, out, ids, forced, embed, E, x_next, s);
+    if (done) return check_launch("sample_step_reg_kernel");
+  }
   const size_t smem = (size_t)V * sizeof(float);
   const int in_smem = smem <= 200 * 1024 ? 1 : 0;
   static bool attr_set = false;
@@ -180,7 +307,6 @@ int sample_step(bool pretrain, const float* logits, const float* u, float temper
     attr_set = true;
   }
   const size_t dyn = in_smem ? smem : 0;
-  ProfScope prof(PROF_SAMPLE, 8.0 * B * V, s);     // algorithmic HBM bytes: read u, write probs (SURVEY 8d)
   if (pretrain)
     sample_step_kernel<true><<<B, 256, dyn, s>>>(logits, u, temperature, V, L, t, out, ids, forced, embed, E,
                                                x_next, in_smem);

@@ -152,86 +152,123 @@ conv_pool_fwd_kernel(const float* __restrict__ emb, int L, int De, int R, int es
 }
 
 // ---------------------------------------------------------------------------------------
-// backward of conv + ReLU + max-pool.  Persistent CTAs loop over captions; each thread owns
-// whole feature columns (weights and their gradient accumulators stay in registers across all
-// captions of the CTA, one global atomic per weight at the end); demb is accumulated in shared
-// memory and written once per caption.
+// backward of conv + ReLU + max-pool, two kernels (both stream dx / pooled / arg once, coalesced):
+//
+//  (a) conv_pool_bwd_demb_kernel: one warp per (caption n, representation r) row of [N*R, F].  Lanes stride over
+//      the feature columns; every lane accumulates into its OWN copy of demb[n, :, r*es .. r*es+es) in shared
+//      memory (layout [entry][lane]: bank = lane, so plain read-modify-write, no atomics), then the 32 copies
+//      are summed with a rotated conflict-free read.
+//  (b) conv_pool_bwd_dw_kernel: thread = feature column, CTA = chunk of rows; conv-weight / bias gradients
+//      accumulate in registers over the chunk, one global atomic per weight per CTA.
 // ---------------------------------------------------------------------------------------
-constexpr int BWD_SLOTS = 4;     // columns per thread: F <= 256 * BWD_SLOTS
 constexpr int BWD_KMAX = 8;      // f * es <= 8 on the register path
 
+template <bool ES1>
 __global__ void __launch_bounds__(256)
-conv_pool_bwd_kernel(const float* __restrict__ emb, const float* __restrict__ pooled,
-                     const uint8_t* __restrict__ arg, const float* __restrict__ dx, int N, int L, int De,
-                     int R, int es, ConvGroups g, int want_param, float* __restrict__ demb) {
+conv_pool_bwd_demb_kernel(const float* __restrict__ pooled, const uint8_t* __restrict__ arg,
+                          const float* __restrict__ dx, int rows /*N*R*/, int L, int De, int R, int es,
+                          ConvGroups g, float* __restrict__ demb) {
   extern __shared__ __align__(16) float sm[];
-  const int F = g.F;
-  float* emb_s = sm;
-  float* demb_s = sm + L * De;
-  // per-thread column slots
-  float w[BWD_SLOTS][BWD_KMAX], dw[BWD_SLOTS][BWD_KMAX], dbias[BWD_SLOTS];
-  int fk[BWD_SLOTS], grp[BWD_SLOTS], cin[BWD_SLOTS];
-#pragma unroll
-  for (int s = 0; s < BWD_SLOTS; ++s) {
-    const int c = threadIdx.x + s * 256;
-    fk[s] = 0; grp[s] = 0; cin[s] = 0; dbias[s] = 0.f;
-#pragma unroll
-    for (int k = 0; k < BWD_KMAX; ++k) { w[s][k] = 0.f; dw[s][k] = 0.f; }
-    if (c < F) {
-      int gi = 0;
-      while (gi + 1 < g.ngroups && c >= g.col0[gi + 1]) ++gi;
-      grp[s] = gi; cin[s] = c - g.col0[gi]; fk[s] = g.f[gi] * es;
-#pragma unroll
-      for (int k = 0; k < BWD_KMAX; ++k)
-        if (k < fk[s]) w[s][k] = g.w[gi][cin[s] * fk[s] + k];
+  const int F = g.F, kmax = g.kmax;
+  const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int LE = L * es;                       // entries of one (n, r) slice of demb
+  float* wk_s = sm;                            // [kmax][F]
+  int* fk_s = reinterpret_cast<int*>(wk_s + kmax * F);        // [F]
+  float* priv = reinterpret_cast<float*>(fk_s + F) + (size_t)warp * LE * 32;   // [LE][32] per warp
+  for (int gi = 0; gi < g.ngroups; ++gi) {
+    const int fk = g.f[gi] * es;
+    for (int i = threadIdx.x; i < g.n[gi] * kmax; i += blockDim.x) {
+      const int c = i / kmax, k = i % kmax;
+      wk_s[k * F + g.col0[gi] + c] = (k < fk) ? g.w[gi][c * fk + k] : 0.f;
     }
+    for (int c = threadIdx.x; c < g.n[gi]; c += blockDim.x) fk_s[g.col0[gi] + c] = fk;
   }
-
-  for (int n = blockIdx.x; n < N; n += gridDim.x) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < L * De; i += blockDim.x) {
-      emb_s[i] = emb[(size_t)n * L * De + i];
-      demb_s[i] = 0.f;
-    }
-    __syncthreads();
-    for (int r = 0; r < R; ++r) {
-      const size_t base = ((size_t)n * R + r) * F;
+  __syncthreads();
+  for (int row = blockIdx.x * nwarps + warp; row < rows; row += gridDim.x * nwarps) {
+    const int n = row / R, r = row % R;
+    for (int e = 0; e < LE; ++e) priv[e * 32 + lane] = 0.f;
+    const size_t base = (size_t)row * F;
+    for (int c0 = 0; c0 < F; c0 += 128) {      // 4 columns per lane in flight
+      float gv[4], pv[4];
+      int av[4];
 #pragma unroll
-      for (int s = 0; s < BWD_SLOTS; ++s) {
-        const int c = threadIdx.x + s * 256;
-        if (c < F) {
-          const float gsd = dx[base + c];
-          const float pv = pooled[base + c];
-          if (pv > 0.f && gsd != 0.f) {
-            const int a = arg[base + c];
+      for (int j = 0; j < 4; ++j) {
+        const int c = c0 + j * 32 + lane;
+        const bool ok = c < F;
+        gv[j] = ok ? dx[base + c] : 0.f;
+        pv[j] = ok ? pooled[base + c] : 0.f;
+        av[j] = ok ? (int)arg[base + c] : 0;
+      }
 #pragma unroll
-            for (int k = 0; k < BWD_KMAX; ++k) {
-              if (k < fk[s]) {
-                const int ei = (a + k / es) * De + r * es + k % es;
-                dw[s][k] = fmaf(gsd, emb_s[ei], dw[s][k]);
-                atomicAdd(&demb_s[ei], w[s][k] * gsd);
-              }
-            }
-            dbias[s] += gsd;
+      for (int j = 0; j < 4; ++j) {
+        const int c = c0 + j * 32 + lane;
+        if (c < F && pv[j] > 0.f && gv[j] != 0.f) {
+          const int fk = fk_s[c];
+          for (int k = 0; k < fk; ++k) {
+            const int e = ES1 ? (av[j] + k) : ((av[j] + k / es) * es + k % es);
+            priv[e * 32 + lane] = fmaf(wk_s[k * F + c], gv[j], priv[e * 32 + lane]);
           }
         }
       }
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < L * De; i += blockDim.x) demb[(size_t)n * L * De + i] = demb_s[i];
+    __syncwarp();
+    // sum the 32 lane-private copies: lane handles entries e = lane, lane+32, ...; rotated column order
+    for (int e = lane; e < LE; e += 32) {
+      float acc = 0.f;
+#pragma unroll 8
+      for (int i = 0; i < 32; ++i) acc += priv[e * 32 + ((i + lane) & 31)];
+      const int t = ES1 ? e : e / es, ee = ES1 ? 0 : e % es;
+      demb[((size_t)n * L + t) * De + r * es + ee] = acc;
+    }
+    __syncwarp();
   }
-  if (want_param) {
+}
+
+template <bool ES1>
+__global__ void __launch_bounds__(256)
+conv_pool_bwd_dw_kernel(const float* __restrict__ emb, const float* __restrict__ pooled,
+                        const uint8_t* __restrict__ arg, const float* __restrict__ dx, int rows, int L, int De,
+                        int R, int es, ConvGroups g, int rows_per_cta) {
+  const int F = g.F;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= F) return;
+  int gi = 0;
+  while (gi + 1 < g.ngroups && c >= g.col0[gi + 1]) ++gi;
+  const int cin = c - g.col0[gi], fk = g.f[gi] * es;
+  float dw[BWD_KMAX];
 #pragma unroll
-    for (int s = 0; s < BWD_SLOTS; ++s) {
-      const int c = threadIdx.x + s * 256;
-      if (c < F) {
+  for (int k = 0; k < BWD_KMAX; ++k) dw[k] = 0.f;
+  float dbias = 0.f;
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+  int n_cur = r0 / R, r_cur = r0 % R;          // (caption, representation) of row rb, advanced incrementally
+  for (int rb = r0; rb < r1; rb += 4) {
+    float gv[4], pv[4];
+    int av[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int row = rb + j;
+      const bool ok = row < r1;
+      const size_t i = (size_t)row * F + c;
+      gv[j] = ok ? dx[i] : 0.f;
+      pv[j] = ok ? pooled[i] : 0.f;
+      av[j] = ok ? (int)arg[i] : 0;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (pv[j] > 0.f && gv[j] != 0.f) {
+        const float* e0 = emb + (size_t)n_cur * L * De + r_cur * es;
 #pragma unroll
         for (int k = 0; k < BWD_KMAX; ++k)
-          if (k < fk[s]) atomicAdd(g.dw[grp[s]] + cin[s] * fk[s] + k, dw[s][k]);
-        atomicAdd(g.db[grp[s]] + cin[s], dbias[s]);
+          if (k < fk) dw[k] = fmaf(gv[j], ES1 ? e0[(av[j] + k) * De] : e0[(av[j] + k / es) * De + k % es], dw[k]);
+        dbias += gv[j];
       }
+      if (++r_cur == R) { r_cur = 0; ++n_cur; }
     }
   }
+#pragma unroll
+  for (int k = 0; k < BWD_KMAX; ++k)
+    if (k < fk) atomicAdd(g.dw[gi] + cin * fk + k, dw[k]);
+  atomicAdd(g.db[gi] + cin, dbias);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -503,7 +540,6 @@ int disc_backward(int mode, const float* dlogit, const uint8_t* keep, float drop
   GIC_TRY(gemm(mode, false, false, (int)rows, d.F, d.F, 1.f, dh, d.F, W_h, d.F, 1.f, dx, d.F, nullptr, s));
   // conv / pool backward
   {
-    GIC_REQUIRE(d.F <= 256 * BWD_SLOTS, GIC_ERR_SHAPE, "disc bwd: at most %d feature columns supported", 256 * BWD_SLOTS);
     GIC_REQUIRE(g.kmax <= BWD_KMAX, GIC_ERR_SHAPE, "disc bwd: filter_size*emb_dim_single <= %d supported", BWD_KMAX);
     if (want_param && !accumulate) {
       for (int i = 0; i < g.ngroups; ++i) {
@@ -511,12 +547,37 @@ int disc_backward(int mode, const float* dlogit, const uint8_t* keep, float drop
         cudaMemsetAsync(g.db[i], 0, (size_t)g.n[i] * sizeof(float), s);
       }
     }
-    const size_t smem = (size_t)2 * d.L * d.De * sizeof(float);
-    GIC_REQUIRE(smem <= 200 * 1024, GIC_ERR_SHAPE, "disc bwd: L*De too large for shared memory");
-    cudaFuncSetAttribute(conv_pool_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    const int grid = min(d.N, 2 * num_sms());
-    conv_pool_bwd_kernel<<<grid, 256, smem, s>>>(emb, pooled, arg, dx, d.N, d.L, d.De, d.R, d.es, g, want_param, demb);
-    GIC_TRY(check_launch("conv_pool_bwd_kernel"));
+    // (a) demb
+    {
+      const size_t fixed = ((size_t)g.kmax + 1) * d.F * 4;
+      const size_t per_warp = (size_t)d.L * d.es * 32 * 4;
+      int nwarps = 8;
+      while (nwarps > 1 && fixed + nwarps * per_warp > 100 * 1024) nwarps >>= 1;
+      const size_t smem = fixed + nwarps * per_warp;
+      GIC_REQUIRE(smem <= 200 * 1024, GIC_ERR_SHAPE, "disc bwd: L*emb_dim_single too large for shared memory");
+      const int grid = min(cdiv((long long)rows, nwarps), 4 * num_sms());
+      if (d.es == 1) {
+        cudaFuncSetAttribute(conv_pool_bwd_demb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        conv_pool_bwd_demb_kernel<true><<<grid, nwarps * 32, smem, s>>>(pooled, arg, dx, (int)rows, d.L, d.De, d.R, d.es, g, demb);
+      } else {
+        cudaFuncSetAttribute(conv_pool_bwd_demb_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        conv_pool_bwd_demb_kernel<false><<<grid, nwarps * 32, smem, s>>>(pooled, arg, dx, (int)rows, d.L, d.De, d.R, d.es, g, demb);
+      }
+      GIC_TRY(check_launch("conv_pool_bwd_demb_kernel"));
+    }
+    // (b) conv weight / bias gradients
+    if (want_param) {
+      const int colb = cdiv(d.F, 256);
+      int chunks = max(1, (4 * num_sms()) / colb);
+      int rpc = cdiv((long long)rows, chunks);
+      rpc = (rpc + 3) & ~3;
+      chunks = cdiv((long long)rows, rpc);
+      if (d.es == 1)
+        conv_pool_bwd_dw_kernel<true><<<dim3(colb, chunks), 256, 0, s>>>(emb, pooled, arg, dx, (int)rows, d.L, d.De, d.R, d.es, g, rpc);
+      else
+        conv_pool_bwd_dw_kernel<false><<<dim3(colb, chunks), 256, 0, s>>>(emb, pooled, arg, dx, (int)rows, d.L, d.De, d.R, d.es, g, rpc);
+      GIC_TRY(check_launch("conv_pool_bwd_dw_kernel"));
+    }
   }
   // embedding backward
   if (want_param) {

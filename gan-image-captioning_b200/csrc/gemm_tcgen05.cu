@@ -111,7 +111,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int nkb = (K + BK - 1) / BK;
+  // split-K: gridDim.z CTAs share one output tile, each owns a contiguous range of k-blocks and adds its partial
+  // sum with fp32 atomics (the host pre-scales C by beta).  kb_lo/kb_hi are this CTA's range.
+  const int nkb_all = (K + BK - 1) / BK;
+  const int kb_lo = (int)(((long long)nkb_all * blockIdx.z) / gridDim.z);
+  const int kb_hi = (int)(((long long)nkb_all * (blockIdx.z + 1)) / gridDim.z);
+  const int nkb = kb_hi - kb_lo;
+  const bool split = gridDim.z > 1;
   constexpr uint32_t TMEM_COLS = (BN <= 32) ? 32 : (BN <= 64) ? 64 : (BN <= 128) ? 128 : 256;
 
   if (warp == 0 && lane == 0) {
@@ -140,7 +146,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint8_t* sa = smem + s * S::STAGE;
         uint8_t* sb = sa + S::A_BYTES;
         mbar_expect_tx(&full[s], S::STAGE);
-        const int k0 = kb * BK;
+        const int k0 = (kb_lo + kb) * BK;
         if (A_MN) {
 #pragma unroll
           for (int j = 0; j < BM / 32; ++j) tma_load_2d(sa + j * (BK * 128), &tmA, &full[s], m0 + 32 * j, k0);
@@ -181,11 +187,15 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       umma_commit(tmem_full);            // accumulator complete
     }
   } else {
-    // ===== epilogue: TMEM -> registers -> global =====
+    // ===== epilogue: TMEM -> registers -> smem transpose -> coalesced global stores =====
+    // tcgen05.ld hands every lane one accumulator ROW (32 consecutive columns); storing that directly would make
+    // each warp store touch 32 different rows.  Each warp transposes its 32 x 32 block through a padded smem
+    // staging tile (the pipeline buffers are idle once tmem_full has fired) so that one store / atomic instruction
+    // covers 128 contiguous bytes of one output row.
     mbar_wait(tmem_full, 0);
     tcgen05_fence_after();
     const int q = warp & 3;              // TMEM lane quarter this warp may access
-    const int m = m0 + q * 32 + lane;
+    float* stg = reinterpret_cast<float*>(smem) + q * (32 * 33);
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t r[32];
@@ -200,33 +210,54 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (m < M) {
-        float* crow = C + (size_t)m * ldc;
+      if (n0 + c0 >= N) continue;        // warp-uniform: nothing to store from this chunk
+      if (split) {
+        // split-K: transpose the warp's 32 x 32 block through smem so one atomic instruction covers 128 contiguous
+        // bytes of one output row (8x fewer L2 atomic sector operations than one row per lane)
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int n = n0 + c0 + j;
-          if (n >= N) break;
-          float v[4];
+        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = alpha * __uint_as_float(r[j]);
+        __syncwarp();
+        const int n = n0 + c0 + lane;
+        const bool n_ok = n < N;
+        const float bv = (bias != nullptr && n_ok && blockIdx.z == 0) ? bias[n] : 0.f;
+        const int m_base = m0 + q * 32;
+#pragma unroll 4
+        for (int i = 0; i < 32; ++i) {
+          const int m = m_base + i;
+          if (m < M && n_ok) atomicAdd(C + (size_t)m * ldc + n, stg[i * 33 + lane] + bv);
+        }
+        __syncwarp();
+      } else {
+        // direct: each lane owns one output row and writes 32 consecutive floats as 8 float4 stores
+        const int m = m0 + q * 32 + lane;
+        if (m < M) {
+          float* crow = C + (size_t)m * ldc;
 #pragma unroll
-          for (int e = 0; e < 4; ++e) v[e] = alpha * __uint_as_float(r[j + e]);
-          if (vecC && n + 3 < N) {
-            if (bias) {
-              const float4 bb = *reinterpret_cast<const float4*>(bias + n);
-              v[0] += bb.x; v[1] += bb.y; v[2] += bb.z; v[3] += bb.w;
-            }
-            if (beta != 0.f) {
-              const float4 cc = *reinterpret_cast<const float4*>(crow + n);
-              v[0] += beta * cc.x; v[1] += beta * cc.y; v[2] += beta * cc.z; v[3] += beta * cc.w;
-            }
-            *reinterpret_cast<float4*>(crow + n) = make_float4(v[0], v[1], v[2], v[3]);
-          } else {
+          for (int j = 0; j < 32; j += 4) {
+            const int n = n0 + c0 + j;
+            if (n >= N) break;
+            float v[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              if (n + e < N) {
-                float x = v[e];
-                if (bias) x += bias[n + e];
-                if (beta != 0.f) x += beta * crow[n + e];
-                crow[n + e] = x;
+            for (int e = 0; e < 4; ++e) v[e] = alpha * __uint_as_float(r[j + e]);
+            if (vecC && n + 3 < N) {
+              if (bias) {
+                const float4 bb = *reinterpret_cast<const float4*>(bias + n);
+                v[0] += bb.x; v[1] += bb.y; v[2] += bb.z; v[3] += bb.w;
+              }
+              if (beta != 0.f) {
+                const float4 cc = *reinterpret_cast<const float4*>(crow + n);
+                v[0] += beta * cc.x; v[1] += beta * cc.y; v[2] += beta * cc.z; v[3] += beta * cc.w;
+              }
+              *reinterpret_cast<float4*>(crow + n) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (n + e < N) {
+                  float x = v[e];
+                  if (bias) x += bias[n + e];
+                  if (beta != 0.f) x += beta * crow[n + e];
+                  crow[n + e] = x;
+                }
               }
             }
           }
@@ -282,7 +313,7 @@ static bool make_map(CUtensorMap* m, const float* base, int rows, int cols, int 
 
 template <int BN, bool A_MN, bool B_MN>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, float alpha, float beta, float* C,
-                  int ldc, const float* bias, cudaStream_t s) {
+                  int ldc, const float* bias, int splits, cudaStream_t s) {
   using S = Smem<BN>;
   static bool attr = false;
   if (!attr) {
@@ -290,7 +321,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, in
     attr = true;
   }
   const int vecC = (aligned16(C) && (ldc % 4 == 0) && (!bias || aligned16(bias))) ? 1 : 0;
-  dim3 grid(cdiv(N, BN), cdiv(M, BM));
+  dim3 grid(cdiv(N, BN), cdiv(M, BM), splits);
   gemm_tf32_kernel<BN, A_MN, B_MN><<<grid, NTHREADS, S::TOTAL, s>>>(ta, tb, M, N, K, alpha, beta, C, ldc, bias, vecC);
   return check_launch("gemm_tf32_kernel");
 }
@@ -330,13 +361,26 @@ int gemm_tc(int mode, bool transA, bool transB, int M, int N, int K, float alpha
     else      ok = make_map(&tb, B, N, K, ldb, BK, BN, rn, false);        // [N rows, K cols], box 32 (K) x BN (N)
   }
   if (!ok) return GIC_OK;
+  // split-K when the output tiles alone cannot fill the machine (long-K / small-MN shapes of the backward pass)
+  int splits = 1;
+  {
+    const int tiles = cdiv(N, BN) * cdiv(M, BM), nkb = cdiv(K, BK);
+    if (tiles * 2 <= num_sms() && nkb >= 8 && (beta == 0.f || beta == 1.f)) {
+      splits = min(min(cdiv(num_sms(), tiles), nkb / 4), 32);
+      if (splits < 1) splits = 1;
+    }
+    if (splits > 1 && beta == 0.f) {
+      cudaError_t e = cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, stream);
+      if (e != cudaSuccess) { set_error("memset2D: %s", cudaGetErrorString(e)); return GIC_ERR_CUDA; }
+    }
+  }
   int rc;
 #define GIC_TC(BN_)                                                                                        \
   do {                                                                                                     \
-    if (!a_mn && !b_mn) rc = launch<BN_, false, false>(ta, tb, M, N, K, alpha, beta, C, ldc, bias, stream); \
-    else if (!a_mn && b_mn) rc = launch<BN_, false, true>(ta, tb, M, N, K, alpha, beta, C, ldc, bias, stream); \
-    else if (a_mn && !b_mn) rc = launch<BN_, true, false>(ta, tb, M, N, K, alpha, beta, C, ldc, bias, stream); \
-    else rc = launch<BN_, true, true>(ta, tb, M, N, K, alpha, beta, C, ldc, bias, stream);                  \
+    if (!a_mn && !b_mn) rc = launch<BN_, false, false>(ta, tb, M, N, K, alpha, beta, C, ldc, bias, splits, stream); \
+    else if (!a_mn && b_mn) rc = launch<BN_, false, true>(ta, tb, M, N, K, alpha, beta, C, ldc, bias, splits, stream); \
+    else if (a_mn && !b_mn) rc = launch<BN_, true, false>(ta, tb, M, N, K, alpha, beta, C, ldc, bias, splits, stream); \
+    else rc = launch<BN_, true, true>(ta, tb, M, N, K, alpha, beta, C, ldc, bias, splits, stream);                  \
   } while (0)
   if (BN == 64) GIC_TC(64); else GIC_TC(128);
 #undef GIC_TC
