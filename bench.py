@@ -335,7 +335,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--mode", default=os.environ.get("GIC_GEMM_MODE", "fp32"), choices=sorted(MODES))
+    ap.add_argument("--mode", default=os.environ.get("GIC_GEMM_MODE", "tf32"), choices=sorted(MODES))
     ap.add_argument("--cpu-sample-rows", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

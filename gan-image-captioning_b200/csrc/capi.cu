@@ -7,7 +7,7 @@ namespace gic {
 // decode.cu
 int gather_rows(const float*, const int64_t*, int, int, int, float*, cudaStream_t);
 int sample_step(bool, const float*, const float*, float, int, int, int, int, float*, int64_t*, const int64_t*,
-                const float*, int, float*, cudaStream_t);
+                const float*, int, float*, cudaStream_t, bool fast_math = false);
 int softmax_bwd(const float*, const float*, float, int, int, float*, cudaStream_t);
 int embed_scatter(const float*, const int64_t*, int, int, int, int, float*, float*, cudaStream_t);
 int bn_fwd(const float*, int, int, const float*, const float*, float, float*, float*, float*, cudaStream_t);
@@ -16,6 +16,9 @@ int bn_bwd(const float*, const float*, int, int, const float*, const float*, con
 int lstm_cell_fwd(const float*, const float*, int, int, float*, float*, float*, float*, int, int, cudaStream_t);
 int lstm_cell_bwd(const float*, const float*, const float*, const float*, long long, const float*, float*, int, int,
                   float*, cudaStream_t);
+// lstm_tcgen05.cu
+int lstm_step_tc(const float*, int, const float*, const float*, const float*, const float*, const float*, const float*,
+                 int, int, float*, float*, float*, float*, int, int, cudaStream_t, bool*);
 // disc.cu
 size_t disc_saved_floats(int, int, int, int, int);
 size_t disc_fwd_workspace_floats(int);
@@ -91,18 +94,27 @@ static int decode_fwd(int mode, const float* features, const float* W_emb, const
       const float* xin = (l == 0) ? saved + sv.xs + (size_t)t * BE : saved + sv.hs(l - 1) + (size_t)(t + 1) * BH;
       const int In = (l == 0) ? E : H;
       const float* hprev = saved + sv.hs(l) + (size_t)t * BH;
-      // gates = x W_ih^T + b_ih + h W_hh^T + b_hh          (src/generator.py:61)
-      GIC_TRY(gemm(mode, false, true, B, 4 * H, In, 1.f, xin, In, W_ih[l], In, 0.f, gates, 4 * H, b_ih[l], s));
-      GIC_TRY(gemm(mode, false, true, B, 4 * H, H, 1.f, hprev, H, W_hh[l], H, 1.f, gates, 4 * H, b_hh[l], s));
-      GIC_TRY(lstm_cell_fwd(gates, saved + sv.cs(l) + (size_t)t * BH, B, H, saved + sv.acts(l) + (size_t)t * BH * 4,
-                            saved + sv.cs(l) + (size_t)(t + 1) * BH, saved + sv.hs(l) + (size_t)(t + 1) * BH,
-                            (l == layers - 1) ? saved + sv.htop : nullptr, L, t, s));
+      float* acts_t = saved + sv.acts(l) + (size_t)t * BH * 4;
+      const float* c_prev = saved + sv.cs(l) + (size_t)t * BH;
+      float* c_new = saved + sv.cs(l) + (size_t)(t + 1) * BH;
+      float* h_new = saved + sv.hs(l) + (size_t)(t + 1) * BH;
+      float* htop = (l == layers - 1) ? saved + sv.htop : nullptr;
+      bool fused = false;
+      if (mode == GEMM_TF32)   // tensor-core mode: both contractions + the cell update in one tcgen05 kernel
+        GIC_TRY(lstm_step_tc(xin, In, hprev, W_ih[l], W_hh[l], b_ih[l], b_hh[l], c_prev, B, H, acts_t, c_new, h_new,
+                             htop, L, t, s, &fused));
+      if (!fused) {
+        // gates = x W_ih^T + b_ih + h W_hh^T + b_hh          (src/generator.py:61)
+        GIC_TRY(gemm(mode, false, true, B, 4 * H, In, 1.f, xin, In, W_ih[l], In, 0.f, gates, 4 * H, b_ih[l], s));
+        GIC_TRY(gemm(mode, false, true, B, 4 * H, H, 1.f, hprev, H, W_hh[l], H, 1.f, gates, 4 * H, b_hh[l], s));
+        GIC_TRY(lstm_cell_fwd(gates, c_prev, B, H, acts_t, c_new, h_new, htop, L, t, s));
+      }
     }
     const float* htop_t = saved + sv.hs(layers - 1) + (size_t)(t + 1) * BH;
     GIC_TRY(gemm(mode, false, true, B, V, H, 1.f, htop_t, H, W_out, H, 0.f, logits, V, b_out, s));   // :64,68
     float* x_next = (t + 1 < L) ? saved + sv.xs + (size_t)(t + 1) * BE : nullptr;
     GIC_TRY(sample_step(pretrain != 0, logits, pretrain ? nullptr : u + (size_t)t * B * V, T, B, V, L, t, out, ids,
-                        forced, W_emb, E, x_next, s));
+                        forced, W_emb, E, x_next, s, /*fast_math=*/mode == GEMM_TF32));
   }
   return GIC_OK;
 }

@@ -172,7 +172,13 @@ sample_step_kernel(const float* __restrict__ logits, const float* __restrict__ u
 // the logits row and the uniform row up front (2 * NV4 outstanding 16-byte loads), keeps its NV4 * 4 perturbed
 // logits in registers through the max / sum / normalise passes, and writes the probabilities with float4 stores.
 // Same arithmetic (accurate logf / expf, true division) and tie rule as sample_step_kernel.
-template <bool PRETRAIN, int NV4>
+// FAST (tensor-core mode only, where the logits already carry TF32 rounding): MUFU-based __logf / __expf and a
+// reciprocal multiply for the outer log / exp / normalisation.  The inner log(u) stays accurate: for u -> 1 its
+// value is tiny and __logf's absolute error would become a relative error of the Gumbel noise.
+template <bool FAST> __device__ __forceinline__ float log_f(float x) { return FAST ? __logf(x) : logf(x); }
+template <bool FAST> __device__ __forceinline__ float exp_f(float x) { return FAST ? __expf(x) : expf(x); }
+
+template <bool PRETRAIN, int NV4, bool FAST>
 __global__ void __launch_bounds__(256)
 sample_step_reg_kernel(const float* __restrict__ logits, const float* __restrict__ u, float temperature,
                        int V, int L, int t, float* __restrict__ out, int64_t* __restrict__ ids,
@@ -201,10 +207,10 @@ sample_step_reg_kernel(const float* __restrict__ logits, const float* __restrict
     if (PRETRAIN) {
       if (threadIdx.x + i * 256 < nv4) orow[threadIdx.x + i * 256] = z[i];       // out = raw logits
     } else {
-      z[i].x = (z[i].x - logf(-logf(uu[i].x + eps) + eps)) * temperature;
-      z[i].y = (z[i].y - logf(-logf(uu[i].y + eps) + eps)) * temperature;
-      z[i].z = (z[i].z - logf(-logf(uu[i].z + eps) + eps)) * temperature;
-      z[i].w = (z[i].w - logf(-logf(uu[i].w + eps) + eps)) * temperature;
+      z[i].x = (z[i].x - log_f<FAST>(-logf(uu[i].x + eps) + eps)) * temperature;
+      z[i].y = (z[i].y - log_f<FAST>(-logf(uu[i].y + eps) + eps)) * temperature;
+      z[i].z = (z[i].z - log_f<FAST>(-logf(uu[i].z + eps) + eps)) * temperature;
+      z[i].w = (z[i].w - log_f<FAST>(-logf(uu[i].w + eps) + eps)) * temperature;
     }
     mx = fmaxf(mx, fmaxf(fmaxf(z[i].x, z[i].y), fmaxf(z[i].z, z[i].w)));
   }
@@ -212,11 +218,12 @@ sample_step_reg_kernel(const float* __restrict__ logits, const float* __restrict
   float sum = 0.f;
 #pragma unroll
   for (int i = 0; i < NV4; ++i) {
-    z[i].x = expf(z[i].x - mx); z[i].y = expf(z[i].y - mx);
-    z[i].z = expf(z[i].z - mx); z[i].w = expf(z[i].w - mx);
+    z[i].x = exp_f<FAST>(z[i].x - mx); z[i].y = exp_f<FAST>(z[i].y - mx);
+    z[i].z = exp_f<FAST>(z[i].z - mx); z[i].w = exp_f<FAST>(z[i].w - mx);
     sum += (z[i].x + z[i].y) + (z[i].z + z[i].w);
   }
   sum = block_sum(sum, red);
+  const float inv = 1.0f / sum;
   float best = -1.f;
   int best_i = 0x7fffffff;
 #pragma unroll
@@ -224,7 +231,8 @@ sample_step_reg_kernel(const float* __restrict__ logits, const float* __restrict
     const int v = threadIdx.x + i * 256;
     if (v < nv4) {
       float4 p;
-      p.x = z[i].x / sum; p.y = z[i].y / sum; p.z = z[i].z / sum; p.w = z[i].w / sum;
+      if (FAST) { p.x = z[i].x * inv; p.y = z[i].y * inv; p.z = z[i].z * inv; p.w = z[i].w * inv; }
+      else { p.x = z[i].x / sum; p.y = z[i].y / sum; p.z = z[i].z / sum; p.w = z[i].w / sum; }
       if (!PRETRAIN) orow[v] = p;
       if (p.x > best) { best = p.x; best_i = 4 * v; }
       if (p.y > best) { best = p.y; best_i = 4 * v + 1; }
@@ -270,13 +278,13 @@ sample_step_reg_kernel(const float* __restrict__ logits, const float* __restrict
   }
 }
 
-template <bool PRETRAIN>
+template <bool PRETRAIN, bool FAST>
 static bool launch_sample_reg(const float* logits, const float* u, float temperature, int B, int V, int L, int t,
                               float* out, int64_t* ids, const int64_t* forced, const float* embed, int E,
                               float* x_next, cudaStream_t s) {
   const int nv4 = V >> 2;
 #define GIC_SAMPLE(NV4_)                                                                                         \
-  sample_step_reg_kernel<PRETRAIN, NV4_><<<B, 256, 0, s>>>(logits, u, temperature, V, L, t, out, ids, forced, embed, \
+  sample_step_reg_kernel<PRETRAIN, NV4_, FAST><<<B, 256, 0, s>>>(logits, u, temperature, V, L, t, out, ids, forced, embed, \
                                                            E, x_next)
   if (nv4 <= 256 * 1) GIC_SAMPLE(1);
   else if (nv4 <= 256 * 2) GIC_SAMPLE(2);
@@ -291,11 +299,13 @@ static bool launch_sample_reg(const float* logits, const float* u, float tempera
 
 int sample_step(bool pretrain, const float* logits, const float* u, float temperature, int B, int V,
                 int L, int t, float* out, int64_t* ids, const int64_t* forced, const float* embed,
-                int E, float* x_next, cudaStream_t s) {
+                int E, float* x_next, cudaStream_t s, bool fast_math) {
   ProfScope prof(PROF_SAMPLE, 8.0 * B * V, s);     // algorithmic HBM bytes: read u, write probs
   if ((V % 4 == 0) && aligned16(logits) && aligned16(out) && (pretrain || aligned16(u))) {
-    const bool done = pretrain ? launch_sample_reg<true>(logits, u, temperature, B, V, L, t, out, ids, forced, embed, E, x_next, s)
-                               : launch_sample_reg<false>(logits, u, temperature, B, V, L, t, out, ids, forced, embed, E, x_next, s);
+    bool done;
+    if (pretrain) done = launch_sample_reg<true, false>(logits, u, temperature, B, V, L, t, out, ids, forced, embed, E, x_next, s);
+    else if (fast_math) done = launch_sample_reg<false, true>(logits, u, temperature, B, V, L, t, out, ids, forced, embed, E, x_next, s);
+    else done = launch_sample_reg<false, false>(logits, u, temperature, B, V, L, t, out, ids, forced, embed, E, x_next, s);
     if (done) return check_launch("sample_step_reg_kernel");
   }
   const size_t smem = (size_t)V * sizeof(float);

@@ -9,90 +9,18 @@
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue
 // (TMEM lane quarter = warp_id % 4).  One 128 x BN output tile per CTA.
-#include <cuda.h>
-
-#include <map>
-#include <tuple>
-
-#include "gic_internal.cuh"
+#include "tcgen05_common.cuh"
 
 namespace gic {
 
 namespace tc {
-
-constexpr int BM = 128;        // UMMA M (cta_group::1)
-constexpr int BK = 32;         // fp32 elements per stage along K = one 128-byte swizzle row
-constexpr int UMMA_K = 8;      // kind::tf32: 32 bytes of K per instruction
-constexpr int NTHREADS = 192;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// Bounded wait: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  for (uint32_t spin = 0;; ++spin) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-    if (done) return;
-    if (spin > (1u << 26)) __trap();
-  }
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-
-// UMMA shared-memory descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
-//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4
-//   [46,48) version = 1 (sm_100) | [61,64) layout type = 2 (SWIZZLE_128B)
-//   layout type 2 = SWIZZLE_128B (16-byte atoms; K-major tiles), 1 = SWIZZLE_128B_BASE32B (32-byte atoms: the only
-//   layout the hardware accepts for MN-major tf32 operands, cutlass sm100_common.inl:92)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)layout << 61;
-  return d;
-}
-
-// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) at [4,6), a/b format TF32 (2) at [7,10),
-// [10,13), a_major [15], b_major [16] (0 = K-major, 1 = MN-major), N >> 3 at [17,23), M >> 4 at [24,29).
-__host__ __device__ constexpr uint32_t make_idesc(int a_mn, int b_mn, int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
-         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-}
 
 template <int BN>
 struct Smem {
   static constexpr int A_BYTES = BM * BK * 4;     // 16 KB
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int STAGE = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN >= 128) ? 6 : 8;
+  static constexpr int STAGES = (196 * 1024 / STAGE) > 8 ? 8 : (196 * 1024 / STAGE);
   static constexpr int TOTAL = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -195,45 +123,36 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     mbar_wait(tmem_full, 0);
     tcgen05_fence_after();
     const int q = warp & 3;              // TMEM lane quarter this warp may access
-    float* stg = reinterpret_cast<float*>(smem) + q * (32 * 33);
+    float* stg = reinterpret_cast<float*>(smem) + q * (32 * 17);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-            "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-            "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-          : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
       if (n0 + c0 >= N) continue;        // warp-uniform: nothing to store from this chunk
       if (split) {
-        // split-K: transpose the warp's 32 x 32 block through smem so one atomic instruction covers 128 contiguous
-        // bytes of one output row (8x fewer L2 atomic sector operations than one row per lane)
+        // split-K: transpose the warp's 32 x 16 block through smem so that one atomic instruction covers two
+        // 64-byte row segments instead of 32 different rows (fewer L2 atomic sector operations)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = alpha * __uint_as_float(r[j]);
+        for (int j = 0; j < 16; ++j) stg[lane * 17 + j] = alpha * __uint_as_float(r[j]);
         __syncwarp();
-        const int n = n0 + c0 + lane;
+        const int cj = lane & 15, rh = lane >> 4;      // column within the chunk, row parity
+        const int n = n0 + c0 + cj;
         const bool n_ok = n < N;
         const float bv = (bias != nullptr && n_ok && blockIdx.z == 0) ? bias[n] : 0.f;
         const int m_base = m0 + q * 32;
 #pragma unroll 4
-        for (int i = 0; i < 32; ++i) {
-          const int m = m_base + i;
-          if (m < M && n_ok) atomicAdd(C + (size_t)m * ldc + n, stg[i * 33 + lane] + bv);
+        for (int i = 0; i < 32; i += 2) {
+          const int m = m_base + i + rh;
+          if (m < M && n_ok) atomicAdd(C + (size_t)m * ldc + n, stg[(i + rh) * 17 + cj] + bv);
         }
         __syncwarp();
       } else {
-        // direct: each lane owns one output row and writes 32 consecutive floats as 8 float4 stores
+        // direct: each lane owns one output row and writes 16 consecutive floats as 4 float4 stores
         const int m = m0 + q * 32 + lane;
         if (m < M) {
           float* crow = C + (size_t)m * ldc;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
+          for (int j = 0; j < 16; j += 4) {
             const int n = n0 + c0 + j;
             if (n >= N) break;
             float v[4];
@@ -273,44 +192,6 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// host side: tensor maps (driver entry point fetched at run time: the library does not link libcuda)
-// ---------------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
-// 2-D fp32 tensor [rows, cols] (cols contiguous, leading dimension ld) with a box of box_cols x box_rows.
-// dtype TFLOAT32: the TMA unit rounds fp32 -> tf32 while staging (unbiased, unlike the MMA's own truncation).
-static bool make_map(CUtensorMap* m, const float* base, int rows, int cols, int ld, int box_cols, int box_rows, bool rn,
-                     bool mn_major) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return false;
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, rn ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base),
-                  dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS;
-}
-
 template <int BN, bool A_MN, bool B_MN>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, float alpha, float beta, float* C,
                   int ldc, const float* bias, int splits, cudaStream_t s) {
@@ -324,15 +205,6 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, in
   dim3 grid(cdiv(N, BN), cdiv(M, BM), splits);
   gemm_tf32_kernel<BN, A_MN, B_MN><<<grid, NTHREADS, S::TOTAL, s>>>(ta, tb, M, N, K, alpha, beta, C, ldc, bias, vecC);
   return check_launch("gemm_tf32_kernel");
-}
-
-static bool tf32_round_in_tma() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("GIC_TMA_TF32_RN");
-    v = (e && e[0] == '0') ? 0 : 1;
-  }
-  return v == 1;
 }
 
 }  // namespace tc
@@ -351,7 +223,20 @@ int gemm_tc(int mode, bool transA, bool transB, int M, int N, int K, float alpha
   const bool rn = tf32_round_in_tma();
   const bool a_mn = transA;       // A stored [K, M]: contiguous along M
   const bool b_mn = !transB;      // B stored [K, N]: contiguous along N
-  const int BN = (N <= 64) ? 64 : 128;
+  // tile width: minimise waves x bytes-per-k-block (the main loop is bound by L2 -> smem traffic, (128 + BN) rows of
+  // 128 B per k-block), e.g. N = 10000, M = 256 -> BN = 144 (140 CTAs, one wave) instead of 128 (158 CTAs, two waves)
+  static const int kBN[6] = {64, 128, 144, 192, 240, 256};
+  int BN = 128;
+  {
+    long long best = -1;
+    for (int i = 0; i < 6; ++i) {
+      const int bn = kBN[i];
+      if (b_mn && (bn % 32)) continue;                 // MN-major B is loaded as 32-wide slabs
+      const long long tiles = (long long)cdiv(N, bn) * cdiv(M, BM);
+      const long long cost = (long long)cdiv(tiles, num_sms()) * (BM + bn) + bn / 64;   // tie-break: smaller tile
+      if (best < 0 || cost < best) { best = cost; BN = bn; }
+    }
+  }
   CUtensorMap ta, tb;
   bool ok;
   if (a_mn) ok = make_map(&ta, A, K, M, lda, 32, BK, rn, true);           // [K rows, M cols], box 32 (M) x 32 (K)
@@ -374,15 +259,24 @@ int gemm_tc(int mode, bool transA, bool transB, int M, int N, int K, float alpha
       if (e != cudaSuccess) { set_error("memset2D: %s", cudaGetErrorString(e)); return GIC_ERR_CUDA; }
     }
   }
-  int rc;
-#define GIC_TC(BN_)                                                                                        \
-  do {                                                                                                     \
+  int rc = GIC_OK;
+#define GIC_TC(BN_)                                                                                                \
+  do {                                                                                                             \
     if (!a_mn && !b_mn) rc = launch<BN_, false, false>(ta, tb, M, N, K, alpha, beta, C, ldc, bias, splits, stream); \
-    else if (!a_mn && b_mn) rc = launch<BN_, false, true>(ta, tb, M, N, K, alpha, beta, C, ldc, bias, splits, stream); \
     else if (a_mn && !b_mn) rc = launch<BN_, true, false>(ta, tb, M, N, K, alpha, beta, C, ldc, bias, splits, stream); \
-    else rc = launch<BN_, true, true>(ta, tb, M, N, K, alpha, beta, C, ldc, bias, splits, stream);                  \
+    else if constexpr ((BN_ % 32) == 0) {                                                                          \
+      if (!a_mn) rc = launch<BN_, false, true>(ta, tb, M, N, K, alpha, beta, C, ldc, bias, splits, stream);          \
+      else rc = launch<BN_, true, true>(ta, tb, M, N, K, alpha, beta, C, ldc, bias, splits, stream);                 \
+    }                                                                                                              \
   } while (0)
-  if (BN == 64) GIC_TC(64); else GIC_TC(128);
+  switch (BN) {
+    case 64: GIC_TC(64); break;
+    case 128: GIC_TC(128); break;
+    case 144: GIC_TC(144); break;
+    case 192: GIC_TC(192); break;
+    case 240: GIC_TC(240); break;
+    default: GIC_TC(256); break;
+  }
 #undef GIC_TC
   if (rc == GIC_OK) *handled = true;
   return rc;

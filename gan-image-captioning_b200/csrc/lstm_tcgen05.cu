@@ -1,0 +1,172 @@
+// Fused LSTM decode step on the tensor cores (sm_100a): one kernel computes
+//     gates = x W_ih^T + h W_hh^T + b_ih + b_hh            (both contractions accumulate into one TMEM tile)
+//     i,f,g,o -> c' = sig(f) c + sig(i) tanh(g),  h' = sig(o) tanh(c')
+// for one layer and one time step (src/generator.py:61).  It replaces two GEMM launches, the [B,4H] gates round
+// trip through HBM and the cell kernel of the unfused path.
+//
+// Tiling: a CTA owns 128 batch rows x 32 hidden units.  Its B operand tile is gate-interleaved: four 32-row slabs
+// of the weight matrix (rows g*H + j0 .. j0+31 for g = i,f,g,o) are TMA-loaded next to each other, so the 128
+// accumulator columns are [i(32) | f(32) | g(32) | o(32)] of the same 32 units and the cell update is an epilogue
+// on the TMEM tile.  The k loop runs over ceil(In/32) blocks of (x, W_ih) followed by ceil(H/32) blocks of
+// (h, W_hh).  Warp roles as in gemm_tcgen05.cu.
+#include "tcgen05_common.cuh"
+
+namespace gic {
+namespace tc {
+
+constexpr int LSTM_STAGE = 2 * BM * BK * 4;     // A 16 KB + B 16 KB
+constexpr int LSTM_STAGES = 6;
+constexpr int LSTM_SMEM = LSTM_STAGES * LSTM_STAGE + 1024 + 256;
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+lstm_step_tf32_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmH,
+                      const __grid_constant__ CUtensorMap tmWih, const __grid_constant__ CUtensorMap tmWhh, int B,
+                      int H, int In, const float* __restrict__ b_ih, const float* __restrict__ b_hh,
+                      const float* __restrict__ c_prev, float* __restrict__ acts, float* __restrict__ c_out,
+                      float* __restrict__ h_out, float* __restrict__ htop, int L, int t) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + LSTM_STAGES * LSTM_STAGE);
+  uint64_t* empty = full + LSTM_STAGES;
+  uint64_t* tmem_full = empty + LSTM_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j0 = blockIdx.x * 32, m0 = blockIdx.y * BM;
+  const int nkb1 = (In + BK - 1) / BK, nkb2 = (H + BK - 1) / BK, nkb = nkb1 + nkb2;
+  constexpr uint32_t TMEM_COLS = 128;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWih) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmH) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWhh) : "memory");
+    for (int s = 0; s < LSTM_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % LSTM_STAGES;
+        const uint32_t ph = (kb / LSTM_STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* sa = smem + s * LSTM_STAGE;
+        uint8_t* sb = sa + BM * BK * 4;
+        mbar_expect_tx(&full[s], LSTM_STAGE);
+        const bool first = kb < nkb1;
+        const int k0 = (first ? kb : kb - nkb1) * BK;
+        tma_load_2d(sa, first ? &tmX : &tmH, &full[s], k0, m0);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) tma_load_2d(sb + g * 4096, first ? &tmWih : &tmWhh, &full[s], k0, g * H + j0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(0, 0, 128);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % LSTM_STAGES;
+        const uint32_t ph = (kb / LSTM_STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        tcgen05_fence_after();
+        const uint32_t sa = smem_u32(smem + s * LSTM_STAGE);
+        const uint32_t sb = sa + BM * BK * 4;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k)
+          umma_tf32(tmem_base, make_desc(sa + k * 32, 16, 1024, 2), make_desc(sb + k * 32, 16, 1024, 2), idesc,
+                    (kb > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&empty[s]);
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    // ===== epilogue: LSTM cell on the accumulator tile =====
+    mbar_wait(tmem_full, 0);
+    tcgen05_fence_after();
+    const int q = warp & 3;
+    const int b = m0 + q * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+    for (int u0 = 0; u0 < 32; u0 += 8) {
+      uint32_t ri[8], rf[8], rg[8], ro[8];
+      tmem_ld8(lane_addr + 0 * 32 + u0, ri);
+      tmem_ld8(lane_addr + 1 * 32 + u0, rf);
+      tmem_ld8(lane_addr + 2 * 32 + u0, rg);
+      tmem_ld8(lane_addr + 3 * 32 + u0, ro);
+      if (b < B) {
+        const int j = j0 + u0;
+        float cp[8], ai[8], af[8], ag[8], ao[8], cn[8], hn[8];
+        *reinterpret_cast<float4*>(cp) = *reinterpret_cast<const float4*>(c_prev + (size_t)b * H + j);
+        *reinterpret_cast<float4*>(cp + 4) = *reinterpret_cast<const float4*>(c_prev + (size_t)b * H + j + 4);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float pi = __uint_as_float(ri[e]) + b_ih[0 * H + j + e] + b_hh[0 * H + j + e];
+          const float pf = __uint_as_float(rf[e]) + b_ih[1 * H + j + e] + b_hh[1 * H + j + e];
+          const float pg = __uint_as_float(rg[e]) + b_ih[2 * H + j + e] + b_hh[2 * H + j + e];
+          const float po = __uint_as_float(ro[e]) + b_ih[3 * H + j + e] + b_hh[3 * H + j + e];
+          ai[e] = sigmoidf_acc(pi); af[e] = sigmoidf_acc(pf); ag[e] = tanhf(pg); ao[e] = sigmoidf_acc(po);
+          cn[e] = af[e] * cp[e] + ai[e] * ag[e];
+          hn[e] = ao[e] * tanhf(cn[e]);
+        }
+        float* arow = acts + (size_t)b * 4 * H + j;
+        auto st8 = [](float* dst, const float* v) {
+          *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        };
+        st8(arow, ai); st8(arow + H, af); st8(arow + 2 * H, ag); st8(arow + 3 * H, ao);
+        st8(c_out + (size_t)b * H + j, cn);
+        st8(h_out + (size_t)b * H + j, hn);
+        if (htop) st8(htop + ((size_t)b * L + t) * H + j, hn);
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+  }
+}
+
+}  // namespace tc
+
+// One LSTM layer / time step on the tensor cores.  handled = false (nothing launched) when the shape does not fit
+// the kernel (H % 32, TMA alignment); the caller then runs the unfused GEMM + cell path.
+int lstm_step_tc(const float* x, int In, const float* h_prev, const float* W_ih, const float* W_hh, const float* b_ih,
+                 const float* b_hh, const float* c_prev, int B, int H, float* acts, float* c_out, float* h_out,
+                 float* htop, int L, int t, cudaStream_t stream, bool* handled) {
+  using namespace tc;
+  *handled = false;
+  if (B <= 0 || (H % 32) || (In % 4) || In < 4) return GIC_OK;
+  const void* ptrs[] = {x, h_prev, W_ih, W_hh, c_prev, acts, c_out, h_out, htop ? htop : h_out};
+  for (const void* p : ptrs)
+    if (!aligned16(p)) return GIC_OK;
+  const bool rn = tf32_round_in_tma();
+  CUtensorMap tx, th, twi, twh;
+  bool ok = make_map(&tx, x, B, In, In, BK, BM, rn, false) && make_map(&th, h_prev, B, H, H, BK, BM, rn, false) &&
+            make_map(&twi, W_ih, 4 * H, In, In, BK, 32, rn, false) && make_map(&twh, W_hh, 4 * H, H, H, BK, 32, rn, false);
+  if (!ok) return GIC_OK;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(lstm_step_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LSTM_SMEM);
+    attr = true;
+  }
+  ProfScope prof(PROF_GEMM, 2.0 * B * 4 * H * (In + H), stream);
+  dim3 grid(H / 32, cdiv(B, BM));
+  lstm_step_tf32_kernel<<<grid, NTHREADS, LSTM_SMEM, stream>>>(tx, th, twi, twh, B, H, In, b_ih, b_hh, c_prev, acts,
+                                                              c_out, h_out, htop, L, t);
+  int rc = check_launch("lstm_step_tf32_kernel");
+  if (rc == GIC_OK) *handled = true;
+  return rc;
+}
+
+}  // namespace gic

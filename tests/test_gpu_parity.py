@@ -498,3 +498,49 @@ def test_empty_batch_and_bad_shapes():
         disc(torch.rand(2, 4, 30, device=dev()))          # L=4 < max filter size 5 (reference also fails)
     with pytest.raises(ValueError):
         disc(torch.rand(2, 8, 31, device=dev()))          # wrong vocab
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core mode (tcgen05 kind::tf32, fp32 accumulate): stated separately from the exact-fp32 mode
+# ------------------------------------------------------------------------------------------------
+MID = dict(B=64, L=16, V=2000, E=64, H=256, layers=1, feat=512, filters=[300, 300, 300])
+
+
+@pytest.fixture
+def tf32_mode():
+    import gic_b200
+    old = gic_b200.get_gemm_mode()
+    gic_b200.set_gemm_mode(gic_b200.GEMM_TF32)
+    yield
+    gic_b200.set_gemm_mode(old)
+
+
+def test_fused_step_tf32_mode_vs_oracle(tf32_mode):
+    """Same step, dense contractions on the tensor cores (TF32 operands rounded to nearest by the TMA unit,
+    fp32 accumulation).  Expected: token ids still bit-exact up to ties; values within 1e-3 of the tensor
+    scale for activations/losses and within 1e-2 for gradients (10-bit mantissa operands); reported."""
+    from gic_b200.training import GANInstructor
+    inp = rp.make_inputs(MID)
+    a = inp["args"]
+    T = 1.0
+    ref = rp.adversarial_step(inp, T, "standard")
+    a.device = "cuda"
+    inst = GANInstructor(a, device="cuda:0")
+    sd = inst.gen.state_dict(); sd.update({k: v.clone() for k, v in inp["gen"].items()}); inst.gen.load_state_dict(sd)
+    inst.disc.load_state_dict({k: v.clone() for k, v in inp["disc"].items()})
+    inst.gen.train(); inst.disc.train(); inst.gen.decoder.temperature = T
+    out = inst.adv_step(inp["captions"], pooled=inp["pooled"], u=inp["u"], keep=inp["keep"], forced_ids=ref["ids"])
+    torch.cuda.synchronize()
+    mism = int((out["ids"].cpu() != ref["ids"]).sum())
+    REPORT["tf32/step/id_mismatches"] = dict(mismatches=mism, total=int(ref["ids"].numel()))
+    assert mism <= 2, f"{mism} token mismatches in TF32 mode"
+    # probabilities amplify the TF32 rounding of the logits by (1 - p) * |logit| * T: 5e-3 of the row scale
+    close("tf32/step/probs", out["probs"], ref["probs"], rtol=5e-3)
+    for k in ("d_real", "d_fake", "g_out", "g_loss", "d_loss", "features"):
+        close(f"tf32/step/{k}", out[k], ref[k], rtol=2e-3)
+    fd, fg = inst._flat_d, inst._flat_g
+    for k, p in inst.disc.named_parameters():
+        close(f"tf32/step/d_grads/{k}", fd.g(p), ref["d_grads"][k], rtol=1e-2, atol=1e-9, outlier_frac=1e-2)
+    for k, p in inst.gen.named_parameters():
+        if k in ref["g_grads"]:
+            close(f"tf32/step/g_grads/{k}", fg.g(p), ref["g_grads"][k], rtol=1e-2, atol=1e-9, outlier_frac=1e-2)
