@@ -60,7 +60,8 @@ def _declare(L):
     L.gic_encoder_bwd.argtypes = [I, P, P, P, P, P, P, P, I, I, I, P, P, P, P, P, I, P]
     L.gic_sample_step.argtypes = [I, P, P, F, I, I, I, I, P, P, P, P, I, P, P]
     for f in (L.gic_decode_saved_floats, L.gic_decode_fwd_workspace_floats, L.gic_decode_bwd_workspace_floats,
-              L.gic_disc_saved_floats, L.gic_disc_fwd_workspace_floats, L.gic_disc_bwd_workspace_floats):
+              L.gic_disc_saved_floats, L.gic_disc_fwd_workspace_floats, L.gic_disc_bwd_workspace_floats,
+              L.gic_disc_bwd_demb_offset_floats):
         f.restype = Z
     L.gic_decode_saved_floats.argtypes = [I] * 5
     L.gic_decode_fwd_workspace_floats.argtypes = [I] * 3
@@ -68,6 +69,9 @@ def _declare(L):
     L.gic_disc_saved_floats.argtypes = [I] * 5
     L.gic_disc_fwd_workspace_floats.argtypes = [I]
     L.gic_disc_bwd_workspace_floats.argtypes = [I] * 5
+    L.gic_disc_bwd_demb_offset_floats.argtypes = [I] * 5
+    L.gic_decode_sample_bwd_factored.argtypes = [I, P, P, P, I, P, P, P, P, P, P, F, I, I, I, I, I, I, P, P, P, P, P, P,
+                                                 P, P, P, P, I, P]
     L.gic_decode_sample_fwd.argtypes = [I, P, P, P, P, P, P, P, P, P, F, I, P, I, I, I, I, I, I, P, P, P, P, P]
     L.gic_decode_sample_bwd.argtypes = [I, P, P, P, P, P, P, P, F, I, I, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P,
                                         I, P]

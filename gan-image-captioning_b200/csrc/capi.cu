@@ -9,6 +9,8 @@ int gather_rows(const float*, const int64_t*, int, int, int, float*, cudaStream_
 int sample_step(bool, const float*, const float*, float, int, int, int, int, float*, int64_t*, const int64_t*,
                 const float*, int, float*, cudaStream_t, bool fast_math = false);
 int softmax_bwd(const float*, const float*, float, int, int, float*, cudaStream_t);
+int rowdot(const float*, const float*, int, int, float*, cudaStream_t);
+int softmax_bwd_dot(const float*, const float*, const float*, float, int, int, float*, cudaStream_t);
 int embed_scatter(const float*, const int64_t*, int, int, int, int, float*, float*, cudaStream_t);
 int bn_fwd(const float*, int, int, const float*, const float*, float, float*, float*, float*, cudaStream_t);
 int bn_bwd(const float*, const float*, int, int, const float*, const float*, const float*, float*, float*, float*,
@@ -16,6 +18,9 @@ int bn_bwd(const float*, const float*, int, int, const float*, const float*, con
 int lstm_cell_fwd(const float*, const float*, int, int, float*, float*, float*, float*, int, int, cudaStream_t);
 int lstm_cell_bwd(const float*, const float*, const float*, const float*, long long, const float*, float*, int, int,
                   float*, cudaStream_t);
+// gemm_dispatch.cu
+int gemm_dz(int, int, int, int, const float*, int, const float*, int, const float*, const float*, float, float*, int,
+            cudaStream_t, bool*);
 // lstm_tcgen05.cu
 int lstm_step_tc(const float*, int, const float*, const float*, const float*, const float*, const float*, const float*,
                  int, int, float*, float*, float*, float*, int, int, cudaStream_t, bool*);
@@ -121,9 +126,9 @@ static int decode_fwd(int mode, const float* features, const float* W_emb, const
 
 // backward workspace (floats):
 //   dlogits[B*L*V] | dHtop[B*L*H] | dG[layers][L][B][4H] | dh_rec[layers][B][H] | dc_rec[layers][B][H]
-//   | dxin[B][H] | dX[L][B][E]
+//   | dxin[B][H] | dX[L][B][E] | dot[B*L]
 struct DecodeBwdWs {
-  size_t dlogits, dhtop, dG, dhrec, dcrec, dxin, dX, total;
+  size_t dlogits, dhtop, dG, dhrec, dcrec, dxin, dX, dot, total;
   DecodeBwdWs(int B, int L, int V, int E, int H, int layers) {
     const size_t BH = (size_t)B * H;
     dlogits = 0;
@@ -133,11 +138,15 @@ struct DecodeBwdWs {
     dcrec = dhrec + (size_t)layers * a4(BH);
     dxin = dcrec + (size_t)layers * a4(BH);
     dX = dxin + a4(BH);
-    total = dX + a4((size_t)L * B * E);
+    dot = dX + a4((size_t)L * B * E);
+    total = dot + a4((size_t)B * L);
   }
 };
 
-static int decode_bwd(int mode, const float* dout, const float* out, const int64_t* fed, const float* W_emb,
+// dout source: dense dout[B,L,V], or (dout == nullptr) the factored form d(emb)[B*L,De] x W_e[De,V] coming out of the
+// discriminator's embedding layer, with emb[B*L,De] = out W_e^T saved by its forward.
+static int decode_bwd(int mode, const float* dout, const float* demb, const float* emb, const float* W_e, int De,
+                      const float* out, const int64_t* fed, const float* W_emb,
                       const float* const* W_ih, const float* const* W_hh, const float* W_out, float T, int pretrain,
                       int B, int L, int V, int E, int H, int layers, const float* saved, float* ws, float* dW_emb,
                       float* const* dW_ih, float* const* dW_hh, float* const* db_ih, float* const* db_hh,
@@ -145,7 +154,7 @@ static int decode_bwd(int mode, const float* dout, const float* out, const int64
   GIC_REQUIRE(B >= 0 && L >= 1 && V >= 1 && E >= 1 && H >= 1 && layers >= 1 && layers <= 8, GIC_ERR_SHAPE,
               "decode_sample_bwd: bad shape");
   if (B == 0) return GIC_OK;
-  GIC_REQUIRE(dout && fed && W_emb && W_ih && W_hh && W_out && saved && ws && dW_emb && dW_ih && dW_hh && db_ih &&
+  GIC_REQUIRE((dout || (demb && emb && W_e && De >= 1)) && fed && W_emb && W_ih && W_hh && W_out && saved && ws && dW_emb && dW_ih && dW_hh && db_ih &&
                   db_hh && dW_out && db_out, GIC_ERR_NULL, "decode_sample_bwd: NULL pointer");
   GIC_REQUIRE(pretrain || out, GIC_ERR_NULL, "decode_sample_bwd: soft captions `out` required");
   const DecodeSaved sv(B, L, E, H, layers);
@@ -157,7 +166,25 @@ static int decode_bwd(int mode, const float* dout, const float* out, const int64
 
   // 1. through the tempered softmax (the Gumbel add is a constant)
   const float* dlogits = dout;
-  if (!pretrain) {
+  if (dout == nullptr) {
+    GIC_REQUIRE(!pretrain, GIC_ERR_UNSUPPORTED, "decode_sample_bwd: factored dout is the adversarial path only");
+    // dz = T p (d(emb) W_e - <d(emb), emb>): d(probs) is never materialised in tensor-core mode
+    if (mode == GEMM_FP32) {
+      // parity mode keeps the reference's own arithmetic: dense d(probs), then sum_v p dp per row (at T = 100 the
+      // softmax saturates and dz is a difference of nearly equal numbers; a different dot product shows up there)
+      GIC_TRY(gemm(mode, false, false, BL, V, De, 1.f, demb, De, W_e, V, 0.f, ws + w.dlogits, V, nullptr, s));
+      GIC_TRY(softmax_bwd(out, ws + w.dlogits, T, BL, V, ws + w.dlogits, s));
+    } else {
+      GIC_TRY(rowdot(demb, emb, BL, De, ws + w.dot, s));
+      bool fused = false;
+      GIC_TRY(gemm_dz(mode, BL, V, De, demb, De, W_e, V, out, ws + w.dot, T, ws + w.dlogits, V, s, &fused));
+      if (!fused) {
+        GIC_TRY(gemm(mode, false, false, BL, V, De, 1.f, demb, De, W_e, V, 0.f, ws + w.dlogits, V, nullptr, s));
+        GIC_TRY(softmax_bwd_dot(out, ws + w.dlogits, ws + w.dot, T, BL, V, ws + w.dlogits, s));
+      }
+    }
+    dlogits = ws + w.dlogits;
+  } else if (!pretrain) {
     GIC_TRY(softmax_bwd(out, dout, T, BL, V, ws + w.dlogits, s));
     dlogits = ws + w.dlogits;
   }
@@ -298,9 +325,29 @@ int gic_decode_sample_bwd(int mode, const float* dout, const float* out, const i
                           float* const* db_ih, float* const* db_hh, float* dW_out, float* db_out, float* dfeatures,
                           int accumulate, gic_stream_t stream) {
   GIC_TRY(require_device());
-  return decode_bwd(mode, dout, out, fed_ids, W_emb, W_ih, W_hh, W_out, temperature, pretrain, B, L, V, E, H, layers,
-                    saved, workspace, dW_emb, dW_ih, dW_hh, db_ih, db_hh, dW_out, db_out, dfeatures, accumulate,
-                    S(stream));
+  return decode_bwd(mode, dout, nullptr, nullptr, nullptr, 0, out, fed_ids, W_emb, W_ih, W_hh, W_out, temperature,
+                    pretrain, B, L, V, E, H, layers, saved, workspace, dW_emb, dW_ih, dW_hh, db_ih, db_hh, dW_out, db_out,
+                    dfeatures, accumulate, S(stream));
+}
+
+int gic_decode_sample_bwd_factored(int mode, const float* demb, const float* emb, const float* W_e, int De,
+                                   const float* out, const int64_t* fed_ids, const float* W_emb,
+                                   const float* const* W_ih, const float* const* W_hh, const float* W_out,
+                                   float temperature, int B, int L, int V, int E, int H, int layers, const float* saved,
+                                   float* workspace, float* dW_emb, float* const* dW_ih, float* const* dW_hh,
+                                   float* const* db_ih, float* const* db_hh, float* dW_out, float* db_out,
+                                   float* dfeatures, int accumulate, gic_stream_t stream) {
+  GIC_TRY(require_device());
+  GIC_REQUIRE(demb && emb && W_e && De >= 1, GIC_ERR_NULL, "decode_sample_bwd_factored: NULL factor");
+  return decode_bwd(mode, nullptr, demb, emb, W_e, De, out, fed_ids, W_emb, W_ih, W_hh, W_out, temperature, 0, B, L, V,
+                    E, H, layers, saved, workspace, dW_emb, dW_ih, dW_hh, db_ih, db_hh, dW_out, db_out, dfeatures,
+                    accumulate, S(stream));
+}
+
+size_t gic_disc_bwd_demb_offset_floats(int N, int L, int De, int R, int F) {
+  (void)L; (void)De;
+  const size_t rows = (size_t)N * R;
+  return a4((size_t)F + 1) + 2 * a4(rows * F) + 2 * a4(F);
 }
 
 size_t gic_disc_saved_floats(int N, int L, int De, int R, int F) { return disc_saved_floats(N, L, De, R, F); }

@@ -53,76 +53,92 @@ __global__ void disc_embed_ids_bwd_kernel(const int64_t* __restrict__ ids, int n
 // the embedding reads are warp broadcasts.  ES1 fast path: float4 over 4 representations.
 // out: pooled[(n*R + r)*F + c] = max_t relu(conv), arg = first t attaining it (uint8).
 // ---------------------------------------------------------------------------------------
-// one (feature column, 4 representations) work item of the ES1 fast path, filter size FK
+// arg value stored when the pooled activation is not positive: ReLU passes no gradient there, so the backward
+// kernels need neither the pooled value nor a time index for that entry.
+constexpr int ARG_DEAD = 255;
+
+// one (feature column, 4 representations) work item of the ES1 fast path, filter size FK.  The FK embedding rows under
+// the filter are kept in a register window that slides one row per time step (one LDS.128 per step instead of FK); the
+// ReLU is hoisted out of the max (max_t relu(x_t) = relu(max_t x_t), same first arg-max whenever the max is positive).
 template <int FK>
 __device__ __forceinline__ void conv_item_es1(const float* emb_s, const float* wk_s, int F, int c, float bias,
                                               int L, int R, int rb, float4& best, int (&a)[4]) {
   float w[FK];
 #pragma unroll
   for (int k = 0; k < FK; ++k) w[k] = wk_s[k * F + c];
-  best = make_float4(-1.f, -1.f, -1.f, -1.f);
+  best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
   a[0] = a[1] = a[2] = a[3] = 0;
   const int T = L - FK + 1;
+  const float4* e4 = reinterpret_cast<const float4*>(emb_s) + rb;     // row t at e4[t * (R / 4)]
+  const int RS = R >> 2;
+  float4 win[FK];
+#pragma unroll
+  for (int k = 0; k < FK - 1; ++k) win[k] = e4[k * RS];
+#pragma unroll 4
   for (int t = 0; t < T; ++t) {
+    win[FK - 1] = e4[(t + FK - 1) * RS];
     float4 acc = make_float4(bias, bias, bias, bias);
 #pragma unroll
     for (int k = 0; k < FK; ++k) {
-      const float4 e = *reinterpret_cast<const float4*>(&emb_s[(t + k) * R + rb * 4]);
-      acc.x = fmaf(w[k], e.x, acc.x);
-      acc.y = fmaf(w[k], e.y, acc.y);
-      acc.z = fmaf(w[k], e.z, acc.z);
-      acc.w = fmaf(w[k], e.w, acc.w);
+      acc.x = fmaf(w[k], win[k].x, acc.x);
+      acc.y = fmaf(w[k], win[k].y, acc.y);
+      acc.z = fmaf(w[k], win[k].z, acc.z);
+      acc.w = fmaf(w[k], win[k].w, acc.w);
     }
-    acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f);
-    acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
     if (acc.x > best.x) { best.x = acc.x; a[0] = t; }
     if (acc.y > best.y) { best.y = acc.y; a[1] = t; }
     if (acc.z > best.z) { best.z = acc.z; a[2] = t; }
     if (acc.w > best.w) { best.w = acc.w; a[3] = t; }
+#pragma unroll
+    for (int k = 0; k < FK - 1; ++k) win[k] = win[k + 1];
   }
+  if (!(best.x > 0.f)) { best.x = 0.f; a[0] = ARG_DEAD; }
+  if (!(best.y > 0.f)) { best.y = 0.f; a[1] = ARG_DEAD; }
+  if (!(best.z > 0.f)) { best.z = 0.f; a[2] = ARG_DEAD; }
+  if (!(best.w > 0.f)) { best.w = 0.f; a[3] = ARG_DEAD; }
 }
 
+// grid = (captions, column slices): CTA (n, y) handles feature columns [y*cs, (y+1)*cs) of caption n for all R
+// representations, so that N * slices CTAs balance over the SMs even at N = 256.
 template <bool ES1>
 __global__ void __launch_bounds__(256)
-conv_pool_fwd_kernel(const float* __restrict__ emb, int L, int De, int R, int es, ConvGroups g,
+conv_pool_fwd_kernel(const float* __restrict__ emb, int L, int De, int R, int es, ConvGroups g, int cs,
                      float* __restrict__ pooled, uint8_t* __restrict__ arg) {
   extern __shared__ __align__(16) float sm[];
   const int F = g.F, kmax = g.kmax;
+  const int c_lo = blockIdx.y * cs, c_hi = min(F, c_lo + cs), CW = c_hi - c_lo;
   float* emb_s = sm;                                // L*De (De % 4 == 0 on the ES1 path)
-  float* wk_s = emb_s + ((L * De + 3) & ~3);        // [kmax][F]
-  float* bias_s = wk_s + kmax * F;                  // [F]
-  int* fk_s = reinterpret_cast<int*>(bias_s + F);   // [F]  f*es per column
+  float* wk_s = emb_s + ((L * De + 3) & ~3);        // [kmax][cs]   (this slice's columns)
+  float* bias_s = wk_s + kmax * cs;                 // [cs]
+  int* fk_s = reinterpret_cast<int*>(bias_s + cs);  // [cs]  f*es per column
   const int n = blockIdx.x;
   for (int i = threadIdx.x; i < L * De; i += blockDim.x) emb_s[i] = emb[(size_t)n * L * De + i];
-  for (int gi = 0; gi < g.ngroups; ++gi) {
+  for (int i = threadIdx.x; i < CW * kmax; i += blockDim.x) {
+    const int cl = i / kmax, k = i % kmax, c = c_lo + cl;
+    int gi = 0;
+    while (gi + 1 < g.ngroups && c >= g.col0[gi + 1]) ++gi;
     const int fk = g.f[gi] * es;
-    for (int i = threadIdx.x; i < g.n[gi] * kmax; i += blockDim.x) {
-      const int c = i / kmax, k = i % kmax;
-      wk_s[k * F + g.col0[gi] + c] = (k < fk) ? g.w[gi][c * fk + k] : 0.f;
-    }
-    for (int c = threadIdx.x; c < g.n[gi]; c += blockDim.x) {
-      bias_s[g.col0[gi] + c] = g.b[gi][c];
-      fk_s[g.col0[gi] + c] = fk;
-    }
+    wk_s[k * cs + cl] = (k < fk) ? g.w[gi][(c - g.col0[gi]) * fk + k] : 0.f;
+    if (k == 0) { bias_s[cl] = g.b[gi][c - g.col0[gi]]; fk_s[cl] = fk; }
   }
   __syncthreads();
 
   if (ES1) {
     const int RB = R / 4;
-    for (int item = threadIdx.x; item < F * RB; item += blockDim.x) {
-      const int c = item % F, rb = item / F;
-      const float bias = bias_s[c];
+    for (int item = threadIdx.x; item < CW * RB; item += blockDim.x) {
+      const int cl = item % CW, rb = item / CW, c = c_lo + cl;
+      const float bias = bias_s[cl];
       float4 best;
       int a[4];
-      switch (fk_s[c]) {   // lanes of a warp share a filter group except at group boundaries
-        case 1: conv_item_es1<1>(emb_s, wk_s, F, c, bias, L, R, rb, best, a); break;
-        case 2: conv_item_es1<2>(emb_s, wk_s, F, c, bias, L, R, rb, best, a); break;
-        case 3: conv_item_es1<3>(emb_s, wk_s, F, c, bias, L, R, rb, best, a); break;
-        case 4: conv_item_es1<4>(emb_s, wk_s, F, c, bias, L, R, rb, best, a); break;
-        case 5: conv_item_es1<5>(emb_s, wk_s, F, c, bias, L, R, rb, best, a); break;
-        case 6: conv_item_es1<6>(emb_s, wk_s, F, c, bias, L, R, rb, best, a); break;
-        case 7: conv_item_es1<7>(emb_s, wk_s, F, c, bias, L, R, rb, best, a); break;
-        default: conv_item_es1<8>(emb_s, wk_s, F, c, bias, L, R, rb, best, a); break;
+      switch (fk_s[cl]) {   // lanes of a warp share a filter group except at group boundaries
+        case 1: conv_item_es1<1>(emb_s, wk_s, cs, cl, bias, L, R, rb, best, a); break;
+        case 2: conv_item_es1<2>(emb_s, wk_s, cs, cl, bias, L, R, rb, best, a); break;
+        case 3: conv_item_es1<3>(emb_s, wk_s, cs, cl, bias, L, R, rb, best, a); break;
+        case 4: conv_item_es1<4>(emb_s, wk_s, cs, cl, bias, L, R, rb, best, a); break;
+        case 5: conv_item_es1<5>(emb_s, wk_s, cs, cl, bias, L, R, rb, best, a); break;
+        case 6: conv_item_es1<6>(emb_s, wk_s, cs, cl, bias, L, R, rb, best, a); break;
+        case 7: conv_item_es1<7>(emb_s, wk_s, cs, cl, bias, L, R, rb, best, a); break;
+        default: conv_item_es1<8>(emb_s, wk_s, cs, cl, bias, L, R, rb, best, a); break;
       }
       const size_t row = (size_t)n * R + rb * 4;
       pooled[(row + 0) * F + c] = best.x; arg[(row + 0) * F + c] = (uint8_t)a[0];
@@ -131,20 +147,20 @@ conv_pool_fwd_kernel(const float* __restrict__ emb, int L, int De, int R, int es
       pooled[(row + 3) * F + c] = best.w; arg[(row + 3) * F + c] = (uint8_t)a[3];
     }
   } else {
-    for (int item = threadIdx.x; item < F * R; item += blockDim.x) {
-      const int c = item % F, r = item / F;
-      const int fk = fk_s[c], f = fk / es;
-      const float bias = bias_s[c];
-      float best = -1.f;
+    for (int item = threadIdx.x; item < CW * R; item += blockDim.x) {
+      const int cl = item % CW, r = item / CW, c = c_lo + cl;
+      const int fk = fk_s[cl], f = fk / es;
+      const float bias = bias_s[cl];
+      float best = -INFINITY;
       int a = 0;
       const int T = L - f + 1;
       for (int t = 0; t < T; ++t) {
         float acc = bias;
         for (int kk = 0; kk < fk; ++kk)
-          acc = fmaf(wk_s[kk * F + c], emb_s[(t + kk / es) * De + r * es + kk % es], acc);
-        acc = fmaxf(acc, 0.f);
+          acc = fmaf(wk_s[kk * cs + cl], emb_s[(t + kk / es) * De + r * es + kk % es], acc);
         if (acc > best) { best = acc; a = t; }
       }
+      if (!(best > 0.f)) { best = 0.f; a = ARG_DEAD; }
       pooled[((size_t)n * R + r) * F + c] = best;
       arg[((size_t)n * R + r) * F + c] = (uint8_t)a;
     }
@@ -163,11 +179,15 @@ conv_pool_fwd_kernel(const float* __restrict__ emb, int L, int De, int R, int es
 // ---------------------------------------------------------------------------------------
 constexpr int BWD_KMAX = 8;      // f * es <= 8 on the register path
 
-template <bool ES1>
+// (a) demb.  One warp per (caption n, representation r) row of [N*R, F].  Each lane owns groups of 4 consecutive
+// feature columns (float4 / uchar4 loads, all of a row's loads issued before any use); every lane accumulates into
+// its OWN copy of demb[n, :, r*es .. r*es+es) in shared memory (layout [entry][lane]: bank = lane, plain
+// read-modify-write, no atomics), then the 32 copies are summed with a rotated conflict-free read.
+// VEC requires F % 4 == 0 and every filter group a multiple of 4 columns wide (a float4 never straddles groups).
+template <bool ES1, bool VEC>
 __global__ void __launch_bounds__(256)
-conv_pool_bwd_demb_kernel(const float* __restrict__ pooled, const uint8_t* __restrict__ arg,
-                          const float* __restrict__ dx, int rows /*N*R*/, int L, int De, int R, int es,
-                          ConvGroups g, float* __restrict__ demb) {
+conv_pool_bwd_demb_kernel(const uint8_t* __restrict__ arg, const float* __restrict__ dx, int rows /*N*R*/, int L,
+                          int De, int R, int es, ConvGroups g, float* __restrict__ demb) {
   extern __shared__ __align__(16) float sm[];
   const int F = g.F, kmax = g.kmax;
   const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -188,25 +208,66 @@ conv_pool_bwd_demb_kernel(const float* __restrict__ pooled, const uint8_t* __res
     const int n = row / R, r = row % R;
     for (int e = 0; e < LE; ++e) priv[e * 32 + lane] = 0.f;
     const size_t base = (size_t)row * F;
-    for (int c0 = 0; c0 < F; c0 += 128) {      // 4 columns per lane in flight
-      float gv[4], pv[4];
-      int av[4];
+    if (VEC) {
+      const int F4 = F >> 2;
+      const float4* dx4 = reinterpret_cast<const float4*>(dx + base);
+      const uchar4* a4 = reinterpret_cast<const uchar4*>(arg + base);
+      for (int q0 = 0; q0 < F4; q0 += 128) {   // 4 float4 groups per lane in flight
+        float4 gv[4];
+        uchar4 av[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c = c0 + j * 32 + lane;
-        const bool ok = c < F;
-        gv[j] = ok ? dx[base + c] : 0.f;
-        pv[j] = ok ? pooled[base + c] : 0.f;
-        av[j] = ok ? (int)arg[base + c] : 0;
-      }
+        for (int j = 0; j < 4; ++j) {
+          const int q = q0 + j * 32 + lane;
+          const bool ok = q < F4;
+          gv[j] = ok ? dx4[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+          av[j] = ok ? a4[q] : make_uchar4(ARG_DEAD, ARG_DEAD, ARG_DEAD, ARG_DEAD);
+        }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c = c0 + j * 32 + lane;
-        if (c < F && pv[j] > 0.f && gv[j] != 0.f) {
+        for (int j = 0; j < 4; ++j) {
+          const int q = q0 + j * 32 + lane;
+          if (q >= F4) continue;
+          const int c = q << 2;
           const int fk = fk_s[c];
+          const float gg[4] = {gv[j].x, gv[j].y, gv[j].z, gv[j].w};
+          const int aa[4] = {av[j].x, av[j].y, av[j].z, av[j].w};
+          bool on[4];
+          bool any = false;
+#pragma unroll
+          for (int e4 = 0; e4 < 4; ++e4) { on[e4] = (aa[e4] != ARG_DEAD) && (gg[e4] != 0.f); any |= on[e4]; }
+          if (!any) continue;
           for (int k = 0; k < fk; ++k) {
-            const int e = ES1 ? (av[j] + k) : ((av[j] + k / es) * es + k % es);
-            priv[e * 32 + lane] = fmaf(wk_s[k * F + c], gv[j], priv[e * 32 + lane]);
+            const float4 w4 = *reinterpret_cast<const float4*>(&wk_s[k * F + c]);   // conflict-free LDS.128
+            const float ww[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int e4 = 0; e4 < 4; ++e4) {
+              if (on[e4]) {
+                const int e = ES1 ? (aa[e4] + k) : ((aa[e4] + k / es) * es + k % es);
+                priv[e * 32 + lane] = fmaf(ww[e4], gg[e4], priv[e * 32 + lane]);
+              }
+            }
+          }
+        }
+      }
+    } else {
+      for (int c0 = 0; c0 < F; c0 += 128) {      // 4 columns per lane in flight
+        float gv[4];
+        int av[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = c0 + j * 32 + lane;
+          const bool ok = c < F;
+          gv[j] = ok ? dx[base + c] : 0.f;
+          av[j] = ok ? (int)arg[base + c] : ARG_DEAD;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = c0 + j * 32 + lane;
+          if (c < F && av[j] != ARG_DEAD && gv[j] != 0.f) {
+            const int fk = fk_s[c];
+            for (int k = 0; k < fk; ++k) {
+              const int e = ES1 ? (av[j] + k) : ((av[j] + k / es) * es + k % es);
+              priv[e * 32 + lane] = fmaf(wk_s[k * F + c], gv[j], priv[e * 32 + lane]);
+            }
           }
         }
       }
@@ -224,14 +285,19 @@ conv_pool_bwd_demb_kernel(const float* __restrict__ pooled, const uint8_t* __res
   }
 }
 
+// (b) conv-weight / bias gradients.  Thread = feature column, CTA = chunk of rows processed RC rows at a time: the
+// RC rows' embedding slices emb[n, :, r*es..] (L*es floats each) are staged in shared memory first, so the gather
+// emb[arg + k] is a shared-memory read instead of L2 traffic; dx / arg loads of all RC rows are issued before use.
+// Weight gradients accumulate in registers over the chunk, one global atomic per weight per CTA.
+constexpr int DW_RC = 8;
 template <bool ES1>
 __global__ void __launch_bounds__(256)
-conv_pool_bwd_dw_kernel(const float* __restrict__ emb, const float* __restrict__ pooled,
-                        const uint8_t* __restrict__ arg, const float* __restrict__ dx, int rows, int L, int De,
-                        int R, int es, ConvGroups g, int rows_per_cta) {
-  const int F = g.F;
+conv_pool_bwd_dw_kernel(const float* __restrict__ emb, const uint8_t* __restrict__ arg, const float* __restrict__ dx,
+                        int rows, int L, int De, int R, int es, ConvGroups g, int rows_per_cta) {
+  extern __shared__ __align__(16) float sm[];   // [DW_RC][L*es]
+  const int F = g.F, LE = L * es;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= F) return;
+  const bool active = c < F;
   int gi = 0;
   while (gi + 1 < g.ngroups && c >= g.col0[gi + 1]) ++gi;
   const int cin = c - g.col0[gi], fk = g.f[gi] * es;
@@ -240,31 +306,38 @@ conv_pool_bwd_dw_kernel(const float* __restrict__ emb, const float* __restrict__
   for (int k = 0; k < BWD_KMAX; ++k) dw[k] = 0.f;
   float dbias = 0.f;
   const int r0 = blockIdx.y * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
-  int n_cur = r0 / R, r_cur = r0 % R;          // (caption, representation) of row rb, advanced incrementally
-  for (int rb = r0; rb < r1; rb += 4) {
-    float gv[4], pv[4];
-    int av[4];
+  for (int rb = r0; rb < r1; rb += DW_RC) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < DW_RC * LE; i += blockDim.x) {
+      const int j = i / LE, e = i % LE, row = rb + j;
+      if (row < r1) {
+        const int n = row / R, r = row % R;
+        sm[i] = emb[((size_t)n * L + e / es) * De + r * es + e % es];
+      }
+    }
+    float gv[DW_RC];
+    int av[DW_RC];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < DW_RC; ++j) {
       const int row = rb + j;
-      const bool ok = row < r1;
+      const bool ok = active && row < r1;
       const size_t i = (size_t)row * F + c;
       gv[j] = ok ? dx[i] : 0.f;
-      pv[j] = ok ? pooled[i] : 0.f;
-      av[j] = ok ? (int)arg[i] : 0;
+      av[j] = ok ? (int)arg[i] : ARG_DEAD;
     }
+    __syncthreads();
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (pv[j] > 0.f && gv[j] != 0.f) {
-        const float* e0 = emb + (size_t)n_cur * L * De + r_cur * es;
+    for (int j = 0; j < DW_RC; ++j) {
+      if (av[j] != ARG_DEAD && gv[j] != 0.f) {
+        const float* e0 = sm + j * LE + av[j] * es;
 #pragma unroll
         for (int k = 0; k < BWD_KMAX; ++k)
-          if (k < fk) dw[k] = fmaf(gv[j], ES1 ? e0[(av[j] + k) * De] : e0[(av[j] + k / es) * De + k % es], dw[k]);
+          if (k < fk) dw[k] = fmaf(gv[j], e0[k], dw[k]);
         dbias += gv[j];
       }
-      if (++r_cur == R) { r_cur = 0; ++n_cur; }
     }
   }
+  if (!active) return;
 #pragma unroll
   for (int k = 0; k < BWD_KMAX; ++k)
     if (k < fk) atomicAdd(g.dw[gi] + cin * fk + k, dw[k]);
@@ -323,6 +396,130 @@ head_fwd_kernel(const float* __restrict__ hpre, const float* __restrict__ pooled
       const float s = warp_sum(acc[m]);
       if (lane == 0) hp.logits[m][row] = s * (hp.keep[m] ? drop_scale : 1.f) + weff[F];
     }
+  }
+}
+
+// float4 variant of head_fwd_kernel for F % 4 == 0: one warp per row, every lane issues all of its loads of the row
+// (up to NQ float4 of hpre and pooled plus the uchar4 mask words) before the first use.
+template <int NQ>
+__global__ void __launch_bounds__(256)
+head_fwd_vec_kernel(const float* __restrict__ hpre, const float* __restrict__ pooled, int rows, int F,
+                    const float* __restrict__ weff, float drop_scale, HeadPtrs hp) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int F4 = F >> 2;
+  const size_t base = (size_t)row * F;
+  const float4* h4 = reinterpret_cast<const float4*>(hpre + base);
+  const float4* x4 = reinterpret_cast<const float4*>(pooled + base);
+  const float4* w4 = reinterpret_cast<const float4*>(weff);
+  float4 hv[NQ], xv[NQ];
+  uchar4 kv[MAX_HEADS][NQ];
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) {
+    const int q = lane + 32 * i;
+    const bool ok = q < F4;
+    hv[i] = ok ? h4[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+    xv[i] = ok ? x4[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int m = 0; m < MAX_HEADS; ++m)
+      if (m < hp.n && hp.keep[m]) kv[m][i] = ok ? reinterpret_cast<const uchar4*>(hp.keep[m] + base)[q] : make_uchar4(0, 0, 0, 0);
+  }
+  float acc[MAX_HEADS] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) {
+    const int q = lane + 32 * i;
+    if (q < F4) {
+      const float4 ww = __ldg(w4 + q);
+      const float hh[4] = {hv[i].x, hv[i].y, hv[i].z, hv[i].w};
+      const float xx[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+      const float wv[4] = {ww.x, ww.y, ww.z, ww.w};
+      float yw[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float sg = sigmoidf_acc(hh[e]);
+        yw[e] = (sg * fmaxf(hh[e], 0.f) + (1.f - sg) * xx[e]) * wv[e];
+      }
+#pragma unroll
+      for (int m = 0; m < MAX_HEADS; ++m) {
+        if (m < hp.n) {
+          if (hp.keep[m]) {
+            const uchar4 k = kv[m][i];
+            acc[m] += (k.x ? yw[0] : 0.f) + (k.y ? yw[1] : 0.f) + (k.z ? yw[2] : 0.f) + (k.w ? yw[3] : 0.f);
+          } else {
+            acc[m] += (yw[0] + yw[1]) + (yw[2] + yw[3]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < MAX_HEADS; ++m) {
+    if (m < hp.n) {
+      const float s = warp_sum(acc[m]);
+      if (lane == 0) hp.logits[m][row] = s * (hp.keep[m] ? drop_scale : 1.f) + weff[F];
+    }
+  }
+}
+
+// float4 variant of head_bwd_kernel (F % 4 == 0): thread = 4 consecutive feature columns, CTA = row chunk, 4 rows of
+// loads in flight per thread.
+__global__ void __launch_bounds__(256)
+head_bwd_vec_kernel(const float* __restrict__ dlogit, const uint8_t* __restrict__ keep, float drop_scale,
+                    const float* __restrict__ hpre, const float* __restrict__ pooled, int rows, int F,
+                    const float* __restrict__ weff, int rows_per_cta, float* __restrict__ dh,
+                    float* __restrict__ dx, float* __restrict__ s_acc, float* __restrict__ dbh_acc) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;      // float4 column group
+  const int F4 = F >> 2;
+  if (q >= F4) return;
+  const int r0 = blockIdx.y * rows_per_cta;
+  const int r1 = min(rows, r0 + rows_per_cta);
+  const float4 w4 = reinterpret_cast<const float4*>(weff)[q];
+  const float wj[4] = {w4.x, w4.y, w4.z, w4.w};
+  const float sc = keep ? drop_scale : 1.f;
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int rb = r0; rb < r1; rb += 4) {
+    float4 hv[4], xv[4];
+    uchar4 kv[4];
+    float dl[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = rb + j;
+      const bool ok = r < r1;
+      const size_t i = (size_t)r * F4 + q;
+      hv[j] = ok ? reinterpret_cast<const float4*>(hpre)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      xv[j] = ok ? reinterpret_cast<const float4*>(pooled)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      kv[j] = (ok && keep) ? reinterpret_cast<const uchar4*>(keep)[i] : make_uchar4(1, 1, 1, 1);
+      dl[j] = ok ? dlogit[r] * sc : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = rb + j;
+      if (r >= r1) break;
+      const float hh[4] = {hv[j].x, hv[j].y, hv[j].z, hv[j].w};
+      const float xx[4] = {xv[j].x, xv[j].y, xv[j].z, xv[j].w};
+      const float kp[4] = {kv[j].x ? 1.f : 0.f, kv[j].y ? 1.f : 0.f, kv[j].z ? 1.f : 0.f, kv[j].w ? 1.f : 0.f};
+      float dhv[4], dxv[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float sg = sigmoidf_acc(hh[e]);
+        const float rl = fmaxf(hh[e], 0.f);
+        const float y = sg * rl + (1.f - sg) * xx[e];
+        const float dy = dl[j] * kp[e] * wj[e];
+        s[e] = fmaf(dl[j] * kp[e], y, s[e]);
+        dhv[e] = dy * (sg * (1.f - sg) * (rl - xx[e]) + (hh[e] > 0.f ? sg : 0.f));
+        dxv[e] = dy * (1.f - sg);
+        sb[e] += dhv[e];
+      }
+      const size_t i = (size_t)r * F4 + q;
+      reinterpret_cast<float4*>(dh)[i] = make_float4(dhv[0], dhv[1], dhv[2], dhv[3]);
+      reinterpret_cast<float4*>(dx)[i] = make_float4(dxv[0], dxv[1], dxv[2], dxv[3]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    atomicAdd(s_acc + 4 * q + e, s[e]);
+    atomicAdd(dbh_acc + 4 * q + e, sb[e]);
   }
 }
 
@@ -467,19 +664,24 @@ int disc_forward(int mode, const float* inp_soft, const int64_t* ids, const Disc
   }
   // 2. conv + relu + max-pool
   {
-    const size_t smem = (((size_t)d.L * d.De + 3) & ~(size_t)3) * 4 + ((size_t)g.kmax + 2) * d.F * 4;
-    GIC_REQUIRE(smem <= 200 * 1024, GIC_ERR_SHAPE, "disc: conv tile needs %zu B of shared memory", smem);
     GIC_REQUIRE(g.kmax <= 16, GIC_ERR_SHAPE, "disc: filter_size*emb_dim_single <= 16 supported");
+    GIC_REQUIRE(d.L <= 254, GIC_ERR_SHAPE, "disc: caption length <= 254 supported");
+    // column slices: enough CTAs to balance the SMs (>= ~6 per SM), slice width a multiple of 32
+    int slices = max(1, min(cdiv(6 * num_sms(), d.N), cdiv(d.F, 32)));
+    int cs = ((cdiv(d.F, slices) + 31) / 32) * 32;
+    slices = cdiv(d.F, cs);
+    const size_t smem = (((size_t)d.L * d.De + 3) & ~(size_t)3) * 4 + ((size_t)g.kmax + 2) * cs * 4;
+    GIC_REQUIRE(smem <= 200 * 1024, GIC_ERR_SHAPE, "disc: conv tile needs %zu B of shared memory", smem);
     ProfScope prof(PROF_CONVPOOL, 5.0 * rows * d.F + 4.0 * d.N * d.L * d.De, s);   // write pooled f32 + arg u8, read emb
     const bool es1 = (d.es == 1) && (d.R % 4 == 0) && g.kmax <= 8;
-    GIC_REQUIRE(d.L <= 255, GIC_ERR_SHAPE, "disc: caption length <= 255 supported");
-    if (es1) {
+    static bool attr = false;
+    if (!attr) {
       cudaFuncSetAttribute(conv_pool_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      conv_pool_fwd_kernel<true><<<d.N, 256, smem, s>>>(emb, d.L, d.De, d.R, d.es, g, pooled, arg);
-    } else {
       cudaFuncSetAttribute(conv_pool_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      conv_pool_fwd_kernel<false><<<d.N, 256, smem, s>>>(emb, d.L, d.De, d.R, d.es, g, pooled, arg);
+      attr = true;
     }
+    if (es1) conv_pool_fwd_kernel<true><<<dim3(d.N, slices), 256, smem, s>>>(emb, d.L, d.De, d.R, d.es, g, cs, pooled, arg);
+    else conv_pool_fwd_kernel<false><<<dim3(d.N, slices), 256, smem, s>>>(emb, d.L, d.De, d.R, d.es, g, cs, pooled, arg);
     GIC_TRY(check_launch("conv_pool_fwd_kernel"));
   }
   // 3. highway pre-activation
@@ -494,7 +696,18 @@ int disc_forward(int mode, const float* inp_soft, const int64_t* ids, const Disc
     hp.logits[m] = (m < n_heads) ? logits[m] : nullptr;
   }
   ProfScope prof(PROF_HEAD, (8.0 + n_heads) * rows * d.F, s);      // read hpre, pooled (f32) + one u8 mask per head
-  head_fwd_kernel<<<cdiv((long long)rows, 8), 256, 0, s>>>(hpre, pooled, (int)rows, d.F, weff, 1.f / (1.f - drop_p), hp);
+  bool vec = (d.F % 4 == 0) && d.F <= 4 * 32 * 8;
+  for (int m = 0; m < n_heads; ++m) vec = vec && (!hp.keep[m] || (reinterpret_cast<uintptr_t>(hp.keep[m]) & 3u) == 0);
+  if (vec) {
+    const int nq = cdiv(d.F / 4, 32);
+    const int grid = cdiv((long long)rows, 8);
+    const float dsc = 1.f / (1.f - drop_p);
+    if (nq <= 2) head_fwd_vec_kernel<2><<<grid, 256, 0, s>>>(hpre, pooled, (int)rows, d.F, weff, dsc, hp);
+    else if (nq <= 4) head_fwd_vec_kernel<4><<<grid, 256, 0, s>>>(hpre, pooled, (int)rows, d.F, weff, dsc, hp);
+    else head_fwd_vec_kernel<8><<<grid, 256, 0, s>>>(hpre, pooled, (int)rows, d.F, weff, dsc, hp);
+  } else {
+    head_fwd_kernel<<<cdiv((long long)rows, 8), 256, 0, s>>>(hpre, pooled, (int)rows, d.F, weff, 1.f / (1.f - drop_p), hp);
+  }
   return check_launch("head_fwd_kernel");
 }
 
@@ -520,7 +733,16 @@ int disc_backward(int mode, const float* dlogit, const uint8_t* keep, float drop
   head_collapse_kernel<<<cdiv(d.F + 1, 256), 256, 0, s>>>(W_f, b_f, W_o, b_o, d.F, d.Hd, weff);
   GIC_TRY(check_launch("head_collapse_kernel"));
   cudaMemsetAsync(sacc, 0, 2 * align4(d.F) * sizeof(float), s);
-  {
+  if ((d.F % 4 == 0) && (!keep || (reinterpret_cast<uintptr_t>(keep) & 3u) == 0)) {
+    const int colb = cdiv(d.F / 4, 256);
+    int chunks = max(1, (6 * num_sms()) / colb);
+    int rpc = cdiv((long long)rows, chunks);
+    rpc = (rpc + 3) & ~3;
+    chunks = cdiv((long long)rows, rpc);
+    head_bwd_vec_kernel<<<dim3(colb, chunks), 256, 0, s>>>(dlogit, keep, 1.f / (1.f - drop_p), hpre, pooled, (int)rows,
+                                                          d.F, weff, rpc, dh, dx, sacc, dbh);
+    GIC_TRY(check_launch("head_bwd_vec_kernel"));
+  } else {
     const int colb = cdiv(d.F, 256);
     int chunks = max(1, (4 * num_sms()) / colb);
     int rpc = cdiv((long long)rows, chunks);
@@ -556,13 +778,20 @@ int disc_backward(int mode, const float* dlogit, const uint8_t* keep, float drop
       const size_t smem = fixed + nwarps * per_warp;
       GIC_REQUIRE(smem <= 200 * 1024, GIC_ERR_SHAPE, "disc bwd: L*emb_dim_single too large for shared memory");
       const int grid = min(cdiv((long long)rows, nwarps), 4 * num_sms());
-      if (d.es == 1) {
-        cudaFuncSetAttribute(conv_pool_bwd_demb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        conv_pool_bwd_demb_kernel<true><<<grid, nwarps * 32, smem, s>>>(pooled, arg, dx, (int)rows, d.L, d.De, d.R, d.es, g, demb);
-      } else {
-        cudaFuncSetAttribute(conv_pool_bwd_demb_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        conv_pool_bwd_demb_kernel<false><<<grid, nwarps * 32, smem, s>>>(pooled, arg, dx, (int)rows, d.L, d.De, d.R, d.es, g, demb);
+      bool vec = (d.F % 4 == 0) && aligned16(dx) && ((reinterpret_cast<uintptr_t>(arg) & 3u) == 0);
+      for (int i = 0; i < g.ngroups; ++i) vec = vec && (g.n[i] % 4 == 0);
+      static bool attr = false;
+      if (!attr) {
+        cudaFuncSetAttribute(conv_pool_bwd_demb_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(conv_pool_bwd_demb_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(conv_pool_bwd_demb_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(conv_pool_bwd_demb_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr = true;
       }
+#define GIC_DEMB(ES1_, VEC_) conv_pool_bwd_demb_kernel<ES1_, VEC_><<<grid, nwarps * 32, smem, s>>>(arg, dx, (int)rows, d.L, d.De, d.R, d.es, g, demb)
+      if (d.es == 1) { if (vec) GIC_DEMB(true, true); else GIC_DEMB(true, false); }
+      else { if (vec) GIC_DEMB(false, true); else GIC_DEMB(false, false); }
+#undef GIC_DEMB
       GIC_TRY(check_launch("conv_pool_bwd_demb_kernel"));
     }
     // (b) conv weight / bias gradients
@@ -570,12 +799,14 @@ int disc_backward(int mode, const float* dlogit, const uint8_t* keep, float drop
       const int colb = cdiv(d.F, 256);
       int chunks = max(1, (4 * num_sms()) / colb);
       int rpc = cdiv((long long)rows, chunks);
-      rpc = (rpc + 3) & ~3;
+      rpc = ((rpc + DW_RC - 1) / DW_RC) * DW_RC;
       chunks = cdiv((long long)rows, rpc);
+      const size_t smem = (size_t)DW_RC * d.L * d.es * 4;
+      GIC_REQUIRE(smem <= 48 * 1024, GIC_ERR_SHAPE, "disc bwd: L*emb_dim_single too large for shared memory");
       if (d.es == 1)
-        conv_pool_bwd_dw_kernel<true><<<dim3(colb, chunks), 256, 0, s>>>(emb, pooled, arg, dx, (int)rows, d.L, d.De, d.R, d.es, g, rpc);
+        conv_pool_bwd_dw_kernel<true><<<dim3(colb, chunks), 256, smem, s>>>(emb, arg, dx, (int)rows, d.L, d.De, d.R, d.es, g, rpc);
       else
-        conv_pool_bwd_dw_kernel<false><<<dim3(colb, chunks), 256, 0, s>>>(emb, pooled, arg, dx, (int)rows, d.L, d.De, d.R, d.es, g, rpc);
+        conv_pool_bwd_dw_kernel<false><<<dim3(colb, chunks), 256, smem, s>>>(emb, arg, dx, (int)rows, d.L, d.De, d.R, d.es, g, rpc);
       GIC_TRY(check_launch("conv_pool_bwd_dw_kernel"));
     }
   }
@@ -608,7 +839,7 @@ static int disc_dims(DiscDims& d, int N, int L, int V, int De, int R, int Hd, co
   d.kmax = g.kmax;
   for (int i = 0; i < g.ngroups; ++i)
     GIC_REQUIRE(L >= g.f[i], GIC_ERR_SHAPE, "disc: caption length %d shorter than filter size %d", L, g.f[i]);
-  GIC_REQUIRE(L <= 255, GIC_ERR_SHAPE, "disc: caption length <= 255 supported");
+  GIC_REQUIRE(L <= 254, GIC_ERR_SHAPE, "disc: caption length <= 254 supported");
   return GIC_OK;
 }
 

@@ -4,26 +4,35 @@
 // for one layer and one time step (src/generator.py:61).  It replaces two GEMM launches, the [B,4H] gates round
 // trip through HBM and the cell kernel of the unfused path.
 //
-// Tiling: a CTA owns 128 batch rows x 32 hidden units.  Its B operand tile is gate-interleaved: four 32-row slabs
-// of the weight matrix (rows g*H + j0 .. j0+31 for g = i,f,g,o) are TMA-loaded next to each other, so the 128
-// accumulator columns are [i(32) | f(32) | g(32) | o(32)] of the same 32 units and the cell update is an epilogue
-// on the TMEM tile.  The k loop runs over ceil(In/32) blocks of (x, W_ih) followed by ceil(H/32) blocks of
+// Tiling: a CTA owns 128 batch rows x U hidden units (U = 8, 16 or 32, chosen so that the grid covers the SMs: at
+// B = 256, H = 512 that is 2 x 64 CTAs of U = 8).  Its B operand tile is gate-interleaved: four U-row slabs of the
+// weight matrix (rows g*H + j0 .. j0+U-1 for g = i,f,g,o) are TMA-loaded next to each other, so the 4U accumulator
+// columns are [i(U) | f(U) | g(U) | o(U)] of the same U units and the cell update is an epilogue on the TMEM tile.  The k loop runs over ceil(In/32) blocks of (x, W_ih) followed by ceil(H/32) blocks of
 // (h, W_hh).  Warp roles as in gemm_tcgen05.cu.
 #include "tcgen05_common.cuh"
 
 namespace gic {
 namespace tc {
 
-constexpr int LSTM_STAGE = 2 * BM * BK * 4;     // A 16 KB + B 16 KB
-constexpr int LSTM_STAGES = 6;
-constexpr int LSTM_SMEM = LSTM_STAGES * LSTM_STAGE + 1024 + 256;
+template <int U>
+struct LstmCfg {
+  static constexpr int A_BYTES = BM * BK * 4;            // 16 KB
+  static constexpr int B_BYTES = 4 * U * BK * 4;         // 4 gates x U rows x 128 B
+  static constexpr int STAGE = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (U == 32) ? 6 : 8;
+  static constexpr int SMEM = STAGES * STAGE + 1024 + 256;
+  static constexpr uint32_t TMEM_COLS = (4 * U < 32) ? 32 : 4 * U;
+};
 
+template <int U>
 __global__ void __launch_bounds__(NTHREADS, 1)
 lstm_step_tf32_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmH,
                       const __grid_constant__ CUtensorMap tmWih, const __grid_constant__ CUtensorMap tmWhh, int B,
                       int H, int In, const float* __restrict__ b_ih, const float* __restrict__ b_hh,
                       const float* __restrict__ c_prev, float* __restrict__ acts, float* __restrict__ c_out,
                       float* __restrict__ h_out, float* __restrict__ htop, int L, int t) {
+  using S = LstmCfg<U>;
+  constexpr int LSTM_STAGES = S::STAGES, LSTM_STAGE = S::STAGE;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + LSTM_STAGES * LSTM_STAGE);
@@ -32,9 +41,9 @@ lstm_step_tf32_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int j0 = blockIdx.x * 32, m0 = blockIdx.y * BM;
+  const int j0 = blockIdx.x * U, m0 = blockIdx.y * BM;
   const int nkb1 = (In + BK - 1) / BK, nkb2 = (H + BK - 1) / BK, nkb = nkb1 + nkb2;
-  constexpr uint32_t TMEM_COLS = 128;
+  constexpr uint32_t TMEM_COLS = S::TMEM_COLS;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
@@ -67,12 +76,12 @@ lstm_step_tf32_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         const int k0 = (first ? kb : kb - nkb1) * BK;
         tma_load_2d(sa, first ? &tmX : &tmH, &full[s], k0, m0);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) tma_load_2d(sb + g * 4096, first ? &tmWih : &tmWhh, &full[s], k0, g * H + j0);
+        for (int g = 0; g < 4; ++g) tma_load_2d(sb + g * (U * 128), first ? &tmWih : &tmWhh, &full[s], k0, g * H + j0);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(0, 0, 128);
+      constexpr uint32_t idesc = make_idesc(0, 0, 4 * U);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % LSTM_STAGES;
         const uint32_t ph = (kb / LSTM_STAGES) & 1;
@@ -96,12 +105,12 @@ lstm_step_tf32_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     const int b = m0 + q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-    for (int u0 = 0; u0 < 32; u0 += 8) {
+    for (int u0 = 0; u0 < U; u0 += 8) {
       uint32_t ri[8], rf[8], rg[8], ro[8];
-      tmem_ld8(lane_addr + 0 * 32 + u0, ri);
-      tmem_ld8(lane_addr + 1 * 32 + u0, rf);
-      tmem_ld8(lane_addr + 2 * 32 + u0, rg);
-      tmem_ld8(lane_addr + 3 * 32 + u0, ro);
+      tmem_ld8(lane_addr + 0 * U + u0, ri);
+      tmem_ld8(lane_addr + 1 * U + u0, rf);
+      tmem_ld8(lane_addr + 2 * U + u0, rg);
+      tmem_ld8(lane_addr + 3 * U + u0, ro);
       if (b < B) {
         const int j = j0 + u0;
         float cp[8], ai[8], af[8], ag[8], ao[8], cn[8], hn[8];
@@ -146,24 +155,32 @@ int lstm_step_tc(const float* x, int In, const float* h_prev, const float* W_ih,
                  float* htop, int L, int t, cudaStream_t stream, bool* handled) {
   using namespace tc;
   *handled = false;
-  if (B <= 0 || (H % 32) || (In % 4) || In < 4) return GIC_OK;
+  if (B <= 0 || (H % 8) || (In % 4) || In < 4) return GIC_OK;
   const void* ptrs[] = {x, h_prev, W_ih, W_hh, c_prev, acts, c_out, h_out, htop ? htop : h_out};
   for (const void* p : ptrs)
     if (!aligned16(p)) return GIC_OK;
+  // units per CTA: the widest tile that still gives at least ~3/4 of the SMs a CTA
+  const int mt = cdiv(B, BM);
+  int U = 32;
+  if ((H % 32) || (H / 32) * mt * 4 < 3 * num_sms()) U = 16;
+  if (U == 16 && ((H % 16) || (H / 16) * mt * 4 < 3 * num_sms())) U = 8;
   const bool rn = tf32_round_in_tma();
   CUtensorMap tx, th, twi, twh;
   bool ok = make_map(&tx, x, B, In, In, BK, BM, rn, false) && make_map(&th, h_prev, B, H, H, BK, BM, rn, false) &&
-            make_map(&twi, W_ih, 4 * H, In, In, BK, 32, rn, false) && make_map(&twh, W_hh, 4 * H, H, H, BK, 32, rn, false);
+            make_map(&twi, W_ih, 4 * H, In, In, BK, U, rn, false) && make_map(&twh, W_hh, 4 * H, H, H, BK, U, rn, false);
   if (!ok) return GIC_OK;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(lstm_step_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LSTM_SMEM);
+    cudaFuncSetAttribute(lstm_step_tf32_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, LstmCfg<8>::SMEM);
+    cudaFuncSetAttribute(lstm_step_tf32_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, LstmCfg<16>::SMEM);
+    cudaFuncSetAttribute(lstm_step_tf32_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, LstmCfg<32>::SMEM);
     attr = true;
   }
   ProfScope prof(PROF_GEMM, 2.0 * B * 4 * H * (In + H), stream);
-  dim3 grid(H / 32, cdiv(B, BM));
-  lstm_step_tf32_kernel<<<grid, NTHREADS, LSTM_SMEM, stream>>>(tx, th, twi, twh, B, H, In, b_ih, b_hh, c_prev, acts,
-                                                              c_out, h_out, htop, L, t);
+  dim3 grid(H / U, mt);
+#define GIC_LSTM(U_) lstm_step_tf32_kernel<U_><<<grid, NTHREADS, LstmCfg<U_>::SMEM, stream>>>(tx, th, twi, twh, B, H, In, b_ih, b_hh, c_prev, acts, c_out, h_out, htop, L, t)
+  if (U == 32) GIC_LSTM(32); else if (U == 16) GIC_LSTM(16); else GIC_LSTM(8);
+#undef GIC_LSTM
   int rc = check_launch("lstm_step_tf32_kernel");
   if (rc == GIC_OK) *handled = true;
   return rc;

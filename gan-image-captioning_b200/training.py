@@ -221,18 +221,23 @@ class GANInstructor:
         disc_bwd(seeds[1], k1, probs, None, saved_f, 1, 1, None)
         g_has_grad = loss_type != "rsgan"          # A14: rsgan's g_loss only sees detached D outputs
         if g_has_grad:
-            dprobs = self._buf("dprobs", B * L * V).view(B, L, V)
-            disc_bwd(seeds[2], k2, probs, None, saved_f, 0, 0, dprobs)
+            # D's input gradient stays factored (demb x W_e): the dense d(probs)[B,L,V] is never written; the
+            # decoder backward fuses demb W_e with the tempered-softmax backward (gic_decode_sample_bwd_factored)
+            disc_bwd(seeds[2], k2, probs, None, saved_f, 0, 0, None)
+            off = lib.gic_disc_bwd_demb_offset_floats(B, L, De, R, Fd)
+            demb = bws[off:off + B * L * De]
+            emb = saved_f[:B * L * De]
             gg = fg.g
             gws = self._buf("dec_bws", lib.gic_decode_bwd_workspace_floats(B, L, V, E, H, layers))
             dfeat = self._buf("dfeat", B * E).view(B, E)
             fed = ids if forced_ids is None else forced_ids
-            _lib.check(lib.gic_decode_sample_bwd(
-                mode, P(dprobs), P(probs), P(fed), P(dec.embed.weight), _lib.ptr_array(W_ih), _lib.ptr_array(W_hh),
-                P(dec.linear.weight), T, 0, B, L, V, E, H, layers, P(dsaved), P(gws), P(gg(dec.embed.weight)),
-                _lib.ptr_array([gg(w) for w in W_ih]), _lib.ptr_array([gg(w) for w in W_hh]),
-                _lib.ptr_array([gg(w) for w in b_ih]), _lib.ptr_array([gg(w) for w in b_hh]),
-                P(gg(dec.linear.weight)), P(gg(dec.linear.bias)), P(dfeat), 0, stream), "gic_decode_sample_bwd")
+            _lib.check(lib.gic_decode_sample_bwd_factored(
+                mode, P(demb), P(emb), P(disc.embeddings.weight), De, P(probs), P(fed), P(dec.embed.weight),
+                _lib.ptr_array(W_ih), _lib.ptr_array(W_hh), P(dec.linear.weight), T, B, L, V, E, H, layers, P(dsaved),
+                P(gws), P(gg(dec.embed.weight)), _lib.ptr_array([gg(w) for w in W_ih]),
+                _lib.ptr_array([gg(w) for w in W_hh]), _lib.ptr_array([gg(w) for w in b_ih]),
+                _lib.ptr_array([gg(w) for w in b_hh]), P(gg(dec.linear.weight)), P(gg(dec.linear.bias)), P(dfeat), 0,
+                stream), "gic_decode_sample_bwd_factored")
             if self.cgan:
                 enc = self.gen.encoder
                 _lib.check(lib.gic_encoder_bwd(mode, P(dfeat), P(pooled), P(lin), P(mean), P(rstd),

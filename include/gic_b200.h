@@ -117,6 +117,20 @@ int gic_decode_sample_bwd(int mode, const float* dout, const float* out, const i
                           float* const* dW_hh, float* const* db_ih, float* const* db_hh, float* dW_out,
                           float* db_out, float* dfeatures, int accumulate, gic_stream_t stream);
 
+/* Same backward with the incoming gradient in factored form (the fused adversarial step): instead of the dense
+ * dout[B,L,V] = d g_loss / d probs it takes demb[B*L,De] = d g_loss / d (probs W_e^T) -- what gic_disc_bwd leaves at
+ * workspace + gic_disc_bwd_demb_offset_floats() when called with dinp = NULL -- together with emb[B*L,De] (the first
+ * B*L*De floats of the discriminator's saved blob) and W_e[De,V].  dz = T p (demb W_e - <demb, emb>) is produced by one
+ * tensor-core kernel with the softmax backward as its epilogue; the dense d(probs) is never written or read.
+ * Same autograd semantics as src/generator.py:69 + src/discriminator.py:40. */
+int gic_decode_sample_bwd_factored(int mode, const float* demb, const float* emb, const float* W_e, int De,
+                                   const float* out, const int64_t* fed_ids, const float* W_emb,
+                                   const float* const* W_ih, const float* const* W_hh, const float* W_out,
+                                   float temperature, int B, int L, int V, int E, int H, int layers, const float* saved,
+                                   float* workspace, float* dW_emb, float* const* dW_ih, float* const* dW_hh,
+                                   float* const* db_ih, float* const* db_hh, float* dW_out, float* db_out,
+                                   float* dfeatures, int accumulate, gic_stream_t stream);
+
 /* ---- Discriminator.forward (src/discriminator.py:34-62) ----
  * Exactly one of inp_soft[N,L,V] (soft / dense one-hot captions) and ids[N,L] (hard tokens: Linear of a one-hot is
  * a column pick, replacing F.one_hot at src/training.py:158) is non-NULL.  De = disc_embed_dim, R = disc_num_rep,
@@ -137,6 +151,8 @@ int gic_disc_fwd(int mode, const float* inp_soft, const int64_t* ids, int N, int
  * (NULL = eval).  want_param: produce parameter gradients (accumulate != 0 adds).  dinp != NULL: also produce the
  * gradient w.r.t. the soft input [N,L,V] (the generator's path). */
 size_t gic_disc_bwd_workspace_floats(int N, int L, int De, int R, int F);
+/* offset (floats) of demb[N,L,De] = d loss / d embedding output inside the backward workspace after gic_disc_bwd */
+size_t gic_disc_bwd_demb_offset_floats(int N, int L, int De, int R, int F);
 int gic_disc_bwd(int mode, const float* dlogits, const uint8_t* keep, float drop_p, const float* inp_soft,
                  const int64_t* ids, int N, int L, int V, int De, int R, int n_groups, const int* filter_sizes,
                  const int* num_filters, const float* W_e, const float* const* conv_w, const float* const* conv_b,

@@ -39,16 +39,29 @@ def bench(mode, tA, tB, M, N, K, iters=200, beta=0.0):
 
 
 if __name__ == "__main__":
-    for K in (32, 128, 512, 2048, 8192):
-        bench(1, 0, 1, 128, 128, K)
-    for K in (32, 512, 2048):
-        bench(1, 0, 1, 256, 2048, K)
-    bench(1, 0, 1, 256, 2048, 512, beta=1.0)
-    bench(1, 0, 1, 256, 10000, 512)
-    bench(1, 0, 1, 16384, 900, 900)
-    bench(1, 0, 0, 16384, 900, 900)
-    bench(1, 1, 0, 900, 900, 16384)
+    print("GIC_GEMM_V1 =", os.environ.get("GIC_GEMM_V1", "0"), flush=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "short":
+        bench(1, 0, 0, 16384, 900, 900, beta=1.0)
+        bench(1, 1, 0, 10000, 512, 5120)
+        bench(1, 0, 0, 5120, 512, 10000)
+        bench(1, 1, 0, 900, 900, 16384)
+        bench(1, 0, 1, 16384, 900, 900)
+        sys.exit(0)
+    # decode
+    bench(1, 0, 1, 256, 10000, 512)          # vocab projection, one step
+    bench(1, 0, 1, 256, 2048, 512)           # gates, one operand
+    bench(1, 0, 0, 256, 512, 2048)           # BPTT dh_rec = dG W_hh
+    # discriminator
+    bench(1, 0, 1, 16384, 900, 900)          # highway fwd
+    bench(1, 0, 0, 16384, 900, 900, beta=1.0)  # dx += dh W_h
+    bench(1, 1, 0, 900, 900, 16384)          # dW_h
+    bench(1, 0, 1, 5120, 64, 10000)          # soft embedding
+    bench(1, 1, 0, 64, 10000, 5120)          # dW_e
+    bench(1, 0, 0, 5120, 10000, 64)          # dinp
+    # generator backward
+    bench(1, 1, 0, 10000, 512, 5120)         # dW_out
+    bench(1, 0, 0, 5120, 512, 10000)         # dhtop
+    bench(1, 1, 0, 2048, 512, 5120)          # dW_ih / dW_hh
+    bench(1, 0, 0, 5120, 512, 2048)          # dX
     bench(1, 0, 1, 8192, 8192, 8192, iters=10)
-    bench(1, 0, 1, 5120, 64, 10000)
-    bench(0, 0, 1, 256, 2048, 512)
-    bench(0, 0, 1, 16384, 900, 900, iters=20)
+    bench(1, 0, 1, 32768, 900, 900, iters=50)
