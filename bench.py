@@ -158,7 +158,8 @@ def workload_config(args, cfg, world):
                         f"vocab {cfg['V']}, E {cfg['E']}, H {cfg['H']}, feat {cfg['feat']} (pooled 7x7x2048 grid), "
                         f"D 64 reps x {sum(cfg['filters'])} filters, loss standard",
             "global_batch": cfg["B"] * world, "seq_len": cfg["L"], "vocab": cfg["V"], "parallelism": f"dp{world}",
-            "gemm_mode": args.mode, "cache": "two 250 MB input sets alternate (each > 126 MB L2)"}
+            "gemm_mode": args.mode, "cache": "two 250 MB input sets alternate (each > 126 MB L2)",
+            "launch": "eager" if args.no_graph else "one CUDA graph per step"}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -206,14 +207,20 @@ def run_ours(args):
     h_caps = [s["caps"].cpu().pin_memory() for s in sets]
     h_pool = [s["pooled"].cpu().pin_memory() for s in sets]
 
+    use_graph = not args.no_graph
+
     def step_resident(i):
         s = sets[i % 2]
-        return inst.adv_step(s["caps"], pooled=s["pooled"], u=s["u"], keep=s["keep"])
+        return inst.adv_step(s["caps"], pooled=s["pooled"], u=s["u"], keep=s["keep"], graph="static" if use_graph else False)
 
     def step_e2e(i):
-        caps = h_caps[i % 2].to(dev, non_blocking=True)
-        pooled = h_pool[i % 2].to(dev, non_blocking=True)
-        r = inst.adv_step(caps, pooled=pooled)                     # uniforms / masks drawn on-device
+        # host buffers in, losses out; with --graph the H2D copies land in the graph's static input buffers
+        if use_graph:
+            r = inst.adv_step(h_caps[i % 2], pooled=h_pool[i % 2], graph=True)
+        else:
+            caps = h_caps[i % 2].to(dev, non_blocking=True)
+            pooled = h_pool[i % 2].to(dev, non_blocking=True)
+            r = inst.adv_step(caps, pooled=pooled)                     # uniforms / masks drawn on-device
         return torch.stack([r["g_loss"], r["d_loss"]]).cpu()      # D2H read of the step's result (syncs)
 
     def timed(fn, steps, warmup, sample_clocks=False):
@@ -235,6 +242,8 @@ def run_ours(args):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         launches = lib.gic_launch_count() - n0
+        if use_graph and launches == 0:
+            launches = steps * getattr(inst, "graph_launches_per_step", 0)     # kernels replayed from the captured step
         clocks = sampler.stop() if sampler else None
         if world > 1:
             dist.barrier()
@@ -267,6 +276,7 @@ def run_ours(args):
     peaks = load_peaks()
     K = C.c_double * 6
     ms_k, work_k, calls_k = K(), K(), (C.c_ulonglong * 6)()
+    use_graph = False          # events around individual launches need the eager path
     step_resident(0); torch.cuda.synchronize()
     psteps = min(args.steps, 3)
     lib.gic_prof_begin()
@@ -338,6 +348,7 @@ def main():
     ap.add_argument("--mode", default=os.environ.get("GIC_GEMM_MODE", "tf32"), choices=sorted(MODES))
     ap.add_argument("--cpu-sample-rows", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from the host instead of replaying the captured step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

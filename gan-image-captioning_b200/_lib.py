@@ -81,6 +81,9 @@ def _declare(L):
     L.gic_gan_loss_fwd_bwd.argtypes = [I, P, P, P, I, P, P, P, P, P]
     L.gic_grad_sqnorm.argtypes = [P, Z, P, P]
     L.gic_clip_adam.argtypes = [P, P, P, P, Z, P, F, F, I, F, F, F, F, P]
+    L.gic_clip_adam_dyn.argtypes = [P, P, P, P, Z, P, F, F, P, F, F, F, P]
+    L.gic_set_temperature_device.restype = None
+    L.gic_set_temperature_device.argtypes = [P]
     for name in header_symbols():      # every declared entry point must be exported
         getattr(L, name)
 

@@ -33,7 +33,8 @@ int scale_inplace(float*, size_t, float, cudaStream_t);
 int gan_loss(int, const float*, const float*, const float*, int, float*, float*, float*, float*, cudaStream_t);
 int grad_sqnorm(const float*, size_t, float*, cudaStream_t);
 int clip_adam(float*, const float*, float*, float*, size_t, const float*, float, float, int, float, float, float,
-              float, cudaStream_t);
+              float, const float*, cudaStream_t);
+void set_temperature_device(const float*);
 const char* last_error();
 unsigned long long launch_count();
 void prof_begin();
@@ -394,7 +395,17 @@ int gic_grad_sqnorm(const float* g, size_t n, float* sqnorm, gic_stream_t stream
 int gic_clip_adam(float* p, const float* g, float* m, float* v, size_t n, const float* sqnorm, float max_norm,
                   float grad_scale, int step, float lr, float beta1, float beta2, float eps, gic_stream_t stream) {
   GIC_TRY(require_device());
-  return clip_adam(p, g, m, v, n, sqnorm, max_norm, grad_scale, step, lr, beta1, beta2, eps, S(stream));
+  return clip_adam(p, g, m, v, n, sqnorm, max_norm, grad_scale, step, lr, beta1, beta2, eps, nullptr, S(stream));
 }
+
+int gic_clip_adam_dyn(float* p, const float* g, float* m, float* v, size_t n, const float* sqnorm, float max_norm,
+                      float grad_scale, const float* bias_corr_dev, float beta1, float beta2, float eps,
+                      gic_stream_t stream) {
+  GIC_TRY(require_device());
+  GIC_REQUIRE(bias_corr_dev, GIC_ERR_NULL, "clip_adam_dyn: NULL bias_corr_dev");
+  return clip_adam(p, g, m, v, n, sqnorm, max_norm, grad_scale, 0, 0.f, beta1, beta2, eps, bias_corr_dev, S(stream));
+}
+
+void gic_set_temperature_device(const float* t_dev) { set_temperature_device(t_dev); }
 
 }  // extern "C"

@@ -6,6 +6,13 @@
 
 namespace gic {
 
+// Temperature source: the by-value argument, or (CUDA-graph replay: by-value arguments are frozen at capture) a device
+// scalar registered with gic_set_temperature_device().
+static const float* g_t_dev = nullptr;
+void set_temperature_device(const float* p) { g_t_dev = p; }
+const float* temperature_device() { return g_t_dev; }
+__device__ __forceinline__ float pick_t(float by_value, const float* t_dev) { return t_dev ? __ldg(t_dev) : by_value; }
+
 // ---------------------------------------------------------------------------------------
 // row gather: out[i, :] = table[ids[i], :]     (nn.Embedding lookup, src/generator.py:75)
 // ---------------------------------------------------------------------------------------
@@ -86,10 +93,11 @@ __global__ void lstm_cell_bwd_kernel(const float* __restrict__ acts, const float
 // ---------------------------------------------------------------------------------------
 template <bool PRETRAIN>
 __global__ void __launch_bounds__(256)
-sample_step_kernel(const float* __restrict__ logits, const float* __restrict__ u, float temperature,
-                   int V, int L, int t, float* __restrict__ out /*[B,L,V]*/, int64_t* __restrict__ ids,
-                   const int64_t* __restrict__ forced, const float* __restrict__ embed, int E,
+sample_step_kernel(const float* __restrict__ logits, const float* __restrict__ u, float temperature_v,
+                   const float* __restrict__ t_dev, int V, int L, int t, float* __restrict__ out /*[B,L,V]*/,
+                   int64_t* __restrict__ ids, const int64_t* __restrict__ forced, const float* __restrict__ embed, int E,
                    float* __restrict__ x_next, int stage_in_smem) {
+  const float temperature = pick_t(temperature_v, t_dev);
   extern __shared__ float zbuf[];
   __shared__ float red[32];
   __shared__ int red_i[32];
@@ -180,10 +188,11 @@ template <bool FAST> __device__ __forceinline__ float exp_f(float x) { return FA
 
 template <bool PRETRAIN, int NV4, bool FAST>
 __global__ void __launch_bounds__(256)
-sample_step_reg_kernel(const float* __restrict__ logits, const float* __restrict__ u, float temperature,
-                       int V, int L, int t, float* __restrict__ out, int64_t* __restrict__ ids,
-                       const int64_t* __restrict__ forced, const float* __restrict__ embed, int E,
-                       float* __restrict__ x_next) {
+sample_step_reg_kernel(const float* __restrict__ logits, const float* __restrict__ u, float temperature_v,
+                       const float* __restrict__ t_dev, int V, int L, int t, float* __restrict__ out,
+                       int64_t* __restrict__ ids, const int64_t* __restrict__ forced, const float* __restrict__ embed,
+                       int E, float* __restrict__ x_next) {
+  const float temperature = pick_t(temperature_v, t_dev);
   __shared__ float red[32];
   __shared__ int red_i[32];
   __shared__ int s_tok;
@@ -284,7 +293,7 @@ static bool launch_sample_reg(const float* logits, const float* u, float tempera
                               float* x_next, cudaStream_t s) {
   const int nv4 = V >> 2;
 #define GIC_SAMPLE(NV4_)                                                                                         \
-  sample_step_reg_kernel<PRETRAIN, NV4_, FAST><<<B, 256, 0, s>>>(logits, u, temperature, V, L, t, out, ids, forced, embed, \
+  sample_step_reg_kernel<PRETRAIN, NV4_, FAST><<<B, 256, 0, s>>>(logits, u, temperature, g_t_dev, V, L, t, out, ids, forced, embed, \
                                                            E, x_next)
   if (nv4 <= 256 * 1) GIC_SAMPLE(1);
   else if (nv4 <= 256 * 2) GIC_SAMPLE(2);
@@ -318,10 +327,10 @@ int sample_step(bool pretrain, const float* logits, const float* u, float temper
   }
   const size_t dyn = in_smem ? smem : 0;
   if (pretrain)
-    sample_step_kernel<true><<<B, 256, dyn, s>>>(logits, u, temperature, V, L, t, out, ids, forced, embed, E,
+    sample_step_kernel<true><<<B, 256, dyn, s>>>(logits, u, temperature, g_t_dev, V, L, t, out, ids, forced, embed, E,
                                                x_next, in_smem);
   else
-    sample_step_kernel<false><<<B, 256, dyn, s>>>(logits, u, temperature, V, L, t, out, ids, forced, embed, E,
+    sample_step_kernel<false><<<B, 256, dyn, s>>>(logits, u, temperature, g_t_dev, V, L, t, out, ids, forced, embed, E,
                                                 x_next, in_smem);
   return check_launch("sample_step_kernel");
 }
@@ -331,7 +340,9 @@ int sample_step(bool pretrain, const float* logits, const float* u, float temper
 // (autograd of F.softmax(gumbel_t * T), src/generator.py:69; the Gumbel add is a constant.)
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-softmax_bwd_kernel(const float* __restrict__ p, const float* dp, float temperature, int V, float* dz) {   // dz may alias dp
+softmax_bwd_kernel(const float* __restrict__ p, const float* dp, float temperature_v, const float* __restrict__ t_dev,
+                   int V, float* dz) {   // dz may alias dp
+  const float temperature = pick_t(temperature_v, t_dev);
   __shared__ float red[32];
   const size_t row = blockIdx.x;
   const float* pr = p + row * V;
@@ -347,15 +358,16 @@ int softmax_bwd(const float* p, const float* dp, float temperature, int rows, in
                 cudaStream_t s) {
   if (rows == 0) return GIC_OK;
   ProfScope prof(PROF_SOFTMAX_BWD, 12.0 * rows * V, s);               // read p, dp; write dz
-  softmax_bwd_kernel<<<rows, 256, 0, s>>>(p, dp, temperature, V, dz);
+  softmax_bwd_kernel<<<rows, 256, 0, s>>>(p, dp, temperature, g_t_dev, V, dz);
   return check_launch("softmax_bwd_kernel");
 }
 
 // Softmax backward with the row dot products already known (factored path: dot = <d(emb), emb>): a pure streaming
 // elementwise pass dz = T * p * (dp - dot[row]), float4, in place over dp.  12 B of HBM traffic per element.
 __global__ void __launch_bounds__(256)
-softmax_bwd_dot_kernel(const float4* __restrict__ p, const float4* dp, const float* __restrict__ dot, float temperature,
-                       int V4, size_t n4, float4* dz) {
+softmax_bwd_dot_kernel(const float4* __restrict__ p, const float4* dp, const float* __restrict__ dot, float temperature_v,
+                       const float* __restrict__ t_dev, int V4, size_t n4, float4* dz) {
+  const float temperature = pick_t(temperature_v, t_dev);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i0 < n4; i0 += 4 * stride) {
     float4 pv[4], dv[4];
@@ -378,7 +390,9 @@ softmax_bwd_dot_kernel(const float4* __restrict__ p, const float4* dp, const flo
   }
 }
 __global__ void softmax_bwd_dot_scalar_kernel(const float* __restrict__ p, const float* dp, const float* __restrict__ dot,
-                                              float temperature, int V, size_t n, float* dz) {
+                                              float temperature_v, const float* __restrict__ t_dev, int V, size_t n,
+                                              float* dz) {
+  const float temperature = pick_t(temperature_v, t_dev);
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     dz[i] = temperature * p[i] * (dp[i] - dot[i / V]);
 }
@@ -391,9 +405,9 @@ int softmax_bwd_dot(const float* p, const float* dp, const float* dot, float tem
     const size_t n4 = n / 4;
     const int grid = (int)min((size_t)num_sms() * 8, (n4 + 1023) / 1024);
     softmax_bwd_dot_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(p), reinterpret_cast<const float4*>(dp), dot,
-                                               temperature, V / 4, n4, reinterpret_cast<float4*>(dz));
+                                               temperature, g_t_dev, V / 4, n4, reinterpret_cast<float4*>(dz));
   } else {
-    softmax_bwd_dot_scalar_kernel<<<num_sms() * 8, 256, 0, s>>>(p, dp, dot, temperature, V, n, dz);
+    softmax_bwd_dot_scalar_kernel<<<num_sms() * 8, 256, 0, s>>>(p, dp, dot, temperature, g_t_dev, V, n, dz);
   }
   return check_launch("softmax_bwd_dot_kernel");
 }

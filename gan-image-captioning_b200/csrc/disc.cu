@@ -211,16 +211,16 @@ conv_pool_bwd_demb_kernel(const uint8_t* __restrict__ arg, const float* __restri
     if (VEC) {
       const int F4 = F >> 2;
       const float4* dx4 = reinterpret_cast<const float4*>(dx + base);
-      const uchar4* a4 = reinterpret_cast<const uchar4*>(arg + base);
+      const uint32_t* a4 = reinterpret_cast<const uint32_t*>(arg + base);
       for (int q0 = 0; q0 < F4; q0 += 128) {   // 4 float4 groups per lane in flight
         float4 gv[4];
-        uchar4 av[4];
+        uint32_t av[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int q = q0 + j * 32 + lane;
           const bool ok = q < F4;
           gv[j] = ok ? dx4[q] : make_float4(0.f, 0.f, 0.f, 0.f);
-          av[j] = ok ? a4[q] : make_uchar4(ARG_DEAD, ARG_DEAD, ARG_DEAD, ARG_DEAD);
+          av[j] = ok ? __ldg(a4 + q) : 0xffffffffu;
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -229,7 +229,7 @@ conv_pool_bwd_demb_kernel(const uint8_t* __restrict__ arg, const float* __restri
           const int c = q << 2;
           const int fk = fk_s[c];
           const float gg[4] = {gv[j].x, gv[j].y, gv[j].z, gv[j].w};
-          const int aa[4] = {av[j].x, av[j].y, av[j].z, av[j].w};
+          const int aa[4] = {(int)(av[j] & 0xffu), (int)((av[j] >> 8) & 0xffu), (int)((av[j] >> 16) & 0xffu), (int)(av[j] >> 24)};
           bool on[4];
           bool any = false;
 #pragma unroll
@@ -414,7 +414,7 @@ head_fwd_vec_kernel(const float* __restrict__ hpre, const float* __restrict__ po
   const float4* x4 = reinterpret_cast<const float4*>(pooled + base);
   const float4* w4 = reinterpret_cast<const float4*>(weff);
   float4 hv[NQ], xv[NQ];
-  uchar4 kv[MAX_HEADS][NQ];
+  uint32_t kv[MAX_HEADS][NQ];      // raw 4-byte mask words: unpacking at load time would serialise the loads
 #pragma unroll
   for (int i = 0; i < NQ; ++i) {
     const int q = lane + 32 * i;
@@ -423,7 +423,7 @@ head_fwd_vec_kernel(const float* __restrict__ hpre, const float* __restrict__ po
     xv[i] = ok ? x4[q] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int m = 0; m < MAX_HEADS; ++m)
-      if (m < hp.n && hp.keep[m]) kv[m][i] = ok ? reinterpret_cast<const uchar4*>(hp.keep[m] + base)[q] : make_uchar4(0, 0, 0, 0);
+      if (m < hp.n && hp.keep[m]) kv[m][i] = ok ? __ldg(reinterpret_cast<const uint32_t*>(hp.keep[m] + base) + q) : 0u;
   }
   float acc[MAX_HEADS] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -444,8 +444,9 @@ head_fwd_vec_kernel(const float* __restrict__ hpre, const float* __restrict__ po
       for (int m = 0; m < MAX_HEADS; ++m) {
         if (m < hp.n) {
           if (hp.keep[m]) {
-            const uchar4 k = kv[m][i];
-            acc[m] += (k.x ? yw[0] : 0.f) + (k.y ? yw[1] : 0.f) + (k.z ? yw[2] : 0.f) + (k.w ? yw[3] : 0.f);
+            const uint32_t k = kv[m][i];
+            acc[m] += ((k & 0xffu) ? yw[0] : 0.f) + ((k & 0xff00u) ? yw[1] : 0.f) + ((k & 0xff0000u) ? yw[2] : 0.f) +
+                      ((k & 0xff000000u) ? yw[3] : 0.f);
           } else {
             acc[m] += (yw[0] + yw[1]) + (yw[2] + yw[3]);
           }
@@ -480,7 +481,7 @@ head_bwd_vec_kernel(const float* __restrict__ dlogit, const uint8_t* __restrict_
   float s[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};
   for (int rb = r0; rb < r1; rb += 4) {
     float4 hv[4], xv[4];
-    uchar4 kv[4];
+    uint32_t kv[4];
     float dl[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -489,7 +490,7 @@ head_bwd_vec_kernel(const float* __restrict__ dlogit, const uint8_t* __restrict_
       const size_t i = (size_t)r * F4 + q;
       hv[j] = ok ? reinterpret_cast<const float4*>(hpre)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
       xv[j] = ok ? reinterpret_cast<const float4*>(pooled)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-      kv[j] = (ok && keep) ? reinterpret_cast<const uchar4*>(keep)[i] : make_uchar4(1, 1, 1, 1);
+      kv[j] = (ok && keep) ? __ldg(reinterpret_cast<const uint32_t*>(keep) + i) : 0x01010101u;
       dl[j] = ok ? dlogit[r] * sc : 0.f;
     }
 #pragma unroll
@@ -498,7 +499,8 @@ head_bwd_vec_kernel(const float* __restrict__ dlogit, const uint8_t* __restrict_
       if (r >= r1) break;
       const float hh[4] = {hv[j].x, hv[j].y, hv[j].z, hv[j].w};
       const float xx[4] = {xv[j].x, xv[j].y, xv[j].z, xv[j].w};
-      const float kp[4] = {kv[j].x ? 1.f : 0.f, kv[j].y ? 1.f : 0.f, kv[j].z ? 1.f : 0.f, kv[j].w ? 1.f : 0.f};
+      const float kp[4] = {(kv[j] & 0xffu) ? 1.f : 0.f, (kv[j] & 0xff00u) ? 1.f : 0.f, (kv[j] & 0xff0000u) ? 1.f : 0.f,
+                           (kv[j] & 0xff000000u) ? 1.f : 0.f};
       float dhv[4], dxv[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {

@@ -25,6 +25,7 @@ struct EpiArgs {
   const float* aux;    // EPI_DZ: p[M, ldc]
   const float* rowv;   // EPI_DZ: dot[M]
   float scalar;        // EPI_DZ: temperature
+  const float* scalar_dev;   // EPI_DZ: temperature read at run time when non-null (CUDA-graph replay)
   int dbg;             // profiling experiments only (GIC_GEMM_DBG): 1 = skip the global stores of the epilogue
   int vec_red;         // C is 16-byte aligned with ldc % 4 == 0: stream-K shares use red.global.add.v4.f32
   int tma_store;       // tmC is valid: full-width chunks of plain stores leave through cp.async.bulk.tensor
@@ -277,6 +278,7 @@ gemm_p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         if (EPI == EPI_DZ) {
           // loads of p first (8 rows in flight), then the stores: p and dz may not alias but the compiler cannot know
           const float* pptr = ea.aux + (size_t)m_base * ea.ldc + n;
+          const float tscal = ea.scalar_dev ? __ldg(ea.scalar_dev) : ea.scalar;
 #pragma unroll
           for (int r0 = 0; r0 < 32; r0 += 8) {
             float pv[8], dv[8];
@@ -289,7 +291,7 @@ gemm_p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 #pragma unroll
             for (int i = 0; i < 8; ++i)
               if ((r0 + i < rows) && n_ok)
-                cptr[(size_t)(r0 + i) * ea.ldc] = ea.scalar * pv[i] * (stg[(r0 + i) * 33 + lane] - dv[i]);
+                cptr[(size_t)(r0 + i) * ea.ldc] = tscal * pv[i] * (stg[(r0 + i) * 33 + lane] - dv[i]);
           }
         } else if (partial) {
           if (ea.vec_red) {
@@ -401,6 +403,7 @@ static bool use_v1() {
 int gemm_tc_persistent(bool transA, bool transB, int M, int N, int K, float alpha, const float* A, int lda,
                        const float* B, int ldb, float beta, float* C, int ldc, const float* bias, int epi,
                        const float* aux, const float* rowv, float scalar, cudaStream_t stream, bool* handled) {
+  extern const float* temperature_device();
   using namespace tc;
   *handled = false;
   if (use_v1() && epi == EPI_STORE) return GIC_OK;
@@ -447,7 +450,7 @@ int gemm_tc_persistent(bool transA, bool transB, int M, int N, int K, float alph
     if (e != cudaSuccess) { set_error("memset2D: %s", cudaGetErrorString(e)); return GIC_ERR_CUDA; }
   }
   EpiArgs ea;
-  ea.alpha = alpha; ea.beta = beta; ea.C = C; ea.ldc = ldc; ea.bias = bias; ea.aux = aux; ea.rowv = rowv; ea.scalar = scalar; ea.dbg = dbg_env;
+  ea.alpha = alpha; ea.beta = beta; ea.C = C; ea.ldc = ldc; ea.bias = bias; ea.aux = aux; ea.rowv = rowv; ea.scalar = scalar; ea.scalar_dev = (epi == EPI_DZ) ? temperature_device() : nullptr; ea.dbg = dbg_env;
   CUtensorMap tcm;
   ea.vec_red = (aligned16(C) && (ldc % 4) == 0 && (!bias || aligned16(bias))) ? 1 : 0;
   ea.tma_store = 0;

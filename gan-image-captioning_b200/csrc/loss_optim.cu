@@ -122,7 +122,9 @@ int grad_sqnorm(const float* g, size_t n, float* out, cudaStream_t s) {
 __global__ void __launch_bounds__(256)
 clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                  float* __restrict__ v, size_t n, const float* __restrict__ sqnorm, float max_norm,
-                 float grad_scale, float lr_over_bc1, float inv_sqrt_bc2, float b1, float b2, float eps) {
+                 float grad_scale, float lr_over_bc1, float inv_sqrt_bc2, const float* __restrict__ bc_dev, float b1,
+                 float b2, float eps) {
+  if (bc_dev) { lr_over_bc1 = __ldg(bc_dev); inv_sqrt_bc2 = __ldg(bc_dev + 1); }
   float coef = grad_scale;
   if (max_norm > 0.f && sqnorm) {
     const float nrm = sqrtf(*sqnorm) * grad_scale;
@@ -139,15 +141,16 @@ clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
 }
 
 int clip_adam(float* p, const float* g, float* m, float* v, size_t n, const float* sqnorm, float max_norm,
-              float grad_scale, int step, float lr, float b1, float b2, float eps, cudaStream_t s) {
+              float grad_scale, int step, float lr, float b1, float b2, float eps, const float* bc_dev, cudaStream_t s) {
   if (n == 0) return GIC_OK;
   GIC_REQUIRE(p && g && m && v, GIC_ERR_NULL, "clip_adam: NULL operand");
-  GIC_REQUIRE(step >= 1, GIC_ERR_SHAPE, "clip_adam: step must be >= 1");
+  GIC_REQUIRE(step >= 1 || bc_dev, GIC_ERR_SHAPE, "clip_adam: step must be >= 1");
+  if (step < 1) step = 1;
   const double bc1 = 1.0 - pow((double)b1, step), bc2 = 1.0 - pow((double)b2, step);
   const int grid = min(cdiv((long long)n, 256), 8 * num_sms());
   ProfScope prof(PROF_ADAM, 28.0 * n, s);                              // read p,g,m,v; write p,m,v
   clip_adam_kernel<<<grid, 256, 0, s>>>(p, g, m, v, n, sqnorm, max_norm, grad_scale, (float)(lr / bc1),
-                                        (float)(1.0 / sqrt(bc2)), b1, b2, eps);
+                                        (float)(1.0 / sqrt(bc2)), bc_dev, b1, b2, eps);
   return check_launch("clip_adam_kernel");
 }
 

@@ -69,6 +69,10 @@ class GANInstructor:
         self._flat_g: Optional[FlatParams] = None
         self._flat_d: Optional[FlatParams] = None
         self._cache = {}
+        self._graphs = {}
+        self._dyn = None          # device scalars of the captured step: [T, D lr/bc1, D 1/sqrt(bc2), G lr/bc1, G 1/sqrt(bc2)]
+        self._dyn_host = None
+        self._in_graph = False
         self.world = 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size()
@@ -119,12 +123,18 @@ class GANInstructor:
     # ---- the fused adversarial step ---------------------------------------------------------------
     @torch.no_grad()
     def adv_step(self, captions, pooled=None, u=None, keep=None, train=True, forced_ids=None, loss_type=None,
-                 update=True):
+                 update=True, graph=False):
         """One adversarial step on a batch (src/training.py:136-169).
 
         captions [B,L] int64 (collate contract); pooled [B,feature_dim] CNN features when conditional;
         u [L,B,V] uniforms and keep [3,B*R,F] dropout keep-masks are drawn on-device when omitted.
-        Returns a dict with g_loss/d_loss (device scalars), ids, probs and the D logits."""
+        Returns a dict with g_loss/d_loss (device scalars), ids, probs and the D logits.
+
+        graph=True replays the whole step as one CUDA graph (captured on first use per batch shape): inputs are
+        copied into static buffers, the temperature and Adam's bias corrections are read from device memory
+        (gic_set_temperature_device / gic_clip_adam_dyn), so one replay call enqueues all ~150 kernels."""
+        if graph:
+            return self._adv_step_graph(captions, pooled, u, keep, loss_type, static=(graph == "static"))
         _lib.require_cuda()
         lib = _lib.lib()
         a, dev = self.args, self.device
@@ -143,6 +153,8 @@ class GANInstructor:
         T = float(dec.temperature)
         stream = _lib.stream()
         P = _lib.ptr
+        if self._in_graph:
+            lib.gic_set_temperature_device(P(self._dyn[0:1]))
 
         # -- step-0 input (:144-147)
         if self.cgan:
@@ -252,29 +264,120 @@ class GANInstructor:
             torch.distributed.all_reduce(fd.grad)
             if g_has_grad:
                 torch.distributed.all_reduce(fg.grad)
-        out["d_sqnorm"] = self._clip_adam(fd, a.disc_lr, update)
+        out["d_sqnorm"] = self._clip_adam(fd, a.disc_lr, update, 1)
         if g_has_grad:
-            out["g_sqnorm"] = self._clip_adam(fg, a.gen_lr, update)
+            out["g_sqnorm"] = self._clip_adam(fg, a.gen_lr, update, 3)
+        out["g_has_grad"] = g_has_grad
+        if self._in_graph:
+            lib.gic_set_temperature_device(None)
         return out
 
-    def _clip_adam(self, fp: FlatParams, lr: float, update: bool):
+    def _clip_adam(self, fp: FlatParams, lr: float, update: bool, dyn_slot: int = 1):
         lib = _lib.lib()
         sq = torch.zeros(1, device=self.device)
         stream = _lib.stream()
         _lib.check(lib.gic_grad_sqnorm(_lib.ptr(fp.grad), fp.n, _lib.ptr(sq), stream), "gic_grad_sqnorm")
-        if update:
+        if update and self._in_graph:
+            _lib.check(lib.gic_clip_adam_dyn(_lib.ptr(fp.flat), _lib.ptr(fp.grad), _lib.ptr(fp.m), _lib.ptr(fp.v), fp.n,
+                                             _lib.ptr(sq), float(self.args.clip_norm), 1.0 / self.world,
+                                             _lib.ptr(self._dyn[dyn_slot:dyn_slot + 2]), 0.9, 0.999, 1e-8, stream),
+                       "gic_clip_adam_dyn")
+        elif update:
             fp.step += 1
             _lib.check(lib.gic_clip_adam(_lib.ptr(fp.flat), _lib.ptr(fp.grad), _lib.ptr(fp.m), _lib.ptr(fp.v), fp.n,
                                          _lib.ptr(sq), float(self.args.clip_norm), 1.0 / self.world, fp.step,
                                          float(lr), 0.9, 0.999, 1e-8, stream), "gic_clip_adam")
         return sq
 
-    def adv_loop(self, what, batches, total_batches=None):
+    # ---- CUDA-graph replay of the fused step -------------------------------------------------------
+    def _adv_step_graph(self, captions, pooled, u, keep, loss_type, static=False):
+        """static=True: the given device tensors themselves are the graph's inputs (no copies; one graph per distinct
+        set of buffers) -- for callers that keep their batches resident."""
+        a, dev = self.args, self.device
+        loss_type = loss_type or a.adv_loss_type
+        B, L = captions.shape
+        key = (B, L, loss_type, pooled is not None, u is not None, keep is not None)
+        if static:
+            key = key + tuple(None if t is None else t.data_ptr() for t in (captions, pooled, u, keep))
+        st = self._graphs.get(key)
+        if self._dyn is None:
+            self._dyn = torch.zeros(8, device=dev)
+            # ring of pinned staging slots: the host may run ahead of the GPU, so a slot is rewritten only after the
+            # copy that read it has executed (event per slot)
+            self._dyn_host = [torch.zeros(8).pin_memory() for _ in range(16)]
+            self._dyn_ev = [None] * 16
+            self._dyn_i = 0
+        if st is None and static:
+            st = dict(captions=captions, pooled=pooled, u=u, keep=keep)
+            self._graphs[key] = st
+        if st is None:
+            st = dict(captions=torch.empty(B, L, dtype=torch.int64, device=dev),
+                      pooled=None if pooled is None else torch.empty(pooled.shape, device=dev),
+                      u=None if u is None else torch.empty(u.shape, device=dev),
+                      keep=None if keep is None else torch.empty(keep.shape, dtype=torch.uint8, device=dev))
+            self._graphs[key] = st
+
+        def load_inputs():
+            if static:
+                return
+            st["captions"].copy_(captions, non_blocking=True)
+            if pooled is not None:
+                st["pooled"].copy_(pooled, non_blocking=True)
+            if u is not None:
+                st["u"].copy_(u, non_blocking=True)
+            if keep is not None:
+                st["keep"].copy_(keep, non_blocking=True)
+
+        def load_scalars():
+            self._ensure_flat()
+            i = self._dyn_i = (self._dyn_i + 1) % 16
+            if self._dyn_ev[i] is not None:
+                self._dyn_ev[i].synchronize()
+            h = self._dyn_host[i]
+            h[0] = float(self.gen.decoder.temperature)
+            for slot, fp, lr in ((1, self._flat_d, a.disc_lr), (3, self._flat_g, a.gen_lr)):
+                t = fp.step + 1
+                h[slot] = lr / (1.0 - 0.9 ** t)
+                h[slot + 1] = 1.0 / (1.0 - 0.999 ** t) ** 0.5
+            self._dyn.copy_(h, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            self._dyn_ev[i] = ev
+
+        load_inputs()
+        if "graph" not in st:
+            # one eager step allocates every cached buffer and compiles nothing new during capture; it is a real
+            # training step (same semantics), so the captured replay starts at step 2
+            out = self.adv_step(st["captions"], pooled=st["pooled"], u=st["u"], keep=st["keep"], loss_type=loss_type)
+            torch.cuda.synchronize(dev)
+            load_scalars()
+            g = torch.cuda.CUDAGraph()
+            n0 = _lib.lib().gic_launch_count()
+            self._in_graph = True
+            try:
+                with torch.cuda.graph(g):
+                    st["out"] = self.adv_step(st["captions"], pooled=st["pooled"], u=st["u"], keep=st["keep"],
+                                              loss_type=loss_type)
+            finally:
+                self._in_graph = False
+                _lib.lib().gic_set_temperature_device(None)
+            st["graph"] = g
+            st["g_has_grad"] = st["out"]["g_has_grad"]
+            self.graph_launches_per_step = int(_lib.lib().gic_launch_count() - n0)   # kernels of ours in one replay
+            return out          # the eager step's results (capture itself does not execute the kernels)
+        load_scalars()
+        st["graph"].replay()
+        self._flat_d.step += 1
+        if st["g_has_grad"]:
+            self._flat_g.step += 1
+        return st["out"]
+
+    def adv_loop(self, what, batches, total_batches=None, graph=False):
         """Body of the reference's adv_loop over an iterable of (pooled_or_None, captions) batches."""
         gen_loss, disc_loss = [], []
         nb = total_batches or (len(batches) if hasattr(batches, "__len__") else 1)
         for i, (pooled, captions) in enumerate(batches, start=1):
-            r = self.adv_step(captions, pooled=pooled, train=(what == "train"))
+            r = self.adv_step(captions, pooled=pooled, train=(what == "train"), graph=(graph and what == "train"))
             gen_loss.append(r["g_loss"])
             disc_loss.append(r["d_loss"])
             self.gen_steps += 1

@@ -175,6 +175,18 @@ int gic_grad_sqnorm(const float* g, size_t n, float* sqnorm, gic_stream_t stream
 int gic_clip_adam(float* p, const float* g, float* m, float* v, size_t n, const float* sqnorm, float max_norm,
                   float grad_scale, int step, float lr, float beta1, float beta2, float eps, gic_stream_t stream);
 
+/* ---- CUDA-graph replay support ----
+ * By-value scalars are frozen when a launch is captured into a CUDA graph, but the reference changes two of them every
+ * batch: the temperature (update_temperature, src/training.py:183,190-191) and Adam's bias corrections (step count).
+ * gic_set_temperature_device(t_dev): while t_dev is non-NULL every entry point that takes `temperature` reads it from
+ *   *t_dev when its kernels run and ignores the by-value argument (process-wide; pass NULL to switch back).
+ * gic_clip_adam_dyn: gic_clip_adam with the step-dependent factors read from device memory:
+ *   bias_corr_dev[0] = lr / (1 - beta1^t), bias_corr_dev[1] = 1 / sqrt(1 - beta2^t). */
+void gic_set_temperature_device(const float* t_dev);
+int gic_clip_adam_dyn(float* p, const float* g, float* m, float* v, size_t n, const float* sqnorm, float max_norm,
+                      float grad_scale, const float* bias_corr_dev, float beta1, float beta2, float eps,
+                      gic_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

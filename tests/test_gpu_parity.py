@@ -544,3 +544,39 @@ def test_fused_step_tf32_mode_vs_oracle(tf32_mode):
     for k, p in inst.gen.named_parameters():
         if k in ref["g_grads"]:
             close(f"tf32/step/g_grads/{k}", fg.g(p), ref["g_grads"][k], rtol=1e-2, atol=1e-9, outlier_frac=1e-2)
+
+
+def test_graph_replay_matches_eager_steps():
+    """CUDA-graph replay of the fused step (device-side temperature and Adam bias corrections) against the same
+    three steps enqueued eagerly: identical inputs, a different temperature per step (update_temperature)."""
+    from gic_b200.training import GANInstructor
+    inp = rp.make_inputs(rp.CONFIGS["c1"])
+    a = inp["args"]; a.device = "cuda"
+
+    def fresh():
+        inst = GANInstructor(a, device="cuda:0")
+        sd = inst.gen.state_dict(); sd.update({k: v.clone() for k, v in inp["gen"].items()}); inst.gen.load_state_dict(sd)
+        inst.disc.load_state_dict({k: v.clone() for k, v in inp["disc"].items()})
+        inst.gen.train(); inst.disc.train()
+        return inst
+    temps = [1.0, 1.7, 3.1, 5.0]
+    caps, pooled = inp["captions"].cuda(), inp["pooled"].cuda()
+    u, keep = inp["u"].cuda(), inp["keep"].to(torch.uint8).cuda()
+    eager, graphed = fresh(), fresh()
+    outs_e, outs_g = [], []
+    for T in temps:
+        eager.gen.decoder.temperature = T
+        r = eager.adv_step(caps, pooled=pooled, u=u, keep=keep)
+        outs_e.append((r["g_loss"].item(), r["d_loss"].item(), r["ids"].clone()))
+        graphed.gen.decoder.temperature = T
+        r = graphed.adv_step(caps, pooled=pooled, u=u, keep=keep, graph=True)
+        outs_g.append((r["g_loss"].item(), r["d_loss"].item(), r["ids"].clone()))
+    torch.cuda.synchronize()
+    assert graphed.graph_launches_per_step > 50
+    for (ge, de, ie), (gg, dg, ig) in zip(outs_e, outs_g):
+        assert abs(ge - gg) <= 1e-6 * max(1.0, abs(ge)) and abs(de - dg) <= 1e-6 * max(1.0, abs(de))
+        assert torch.equal(ie, ig)
+    for (k, pe), (_, pg) in zip(eager.disc.named_parameters(), graphed.disc.named_parameters()):
+        close(f"graph/disc/{k}", pg, pe.detach().cpu(), rtol=1e-5, atol=len(temps) * ADAM_ATOL)   # atomics order differs run to run
+    for (k, pe), (_, pg) in zip(eager.gen.named_parameters(), graphed.gen.named_parameters()):
+        close(f"graph/gen/{k}", pg, pe.detach().cpu(), rtol=1e-5, atol=len(temps) * ADAM_ATOL)
