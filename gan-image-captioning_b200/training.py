@@ -11,6 +11,7 @@ Data parallel: one process per GPU, each rank owns B/world rows; the only exchan
 (sum) of the flat G and D gradient buffers before the clip."""
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -73,6 +74,8 @@ class GANInstructor:
         self._dyn = None          # device scalars of the captured step: [T, D lr/bc1, D 1/sqrt(bc2), G lr/bc1, G 1/sqrt(bc2)]
         self._dyn_host = None
         self._in_graph = False
+        self._side = None
+        self.overlap = os.environ.get("GIC_NO_OVERLAP", "0") != "1"
         self.world = 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size()
@@ -88,6 +91,11 @@ class GANInstructor:
         if model is not None:
             torch.nn.utils.clip_grad_norm_(model.parameters(), self.args.clip_norm)
         opt.step()
+
+    def _side_stream(self):
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
 
     # ---- flat buffers ---------------------------------------------------------------------------
     def _gen_params(self):
@@ -156,6 +164,29 @@ class GANInstructor:
         if self._in_graph:
             lib.gic_set_temperature_device(P(self._dyn[0:1]))
 
+        # -- discriminator on the real captions (hard tokens, :158,162): independent of the decode, so it runs on a
+        #    side stream underneath the latency-bound autoregressive loop
+        if train:
+            if keep is None:
+                keep = torch.rand(3, B * R, Fd, device=dev) >= disc.dropout.p
+            keep = keep.to(dev).to(torch.uint8).contiguous()
+            k0, k1, k2 = keep[0], keep[1], keep[2]
+        else:
+            k0 = k1 = k2 = None
+        cw = [c.weight for c in disc.convs]
+        cb = [c.bias for c in disc.convs]
+        dW = (disc.embeddings.weight, cw, cb, disc.highway.weight, disc.highway.bias, disc.feature2out.weight,
+              disc.feature2out.bias, disc.out2logits.weight, disc.out2logits.bias)
+        drop_p = disc.dropout.p
+        main = torch.cuda.current_stream()
+        side = self._side_stream() if (train and self.overlap) else None
+        if side is not None:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                (d_real,), saved_r = disc_fwd_raw(lib, mode, None, captions, B, L, V, De, R, fsz, nfl, *dW, [k0], drop_p,
+                                                  dev)
+        else:
+            (d_real,), saved_r = disc_fwd_raw(lib, mode, None, captions, B, L, V, De, R, fsz, nfl, *dW, [k0], drop_p, dev)
         # -- step-0 input (:144-147)
         if self.cgan:
             enc = self.gen.encoder
@@ -185,22 +216,11 @@ class GANInstructor:
                                              P(dec.linear.weight), P(dec.linear.bias), P(u), T, 0, P(forced_ids), B, L,
                                              V, E, H, layers, P(probs), P(ids), P(dsaved), P(dws), stream),
                    "gic_decode_sample_fwd")
-        # -- discriminator: real (hard tokens) and fake/gen (shared trunk, two dropout masks) (:158-164)
-        if train:
-            if keep is None:
-                keep = torch.rand(3, B * R, Fd, device=dev) >= disc.dropout.p
-            keep = keep.to(dev).to(torch.uint8).contiguous()
-            k0, k1, k2 = keep[0], keep[1], keep[2]
-        else:
-            k0 = k1 = k2 = None
-        cw = [c.weight for c in disc.convs]
-        cb = [c.bias for c in disc.convs]
-        dW = (disc.embeddings.weight, cw, cb, disc.highway.weight, disc.highway.bias, disc.feature2out.weight,
-              disc.feature2out.bias, disc.out2logits.weight, disc.out2logits.bias)
-        drop_p = disc.dropout.p
-        (d_real,), saved_r = disc_fwd_raw(lib, mode, None, captions, B, L, V, De, R, fsz, nfl, *dW, [k0], drop_p, dev)
+        # -- discriminator on the generated captions: fake / gen share one trunk, two dropout masks (:163-164)
         (d_fake, g_out), saved_f = disc_fwd_raw(lib, mode, probs, None, B, L, V, De, R, fsz, nfl, *dW, [k1, k2],
                                                 drop_p, dev)
+        if side is not None:
+            main.wait_stream(side)
         # -- losses + seeds (:165)
         n = B * R
         losses = torch.empty(2, device=dev)
@@ -217,7 +237,7 @@ class GANInstructor:
         g = fd.g
         dcw, dcb = [g(c.weight) for c in disc.convs], [g(c.bias) for c in disc.convs]
 
-        def disc_bwd(seed, kp, inp, idz, saved, want_param, acc, dinp):
+        def disc_bwd(seed, kp, inp, idz, saved, want_param, acc, dinp, bws, stream):
             _lib.check(lib.gic_disc_bwd(mode, P(seed), P(kp), drop_p, P(inp), P(idz), B, L, V, De, R, len(fsz),
                                         _lib.int_array(fsz), _lib.int_array(nfl), P(disc.embeddings.weight),
                                         _lib.ptr_array(cw), _lib.ptr_array(cb), P(disc.highway.weight),
@@ -229,15 +249,14 @@ class GANInstructor:
                                         P(g(disc.feature2out.bias)), P(g(disc.out2logits.weight)),
                                         P(g(disc.out2logits.bias)), P(dinp), want_param, acc, stream), "gic_disc_bwd")
 
-        disc_bwd(seeds[0], k0, None, captions, saved_r, 1, 0, None)
-        disc_bwd(seeds[1], k1, probs, None, saved_f, 1, 1, None)
         g_has_grad = loss_type != "rsgan"          # A14: rsgan's g_loss only sees detached D outputs
-        if g_has_grad:
+
+        def gen_chain(ws_d, st):
             # D's input gradient stays factored (demb x W_e): the dense d(probs)[B,L,V] is never written; the
             # decoder backward fuses demb W_e with the tempered-softmax backward (gic_decode_sample_bwd_factored)
-            disc_bwd(seeds[2], k2, probs, None, saved_f, 0, 0, None)
+            disc_bwd(seeds[2], k2, probs, None, saved_f, 0, 0, None, ws_d, st)
             off = lib.gic_disc_bwd_demb_offset_floats(B, L, De, R, Fd)
-            demb = bws[off:off + B * L * De]
+            demb = ws_d[off:off + B * L * De]
             emb = saved_f[:B * L * De]
             gg = fg.g
             gws = self._buf("dec_bws", lib.gic_decode_bwd_workspace_floats(B, L, V, E, H, layers))
@@ -249,24 +268,51 @@ class GANInstructor:
                 P(gws), P(gg(dec.embed.weight)), _lib.ptr_array([gg(w) for w in W_ih]),
                 _lib.ptr_array([gg(w) for w in W_hh]), _lib.ptr_array([gg(w) for w in b_ih]),
                 _lib.ptr_array([gg(w) for w in b_hh]), P(gg(dec.linear.weight)), P(gg(dec.linear.bias)), P(dfeat), 0,
-                stream), "gic_decode_sample_bwd_factored")
+                st), "gic_decode_sample_bwd_factored")
             if self.cgan:
                 enc = self.gen.encoder
                 _lib.check(lib.gic_encoder_bwd(mode, P(dfeat), P(pooled), P(lin), P(mean), P(rstd),
                                                P(enc.linear.weight), P(enc.bn.weight), B, pooled.shape[1], E,
                                                P(self._buf("enc_dlin", B * E)), P(gg(enc.linear.weight)),
                                                P(gg(enc.linear.bias)), P(gg(enc.bn.weight)), P(gg(enc.bn.bias)), 0,
-                                               stream), "gic_encoder_bwd")
+                                               st), "gic_encoder_bwd")
             else:
                 gg(dec.embed.weight)[1] += dfeat.sum(0)      # features = embed(<S>) for every row (:147)
-        # -- data-parallel exchange: summed gradients, averaged inside the optimizer kernel
-        if self.world > 1:
-            torch.distributed.all_reduce(fd.grad)
+
+        # Two independent chains after the loss: D parameter gradients (real, then fake accumulated) and the generator
+        # chain (D input gradient -> decoder BPTT).  The generator chain is latency-bound (L serial BPTT steps), so it
+        # runs on a side stream under the D chain.  Q1: both read the PRE-update weights, so D's Adam waits for the
+        # generator chain's last read of D weights.
+        if side is not None and g_has_grad:
+            bws2 = self._buf("disc_bws2", lib.gic_disc_bwd_workspace_floats(B, L, De, R, Fd))
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                gen_chain(bws2, side.cuda_stream)
+                gen_done = torch.cuda.Event()
+                gen_done.record(side)
+                if self.world > 1:
+                    torch.distributed.all_reduce(fg.grad)
+                out["g_sqnorm"] = self._clip_adam(fg, a.gen_lr, update, 3)
+            disc_bwd(seeds[0], k0, None, captions, saved_r, 1, 0, None, bws, stream)
+            disc_bwd(seeds[1], k1, probs, None, saved_f, 1, 1, None, bws, stream)
+            if self.world > 1:
+                torch.distributed.all_reduce(fd.grad)
+            main.wait_event(gen_done)
+            out["d_sqnorm"] = self._clip_adam(fd, a.disc_lr, update, 1)
+            main.wait_stream(side)
+        else:
+            disc_bwd(seeds[0], k0, None, captions, saved_r, 1, 0, None, bws, stream)
+            disc_bwd(seeds[1], k1, probs, None, saved_f, 1, 1, None, bws, stream)
             if g_has_grad:
-                torch.distributed.all_reduce(fg.grad)
-        out["d_sqnorm"] = self._clip_adam(fd, a.disc_lr, update, 1)
-        if g_has_grad:
-            out["g_sqnorm"] = self._clip_adam(fg, a.gen_lr, update, 3)
+                gen_chain(bws, stream)
+            # -- data-parallel exchange: summed gradients, averaged inside the optimizer kernel
+            if self.world > 1:
+                torch.distributed.all_reduce(fd.grad)
+                if g_has_grad:
+                    torch.distributed.all_reduce(fg.grad)
+            out["d_sqnorm"] = self._clip_adam(fd, a.disc_lr, update, 1)
+            if g_has_grad:
+                out["g_sqnorm"] = self._clip_adam(fg, a.gen_lr, update, 3)
         out["g_has_grad"] = g_has_grad
         if self._in_graph:
             lib.gic_set_temperature_device(None)
