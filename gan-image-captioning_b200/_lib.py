@@ -82,6 +82,13 @@ def _declare(L):
     L.gic_grad_sqnorm.argtypes = [P, Z, P, P]
     L.gic_clip_adam.argtypes = [P, P, P, P, Z, P, F, F, I, F, F, F, F, P]
     L.gic_clip_adam_dyn.argtypes = [P, P, P, P, Z, P, F, F, P, F, F, F, P]
+    L.gic_decode_sample_cdf_fwd.argtypes = [I, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, P, P, P, P, P, P]
+    L.gic_sample_cdf_step.argtypes = [P, P, I, I, I, I, P, P, P, P, P, I, P, P]
+    L.gic_decode_rollouts_workspace_floats.restype = Z
+    L.gic_decode_rollouts_workspace_floats.argtypes = [I] * 6
+    L.gic_decode_rollouts.argtypes = [I, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, P, P, P]
+    L.gic_rollout_rewards.argtypes = [P, P, I, I, I, I, P, P]
+    L.gic_pg_loss_fwd_bwd.argtypes = [P, P, P, I, I, I, I, P, P, P, P]
     L.gic_set_temperature_device.restype = None
     L.gic_set_temperature_device.argtypes = [P]
     for name in header_symbols():      # every declared entry point must be exported

@@ -10,6 +10,10 @@ int sample_step(bool, const float*, const float*, float, int, int, int, int, flo
                 const float*, int, float*, cudaStream_t, bool fast_math = false);
 int softmax_bwd(const float*, const float*, float, int, int, float*, cudaStream_t);
 int rowdot(const float*, const float*, int, int, float*, cudaStream_t);
+int sample_cdf_step(const float*, const float*, int, int, int, int, long long, float*, int64_t*, float*, const int64_t*,
+                    const float*, int, float*, cudaStream_t);
+int rollout_init(const float*, const float*, const int64_t*, const float*, int, int, int, int, int, int, int, float*,
+                 float*, float*, int64_t*, cudaStream_t);
 int softmax_bwd_dot(const float*, const float*, const float*, float, int, int, float*, cudaStream_t);
 int embed_scatter(const float*, const int64_t*, int, int, int, int, float*, float*, cudaStream_t);
 int bn_fwd(const float*, int, int, const float*, const float*, float, float*, float*, float*, cudaStream_t);
@@ -32,6 +36,8 @@ int scale_inplace(float*, size_t, float, cudaStream_t);
 // loss_optim.cu
 int gan_loss(int, const float*, const float*, const float*, int, float*, float*, float*, float*, cudaStream_t);
 int grad_sqnorm(const float*, size_t, float*, cudaStream_t);
+int rollout_q(const float*, const float*, int, int, int, int, float*, cudaStream_t);
+int pg_loss(const float*, const int64_t*, const float*, int, int, int, int, float*, float*, float*, cudaStream_t);
 int clip_adam(float*, const float*, float*, float*, size_t, const float*, float, float, int, float, float, float,
               float, const float*, cudaStream_t);
 void set_temperature_device(const float*);
@@ -75,17 +81,19 @@ struct DecodeSaved {
   size_t acts(int l) const { return acts0 + (size_t)l * per_layer; }
 };
 
+// pretrain: 0 = Gumbel-softmax (u[L,B,V], out = soft captions), 1 = pretrain (out = logits, greedy), 2 = inverse-CDF
+// categorical sampling (EXTENSION: u[L,B], out = logits or NULL, logp[B,L] or NULL)
 static int decode_fwd(int mode, const float* features, const float* W_emb, const float* const* W_ih,
                       const float* const* W_hh, const float* const* b_ih, const float* const* b_hh,
                       const float* W_out, const float* b_out, const float* u, float T, int pretrain,
                       const int64_t* forced, int B, int L, int V, int E, int H, int layers, float* out, int64_t* ids,
-                      float* saved, float* ws, cudaStream_t s) {
+                      float* saved, float* ws, cudaStream_t s, float* logp = nullptr) {
   GIC_REQUIRE(B >= 0 && L >= 1 && V >= 1 && E >= 1 && H >= 1 && layers >= 1 && layers <= 8, GIC_ERR_SHAPE,
               "decode_sample_fwd: bad shape B=%d L=%d V=%d E=%d H=%d layers=%d", B, L, V, E, H, layers);
   if (B == 0) return GIC_OK;
-  GIC_REQUIRE(features && W_emb && W_ih && W_hh && b_ih && b_hh && W_out && b_out && out && ids && saved && ws,
-              GIC_ERR_NULL, "decode_sample_fwd: NULL pointer");
-  GIC_REQUIRE(pretrain || u, GIC_ERR_NULL, "decode_sample_fwd: uniforms u[L,B,V] required in adversarial mode");
+  GIC_REQUIRE(features && W_emb && W_ih && W_hh && b_ih && b_hh && W_out && b_out && (out || pretrain == 2) && ids &&
+                  saved && ws, GIC_ERR_NULL, "decode_sample_fwd: NULL pointer");
+  GIC_REQUIRE(pretrain == 1 || u, GIC_ERR_NULL, "decode_sample_fwd: uniforms required when sampling");
   const DecodeSaved sv(B, L, E, H, layers);
   const size_t BH = (size_t)B * H, BE = (size_t)B * E;
   float* gates = ws;                         // [B,4H]
@@ -119,8 +127,11 @@ static int decode_fwd(int mode, const float* features, const float* W_emb, const
     const float* htop_t = saved + sv.hs(layers - 1) + (size_t)(t + 1) * BH;
     GIC_TRY(gemm(mode, false, true, B, V, H, 1.f, htop_t, H, W_out, H, 0.f, logits, V, b_out, s));   // :64,68
     float* x_next = (t + 1 < L) ? saved + sv.xs + (size_t)(t + 1) * BE : nullptr;
-    GIC_TRY(sample_step(pretrain != 0, logits, pretrain ? nullptr : u + (size_t)t * B * V, T, B, V, L, t, out, ids,
-                        forced, W_emb, E, x_next, s, /*fast_math=*/mode == GEMM_TF32));
+    if (pretrain == 2)
+      GIC_TRY(sample_cdf_step(logits, u + (size_t)t * B, B, V, L, t, L, out, ids, logp, forced, W_emb, E, x_next, s));
+    else
+      GIC_TRY(sample_step(pretrain != 0, logits, pretrain ? nullptr : u + (size_t)t * B * V, T, B, V, L, t, out, ids,
+                          forced, W_emb, E, x_next, s, /*fast_math=*/mode == GEMM_TF32));
   }
   return GIC_OK;
 }
@@ -231,6 +242,68 @@ static int decode_bwd(int mode, const float* dout, const float* demb, const floa
   return GIC_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// EXTENSION: Monte-Carlo rollouts (SeqGAN-style search; SURVEY.md 8a row B2, not in the reference).
+// For every prefix length t = 1..L-1 of the sampled captions main_ids[B,L], n continuations are sampled with the
+// generator policy (inverse-CDF sampling, one uniform per row and step).  Row (t-1)*B*n + b*n + j of roll_ids[Mmax,L]
+// holds the j-th completed caption of prefix t of image b.  The active set grows by B*n rows per step and is always a
+// contiguous prefix of the row space, so every step is ONE batched LSTM step + vocab projection over all live rollouts
+// (up to (L-1)*B*n rows): the shapes that make the decode GEMMs tensor-bound.
+// workspace: h[2][Mmax,H] | c[Mmax,H] | x[Mmax,E] | gates[Mmax,4H] (fp32 mode) | logits[chunk,V]
+// ---------------------------------------------------------------------------------------------------------
+struct RolloutWs {
+  size_t h0, h1, c, x, gates, logits, total;
+  int chunk;
+  RolloutWs(int B, int L, int V, int E, int H, int n) {
+    const size_t M = (size_t)(L - 1) * B * n;
+    chunk = (int)(M < 8192 ? M : 8192);
+    h0 = 0; h1 = a4(M * H); c = h1 + a4(M * H); x = c + a4(M * H); gates = x + a4(M * E);
+    logits = gates + a4(M * 4 * H);
+    total = logits + a4((size_t)chunk * V);
+  }
+};
+
+static int decode_rollouts(int mode, const float* saved, const int64_t* main_ids, const float* W_emb, const float* W_ih,
+                           const float* W_hh, const float* b_ih, const float* b_hh, const float* W_out,
+                           const float* b_out, const float* u_roll, int B, int L, int V, int E, int H, int n,
+                           int64_t* roll_ids, float* ws, cudaStream_t s) {
+  GIC_REQUIRE(B >= 1 && L >= 2 && V >= 1 && E >= 1 && H >= 1 && n >= 1, GIC_ERR_SHAPE, "decode_rollouts: bad shape");
+  GIC_REQUIRE(saved && main_ids && W_emb && W_ih && W_hh && b_ih && b_hh && W_out && b_out && u_roll && roll_ids && ws,
+              GIC_ERR_NULL, "decode_rollouts: NULL pointer");
+  const DecodeSaved sv(B, L, E, H, 1);
+  const RolloutWs w(B, L, V, E, H, n);
+  const size_t BH = (size_t)B * H, G = (size_t)B * n, Mmax = (size_t)(L - 1) * G;
+  float* hbuf[2] = {ws + w.h0, ws + w.h1};
+  float* c = ws + w.c;
+  float* x = ws + w.x;
+  int cur = 0;
+  for (int t = 1; t < L; ++t) {
+    // group t joins: state after t steps of the sampled caption, next input = embed(token t-1)
+    const size_t r0 = (size_t)(t - 1) * G;
+    GIC_TRY(rollout_init(saved + sv.hs(0) + (size_t)t * BH, saved + sv.cs(0) + (size_t)t * BH, main_ids, W_emb, B, n, L, t,
+                         H, E, V, hbuf[cur] + r0 * H, c + r0 * H, x + r0 * E, roll_ids + r0 * L, s));
+    const int M = (int)((size_t)t * G);                       // live rows
+    float* hn = hbuf[cur ^ 1];
+    bool fused = false;
+    if (mode == GEMM_TF32)
+      GIC_TRY(lstm_step_tc(x, E, hbuf[cur], W_ih, W_hh, b_ih, b_hh, c, M, H, nullptr, c, hn, nullptr, L, t, s, &fused));
+    if (!fused) {
+      float* gates = ws + w.gates;
+      GIC_TRY(gemm(mode, false, true, M, 4 * H, E, 1.f, x, E, W_ih, E, 0.f, gates, 4 * H, b_ih, s));
+      GIC_TRY(gemm(mode, false, true, M, 4 * H, H, 1.f, hbuf[cur], H, W_hh, H, 1.f, gates, 4 * H, b_hh, s));
+      GIC_TRY(lstm_cell_fwd(gates, c, M, H, nullptr, c, hn, nullptr, L, t, s));
+    }
+    for (int m0 = 0; m0 < M; m0 += w.chunk) {
+      const int mc = (M - m0 < w.chunk) ? (M - m0) : w.chunk;
+      GIC_TRY(gemm(mode, false, true, mc, V, H, 1.f, hn + (size_t)m0 * H, H, W_out, H, 0.f, ws + w.logits, V, b_out, s));
+      GIC_TRY(sample_cdf_step(ws + w.logits, u_roll + (size_t)t * Mmax + m0, mc, V, L, t, L, nullptr,
+                              roll_ids + (size_t)m0 * L, nullptr, nullptr, W_emb, E, x + (size_t)m0 * E, s));
+    }
+    cur ^= 1;
+  }
+  return GIC_OK;
+}
+
 static int require_device() {
   static int cached = -1;
   if (cached == GIC_OK) return GIC_OK;
@@ -303,6 +376,17 @@ int gic_sample_step(int pretrain, const float* logits, const float* u, float tem
                      S(stream));
 }
 
+int gic_sample_cdf_step(const float* logits, const float* u, int B, int V, int L, int t, float* out, int64_t* ids,
+                        float* logp, const int64_t* forced_ids, const float* embed, int E, float* x_next,
+                        gic_stream_t stream) {
+  GIC_TRY(require_device());
+  GIC_REQUIRE(B >= 0 && V >= 1 && L >= 1 && t >= 0 && t < L, GIC_ERR_SHAPE, "sample_cdf_step: bad shape");
+  if (B == 0) return GIC_OK;
+  GIC_REQUIRE(logits && u && ids, GIC_ERR_NULL, "sample_cdf_step: NULL pointer");
+  GIC_REQUIRE(!x_next || embed, GIC_ERR_NULL, "sample_cdf_step: embed table required for x_next");
+  return sample_cdf_step(logits, u, B, V, L, t, L, out, ids, logp, forced_ids, embed, E, x_next, S(stream));
+}
+
 size_t gic_decode_saved_floats(int B, int L, int E, int H, int layers) { return DecodeSaved(B, L, E, H, layers).total; }
 size_t gic_decode_fwd_workspace_floats(int B, int V, int H) { return a4((size_t)4 * B * H) + a4((size_t)B * V); }
 size_t gic_decode_bwd_workspace_floats(int B, int L, int V, int E, int H, int layers) {
@@ -349,6 +433,41 @@ size_t gic_disc_bwd_demb_offset_floats(int N, int L, int De, int R, int F) {
   (void)L; (void)De;
   const size_t rows = (size_t)N * R;
   return a4((size_t)F + 1) + 2 * a4(rows * F) + 2 * a4(F);
+}
+
+int gic_decode_sample_cdf_fwd(int mode, const float* features, const float* W_emb, const float* const* W_ih,
+                              const float* const* W_hh, const float* const* b_ih, const float* const* b_hh,
+                              const float* W_out, const float* b_out, const float* u, const int64_t* forced_ids, int B,
+                              int L, int V, int E, int H, int layers, float* logits_out, int64_t* ids, float* logp,
+                              float* saved, float* workspace, gic_stream_t stream) {
+  GIC_TRY(require_device());
+  return decode_fwd(mode, features, W_emb, W_ih, W_hh, b_ih, b_hh, W_out, b_out, u, 1.f, 2, forced_ids, B, L, V, E, H,
+                    layers, logits_out, ids, saved, workspace, S(stream), logp);
+}
+
+size_t gic_decode_rollouts_workspace_floats(int B, int L, int V, int E, int H, int n_roll) {
+  return RolloutWs(B, L, V, E, H, n_roll).total;
+}
+
+int gic_decode_rollouts(int mode, const float* saved, const int64_t* main_ids, const float* W_emb, const float* W_ih,
+                        const float* W_hh, const float* b_ih, const float* b_hh, const float* W_out,
+                        const float* b_out, const float* u_roll, int B, int L, int V, int E, int H, int n_roll,
+                        int64_t* roll_ids, float* workspace, gic_stream_t stream) {
+  GIC_TRY(require_device());
+  return decode_rollouts(mode, saved, main_ids, W_emb, W_ih, W_hh, b_ih, b_hh, W_out, b_out, u_roll, B, L, V, E, H,
+                         n_roll, roll_ids, workspace, S(stream));
+}
+
+int gic_rollout_rewards(const float* roll_logits, const float* main_logits, int B, int L, int n_roll, int R, float* Q,
+                        gic_stream_t stream) {
+  GIC_TRY(require_device());
+  return rollout_q(roll_logits, main_logits, B, L, n_roll, R, Q, S(stream));
+}
+
+int gic_pg_loss_fwd_bwd(const float* logits, const int64_t* ids, const float* Q, int baseline_mode, int B, int L, int V,
+                        float* loss, float* dlogits, float* logp, gic_stream_t stream) {
+  GIC_TRY(require_device());
+  return pg_loss(logits, ids, Q, baseline_mode, B, L, V, loss, dlogits, logp, S(stream));
 }
 
 size_t gic_disc_saved_floats(int N, int L, int De, int R, int F) { return disc_saved_floats(N, L, De, R, F); }

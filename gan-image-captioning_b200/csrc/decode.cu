@@ -51,8 +51,10 @@ __global__ void lstm_cell_fwd_kernel(const float* __restrict__ gates, const floa
   const float o_ = sigmoidf_acc(g[3 * H + j]);
   const float c = f_ * c_prev[idx] + i_ * g_;
   const float h = o_ * tanhf(c);
-  float* a = acts + (size_t)b * 4 * H;
-  a[j] = i_; a[H + j] = f_; a[2 * H + j] = g_; a[3 * H + j] = o_;
+  if (acts) {
+    float* a = acts + (size_t)b * 4 * H;
+    a[j] = i_; a[H + j] = f_; a[2 * H + j] = g_; a[3 * H + j] = o_;
+  }
   c_new[idx] = c;
   h_new[idx] = h;
   if (htop) htop[((size_t)b * L + t) * H + j] = h;
@@ -333,6 +335,142 @@ int sample_step(bool pretrain, const float* logits, const float* u, float temper
     sample_step_kernel<false><<<B, 256, dyn, s>>>(logits, u, temperature, g_t_dev, V, L, t, out, ids, forced, embed, E,
                                                 x_next, in_smem);
   return check_launch("sample_step_kernel");
+}
+
+// ---------------------------------------------------------------------------------------
+// EXTENSION (north-star stage 2/3, not in the reference: SURVEY.md 8a row B2): fused vocab softmax + categorical
+// sample by inverse CDF from ONE caller-supplied uniform per row.  token = first index whose cumulative probability
+// exceeds u (clamped to V-1); also returns log pi(token) for the policy-gradient loss.  Nothing of size [B,V] is
+// written unless `out` (raw logits, kept for the backward of the sampled caption) is given.
+// One CTA (256 threads) per row.  Order of the cumulative sum: element e belongs to segment e / 128 (a warp's float4
+// sweep); segments are summed in index order by one thread, the hit segment is resolved by a warp scan, the hit
+// float4 sequentially.  All in unnormalised exp space against the target u * sum.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sample_cdf_kernel(const float* __restrict__ logits, const float* __restrict__ u, int V, int L, int t,
+                  long long id_stride /*elements between rows of ids*/, float* __restrict__ out /*[rows,L,V] or null*/,
+                  int64_t* __restrict__ ids, float* __restrict__ logp /*[rows,L] or null*/,
+                  const int64_t* __restrict__ forced, const float* __restrict__ embed, int E,
+                  float* __restrict__ x_next) {
+  extern __shared__ float seg_s[];          // [nseg] partial sums, nseg = ceil(V / 128)
+  __shared__ float red[32];
+  __shared__ int s_seg, s_tok;
+  __shared__ float s_before, s_sum, s_max;
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* lrow = logits + (size_t)b * V;
+  const int nseg = (V + 127) >> 7;
+  // pass 1: max
+  float mx = -INFINITY;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) mx = fmaxf(mx, lrow[v]);
+  mx = block_max(mx, red);
+  // pass 2: per-segment sums of exp (segment = 128 consecutive elements = one warp sweep of 4 per lane)
+  float tot = 0.f;
+  for (int sgi = warp; sgi < nseg; sgi += 8) {
+    const int v0 = sgi * 128 + lane * 4;
+    float e = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (v0 + j < V) e += expf(lrow[v0 + j] - mx);
+    e = warp_sum(e);
+    if (lane == 0) seg_s[sgi] = e;
+    tot += e;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float S = 0.f;
+    for (int i = 0; i < nseg; ++i) S += seg_s[i];
+    const float target = u[b] * S;
+    float acc = 0.f;
+    int hit = -1;
+    for (int i = 0; i < nseg; ++i) {
+      const float nxt = acc + seg_s[i];
+      if (nxt > target) { hit = i; break; }
+      acc = nxt;
+    }
+    s_seg = hit; s_before = acc; s_sum = S; s_max = mx;
+    s_tok = (hit < 0) ? V - 1 : min(V - 1, hit * 128 + 127);     // u beyond the total mass -> last token
+  }
+  __syncthreads();
+  (void)tot;
+  if (warp == 0 && s_seg >= 0) {
+    const int sgi = s_seg;
+    const float target = u[b] * s_sum;
+    const int v0 = sgi * 128 + lane * 4;
+    float e[4];
+    float mine = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { e[j] = (v0 + j < V) ? expf(lrow[v0 + j] - mx) : 0.f; mine += e[j]; }
+    float inc = mine;                                            // inclusive warp scan of the lanes' sums
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float y = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += y;
+    }
+    const bool hit = (s_before + inc > target);
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (m != 0u && lane == (__ffs(m) - 1)) {
+      float acc = s_before + (inc - mine);
+      int tok = min(V - 1, v0 + 3);
+      for (int j = 0; j < 4; ++j) {
+        acc += e[j];
+        if (acc > target) { tok = v0 + j; break; }
+      }
+      s_tok = min(tok, V - 1);
+    }
+  }
+  __syncthreads();
+  const int tok = s_tok;
+  if (threadIdx.x == 0) {
+    ids[(size_t)b * id_stride + t] = tok;
+    if (logp) logp[(size_t)b * L + t] = (lrow[tok] - s_max) - logf(s_sum);
+  }
+  if (out) {
+    float* orow = out + ((size_t)b * L + t) * V;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) orow[v] = lrow[v];
+  }
+  if (x_next) {
+    int fed = tok;
+    if (forced) {
+      const int64_t f = forced[(size_t)b * id_stride + t];
+      fed = (f >= 0 && f < V) ? (int)f : 0;
+    }
+    const float* src = embed + (size_t)fed * E;
+    float* dst = x_next + (size_t)b * E;
+    for (int e = threadIdx.x; e < E; e += blockDim.x) dst[e] = src[e];
+  }
+}
+
+int sample_cdf_step(const float* logits, const float* u, int rows, int V, int L, int t, long long id_stride, float* out,
+                    int64_t* ids, float* logp, const int64_t* forced, const float* embed, int E, float* x_next,
+                    cudaStream_t s) {
+  if (rows == 0) return GIC_OK;
+  ProfScope prof(PROF_SAMPLE, 4.0 * rows * V, s);
+  const size_t smem = (size_t)((V + 127) >> 7) * sizeof(float);
+  sample_cdf_kernel<<<rows, 256, smem, s>>>(logits, u, V, L, t, id_stride, out, ids, logp, forced, embed, E, x_next);
+  return check_launch("sample_cdf_kernel");
+}
+
+// rollout group initialisation (SeqGAN-style Monte-Carlo search): rows of group t replicate the sampled caption's state
+// after t steps n times: h <- hs[t][b], c <- cs[t][b], x <- embed(ids[b][t-1]), prefix ids copied.
+__global__ void rollout_init_kernel(const float* __restrict__ hs_t, const float* __restrict__ cs_t,
+                                    const int64_t* __restrict__ main_ids, const float* __restrict__ embed, int B, int n,
+                                    int L, int t, int H, int E, int V, float* __restrict__ h, float* __restrict__ c,
+                                    float* __restrict__ x, int64_t* __restrict__ roll_ids) {
+  const int r = blockIdx.x;                  // row within the group: b * n + j
+  const int b = r / n;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    h[(size_t)r * H + i] = hs_t[(size_t)b * H + i];
+    c[(size_t)r * H + i] = cs_t[(size_t)b * H + i];
+  }
+  int64_t tok = main_ids[(size_t)b * L + (t - 1)];
+  if (tok < 0 || tok >= V) tok = 0;
+  for (int i = threadIdx.x; i < E; i += blockDim.x) x[(size_t)r * E + i] = embed[(size_t)tok * E + i];
+  for (int i = threadIdx.x; i < t; i += blockDim.x) roll_ids[(size_t)r * L + i] = main_ids[(size_t)b * L + i];
+}
+int rollout_init(const float* hs_t, const float* cs_t, const int64_t* main_ids, const float* embed, int B, int n, int L,
+                 int t, int H, int E, int V, float* h, float* c, float* x, int64_t* roll_ids, cudaStream_t s) {
+  rollout_init_kernel<<<B * n, 128, 0, s>>>(hs_t, cs_t, main_ids, embed, B, n, L, t, H, E, V, h, c, x, roll_ids);
+  return check_launch("rollout_init_kernel");
 }
 
 // ---------------------------------------------------------------------------------------

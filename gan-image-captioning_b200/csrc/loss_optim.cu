@@ -76,6 +76,89 @@ int gan_loss(int type, const float* d_real, const float* d_fake, const float* g_
 }
 
 // ---------------------------------------------------------------------------------------
+// EXTENSION (north-star stage 4, not in the reference: SURVEY.md 8a rows B2/B3) -- SeqGAN-style reward, baseline and
+// log-prob-weighted policy-gradient loss with its backward.
+//   reward of a scored caption  = mean over the R representations of sigmoid(D logit)
+//   Q[b, t-1] (value of the prefix of length t, t = 1..L-1) = mean over the n rollouts started from that prefix;
+//   Q[b, L-1] = reward of the sampled caption itself.
+// Rollout rows are ordered (t-1) * B*n + b*n + j (gic_decode_rollouts).
+// ---------------------------------------------------------------------------------------
+__global__ void rollout_q_kernel(const float* __restrict__ roll_logits /*[(L-1)*B*n*R]*/,
+                                 const float* __restrict__ main_logits /*[B*R]*/, int B, int L, int n, int R,
+                                 float* __restrict__ Q /*[B,L]*/) {
+  const int b = blockIdx.x / L, t = blockIdx.x % L;       // t = prefix length - 1
+  __shared__ float red[32];
+  float s = 0.f;
+  int cnt;
+  if (t == L - 1) {
+    cnt = R;
+    for (int i = threadIdx.x; i < R; i += blockDim.x) s += sigmoidf_acc(main_logits[(size_t)b * R + i]);
+  } else {
+    cnt = n * R;
+    const float* base = roll_logits + ((size_t)t * B * n + (size_t)b * n) * R;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) s += sigmoidf_acc(base[i]);
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) Q[(size_t)b * L + t] = s / (float)cnt;
+}
+
+int rollout_q(const float* roll_logits, const float* main_logits, int B, int L, int n, int R, float* Q, cudaStream_t s) {
+  GIC_REQUIRE(B >= 1 && L >= 1 && n >= 1 && R >= 1, GIC_ERR_SHAPE, "rollout_rewards: bad shape");
+  GIC_REQUIRE((L == 1 || roll_logits) && main_logits && Q, GIC_ERR_NULL, "rollout_rewards: NULL operand");
+  rollout_q_kernel<<<B * L, 128, 0, s>>>(roll_logits, main_logits, B, L, n, R, Q);
+  return check_launch("rollout_q_kernel");
+}
+
+// loss = -(1 / (B L)) sum_{b,t} log pi(y_bt) (Q_bt - base_t),  base_t = mean_b Q_bt (baseline_mode 1) or 0;
+// dlogits[b,t,v] = (A_bt / (B L)) (softmax(logits_bt)_v - [v == y_bt]).  One CTA per (b, t) row; losses[0] += row loss.
+__global__ void __launch_bounds__(256)
+pg_loss_kernel(const float* __restrict__ logits, const int64_t* __restrict__ ids, const float* __restrict__ Q,
+               int baseline_mode, int B, int L, int V, float* __restrict__ loss, float* __restrict__ dlogits,
+               float* __restrict__ logp_out /*[B,L] or null*/) {
+  __shared__ float red[32];
+  const int row = blockIdx.x, t = row % L;
+  const float* lr = logits + (size_t)row * V;
+  float base = 0.f;
+  if (baseline_mode == 1) {
+    float s = 0.f;
+    for (int i = threadIdx.x; i < B; i += blockDim.x) s += Q[(size_t)i * L + t];
+    base = block_sum(s, red) / (float)B;
+  }
+  float mx = -INFINITY;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) mx = fmaxf(mx, lr[v]);
+  mx = block_max(mx, red);
+  float sum = 0.f;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) sum += expf(lr[v] - mx);
+  sum = block_sum(sum, red);
+  int64_t y = ids[row];
+  if (y < 0 || y >= V) y = 0;
+  const float adv = Q[row] - base;
+  const float scale = adv / (float)((size_t)B * L);
+  if (dlogits) {
+    float* dr = dlogits + (size_t)row * V;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+      const float p = expf(lr[v] - mx) / sum;
+      dr[v] = scale * (p - (v == (int)y ? 1.f : 0.f));
+    }
+  }
+  if (threadIdx.x == 0) {
+    const float lp = (lr[y] - mx) - logf(sum);
+    if (logp_out) logp_out[row] = lp;
+    atomicAdd(loss, -lp * scale);
+  }
+}
+
+int pg_loss(const float* logits, const int64_t* ids, const float* Q, int baseline_mode, int B, int L, int V, float* loss,
+            float* dlogits, float* logp, cudaStream_t s) {
+  GIC_REQUIRE(B >= 1 && L >= 1 && V >= 1, GIC_ERR_SHAPE, "pg_loss: bad shape");
+  GIC_REQUIRE(logits && ids && Q && loss, GIC_ERR_NULL, "pg_loss: NULL operand");
+  GIC_REQUIRE(baseline_mode == 0 || baseline_mode == 1, GIC_ERR_UNSUPPORTED, "pg_loss: baseline mode %d", baseline_mode);
+  cudaMemsetAsync(loss, 0, sizeof(float), s);
+  pg_loss_kernel<<<B * L, 256, 0, s>>>(logits, ids, Q, baseline_mode, B, L, V, loss, dlogits, logp);
+  return check_launch("pg_loss_kernel");
+}
+
+// ---------------------------------------------------------------------------------------
 // global L2 norm (squared, accumulated into *out which the caller zeroes) over a flat buffer
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)

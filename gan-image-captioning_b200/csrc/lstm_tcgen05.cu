@@ -126,12 +126,14 @@ lstm_step_tf32_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           cn[e] = af[e] * cp[e] + ai[e] * ag[e];
           hn[e] = ao[e] * tanhf(cn[e]);
         }
-        float* arow = acts + (size_t)b * 4 * H + j;
         auto st8 = [](float* dst, const float* v) {
           *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
           *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
         };
-        st8(arow, ai); st8(arow + H, af); st8(arow + 2 * H, ag); st8(arow + 3 * H, ao);
+        if (acts) {                  // saved for the backward pass; rollouts (no backward) pass nullptr
+          float* arow = acts + (size_t)b * 4 * H + j;
+          st8(arow, ai); st8(arow + H, af); st8(arow + 2 * H, ag); st8(arow + 3 * H, ao);
+        }
         st8(c_out + (size_t)b * H + j, cn);
         st8(h_out + (size_t)b * H + j, hn);
         if (htop) st8(htop + ((size_t)b * L + t) * H + j, hn);
@@ -156,7 +158,7 @@ int lstm_step_tc(const float* x, int In, const float* h_prev, const float* W_ih,
   using namespace tc;
   *handled = false;
   if (B <= 0 || (H % 8) || (In % 4) || In < 4) return GIC_OK;
-  const void* ptrs[] = {x, h_prev, W_ih, W_hh, c_prev, acts, c_out, h_out, htop ? htop : h_out};
+  const void* ptrs[] = {x, h_prev, W_ih, W_hh, c_prev, acts ? acts : h_out, c_out, h_out, htop ? htop : h_out};
   for (const void* p : ptrs)
     if (!aligned16(p)) return GIC_OK;
   // units per CTA: the widest tile that still gives at least ~3/4 of the SMs a CTA

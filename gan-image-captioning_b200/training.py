@@ -418,6 +418,133 @@ class GANInstructor:
             self._flat_g.step += 1
         return st["out"]
 
+    # ---- EXTENSION: SeqGAN-style policy-gradient step (north-star stages 2-4; not in the reference) -------------
+    @torch.no_grad()
+    def pg_step(self, captions, pooled=None, u=None, u_roll=None, keep=None, n_roll=16, baseline_mode=1, update=True,
+                d_update=True, score_chunk=2048):
+        """Generator update by REINFORCE with Monte-Carlo rollouts, discriminator update on hard captions.
+
+        1. captions are sampled by inverse CDF (u[L,B]); 2. for every prefix n_roll continuations are rolled out
+        (u_roll[L, (L-1)*B*n_roll]) -- one batched LSTM step + vocab projection over all live rollouts per position;
+        3. the discriminator scores all rollouts (hard-token gather path, eval mode) -> Q[B,L]; 4. fused
+        reward/baseline/log-prob-weighted loss + backward through the decoder; clip + Adam.  5. (d_update) D step on
+        real vs sampled captions with the 'standard' BCE loss.  Returns ids, roll_ids, Q, pg_loss, logp, d_loss."""
+        _lib.require_cuda()
+        lib = _lib.lib()
+        a, dev = self.args, self.device
+        mode = gic_b200.get_gemm_mode()
+        self._ensure_flat()
+        fg, fd = self._flat_g, self._flat_d
+        dec, disc = self.gen.decoder, self.disc
+        captions = captions.to(dev).long().contiguous()
+        B, L = captions.shape
+        V, E, H, layers = a.vocab_size, a.gen_embed_dim, a.gen_hidden_dim, a.gen_num_layers
+        if layers != 1:
+            raise NotImplementedError("rollouts support a single-layer decoder")
+        De, R, Fd = a.disc_embed_dim, a.disc_num_rep, sum(a.disc_num_filters)
+        fsz, nfl = list(a.disc_filter_sizes), list(a.disc_num_filters)
+        stream = _lib.stream()
+        P = _lib.ptr
+        n = int(n_roll)
+        Mmax = (L - 1) * B * n
+        if self.cgan:
+            feats = self.gen.encoder(pooled.to(dev).float()).detach().contiguous()
+        else:
+            feats = dec.embed.weight[1].expand(B, E).contiguous()
+        if u is None:
+            u = torch.rand(L, B, device=dev)
+        if u_roll is None:
+            u_roll = torch.rand(L, Mmax, device=dev)
+        u, u_roll = u.to(dev).float().contiguous(), u_roll.to(dev).float().contiguous()
+        logits = self._buf("pg_logits", B * L * V).view(B, L, V)
+        ids = torch.empty(B, L, dtype=torch.int64, device=dev)
+        logp = torch.empty(B, L, device=dev)
+        dsaved = self._buf("dec_saved", lib.gic_decode_saved_floats(B, L, E, H, layers))
+        dws = self._buf("dec_ws", lib.gic_decode_fwd_workspace_floats(B, V, H))
+        lp = dec.lstm_params()
+        W_ih, W_hh, b_ih, b_hh = lp[0::4], lp[1::4], lp[2::4], lp[3::4]
+        _lib.check(lib.gic_decode_sample_cdf_fwd(mode, P(feats), P(dec.embed.weight), _lib.ptr_array(W_ih),
+                                                 _lib.ptr_array(W_hh), _lib.ptr_array(b_ih), _lib.ptr_array(b_hh),
+                                                 P(dec.linear.weight), P(dec.linear.bias), P(u), None, B, L, V, E, H,
+                                                 layers, P(logits), P(ids), P(logp), P(dsaved), P(dws), stream),
+                   "gic_decode_sample_cdf_fwd")
+        roll_ids = torch.empty(Mmax, L, dtype=torch.int64, device=dev)
+        rws = self._buf("roll_ws", lib.gic_decode_rollouts_workspace_floats(B, L, V, E, H, n))
+        _lib.check(lib.gic_decode_rollouts(mode, P(dsaved), P(ids), P(dec.embed.weight), P(W_ih[0]), P(W_hh[0]),
+                                           P(b_ih[0]), P(b_hh[0]), P(dec.linear.weight), P(dec.linear.bias), P(u_roll),
+                                           B, L, V, E, H, n, P(roll_ids), P(rws), stream), "gic_decode_rollouts")
+        # -- D scores of every rollout and of the captions themselves (eval mode, hard-token gather path)
+        cw = [c.weight for c in disc.convs]
+        cb = [c.bias for c in disc.convs]
+        dW = (disc.embeddings.weight, cw, cb, disc.highway.weight, disc.highway.bias, disc.feature2out.weight,
+              disc.feature2out.bias, disc.out2logits.weight, disc.out2logits.bias)
+        drop_p = disc.dropout.p
+        roll_logits = torch.empty(Mmax * R, device=dev)
+        for m0 in range(0, Mmax, score_chunk):
+            mc = min(score_chunk, Mmax - m0)
+            (lg,), _ = disc_fwd_raw(lib, mode, None, roll_ids[m0:m0 + mc], mc, L, V, De, R, fsz, nfl, *dW, [None], drop_p, dev)
+            roll_logits[m0 * R:(m0 + mc) * R] = lg
+        (main_logits,), _ = disc_fwd_raw(lib, mode, None, ids, B, L, V, De, R, fsz, nfl, *dW, [None], drop_p, dev)
+        Q = torch.empty(B, L, device=dev)
+        _lib.check(lib.gic_rollout_rewards(P(roll_logits), P(main_logits), B, L, n, R, P(Q), stream), "gic_rollout_rewards")
+        # -- fused reward/baseline/log-prob-weighted loss and its backward; decoder backward w.r.t. the logits
+        loss = torch.empty(1, device=dev)
+        dlogits = self._buf("pg_dlogits", B * L * V).view(B, L, V)
+        _lib.check(lib.gic_pg_loss_fwd_bwd(P(logits), P(ids), P(Q), int(baseline_mode), B, L, V, P(loss), P(dlogits), None,
+                                           stream), "gic_pg_loss_fwd_bwd")
+        gg = fg.g
+        gws = self._buf("dec_bws", lib.gic_decode_bwd_workspace_floats(B, L, V, E, H, layers))
+        dfeat = self._buf("dfeat", B * E).view(B, E)
+        _lib.check(lib.gic_decode_sample_bwd(
+            mode, P(dlogits), None, P(ids), P(dec.embed.weight), _lib.ptr_array(W_ih), _lib.ptr_array(W_hh),
+            P(dec.linear.weight), 1.0, 1, B, L, V, E, H, layers, P(dsaved), P(gws), P(gg(dec.embed.weight)),
+            _lib.ptr_array([gg(w) for w in W_ih]), _lib.ptr_array([gg(w) for w in W_hh]),
+            _lib.ptr_array([gg(w) for w in b_ih]), _lib.ptr_array([gg(w) for w in b_hh]), P(gg(dec.linear.weight)),
+            P(gg(dec.linear.bias)), P(dfeat), 0, stream), "gic_decode_sample_bwd")
+        if self.cgan:
+            enc = self.gen.encoder
+            for p_ in (enc.linear.weight, enc.linear.bias, enc.bn.weight, enc.bn.bias):
+                gg(p_).zero_()                       # the encoder projection is not trained by the PG step here
+        else:
+            gg(dec.embed.weight)[1] += dfeat.sum(0)
+        out = dict(ids=ids, roll_ids=roll_ids, Q=Q, pg_loss=loss[0], logp=logp, logits=logits, roll_logits=roll_logits,
+                   main_logits=main_logits)
+        if self.world > 1:
+            torch.distributed.all_reduce(fg.grad)
+        out["g_sqnorm"] = self._clip_adam(fg, a.gen_lr, update, 3)
+        if d_update:
+            # -- discriminator step on hard captions: real vs sampled ('standard' BCE), two dropout masks
+            if keep is None:
+                keep = torch.rand(2, B * R, Fd, device=dev) >= drop_p
+            keep = keep.to(dev).to(torch.uint8).contiguous()
+            (d_real,), saved_r = disc_fwd_raw(lib, mode, None, captions, B, L, V, De, R, fsz, nfl, *dW, [keep[0]], drop_p, dev)
+            (d_fake,), saved_f = disc_fwd_raw(lib, mode, None, ids, B, L, V, De, R, fsz, nfl, *dW, [keep[1]], drop_p, dev)
+            nn_ = B * R
+            losses = torch.empty(2, device=dev)
+            seeds = self._buf("seeds", 3 * nn_).view(3, nn_)
+            _lib.check(lib.gic_gan_loss_fwd_bwd(_lib.LOSS_TYPES["standard"], P(d_real), P(d_fake), P(d_fake), nn_,
+                                                P(losses), P(seeds[0]), P(seeds[1]), P(seeds[2]), stream),
+                       "gic_gan_loss_fwd_bwd")
+            bws = self._buf("disc_bws", lib.gic_disc_bwd_workspace_floats(B, L, De, R, Fd))
+            g = fd.g
+            dcw, dcb = [g(c.weight) for c in disc.convs], [g(c.bias) for c in disc.convs]
+            for seed, kp, idz, saved, acc in ((seeds[0], keep[0], captions, saved_r, 0), (seeds[1], keep[1], ids, saved_f, 1)):
+                _lib.check(lib.gic_disc_bwd(mode, P(seed), P(kp), drop_p, None, P(idz), B, L, V, De, R, len(fsz),
+                                            _lib.int_array(fsz), _lib.int_array(nfl), P(disc.embeddings.weight),
+                                            _lib.ptr_array(cw), _lib.ptr_array(cb), P(disc.highway.weight),
+                                            P(disc.feature2out.weight), P(disc.feature2out.bias),
+                                            disc.feature2out.weight.shape[0], P(disc.out2logits.weight),
+                                            P(disc.out2logits.bias), P(saved), P(bws), P(g(disc.embeddings.weight)),
+                                            _lib.ptr_array(dcw), _lib.ptr_array(dcb), P(g(disc.highway.weight)),
+                                            P(g(disc.highway.bias)), P(g(disc.feature2out.weight)),
+                                            P(g(disc.feature2out.bias)), P(g(disc.out2logits.weight)),
+                                            P(g(disc.out2logits.bias)), None, 1, acc, stream), "gic_disc_bwd")
+            if self.world > 1:
+                torch.distributed.all_reduce(fd.grad)
+            out["d_loss"] = losses[1]
+            out["d_sqnorm"] = self._clip_adam(fd, a.disc_lr, update, 1)
+        return out
+
     def adv_loop(self, what, batches, total_batches=None, graph=False):
         """Body of the reference's adv_loop over an iterable of (pooled_or_None, captions) batches."""
         gen_loss, disc_loss = [], []

@@ -175,6 +175,44 @@ int gic_grad_sqnorm(const float* g, size_t n, float* sqnorm, gic_stream_t stream
 int gic_clip_adam(float* p, const float* g, float* m, float* v, size_t n, const float* sqnorm, float max_norm,
                   float grad_scale, int step, float lr, float beta1, float beta2, float eps, gic_stream_t stream);
 
+/* ==== EXTENSIONS beyond the reference (north-star stages 2-4).  The reference has no
+ * rollouts, no inverse-CDF sampler and no policy-gradient loss: these entry points are defined by
+ * this library and its oracle (oracle/ref_ext.py), "parity unpinned by reference". ====
+ *
+ * gic_decode_sample_cdf_fwd: Decoder.sample's loop (src/generator.py:55-81) with the token drawn by inverse CDF from
+ *   softmax(logits) and ONE uniform per row and step, u[L,B]; token = first index whose cumulative probability exceeds
+ *   u.  logits_out[B,L,V] (raw logits, for the backward via gic_decode_sample_bwd(pretrain = 1)) and logp[B,L]
+ *   (log pi(token)) may be NULL.  saved / workspace sizes as for gic_decode_sample_fwd.
+ * gic_decode_rollouts: for every prefix length t = 1..L-1 of main_ids[B,L], n_roll continuations sampled with the same
+ *   policy (single-layer decoder).  saved = the blob gic_decode_sample_cdf_fwd filled for those captions.
+ *   u_roll[L, Mmax] with Mmax = (L-1)*B*n_roll: row m at step s reads u_roll[s*Mmax + m].  roll_ids[Mmax, L]: row
+ *   (t-1)*B*n + b*n + j = j-th completion of prefix t of caption b (positions < t copied from main_ids).
+ * gic_rollout_rewards: Q[b,t-1] = mean over rollouts j and representations r of sigmoid(D logit) for prefix length
+ *   t < L; Q[b,L-1] = the sampled caption's own mean sigmoid(D logit).  roll_logits[Mmax*R], main_logits[B*R] come
+ *   from gic_disc_fwd(ids = ...) in eval mode.
+ * gic_pg_loss_fwd_bwd: loss[0] = -(1/(B L)) sum log pi(y_bt) (Q_bt - base_t), base_t = mean_b Q_bt (baseline_mode 1) or
+ *   0 (mode 0); dlogits[B,L,V] = d loss / d logits (may be NULL); logp[B,L] optional. */
+/* one fused vocab-softmax + inverse-CDF sample step (the kernel gic_decode_sample_cdf_fwd / gic_decode_rollouts run
+ * per position): u[B] one uniform per row; out row (b,t) of [B,L,V] = raw logits (NULL: nothing of size V is written);
+ * ids[b,t] = token; logp[b,t] = log softmax(logits)[token]; x_next[B,E] = embed[fed token] (NULL to skip). */
+int gic_sample_cdf_step(const float* logits, const float* u, int B, int V, int L, int t, float* out, int64_t* ids,
+                        float* logp, const int64_t* forced_ids, const float* embed, int E, float* x_next,
+                        gic_stream_t stream);
+int gic_decode_sample_cdf_fwd(int mode, const float* features, const float* W_emb, const float* const* W_ih,
+                              const float* const* W_hh, const float* const* b_ih, const float* const* b_hh,
+                              const float* W_out, const float* b_out, const float* u, const int64_t* forced_ids, int B,
+                              int L, int V, int E, int H, int layers, float* logits_out, int64_t* ids, float* logp,
+                              float* saved, float* workspace, gic_stream_t stream);
+size_t gic_decode_rollouts_workspace_floats(int B, int L, int V, int E, int H, int n_roll);
+int gic_decode_rollouts(int mode, const float* saved, const int64_t* main_ids, const float* W_emb, const float* W_ih,
+                        const float* W_hh, const float* b_ih, const float* b_hh, const float* W_out,
+                        const float* b_out, const float* u_roll, int B, int L, int V, int E, int H, int n_roll,
+                        int64_t* roll_ids, float* workspace, gic_stream_t stream);
+int gic_rollout_rewards(const float* roll_logits, const float* main_logits, int B, int L, int n_roll, int R, float* Q,
+                        gic_stream_t stream);
+int gic_pg_loss_fwd_bwd(const float* logits, const int64_t* ids, const float* Q, int baseline_mode, int B, int L, int V,
+                        float* loss, float* dlogits, float* logp, gic_stream_t stream);
+
 /* ---- CUDA-graph replay support ----
  * By-value scalars are frozen when a launch is captured into a CUDA graph, but the reference changes two of them every
  * batch: the temperature (update_temperature, src/training.py:183,190-191) and Adam's bias corrections (step count).
