@@ -18,7 +18,7 @@ import torch
 import torch.nn as nn
 
 import gic_b200
-from . import _lib
+from . import _lib, parallel
 from .discriminator import Discriminator, disc_fwd_raw
 from .generator import Generator
 from .utils import get_fixed_temperature, get_losses
@@ -291,12 +291,12 @@ class GANInstructor:
                 gen_done = torch.cuda.Event()
                 gen_done.record(side)
                 if self.world > 1:
-                    torch.distributed.all_reduce(fg.grad)
+                    parallel.allreduce_sum_(fg.grad)
                 out["g_sqnorm"] = self._clip_adam(fg, a.gen_lr, update, 3)
             disc_bwd(seeds[0], k0, None, captions, saved_r, 1, 0, None, bws, stream)
             disc_bwd(seeds[1], k1, probs, None, saved_f, 1, 1, None, bws, stream)
             if self.world > 1:
-                torch.distributed.all_reduce(fd.grad)
+                parallel.allreduce_sum_(fd.grad)
             main.wait_event(gen_done)
             out["d_sqnorm"] = self._clip_adam(fd, a.disc_lr, update, 1)
             main.wait_stream(side)
@@ -307,9 +307,9 @@ class GANInstructor:
                 gen_chain(bws, stream)
             # -- data-parallel exchange: summed gradients, averaged inside the optimizer kernel
             if self.world > 1:
-                torch.distributed.all_reduce(fd.grad)
+                parallel.allreduce_sum_(fd.grad)
                 if g_has_grad:
-                    torch.distributed.all_reduce(fg.grad)
+                    parallel.allreduce_sum_(fg.grad)
             out["d_sqnorm"] = self._clip_adam(fd, a.disc_lr, update, 1)
             if g_has_grad:
                 out["g_sqnorm"] = self._clip_adam(fg, a.gen_lr, update, 3)
@@ -510,7 +510,7 @@ class GANInstructor:
         out = dict(ids=ids, roll_ids=roll_ids, Q=Q, pg_loss=loss[0], logp=logp, logits=logits, roll_logits=roll_logits,
                    main_logits=main_logits)
         if self.world > 1:
-            torch.distributed.all_reduce(fg.grad)
+            parallel.allreduce_sum_(fg.grad)
         out["g_sqnorm"] = self._clip_adam(fg, a.gen_lr, update, 3)
         if d_update:
             # -- discriminator step on hard captions: real vs sampled ('standard' BCE), two dropout masks
@@ -540,7 +540,7 @@ class GANInstructor:
                                             P(g(disc.feature2out.bias)), P(g(disc.out2logits.weight)),
                                             P(g(disc.out2logits.bias)), None, 1, acc, stream), "gic_disc_bwd")
             if self.world > 1:
-                torch.distributed.all_reduce(fd.grad)
+                parallel.allreduce_sum_(fd.grad)
             out["d_loss"] = losses[1]
             out["d_sqnorm"] = self._clip_adam(fd, a.disc_lr, update, 1)
         return out
