@@ -307,9 +307,23 @@ def run_ours(args):
             hbm[nm] = {"achieved_GBps": gbs, "frac_of_hbm_peak": gbs / peaks["hbm"], "ms_per_step": c["ms_per_step"],
                        "launches_per_step": c["calls_per_step"]}
 
+    def shutdown():
+        """Release the captured graphs before tearing NCCL down; a watchdog ends the process if the teardown of a
+        communicator that was captured into CUDA graphs does not return (observed with NCCL 2.28 + torch 2.11)."""
+        if world <= 1:
+            return
+        inst._graphs.clear()
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        t = threading.Timer(15.0, lambda: os._exit(0))
+        t.daemon = True
+        t.start()
+        dist.destroy_process_group()
+        t.cancel()
+
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        shutdown()
         return
 
     # CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload on the host cores
@@ -334,8 +348,7 @@ def run_ours(args):
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown()
 
 
 def main():
