@@ -19,6 +19,19 @@ LOSS_TYPES = {"standard": 0, "JS": 1, "KL": 2, "hinge": 3, "tv": 4, "rsgan": 5}
 _lib = None
 
 
+class AttnBlock(C.Structure):
+    """gic_attn_t of include/gic_b200.h."""
+    _fields_ = [("grid", C.c_void_p), ("P", C.c_int), ("Cf", C.c_int), ("Da", C.c_int), ("W_k", C.c_void_p),
+                ("W_v", C.c_void_p), ("W_q", C.c_void_p), ("w_e", C.c_void_p), ("saved", C.c_void_p), ("ws", C.c_void_p),
+                ("dW_k", C.c_void_p), ("dW_v", C.c_void_p), ("dW_q", C.c_void_p), ("dw_e", C.c_void_p)]
+
+
+def attn_block(grid, W_k, W_v, W_q, w_e, saved, ws=None, dW_k=None, dW_v=None, dW_q=None, dw_e=None):
+    B, Pn, Cf = grid.shape
+    return AttnBlock(ptr(grid), Pn, Cf, W_k.shape[0], ptr(W_k), ptr(W_v), ptr(W_q), ptr(w_e), ptr(saved), ptr(ws),
+                     ptr(dW_k), ptr(dW_v), ptr(dW_q), ptr(dw_e))
+
+
 class GicError(RuntimeError):
     pass
 
@@ -83,6 +96,13 @@ def _declare(L):
     L.gic_clip_adam.argtypes = [P, P, P, P, Z, P, F, F, I, F, F, F, F, P]
     L.gic_clip_adam_dyn.argtypes = [P, P, P, P, Z, P, F, F, P, F, F, F, P]
     L.gic_decode_sample_cdf_fwd.argtypes = [I, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, P, P, P, P, P, P]
+    L.gic_attn_saved_floats.restype = Z
+    L.gic_attn_saved_floats.argtypes = [I] * 5
+    L.gic_attn_bwd_workspace_floats.restype = Z
+    L.gic_attn_bwd_workspace_floats.argtypes = [I] * 5
+    L.gic_decode_sample_fwd_attn.argtypes = [P] + [I, P, P, P, P, P, P, P, P, P, F, I, P, I, I, I, I, I, I, P, P, P, P, P]
+    L.gic_decode_sample_bwd_attn.argtypes = [P, I, P, P, P, P, I, P, P, P, P, P, P, F, I, I, I, I, I, I, I, P, P, P, P, P,
+                                             P, P, P, P, P, P]
     L.gic_sample_cdf_step.argtypes = [P, P, I, I, I, I, P, P, P, P, P, I, P, P]
     L.gic_decode_rollouts_workspace_floats.restype = Z
     L.gic_decode_rollouts_workspace_floats.argtypes = [I] * 6

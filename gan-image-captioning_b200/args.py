@@ -59,6 +59,10 @@ def build_parser() -> argparse.ArgumentParser:
     r.add_argument("--log-file", type=str, default="log")
     # extension (not in the reference): width of the pooled CNN feature fed to Encoder.linear
     r.add_argument("--feature-dim", type=int, default=512)
+    # extension (north-star attention cell): additive attention over a [P, feature-channels] grid
+    r.add_argument("--gen-attention", type=int, default=0)
+    r.add_argument("--attn-dim", type=int, default=256)
+    r.add_argument("--feature-channels", type=int, default=2048)
     return p
 
 

@@ -25,6 +25,10 @@ int lstm_cell_bwd(const float*, const float*, const float*, const float*, long l
 // gemm_dispatch.cu
 int gemm_dz(int, int, int, int, const float*, int, const float*, int, const float*, const float*, float, float*, int,
             cudaStream_t, bool*);
+// attn.cu
+int attn_fwd(const float*, const float*, const float*, const float*, int, int, int, int, float*, float*, cudaStream_t);
+int attn_bwd(const float*, const float*, const float*, const float*, const float*, const float*, int, int, int, int,
+             float*, float*, float*, float*, cudaStream_t);
 // lstm_tcgen05.cu
 int lstm_step_tc(const float*, int, const float*, const float*, const float*, const float*, const float*, const float*,
                  int, int, float*, float*, float*, float*, int, int, cudaStream_t, bool*);
@@ -61,6 +65,18 @@ int disc_bwd_entry(int mode, const float* dlogits, const uint8_t* keep, float dr
 
 static size_t a4(size_t x) { return (x + 3) & ~(size_t)3; }
 
+// attention saved layout (floats): Ak[B,P,Da] | Av[B,P,E] | q[L,B,Da] | alpha[L,B,P]
+// attention backward workspace:    dAk[B,P,Da] | dAv[B,P,E] | dq[L,B,Da]
+struct AttnLayout {
+  size_t Ak, Av, q, alpha, total;      // saved
+  size_t dAk, dAv, dq, ws_total;       // workspace
+  AttnLayout(int B, int L, int P, int Da, int E) {
+    Ak = 0; Av = a4((size_t)B * P * Da); q = Av + a4((size_t)B * P * E); alpha = q + a4((size_t)L * B * Da);
+    total = alpha + a4((size_t)L * B * P);
+    dAk = 0; dAv = a4((size_t)B * P * Da); dq = dAv + a4((size_t)B * P * E); ws_total = dq + a4((size_t)L * B * Da);
+  }
+};
+
 // saved-for-backward layout of the decode (floats):
 //   xs[L][B][E] | per layer l: hs[l][(L+1)][B][H], cs[l][(L+1)][B][H], acts[l][L][B][4H] | htop[B][L][H]
 struct DecodeSaved {
@@ -87,7 +103,7 @@ static int decode_fwd(int mode, const float* features, const float* W_emb, const
                       const float* const* W_hh, const float* const* b_ih, const float* const* b_hh,
                       const float* W_out, const float* b_out, const float* u, float T, int pretrain,
                       const int64_t* forced, int B, int L, int V, int E, int H, int layers, float* out, int64_t* ids,
-                      float* saved, float* ws, cudaStream_t s, float* logp = nullptr) {
+                      float* saved, float* ws, cudaStream_t s, float* logp = nullptr, const gic_attn_t* at = nullptr) {
   GIC_REQUIRE(B >= 0 && L >= 1 && V >= 1 && E >= 1 && H >= 1 && layers >= 1 && layers <= 8, GIC_ERR_SHAPE,
               "decode_sample_fwd: bad shape B=%d L=%d V=%d E=%d H=%d layers=%d", B, L, V, E, H, layers);
   if (B == 0) return GIC_OK;
@@ -103,7 +119,25 @@ static int decode_fwd(int mode, const float* features, const float* W_emb, const
     cudaMemsetAsync(saved + sv.hs(l), 0, BH * sizeof(float), s);
     cudaMemsetAsync(saved + sv.cs(l), 0, BH * sizeof(float), s);
   }
+  const AttnLayout al(B, L, at ? at->P : 1, at ? at->Da : 1, E);
+  if (at) {
+    GIC_REQUIRE(at->grid && at->W_k && at->W_v && at->W_q && at->w_e && at->saved && at->P >= 1 && at->Cf >= 1 && at->Da >= 1,
+                GIC_ERR_NULL, "decode_sample_fwd_attn: incomplete attention block");
+    // once per image: key / value projections of the feature grid
+    GIC_TRY(gemm(mode, false, true, B * at->P, at->Da, at->Cf, 1.f, at->grid, at->Cf, at->W_k, at->Cf, 0.f, at->saved + al.Ak,
+                 at->Da, nullptr, s));
+    GIC_TRY(gemm(mode, false, true, B * at->P, E, at->Cf, 1.f, at->grid, at->Cf, at->W_v, at->Cf, 0.f, at->saved + al.Av, E,
+                 nullptr, s));
+  }
   for (int t = 0; t < L; ++t) {
+    if (at) {
+      // q_t = h_{t-1} W_q^T (top... layer 0 state), scores / softmax over the P locations / context added to x_t
+      float* q_t = at->saved + al.q + (size_t)t * B * at->Da;
+      GIC_TRY(gemm(mode, false, true, B, at->Da, H, 1.f, saved + sv.hs(0) + (size_t)t * BH, H, at->W_q, H, 0.f, q_t, at->Da,
+                   nullptr, s));
+      GIC_TRY(attn_fwd(at->saved + al.Ak, at->saved + al.Av, q_t, at->w_e, B, at->P, at->Da, E,
+                       saved + sv.xs + (size_t)t * BE, at->saved + al.alpha + (size_t)t * B * at->P, s));
+    }
     for (int l = 0; l < layers; ++l) {
       const float* xin = (l == 0) ? saved + sv.xs + (size_t)t * BE : saved + sv.hs(l - 1) + (size_t)(t + 1) * BH;
       const int In = (l == 0) ? E : H;
@@ -162,9 +196,18 @@ static int decode_bwd(int mode, const float* dout, const float* demb, const floa
                       const float* const* W_ih, const float* const* W_hh, const float* W_out, float T, int pretrain,
                       int B, int L, int V, int E, int H, int layers, const float* saved, float* ws, float* dW_emb,
                       float* const* dW_ih, float* const* dW_hh, float* const* db_ih, float* const* db_hh,
-                      float* dW_out, float* db_out, float* dfeat, int accumulate, cudaStream_t s) {
+                      float* dW_out, float* db_out, float* dfeat, int accumulate, cudaStream_t s,
+                      const gic_attn_t* at = nullptr) {
   GIC_REQUIRE(B >= 0 && L >= 1 && V >= 1 && E >= 1 && H >= 1 && layers >= 1 && layers <= 8, GIC_ERR_SHAPE,
               "decode_sample_bwd: bad shape");
+  const AttnLayout al(B, L, at ? at->P : 1, at ? at->Da : 1, E);
+  if (at) {
+    GIC_REQUIRE(at->grid && at->W_k && at->W_v && at->W_q && at->w_e && at->saved && at->ws && at->dW_k && at->dW_v &&
+                    at->dW_q && at->dw_e, GIC_ERR_NULL, "decode_sample_bwd_attn: incomplete attention block");
+    GIC_REQUIRE(!accumulate, GIC_ERR_UNSUPPORTED, "decode_sample_bwd_attn: accumulate is not supported");
+    cudaMemsetAsync(at->ws + al.dAk, 0, (al.dq - al.dAk) * sizeof(float), s);      // dAk, dAv accumulate over t
+    cudaMemsetAsync(at->dw_e, 0, (size_t)at->Da * sizeof(float), s);
+  }
   if (B == 0) return GIC_OK;
   GIC_REQUIRE((dout || (demb && emb && W_e && De >= 1)) && fed && W_emb && W_ih && W_hh && W_out && saved && ws && dW_emb && dW_ih && dW_hh && db_ih &&
                   db_hh && dW_out && db_out, GIC_ERR_NULL, "decode_sample_bwd: NULL pointer");
@@ -219,6 +262,17 @@ static int decode_bwd(int mode, const float* dout, const float* demb, const floa
       // recurrent gradient for step t-1: dh_rec = dgates W_hh    ([B,4H] x [4H,H])
       if (t > 0)
         GIC_TRY(gemm(mode, false, false, B, H, 4 * H, 1.f, dG_lt, 4 * H, W_hh[l], H, 0.f, dhrec, H, nullptr, s));
+      if (at && l == 0) {
+        // attention: dx'_t = dG_t W_ih (per step: dq_t feeds the recurrent gradient), then the attention backward
+        float* dXt = ws + w.dX + (size_t)t * BE;
+        float* dq_t = at->ws + al.dq + (size_t)t * B * at->Da;
+        GIC_TRY(gemm(mode, false, false, B, E, 4 * H, 1.f, dG_lt, 4 * H, W_ih[0], E, 0.f, dXt, E, nullptr, s));
+        GIC_TRY(attn_bwd(dXt, at->saved + al.alpha + (size_t)t * B * at->P, at->saved + al.q + (size_t)t * B * at->Da,
+                         at->saved + al.Ak, at->saved + al.Av, at->w_e, B, at->P, at->Da, E, dq_t, at->ws + al.dAk,
+                         at->ws + al.dAv, at->dw_e, s));
+        if (t > 0)   // q_t = h_{t-1} W_q^T: dh_{t-1} += dq_t W_q
+          GIC_TRY(gemm(mode, false, false, B, H, at->Da, 1.f, dq_t, at->Da, at->W_q, H, 1.f, dhrec, H, nullptr, s));
+      }
       // gradient to the layer below at the same step
       if (l > 0)
         GIC_TRY(gemm(mode, false, false, B, H, 4 * H, 1.f, dG_lt, 4 * H, W_ih[l], H, 0.f, ws + w.dxin, H, nullptr, s));
@@ -235,7 +289,17 @@ static int decode_bwd(int mode, const float* dout, const float* demb, const floa
     GIC_TRY(colsum_f32(dG_l, L * B, 4 * H, 4 * H, 1.f, accumulate != 0, db_hh[l], s));
   }
   // 5. input gradients: dX[L*B,E] = dG[0] W_ih[0]; t = 0 -> dfeatures, t >= 1 -> embedding rows
-  GIC_TRY(gemm(mode, false, false, L * B, E, 4 * H, 1.f, ws + w.dG, 4 * H, W_ih[0], E, 0.f, ws + w.dX, E, nullptr, s));
+  if (!at)
+    GIC_TRY(gemm(mode, false, false, L * B, E, 4 * H, 1.f, ws + w.dG, 4 * H, W_ih[0], E, 0.f, ws + w.dX, E, nullptr, s));
+  else {
+    // attention parameter gradients: dW_q = sum_t dq_t^T h_{t-1} (step 0 sees h = 0), dW_k = dAk^T grid, dW_v = dAv^T grid
+    GIC_TRY(gemm(mode, true, false, at->Da, H, L * B, 1.f, at->ws + al.dq, at->Da, saved + sv.hs(0), H, 0.f, at->dW_q, H,
+                 nullptr, s));
+    GIC_TRY(gemm(mode, true, false, at->Da, at->Cf, B * at->P, 1.f, at->ws + al.dAk, at->Da, at->grid, at->Cf, 0.f, at->dW_k,
+                 at->Cf, nullptr, s));
+    GIC_TRY(gemm(mode, true, false, E, at->Cf, B * at->P, 1.f, at->ws + al.dAv, E, at->grid, at->Cf, 0.f, at->dW_v, at->Cf,
+                 nullptr, s));
+  }
   if (!accumulate) cudaMemsetAsync(dW_emb, 0, (size_t)V * E * sizeof(float), s);
   GIC_TRY(embed_scatter(ws + w.dX, fed, B, L, E, V, dW_emb, dfeat, s));
   (void)BE;
@@ -374,6 +438,35 @@ int gic_sample_step(int pretrain, const float* logits, const float* u, float tem
   GIC_REQUIRE(!x_next || embed, GIC_ERR_NULL, "sample_step: embed table required for x_next");
   return sample_step(pretrain != 0, logits, u, temperature, B, V, L, t, out, ids, forced_ids, embed, E, x_next,
                      S(stream));
+}
+
+size_t gic_attn_saved_floats(int B, int L, int P, int Da, int E) { return AttnLayout(B, L, P, Da, E).total; }
+size_t gic_attn_bwd_workspace_floats(int B, int L, int P, int Da, int E) { return AttnLayout(B, L, P, Da, E).ws_total; }
+
+int gic_decode_sample_fwd_attn(const gic_attn_t* attn, int mode, const float* features, const float* W_emb,
+                               const float* const* W_ih, const float* const* W_hh, const float* const* b_ih,
+                               const float* const* b_hh, const float* W_out, const float* b_out, const float* u,
+                               float temperature, int pretrain, const int64_t* forced_ids, int B, int L, int V, int E,
+                               int H, int layers, float* out, int64_t* ids, float* saved, float* workspace,
+                               gic_stream_t stream) {
+  GIC_TRY(require_device());
+  GIC_REQUIRE(attn, GIC_ERR_NULL, "decode_sample_fwd_attn: NULL attention block");
+  return decode_fwd(mode, features, W_emb, W_ih, W_hh, b_ih, b_hh, W_out, b_out, u, temperature, pretrain, forced_ids,
+                    B, L, V, E, H, layers, out, ids, saved, workspace, S(stream), nullptr, attn);
+}
+
+int gic_decode_sample_bwd_attn(const gic_attn_t* attn, int mode, const float* dout, const float* demb, const float* emb,
+                               const float* W_e, int De, const float* out, const int64_t* fed_ids, const float* W_emb,
+                               const float* const* W_ih, const float* const* W_hh, const float* W_out,
+                               float temperature, int pretrain, int B, int L, int V, int E, int H, int layers,
+                               const float* saved, float* workspace, float* dW_emb, float* const* dW_ih,
+                               float* const* dW_hh, float* const* db_ih, float* const* db_hh, float* dW_out,
+                               float* db_out, float* dfeatures, gic_stream_t stream) {
+  GIC_TRY(require_device());
+  GIC_REQUIRE(attn, GIC_ERR_NULL, "decode_sample_bwd_attn: NULL attention block");
+  return decode_bwd(mode, dout, demb, emb, W_e, De, out, fed_ids, W_emb, W_ih, W_hh, W_out, temperature, pretrain, B, L,
+                    V, E, H, layers, saved, workspace, dW_emb, dW_ih, dW_hh, db_ih, db_hh, dW_out, db_out, dfeatures, 0,
+                    S(stream), attn);
 }
 
 int gic_sample_cdf_step(const float* logits, const float* u, int B, int V, int L, int t, float* out, int64_t* ids,

@@ -141,6 +141,68 @@ class _DecodeSample(torch.autograd.Function):
         return (dfeat, None, None, None, None, None, None, None, dW_emb, dW_out, db_out, *lstm_grads)
 
 
+class _DecodeSampleAttn(torch.autograd.Function):
+    """Decoder.sample with the attention cell (EXTENSION) through gic_decode_sample_{fwd,bwd}_attn."""
+
+    @staticmethod
+    def forward(ctx, features, grid, u, temperature, L, forced_ids, mode, W_k, W_v, W_q, w_e, W_emb, W_out, b_out, W_ih,
+                W_hh, b_ih, b_hh):
+        _lib.require_cuda()
+        lib = _lib.lib()
+        dev = features.device
+        features, grid, u = _f32c(features), _f32c(grid), _f32c(u)
+        W_k, W_v, W_q, w_e, W_emb, W_out, b_out, W_ih, W_hh, b_ih, b_hh = map(
+            _f32c, (W_k, W_v, W_q, w_e, W_emb, W_out, b_out, W_ih, W_hh, b_ih, b_hh))
+        B, E = features.shape
+        V, H = W_out.shape
+        Pn, Da = grid.shape[1], W_k.shape[0]
+        if forced_ids is not None:
+            forced_ids = forced_ids.detach().contiguous().long()
+        out = torch.empty(B, L, V, device=dev)
+        ids = torch.empty(B, L, dtype=torch.int64, device=dev)
+        saved = torch.empty(lib.gic_decode_saved_floats(B, L, E, H, 1), device=dev)
+        asaved = torch.empty(lib.gic_attn_saved_floats(B, L, Pn, Da, E), device=dev)
+        ws = torch.empty(lib.gic_decode_fwd_workspace_floats(B, V, H), device=dev)
+        blk = _lib.attn_block(grid, W_k, W_v, W_q, w_e.reshape(-1), asaved)
+        import ctypes as C
+        _lib.check(lib.gic_decode_sample_fwd_attn(
+            C.byref(blk), mode, _lib.ptr(features), _lib.ptr(W_emb), _lib.ptr_array([W_ih]), _lib.ptr_array([W_hh]),
+            _lib.ptr_array([b_ih]), _lib.ptr_array([b_hh]), _lib.ptr(W_out), _lib.ptr(b_out), _lib.ptr(u),
+            float(temperature), 0, _lib.ptr(forced_ids), B, L, V, E, H, 1, _lib.ptr(out), _lib.ptr(ids), _lib.ptr(saved),
+            _lib.ptr(ws), _lib.stream()), "gic_decode_sample_fwd_attn")
+        fed = ids if forced_ids is None else forced_ids
+        ctx.save_for_backward(out, fed, saved, asaved, grid, W_k, W_v, W_q, w_e, W_emb, W_out, W_ih, W_hh)
+        ctx.dims = (B, L, V, E, H, Pn, Da, float(temperature), mode)
+        ctx.mark_non_differentiable(ids)
+        return out, ids
+
+    @staticmethod
+    def backward(ctx, dout, _dids):
+        import ctypes as C
+        lib = _lib.lib()
+        B, L, V, E, H, Pn, Da, T, mode = ctx.dims
+        out, fed, saved, asaved, grid, W_k, W_v, W_q, w_e, W_emb, W_out, W_ih, W_hh = ctx.saved_tensors
+        dev = out.device
+        dout = _f32c(dout)
+        ws = torch.empty(lib.gic_decode_bwd_workspace_floats(B, L, V, E, H, 1), device=dev)
+        aws = torch.empty(lib.gic_attn_bwd_workspace_floats(B, L, Pn, Da, E), device=dev)
+        dW_k, dW_v, dW_q, dw_e = (torch.empty_like(t) for t in (W_k, W_v, W_q, w_e))
+        dW_emb, dW_out = torch.empty_like(W_emb), torch.empty_like(W_out)
+        db_out = torch.empty(V, device=dev)
+        dW_ih, dW_hh = torch.empty_like(W_ih), torch.empty_like(W_hh)
+        db_ih, db_hh = torch.empty(4 * H, device=dev), torch.empty(4 * H, device=dev)
+        dfeat = torch.empty(B, E, device=dev)
+        blk = _lib.attn_block(grid, W_k, W_v, W_q, w_e.reshape(-1), asaved, aws, dW_k, dW_v, dW_q, dw_e)
+        _lib.check(lib.gic_decode_sample_bwd_attn(
+            C.byref(blk), mode, _lib.ptr(dout), None, None, None, 0, _lib.ptr(out), _lib.ptr(fed), _lib.ptr(W_emb),
+            _lib.ptr_array([W_ih]), _lib.ptr_array([W_hh]), _lib.ptr(W_out), T, 0, B, L, V, E, H, 1, _lib.ptr(saved),
+            _lib.ptr(ws), _lib.ptr(dW_emb), _lib.ptr_array([dW_ih]), _lib.ptr_array([dW_hh]), _lib.ptr_array([db_ih]),
+            _lib.ptr_array([db_hh]), _lib.ptr(dW_out), _lib.ptr(db_out), _lib.ptr(dfeat), _lib.stream()),
+            "gic_decode_sample_bwd_attn")
+        return (dfeat, None, None, None, None, None, None, dW_k, dW_v, dW_q, dw_e, dW_emb, dW_out, db_out, dW_ih, dW_hh,
+                db_ih, db_hh)
+
+
 class Decoder(nn.Module):
     """LSTM caption decoder (src/generator.py:27-96).  ``embed``/``lstm``/``linear`` are parameter
     containers with the reference's state_dict keys; ``sample`` runs on the B200 kernels."""
@@ -153,6 +215,15 @@ class Decoder(nn.Module):
         self.max_seq_length = args.max_seq_len
         self.temperature = args.temperature
         self.args = args
+        # EXTENSION: additive attention over the CNN feature grid; off by default so that the
+        # reference's state_dict is unchanged
+        self.attention = bool(getattr(args, "gen_attention", 0))
+        if self.attention:
+            Cf, Da = args.feature_channels, args.attn_dim
+            self.attn_k = nn.Linear(Cf, Da, bias=False)
+            self.attn_v = nn.Linear(Cf, args.gen_embed_dim, bias=False)
+            self.attn_q = nn.Linear(args.gen_hidden_dim, Da, bias=False)
+            self.attn_e = nn.Linear(Da, 1, bias=False)
 
     def lstm_params(self):
         ps = []
@@ -161,7 +232,10 @@ class Decoder(nn.Module):
                    getattr(self.lstm, f"bias_ih_l{l}"), getattr(self.lstm, f"bias_hh_l{l}")]
         return ps
 
-    def sample(self, features, states=None, pretrain=False, max_caption_len=34, u=None, forced_ids=None):
+    def attn_params(self):
+        return [self.attn_k.weight, self.attn_v.weight, self.attn_q.weight, self.attn_e.weight]
+
+    def sample(self, features, states=None, pretrain=False, max_caption_len=34, u=None, forced_ids=None, grid=None):
         """Generate captions (src/generator.py:55-81) -> (outputs[B,L,V], sampled_ids[B,L]).
 
         Extensions over the reference signature (keyword-only in spirit): ``u[L,B,V]`` supplies the
@@ -172,6 +246,14 @@ class Decoder(nn.Module):
         L = int(max_caption_len)
         if u is None and not pretrain:
             u = torch.rand(L, features.shape[0], self.linear.out_features, device=features.device)
+        if grid is not None:
+            if not self.attention:
+                raise ValueError("a feature grid was given but the decoder was built without --gen-attention 1")
+            if pretrain or self.lstm.num_layers != 1:
+                raise NotImplementedError("the attention cell is implemented for single-layer adversarial decoding")
+            return _DecodeSampleAttn.apply(features, grid, u, float(self.temperature), L, forced_ids,
+                                           gic_b200.get_gemm_mode(), *self.attn_params(), self.embed.weight,
+                                           self.linear.weight, self.linear.bias, *self.lstm_params())
         return _DecodeSample.apply(features, u, float(self.temperature), bool(pretrain), L, forced_ids,
                                    gic_b200.get_gemm_mode(), self.lstm.num_layers, self.embed.weight,
                                    self.linear.weight, self.linear.bias, *self.lstm_params())

@@ -101,6 +101,8 @@ class GANInstructor:
     def _gen_params(self):
         dec = self.gen.decoder
         ps = [dec.embed.weight, *dec.lstm_params(), dec.linear.weight, dec.linear.bias]
+        if dec.attention:
+            ps += dec.attn_params()
         if self.cgan:
             enc = self.gen.encoder
             ps += [enc.linear.weight, enc.linear.bias, enc.bn.weight, enc.bn.bias]
@@ -131,7 +133,7 @@ class GANInstructor:
     # ---- the fused adversarial step ---------------------------------------------------------------
     @torch.no_grad()
     def adv_step(self, captions, pooled=None, u=None, keep=None, train=True, forced_ids=None, loss_type=None,
-                 update=True, graph=False):
+                 update=True, graph=False, grid=None):
         """One adversarial step on a batch (src/training.py:136-169).
 
         captions [B,L] int64 (collate contract); pooled [B,feature_dim] CNN features when conditional;
@@ -142,6 +144,8 @@ class GANInstructor:
         copied into static buffers, the temperature and Adam's bias corrections are read from device memory
         (gic_set_temperature_device / gic_clip_adam_dyn), so one replay call enqueues all ~150 kernels."""
         if graph:
+            if grid is not None:
+                raise NotImplementedError("graph replay with the attention grid: pass graph=False")
             return self._adv_step_graph(captions, pooled, u, keep, loss_type, static=(graph == "static"))
         _lib.require_cuda()
         lib = _lib.lib()
@@ -188,6 +192,17 @@ class GANInstructor:
         else:
             (d_real,), saved_r = disc_fwd_raw(lib, mode, None, captions, B, L, V, De, R, fsz, nfl, *dW, [k0], drop_p, dev)
         # -- step-0 input (:144-147)
+        attn = grid is not None
+        if attn:
+            import ctypes as C
+            if not dec.attention or layers != 1:
+                raise ValueError("grid given: build the generator with gen_attention=1 and one LSTM layer")
+            grid = grid.to(dev).float().contiguous()
+            if pooled is None and self.cgan:
+                pooled = grid.mean(1)                       # the reference's pooled feature = mean over the locations
+            Pn, Da = grid.shape[1], a.attn_dim
+            asaved = self._buf("attn_saved", lib.gic_attn_saved_floats(B, L, Pn, Da, E))
+            we = dec.attn_e.weight.view(-1)
         if self.cgan:
             enc = self.gen.encoder
             pooled = pooled.to(dev).float().contiguous()
@@ -211,11 +226,19 @@ class GANInstructor:
         W_ih, W_hh, b_ih, b_hh = lp[0::4], lp[1::4], lp[2::4], lp[3::4]
         if forced_ids is not None:
             forced_ids = forced_ids.to(dev).long().contiguous()
-        _lib.check(lib.gic_decode_sample_fwd(mode, P(feats), P(dec.embed.weight), _lib.ptr_array(W_ih),
-                                             _lib.ptr_array(W_hh), _lib.ptr_array(b_ih), _lib.ptr_array(b_hh),
-                                             P(dec.linear.weight), P(dec.linear.bias), P(u), T, 0, P(forced_ids), B, L,
-                                             V, E, H, layers, P(probs), P(ids), P(dsaved), P(dws), stream),
-                   "gic_decode_sample_fwd")
+        if attn:
+            blk = _lib.attn_block(grid, dec.attn_k.weight, dec.attn_v.weight, dec.attn_q.weight, we, asaved)
+            _lib.check(lib.gic_decode_sample_fwd_attn(C.byref(blk), mode, P(feats), P(dec.embed.weight),
+                                                      _lib.ptr_array(W_ih), _lib.ptr_array(W_hh), _lib.ptr_array(b_ih),
+                                                      _lib.ptr_array(b_hh), P(dec.linear.weight), P(dec.linear.bias),
+                                                      P(u), T, 0, P(forced_ids), B, L, V, E, H, layers, P(probs), P(ids),
+                                                      P(dsaved), P(dws), stream), "gic_decode_sample_fwd_attn")
+        else:
+            _lib.check(lib.gic_decode_sample_fwd(mode, P(feats), P(dec.embed.weight), _lib.ptr_array(W_ih),
+                                                 _lib.ptr_array(W_hh), _lib.ptr_array(b_ih), _lib.ptr_array(b_hh),
+                                                 P(dec.linear.weight), P(dec.linear.bias), P(u), T, 0, P(forced_ids), B,
+                                                 L, V, E, H, layers, P(probs), P(ids), P(dsaved), P(dws), stream),
+                       "gic_decode_sample_fwd")
         # -- discriminator on the generated captions: fake / gen share one trunk, two dropout masks (:163-164)
         (d_fake, g_out), saved_f = disc_fwd_raw(lib, mode, probs, None, B, L, V, De, R, fsz, nfl, *dW, [k1, k2],
                                                 drop_p, dev)
@@ -262,13 +285,26 @@ class GANInstructor:
             gws = self._buf("dec_bws", lib.gic_decode_bwd_workspace_floats(B, L, V, E, H, layers))
             dfeat = self._buf("dfeat", B * E).view(B, E)
             fed = ids if forced_ids is None else forced_ids
-            _lib.check(lib.gic_decode_sample_bwd_factored(
-                mode, P(demb), P(emb), P(disc.embeddings.weight), De, P(probs), P(fed), P(dec.embed.weight),
-                _lib.ptr_array(W_ih), _lib.ptr_array(W_hh), P(dec.linear.weight), T, B, L, V, E, H, layers, P(dsaved),
-                P(gws), P(gg(dec.embed.weight)), _lib.ptr_array([gg(w) for w in W_ih]),
-                _lib.ptr_array([gg(w) for w in W_hh]), _lib.ptr_array([gg(w) for w in b_ih]),
-                _lib.ptr_array([gg(w) for w in b_hh]), P(gg(dec.linear.weight)), P(gg(dec.linear.bias)), P(dfeat), 0,
-                st), "gic_decode_sample_bwd_factored")
+            if attn:
+                aws = self._buf("attn_ws", lib.gic_attn_bwd_workspace_floats(B, L, Pn, Da, E))
+                blk = _lib.attn_block(grid, dec.attn_k.weight, dec.attn_v.weight, dec.attn_q.weight, we, asaved, aws,
+                                      gg(dec.attn_k.weight), gg(dec.attn_v.weight), gg(dec.attn_q.weight),
+                                      gg(dec.attn_e.weight).view(-1))
+                _lib.check(lib.gic_decode_sample_bwd_attn(
+                    C.byref(blk), mode, None, P(demb), P(emb), P(disc.embeddings.weight), De, P(probs), P(fed),
+                    P(dec.embed.weight), _lib.ptr_array(W_ih), _lib.ptr_array(W_hh), P(dec.linear.weight), T, 0, B, L, V,
+                    E, H, layers, P(dsaved), P(gws), P(gg(dec.embed.weight)), _lib.ptr_array([gg(w) for w in W_ih]),
+                    _lib.ptr_array([gg(w) for w in W_hh]), _lib.ptr_array([gg(w) for w in b_ih]),
+                    _lib.ptr_array([gg(w) for w in b_hh]), P(gg(dec.linear.weight)), P(gg(dec.linear.bias)), P(dfeat),
+                    st), "gic_decode_sample_bwd_attn")
+            else:
+                _lib.check(lib.gic_decode_sample_bwd_factored(
+                    mode, P(demb), P(emb), P(disc.embeddings.weight), De, P(probs), P(fed), P(dec.embed.weight),
+                    _lib.ptr_array(W_ih), _lib.ptr_array(W_hh), P(dec.linear.weight), T, B, L, V, E, H, layers,
+                    P(dsaved), P(gws), P(gg(dec.embed.weight)), _lib.ptr_array([gg(w) for w in W_ih]),
+                    _lib.ptr_array([gg(w) for w in W_hh]), _lib.ptr_array([gg(w) for w in b_ih]),
+                    _lib.ptr_array([gg(w) for w in b_hh]), P(gg(dec.linear.weight)), P(gg(dec.linear.bias)), P(dfeat), 0,
+                    st), "gic_decode_sample_bwd_factored")
             if self.cgan:
                 enc = self.gen.encoder
                 _lib.check(lib.gic_encoder_bwd(mode, P(dfeat), P(pooled), P(lin), P(mean), P(rstd),

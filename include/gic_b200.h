@@ -213,6 +213,44 @@ int gic_rollout_rewards(const float* roll_logits, const float* main_logits, int 
 int gic_pg_loss_fwd_bwd(const float* logits, const int64_t* ids, const float* Q, int baseline_mode, int B, int L, int V,
                         float* loss, float* dlogits, float* logp, gic_stream_t stream);
 
+/* ---- B1 (EXTENSION, parity unpinned by reference): additive attention over the CNN feature grid in the decode step.
+ * The reference feeds one pooled vector at step 0 (src/generator.py:19-25,58) and has no attention.  Definition:
+ *   once per image: Ak = grid W_k^T [B,P,Da], Av = grid W_v^T [B,P,E];  every step: q = h_{t-1} W_q^T,
+ *   s_l = w_e . tanh(Ak_l + q), alpha = softmax_l(s), LSTM input x'_t = x_t + sum_l alpha_l Av_l.
+ * gic_attn_t carries the grid, the four parameters, a saved blob (gic_attn_saved_floats) filled by the forward and,
+ * for the backward, a workspace (gic_attn_bwd_workspace_floats) and the four gradient outputs (overwritten).
+ * The *_attn entry points take the same arguments as gic_decode_sample_fwd / _bwd (dout, or dout = NULL and the
+ * factored demb / emb / W_e / De of gic_decode_sample_bwd_factored). */
+typedef struct gic_attn_t {
+  const float* grid;      /* [B, P, Cf] CNN feature grid */
+  int P, Cf, Da;          /* locations, channels, attention width */
+  const float* W_k;       /* [Da, Cf] */
+  const float* W_v;       /* [E, Cf]  */
+  const float* W_q;       /* [Da, H]  */
+  const float* w_e;       /* [Da]     */
+  float* saved;           /* gic_attn_saved_floats(B, L, P, Da, E) */
+  float* ws;              /* backward only: gic_attn_bwd_workspace_floats(B, L, P, Da, E) */
+  float* dW_k;            /* backward only */
+  float* dW_v;
+  float* dW_q;
+  float* dw_e;
+} gic_attn_t;
+size_t gic_attn_saved_floats(int B, int L, int P, int Da, int E);
+size_t gic_attn_bwd_workspace_floats(int B, int L, int P, int Da, int E);
+int gic_decode_sample_fwd_attn(const gic_attn_t* attn, int mode, const float* features, const float* W_emb,
+                               const float* const* W_ih, const float* const* W_hh, const float* const* b_ih,
+                               const float* const* b_hh, const float* W_out, const float* b_out, const float* u,
+                               float temperature, int pretrain, const int64_t* forced_ids, int B, int L, int V, int E,
+                               int H, int layers, float* out, int64_t* ids, float* saved, float* workspace,
+                               gic_stream_t stream);
+int gic_decode_sample_bwd_attn(const gic_attn_t* attn, int mode, const float* dout, const float* demb, const float* emb,
+                               const float* W_e, int De, const float* out, const int64_t* fed_ids, const float* W_emb,
+                               const float* const* W_ih, const float* const* W_hh, const float* W_out,
+                               float temperature, int pretrain, int B, int L, int V, int E, int H, int layers,
+                               const float* saved, float* workspace, float* dW_emb, float* const* dW_ih,
+                               float* const* dW_hh, float* const* db_ih, float* const* db_hh, float* dW_out,
+                               float* db_out, float* dfeatures, gic_stream_t stream);
+
 /* ---- CUDA-graph replay support ----
  * By-value scalars are frozen when a launch is captured into a CUDA graph, but the reference changes two of them every
  * batch: the temperature (update_temperature, src/training.py:183,190-191) and Adam's bias corrections (step count).

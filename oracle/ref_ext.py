@@ -117,3 +117,51 @@ def pg_step(inp, u_main, u_roll, n, baseline_mode=1):
     g_grads = {k: g for k, g in zip(names, grads) if g is not None}
     return dict(logits=logits, ids=ids, logp=logp, roll_ids=roll, roll_logits=roll_logits, main_logits=main_logits, Q=Q,
                 loss=loss.detach(), g_grads=g_grads, features=feats)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# B1 (EXTENSION, parity unpinned by reference): additive attention over the CNN feature grid.
+# The reference feeds ONE pooled vector at step 0 and has no attention (src/generator.py:19-25,58); its report
+# describes grid cross-attention only for a Transformer variant whose code is not in the repository.  north_star
+# asks for "the per-step RNN/attention cell over the CNN image-feature grid", so the cell is defined here:
+#   once per image:  Ak = grid W_k^T [B,P,Da],  Av = grid W_v^T [B,P,E]            (P = 49 locations, 2048 channels)
+#   every step t:    q = h_{t-1} W_q^T;  s_l = w_e . tanh(Ak_l + q);  alpha = softmax_l(s);  ctx = sum_l alpha_l Av_l
+#                    LSTM input x'_t = x_t + ctx   (x_0 = projected pooled feature, x_t = embed(token_{t-1}))
+# Everything after the LSTM input (cell, vocab projection, Gumbel-softmax sampling) is the reference-pinned path.
+# --------------------------------------------------------------------------------------------------------------
+ATTN_KEYS = ("decoder.attn_k.weight", "decoder.attn_v.weight", "decoder.attn_q.weight", "decoder.attn_e.weight")
+
+
+def attn_param_shapes(a, Cf, Da):
+    return [("decoder.attn_k.weight", (Da, Cf)), ("decoder.attn_v.weight", (a.gen_embed_dim, Cf)),
+            ("decoder.attn_q.weight", (Da, a.gen_hidden_dim)), ("decoder.attn_e.weight", (Da,))]
+
+
+def attention_context(p, Ak, Av, h_prev):
+    q = F.linear(h_prev, p["decoder.attn_q.weight"])                            # [B,Da]
+    s = (torch.tanh(Ak + q[:, None, :]) * p["decoder.attn_e.weight"].reshape(-1)).sum(-1)    # [B,P]
+    alpha = F.softmax(s, dim=-1)
+    return (alpha[:, :, None] * Av).sum(1), alpha
+
+
+def decoder_sample_attn(p, features, grid, u, temperature, L, forced_ids=None):
+    """Single-layer Decoder.sample with the attention cell.  Returns probs[B,L,V], ids[B,L], alphas[B,L,P]."""
+    B = features.shape[0]
+    H = p["decoder.lstm.weight_hh_l0"].shape[1]
+    Ak = F.linear(grid, p["decoder.attn_k.weight"])
+    Av = F.linear(grid, p["decoder.attn_v.weight"])
+    h = features.new_zeros(B, H)
+    c = features.new_zeros(B, H)
+    x = features
+    outs, ids, alphas = [], [], []
+    for t in range(L):
+        ctx, alpha = attention_context(p, Ak, Av, h)
+        h, c = rp.lstm_cell(x + ctx, h, c, p["decoder.lstm.weight_ih_l0"], p["decoder.lstm.weight_hh_l0"],
+                            p["decoder.lstm.bias_ih_l0"], p["decoder.lstm.bias_hh_l0"])
+        logits = F.linear(h, p["decoder.linear.weight"], p["decoder.linear.bias"])
+        pred = F.softmax((logits + rp.gumbel_noise(u[t])) * temperature, dim=-1)
+        tok = pred.max(1)[1]
+        outs.append(pred); ids.append(tok); alphas.append(alpha)
+        fed = tok if forced_ids is None else forced_ids[:, t]
+        x = p["decoder.embed.weight"][fed.detach()]
+    return torch.stack(outs, 1), torch.stack(ids, 1), torch.stack(alphas, 1)

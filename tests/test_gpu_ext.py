@@ -209,3 +209,132 @@ def test_pg_step_full_update_and_properties_c3_shape():
     assert not torch.equal(inst.disc.highway.weight.detach(), d0)
     # log pi of the sampled tokens is a log-probability
     assert float(out["logp"].max()) <= 0.0
+
+
+# ------------------------------------------------------------------------------------------------------------
+# B1: attention cell over the CNN feature grid (definition: oracle/ref_ext.py; parity unpinned by reference)
+# ------------------------------------------------------------------------------------------------------------
+def _attn_setup(B=4, Lc=6, V=40, E=16, H=32, Pn=9, Cf=24, Da=12, seed=5):
+    from gic_b200.args import default_args
+    import gic_b200.generator as G
+    a = default_args(vocab_size=V, gen_embed_dim=E, gen_hidden_dim=H, gen_attention=1, attn_dim=Da, feature_channels=Cf,
+                     device="cuda")
+    torch.manual_seed(seed)
+    gen = G.Generator(a).cuda()
+    # larger attention weights than the U(-0.05, 0.05) init so that alpha is far from uniform
+    with torch.no_grad():
+        for p in gen.decoder.attn_params():
+            p.mul_(12.0)
+    g = torch.Generator().manual_seed(seed)
+    feats = torch.randn(B, E, generator=g) * 0.5
+    grid = torch.randn(B, Pn, Cf, generator=g)
+    u = torch.rand(Lc, B, V, generator=g)
+    return a, gen, feats, grid, u
+
+
+@pytest.mark.parametrize("T", [1.0, 4.0])
+def test_attention_decode_forward_backward_vs_oracle(T):
+    a, gen, feats, grid, u = _attn_setup()
+    Lc = u.shape[0]
+    p_cpu = {k: v.detach().cpu().clone() for k, v in gen.state_dict().items()}
+    ref_p, ref_ids, ref_alpha = rx.decoder_sample_attn(p_cpu, feats, grid, u, T, Lc)
+    gen.decoder.temperature = T
+    fd, gd = feats.cuda().requires_grad_(True), grid.cuda()
+    out, ids = gen.decoder.sample(fd, max_caption_len=Lc, u=u.cuda(), forced_ids=ref_ids.cuda(), grid=gd)
+    torch.cuda.synchronize()
+    assert torch.equal(ids.cpu(), ref_ids)
+    close(f"attn/T{T}/probs", out, ref_p)
+    # backward of a fixed linear functional of the soft captions: autograd on the oracle vs the CUDA backward
+    g = torch.Generator().manual_seed(99)
+    Rw = torch.randn(out.shape, generator=g)
+    pr = {k: v.clone().requires_grad_(True) for k, v in p_cpu.items() if k.startswith("decoder.")}
+    f_cpu = feats.clone().requires_grad_(True)
+    pp, _, _ = rx.decoder_sample_attn(pr, f_cpu, grid, u, T, Lc, forced_ids=ref_ids)
+    loss = (pp * Rw).sum()
+    names = sorted(pr)
+    grads = torch.autograd.grad(loss, [pr[k] for k in names] + [f_cpu], allow_unused=True)
+    (out * Rw.cuda()).sum().backward()
+    torch.cuda.synchronize()
+    sd = dict(gen.named_parameters())
+    for k, gref in zip(names, grads[:-1]):
+        if gref is None:
+            continue
+        got = sd[k].grad
+        assert got is not None, k
+        close(f"attn/T{T}/grad/{k}", got.reshape(-1), gref.reshape(-1), rtol=2e-3, atol=1e-7)
+    close(f"attn/T{T}/grad/features", fd.grad, grads[-1], rtol=2e-3, atol=1e-7)
+
+
+def test_attention_weights_are_a_distribution():
+    """Property at a larger shape (P = 49 locations, 2048 channels): the saved alphas sum to 1 per (step, caption)."""
+    import ctypes as C
+    L = L_()
+    a, gen, feats, grid, u = _attn_setup(B=8, Lc=5, V=200, E=32, H=64, Pn=49, Cf=2048, Da=64, seed=7)
+    lib = L.lib()
+    d = torch.device("cuda:0")
+    B, E = feats.shape
+    Lc, V, H, Pn, Da = u.shape[0], 200, 64, 49, 64
+    dec = gen.decoder
+    saved = torch.empty(lib.gic_decode_saved_floats(B, Lc, E, H, 1), device=d)
+    asaved = torch.zeros(lib.gic_attn_saved_floats(B, Lc, Pn, Da, E), device=d)
+    ws = torch.empty(lib.gic_decode_fwd_workspace_floats(B, V, H), device=d)
+    out = torch.empty(B, Lc, V, device=d); ids = torch.empty(B, Lc, dtype=torch.int64, device=d)
+    gd, fd, ud = grid.to(d), feats.to(d), u.to(d)
+    we = dec.attn_e.weight.detach().reshape(-1).contiguous()
+    blk = L.attn_block(gd, dec.attn_k.weight.detach(), dec.attn_v.weight.detach(), dec.attn_q.weight.detach(), we, asaved)
+    lp = [p.detach() for p in dec.lstm_params()]
+    L.check(lib.gic_decode_sample_fwd_attn(C.byref(blk), 0, L.ptr(fd), L.ptr(dec.embed.weight.detach()), L.ptr_array([lp[0]]),
+                                           L.ptr_array([lp[1]]), L.ptr_array([lp[2]]), L.ptr_array([lp[3]]),
+                                           L.ptr(dec.linear.weight.detach()), L.ptr(dec.linear.bias.detach()), L.ptr(ud), 1.0, 0,
+                                           None, B, Lc, V, E, H, 1, L.ptr(out), L.ptr(ids), L.ptr(saved), L.ptr(ws), L.stream()),
+            "fwd_attn")
+    torch.cuda.synchronize()
+    a4 = lambda x: (x + 3) & ~3
+    off = a4(B * Pn * Da) + a4(B * Pn * E) + a4(Lc * B * Da)
+    alpha = asaved[off:off + Lc * B * Pn].view(Lc, B, Pn).cpu()
+    assert float((alpha.sum(-1) - 1).abs().max()) < 1e-5 and float(alpha.min()) >= 0.0
+    assert float((out.sum(-1).cpu() - 1).abs().max()) < 1e-4
+
+
+def test_adv_step_with_attention_grid_runs_and_trains_attention_params():
+    """Fused adversarial step with the attention cell: the step runs, every attention parameter receives a finite,
+    non-zero gradient and is updated; the fused (factored) generator backward agrees with the autograd-driven one."""
+    from gic_b200.args import default_args
+    from gic_b200.training import GANInstructor
+    B, Lc, V = 6, 8, 60
+    a = default_args(vocab_size=V, gen_embed_dim=16, gen_hidden_dim=32, gen_attention=1, attn_dim=12, feature_channels=24,
+                     conditional_gan=1, feature_dim=24, disc_num_filters=[20, 24, 28], device="cuda")
+    torch.manual_seed(3)
+    inst = GANInstructor(a, device="cuda:0")
+    inst.gen.train(); inst.disc.train(); inst.gen.decoder.temperature = 2.0
+    with torch.no_grad():
+        for p in inst.gen.decoder.attn_params():
+            p.mul_(12.0)
+    g = torch.Generator().manual_seed(4)
+    caps = torch.randint(4, V, (B, Lc), generator=g)
+    grid = torch.randn(B, 9, 24, generator=g)
+    u = torch.rand(Lc, B, V, generator=g)
+    keep = (torch.rand(3, B * 64, 72, generator=g) >= 0.2)
+    before = [p.detach().clone() for p in inst.gen.decoder.attn_params()]
+    out = inst.adv_step(caps, grid=grid, u=u, keep=keep, update=False)
+    torch.cuda.synchronize()
+    fg = inst._flat_g
+    fused = {k: fg.g(p).clone() for k, p in inst.gen.named_parameters() if k.startswith("decoder.")}
+    for k in ("decoder.attn_k.weight", "decoder.attn_v.weight", "decoder.attn_q.weight", "decoder.attn_e.weight"):
+        assert torch.isfinite(fused[k]).all() and float(fused[k].abs().max()) > 0, k
+    # autograd-driven path on the same modules (dense d(probs) through Discriminator.forward)
+    from gic_b200.utils import get_losses
+    inst.gen.zero_grad(); inst.disc.zero_grad()
+    feats = inst.gen.encoder(grid.cuda().mean(1))
+    probs, ids = inst.gen.decoder.sample(feats, max_caption_len=Lc, u=u.cuda(), grid=grid.cuda())
+    assert torch.equal(ids, out["ids"])
+    g_out = inst.disc(probs, keep=keep[2].cuda())
+    g_loss, _ = get_losses(out["d_real"], out["d_fake"], g_out, "standard")
+    g_loss.backward()
+    for k, p in inst.gen.named_parameters():
+        if k.startswith("decoder.") and p.grad is not None:
+            close(f"attn_step/{k}", fused[k], p.grad.detach().cpu(), rtol=2e-3, atol=1e-9)
+    inst.adv_step(caps, grid=grid, u=u, keep=keep)
+    torch.cuda.synchronize()
+    for b0, p in zip(before, inst.gen.decoder.attn_params()):
+        assert not torch.equal(b0, p.detach())
