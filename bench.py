@@ -37,6 +37,10 @@ WORKLOADS = {
     "c2": dict(B=256, L=20, V=10000, E=512, H=512, layers=1, feat=2048, filters=[300, 300, 300]),
     # BASELINE.json configs[0] (args.py defaults; CPU-runnable)
     "c1": dict(B=8, L=16, V=1000, E=32, H=512, layers=1, feat=2048, filters=[300, 300, 300]),
+    # BASELINE.json configs[2]: SeqGAN-style reward, 128 captions x 16 rollouts per prefix (secondary line: --workload c3)
+    "c3": dict(B=128, L=20, V=10000, E=512, H=512, layers=1, feat=0, filters=[300, 300, 300], n_roll=16),
+    # BASELINE.json configs[4]: discriminator-only step, 4096 real + 4096 fake captions of length 32 (--workload c5)
+    "c5": dict(B=4096, L=32, V=10000, E=512, H=512, layers=1, feat=0, filters=[300, 300, 300]),
 }
 MODES = {"fp32": 0, "tf32": 1, "tf32x3": 2}
 DTYPE_NAME = {"fp32": "f32", "tf32": "tf32 (fp32 accumulate)", "tf32x3": "f32 (3xTF32 tensor-core split, fp32 accumulate)"}
@@ -274,8 +278,9 @@ def run_ours(args):
 
     # roofline of the dominant kernel class: instrumented steps (events around every launch of the class)
     peaks = load_peaks()
-    K = C.c_double * 6
-    ms_k, work_k, calls_k = K(), K(), (C.c_ulonglong * 6)()
+    NK = 8
+    K = C.c_double * NK
+    ms_k, work_k, calls_k = K(), K(), (C.c_ulonglong * NK)()
     use_graph = False          # events around individual launches need the eager path
     step_resident(0); torch.cuda.synchronize()
     psteps = min(args.steps, 3)
@@ -284,21 +289,38 @@ def run_ours(args):
         step_resident(i)
     torch.cuda.synchronize()
     lib.gic_prof_end(ms_k, work_k, calls_k)
-    names = ["gemm", "sample_step", "conv_pool_fwd", "softmax_bwd", "clip_adam", "head_fwd"]
+    names = ["gemm_other", "sample_step", "conv_pool_fwd", "softmax_bwd", "clip_adam", "head_fwd", "gemm_disc", "gemm_decode"]
     classes = {}
     for k, nm in enumerate(names):
         if calls_k[k]:
             classes[nm] = dict(ms_per_step=ms_k[k] / psteps, calls_per_step=calls_k[k] / psteps,
                                work_per_step=work_k[k] / psteps)
-    g = classes.get("gemm")
+    # dominant kernel: the discriminator's [B*R, F] x [F, F] contractions (highway forward, dx, dW_h): 7 launches of
+    # 2*B*R*F*F flop each (2*R*F^2 per caption), the FLOP-dominant kernel of the step
+    g = classes.get("gemm_disc")
     roofline = None
     if g:
-        ach = g["work_per_step"] / (g["ms_per_step"] * 1e-3) / 1e12
-        roofline = {"kernel": "gemm (tcgen05)" if args.mode != "fp32" else "sgemm_kernel (fp32 FFMA)", "bound": "tensor",
-                    "achieved": ach, "peak": peaks["tf"], "unit": "TFLOP/s", "frac": ach / peaks["tf"],
-                    "traffic": None, "peak_source": peaks["src"] + ", sustained bf16 dense",
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r1", "traffic.json")
+        if args.workload == "c2" and os.path.exists(tp):
+            tj = json.load(open(tp))
+            traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
+        flops_launch = g["work_per_step"] / g["calls_per_step"]
+        us_launch = g["ms_per_step"] * 1e3 / g["calls_per_step"]
+        ach = flops_launch / (us_launch * 1e-6) / 1e12
+        roofline = {"kernel": ("gemm_p_kernel (tcgen05 kind::tf32, persistent): discriminator highway / dx / dW_h, "
+                               f"{B * R}x{Fd}x{Fd}") if args.mode != "fp32" else "sgemm_kernel (fp32 FFMA)",
+                    "bound": "tensor", "achieved": ach, "peak": peaks["tf"], "unit": "TFLOP/s", "frac": ach / peaks["tf"],
+                    "traffic": traffic, "peak_source": peaks["src"] + ", sustained bf16 dense (TF32 runs at half that rate)",
                     "share_of_step": g["ms_per_step"] / ms_step, "launches_per_step": g["calls_per_step"],
-                    "algorithmic_flops_per_step": g["work_per_step"]}
+                    "algorithmic_flops_per_launch": flops_launch, "us_per_launch": us_launch}
+    tensor_classes = {}
+    for nm in ("gemm_disc", "gemm_decode", "gemm_other"):
+        c = classes.get(nm)
+        if c:
+            tf = c["work_per_step"] / (c["ms_per_step"] * 1e-3) / 1e12
+            tensor_classes[nm] = {"achieved_TFLOPs": tf, "frac_of_bf16_peak": tf / peaks["tf"], "ms_per_step": c["ms_per_step"],
+                                  "launches_per_step": c["calls_per_step"]}
     hbm = {}
     for nm in ("sample_step", "conv_pool_fwd", "softmax_bwd", "clip_adam", "head_fwd"):
         c = classes.get(nm)
@@ -344,11 +366,74 @@ def run_ours(args):
         "tokens_per_sec": tokens_per_sec, "decode_ms": dms / args.steps,
         "e2e": {"value": e2e_val, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                 "ms_per_step": e2e_ms / args.steps},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "hbm_kernels": hbm,
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "tensor_kernels": tensor_classes,
+        "hbm_kernels": hbm,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
     shutdown()
+
+
+def run_secondary(args):
+    """Secondary workloads (not the headline line): c3 = policy-gradient step with Monte-Carlo rollouts (tokens/s counts
+    every sampled row-step), c5 = discriminator-only step on hard captions."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import gic_b200
+    from gic_b200.args import default_args
+    from gic_b200.training import GANInstructor
+    gic_b200.set_gemm_mode(MODES[args.mode])
+    cfg = WORKLOADS[args.workload]
+    B, L, V = cfg["B"], cfg["L"], cfg["V"]
+    a = default_args(vocab_size=V, gen_embed_dim=cfg["E"], gen_hidden_dim=cfg["H"], disc_num_filters=list(cfg["filters"]),
+                     conditional_gan=0, device="cuda")
+    torch.manual_seed(1008)
+    inst = GANInstructor(a, device=dev)
+    inst.gen.train(); inst.disc.train()
+    g = torch.Generator(device=dev).manual_seed(1008 + rank)
+    caps = torch.randint(4, V, (B, L), generator=g, device=dev); caps[:, 0] = 1; caps[:, L - 1] = 2
+    if args.workload == "c3":
+        n = cfg["n_roll"]
+        Mmax = (L - 1) * B * n
+        sets = [dict(u=torch.rand(L, B, generator=g, device=dev), ur=torch.rand(L, Mmax, generator=g, device=dev)) for _ in range(2)]
+        units = B * L + B * n * (L * (L - 1) // 2)               # sampled row-steps per step (SURVEY.md 8a row B2)
+        fn = lambda i: inst.pg_step(caps, u=sets[i % 2]["u"], u_roll=sets[i % 2]["ur"], n_roll=n)
+        metric, unit = "sampled_caption_tokens_per_sec", "tokens/s"
+    else:
+        fake = torch.randint(4, V, (B, L), generator=g, device=dev)
+        keeps = [(torch.rand(2, B * 64, sum(cfg["filters"]), generator=g, device=dev) >= 0.2).to(torch.uint8) for _ in range(2)]
+        units = 1
+        fn = lambda i: inst.disc_step(caps, fake, keep=keeps[i % 2])
+        metric, unit = "discriminator_steps_per_sec", "steps/s"
+    for i in range(max(args.warmup, 3)):
+        fn(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        fn(i)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    if rank == 0:
+        print(json.dumps({"metric": metric, "value": world * units * args.steps / (ms * 1e-3), "unit": unit, "n_gpus": world,
+                          "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE_NAME[args.mode],
+                          "data": "synthetic", "config": {"workload": args.workload, **{k: v for k, v in cfg.items()}},
+                          "secondary": True}), flush=True)
+    if world > 1:
+        torch.cuda.synchronize(); dist.barrier()
+        t = threading.Timer(15.0, lambda: os._exit(0)); t.daemon = True; t.start()
+        dist.destroy_process_group(); t.cancel()
 
 
 def main():
@@ -366,6 +451,8 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload in ("c3", "c5"):
+        run_secondary(args)
     else:
         run_ours(args)
 

@@ -108,6 +108,7 @@ def _declare(L):
     L.gic_decode_rollouts_workspace_floats.argtypes = [I] * 6
     L.gic_decode_rollouts.argtypes = [I, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, P, P, P]
     L.gic_rollout_rewards.argtypes = [P, P, I, I, I, I, P, P]
+    L.gic_ce_loss_fwd_bwd.argtypes = [P, P, I, I, I, P, P, P]
     L.gic_pg_loss_fwd_bwd.argtypes = [P, P, P, I, I, I, I, P, P, P, P]
     L.gic_set_temperature_device.restype = None
     L.gic_set_temperature_device.argtypes = [P]

@@ -159,7 +159,7 @@ static int decode_fwd(int mode, const float* features, const float* W_emb, const
       }
     }
     const float* htop_t = saved + sv.hs(layers - 1) + (size_t)(t + 1) * BH;
-    GIC_TRY(gemm(mode, false, true, B, V, H, 1.f, htop_t, H, W_out, H, 0.f, logits, V, b_out, s));   // :64,68
+    GIC_TRY(gemm(mode, false, true, B, V, H, 1.f, htop_t, H, W_out, H, 0.f, logits, V, b_out, s, PROF_GEMM_DECODE));   // :64,68
     float* x_next = (t + 1 < L) ? saved + sv.xs + (size_t)(t + 1) * BE : nullptr;
     if (pretrain == 2)
       GIC_TRY(sample_cdf_step(logits, u + (size_t)t * B, B, V, L, t, L, out, ids, logp, forced, W_emb, E, x_next, s));
@@ -555,6 +555,12 @@ int gic_rollout_rewards(const float* roll_logits, const float* main_logits, int 
                         gic_stream_t stream) {
   GIC_TRY(require_device());
   return rollout_q(roll_logits, main_logits, B, L, n_roll, R, Q, S(stream));
+}
+
+int gic_ce_loss_fwd_bwd(const float* logits, const int64_t* targets, int B, int L, int V, float* loss, float* dlogits,
+                        gic_stream_t stream) {
+  GIC_TRY(require_device());
+  return pg_loss(logits, targets, nullptr, 0, B, L, V, loss, dlogits, nullptr, S(stream));
 }
 
 int gic_pg_loss_fwd_bwd(const float* logits, const int64_t* ids, const float* Q, int baseline_mode, int B, int L, int V,

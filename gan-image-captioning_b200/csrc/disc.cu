@@ -687,7 +687,7 @@ int disc_forward(int mode, const float* inp_soft, const int64_t* ids, const Disc
     GIC_TRY(check_launch("conv_pool_fwd_kernel"));
   }
   // 3. highway pre-activation
-  GIC_TRY(gemm(mode, false, true, (int)rows, d.F, d.F, 1.f, pooled, d.F, W_h, d.F, 0.f, hpre, d.F, b_h, s));
+  GIC_TRY(gemm(mode, false, true, (int)rows, d.F, d.F, 1.f, pooled, d.F, W_h, d.F, 0.f, hpre, d.F, b_h, s, PROF_GEMM_D));
   // 4. collapsed head
   head_collapse_kernel<<<cdiv(d.F + 1, 256), 256, 0, s>>>(W_f, b_f, W_o, b_o, d.F, d.Hd, weff);
   GIC_TRY(check_launch("head_collapse_kernel"));
@@ -758,10 +758,10 @@ int disc_backward(int mode, const float* dlogit, const uint8_t* keep, float drop
                                                 db_f, dW_o, db_o, db_h);
     GIC_TRY(check_launch("head_param_grads_kernel"));
     // dW_h[F,F] (+)= dh^T [F, rows] * pooled [rows, F]
-    GIC_TRY(gemm(mode, true, false, d.F, d.F, (int)rows, 1.f, dh, d.F, pooled, d.F, beta, dW_h, d.F, nullptr, s));
+    GIC_TRY(gemm(mode, true, false, d.F, d.F, (int)rows, 1.f, dh, d.F, pooled, d.F, beta, dW_h, d.F, nullptr, s, PROF_GEMM_D));
   }
   // dx += dh * W_h        ([rows,F] x [F,F], W_h is [out,in] so this is the non-transposed product)
-  GIC_TRY(gemm(mode, false, false, (int)rows, d.F, d.F, 1.f, dh, d.F, W_h, d.F, 1.f, dx, d.F, nullptr, s));
+  GIC_TRY(gemm(mode, false, false, (int)rows, d.F, d.F, 1.f, dh, d.F, W_h, d.F, 1.f, dx, d.F, nullptr, s, PROF_GEMM_D));
   // conv / pool backward
   {
     GIC_REQUIRE(g.kmax <= BWD_KMAX, GIC_ERR_SHAPE, "disc bwd: filter_size*emb_dim_single <= %d supported", BWD_KMAX);

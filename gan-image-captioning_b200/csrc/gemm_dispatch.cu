@@ -58,8 +58,8 @@ int gemm_dz(int mode, int M, int N, int K, const float* demb, int lda, const flo
 }
 
 int gemm(int mode, bool transA, bool transB, int M, int N, int K, float alpha, const float* A, int lda,
-         const float* B, int ldb, float beta, float* C, int ldc, const float* bias, cudaStream_t stream) {
-  ProfScope prof(PROF_GEMM, 2.0 * M * N * K, stream);
+         const float* B, int ldb, float beta, float* C, int ldc, const float* bias, cudaStream_t stream, int prof_kind) {
+  ProfScope prof(prof_kind, 2.0 * M * N * K, stream);
   if (mode != GEMM_FP32) {
     bool handled = false;
     int rc = GIC_OK;

@@ -34,7 +34,7 @@ int num_sms();
 
 // ---- optional per-kernel-class device timing (bench.py roofline): CUDA events on the launching stream ----
 enum ProfKind : int { PROF_GEMM = 0, PROF_SAMPLE = 1, PROF_CONVPOOL = 2, PROF_SOFTMAX_BWD = 3, PROF_ADAM = 4,
-                      PROF_HEAD = 5, PROF_KINDS = 6 };
+                      PROF_HEAD = 5, PROF_GEMM_D = 6, PROF_GEMM_DECODE = 7, PROF_KINDS = 8 };
 bool prof_enabled();
 void prof_open(int kind, double work, cudaStream_t s);    // work = algorithmic flops (GEMM) or bytes
 void prof_close(cudaStream_t s);
@@ -62,7 +62,7 @@ enum GemmMode : int {
 // Dispatching GEMM used by the path: routes to tcgen05 when the mode/shape allow, else FFMA.
 int gemm(int mode, bool transA, bool transB, int M, int N, int K, float alpha, const float* A,
          int lda, const float* B, int ldb, float beta, float* C, int ldc, const float* bias,
-         cudaStream_t stream);
+         cudaStream_t stream, int prof_kind = PROF_GEMM);
 
 // out[N] (+)= scale * sum_rows A[M,N]
 int colsum_f32(const float* A, int M, int N, int lda, float scale, bool accumulate, float* out,

@@ -119,7 +119,7 @@ pg_loss_kernel(const float* __restrict__ logits, const int64_t* __restrict__ ids
   const int row = blockIdx.x, t = row % L;
   const float* lr = logits + (size_t)row * V;
   float base = 0.f;
-  if (baseline_mode == 1) {
+  if (baseline_mode == 1 && Q) {
     float s = 0.f;
     for (int i = threadIdx.x; i < B; i += blockDim.x) s += Q[(size_t)i * L + t];
     base = block_sum(s, red) / (float)B;
@@ -132,7 +132,7 @@ pg_loss_kernel(const float* __restrict__ logits, const int64_t* __restrict__ ids
   sum = block_sum(sum, red);
   int64_t y = ids[row];
   if (y < 0 || y >= V) y = 0;
-  const float adv = Q[row] - base;
+  const float adv = Q ? (Q[row] - base) : 1.f;            // Q == nullptr: plain cross entropy (weight 1)
   const float scale = adv / (float)((size_t)B * L);
   if (dlogits) {
     float* dr = dlogits + (size_t)row * V;
@@ -151,7 +151,7 @@ pg_loss_kernel(const float* __restrict__ logits, const int64_t* __restrict__ ids
 int pg_loss(const float* logits, const int64_t* ids, const float* Q, int baseline_mode, int B, int L, int V, float* loss,
             float* dlogits, float* logp, cudaStream_t s) {
   GIC_REQUIRE(B >= 1 && L >= 1 && V >= 1, GIC_ERR_SHAPE, "pg_loss: bad shape");
-  GIC_REQUIRE(logits && ids && Q && loss, GIC_ERR_NULL, "pg_loss: NULL operand");
+  GIC_REQUIRE(logits && ids && loss, GIC_ERR_NULL, "pg_loss: NULL operand");
   GIC_REQUIRE(baseline_mode == 0 || baseline_mode == 1, GIC_ERR_UNSUPPORTED, "pg_loss: baseline mode %d", baseline_mode);
   cudaMemsetAsync(loss, 0, sizeof(float), s);
   pg_loss_kernel<<<B * L, 256, 0, s>>>(logits, ids, Q, baseline_mode, B, L, V, loss, dlogits, logp);

@@ -178,7 +178,7 @@ int lstm_step_tc(const float* x, int In, const float* h_prev, const float* W_ih,
     cudaFuncSetAttribute(lstm_step_tf32_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, LstmCfg<32>::SMEM);
     attr = true;
   }
-  ProfScope prof(PROF_GEMM, 2.0 * B * 4 * H * (In + H), stream);
+  ProfScope prof(PROF_GEMM_DECODE, 2.0 * B * 4 * H * (In + H), stream);
   dim3 grid(H / U, mt);
 #define GIC_LSTM(U_) lstm_step_tf32_kernel<U_><<<grid, NTHREADS, LstmCfg<U_>::SMEM, stream>>>(tx, th, twi, twh, B, H, In, b_ih, b_hh, c_prev, acts, c_out, h_out, htop, L, t)
   if (U == 32) GIC_LSTM(32); else if (U == 16) GIC_LSTM(16); else GIC_LSTM(8);

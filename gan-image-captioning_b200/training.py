@@ -454,6 +454,128 @@ class GANInstructor:
             self._flat_g.step += 1
         return st["out"]
 
+    # ---- generator pre-training step (src/training.py:53-95) -------------------------------
+    @torch.no_grad()
+    def pretrain_step(self, captions, pooled=None, update=True):
+        """Free-running greedy decode (sample(pretrain=True), :71) -> CrossEntropyLoss over all positions incl. PAD
+        (:81-83) -> optimize(pretrain_opt, loss, gen) (:86): clip 5.0 + Adam(lr = pretrain_lr) with its own moments."""
+        _lib.require_cuda()
+        lib = _lib.lib()
+        a, dev = self.args, self.device
+        mode = gic_b200.get_gemm_mode()
+        self._ensure_flat()
+        fg = self._flat_g
+        dec = self.gen.decoder
+        captions = captions.to(dev).long().contiguous()
+        B, L = captions.shape
+        V, E, H, layers = a.vocab_size, a.gen_embed_dim, a.gen_hidden_dim, a.gen_num_layers
+        stream = _lib.stream()
+        P = _lib.ptr
+        if self.cgan:
+            enc = self.gen.encoder
+            pooled = pooled.to(dev).float().contiguous()
+            Fin = pooled.shape[1]
+            lin, mean, rstd = self._buf("enc_lin", B * E).view(B, E), self._buf("enc_mean", E), self._buf("enc_rstd", E)
+            feats = self._buf("feats", B * E).view(B, E)
+            _lib.check(lib.gic_encoder_fwd(mode, P(pooled), B, Fin, E, P(enc.linear.weight), P(enc.linear.bias),
+                                           P(enc.bn.weight), P(enc.bn.bias), enc.bn.eps, P(lin), P(mean), P(rstd),
+                                           P(feats), stream), "gic_encoder_fwd")
+        else:
+            feats = dec.embed.weight[1].expand(B, E).contiguous()
+        logits = self._buf("pg_logits", B * L * V).view(B, L, V)
+        ids = torch.empty(B, L, dtype=torch.int64, device=dev)
+        dsaved = self._buf("dec_saved", lib.gic_decode_saved_floats(B, L, E, H, layers))
+        dws = self._buf("dec_ws", lib.gic_decode_fwd_workspace_floats(B, V, H))
+        lp = dec.lstm_params()
+        W_ih, W_hh, b_ih, b_hh = lp[0::4], lp[1::4], lp[2::4], lp[3::4]
+        _lib.check(lib.gic_decode_sample_fwd(mode, P(feats), P(dec.embed.weight), _lib.ptr_array(W_ih),
+                                             _lib.ptr_array(W_hh), _lib.ptr_array(b_ih), _lib.ptr_array(b_hh),
+                                             P(dec.linear.weight), P(dec.linear.bias), None, 1.0, 1, None, B, L, V, E, H,
+                                             layers, P(logits), P(ids), P(dsaved), P(dws), stream), "gic_decode_sample_fwd")
+        loss = torch.empty(1, device=dev)
+        dlogits = self._buf("pg_dlogits", B * L * V).view(B, L, V)
+        _lib.check(lib.gic_ce_loss_fwd_bwd(P(logits), P(captions), B, L, V, P(loss), P(dlogits), stream), "gic_ce_loss_fwd_bwd")
+        gg = fg.g
+        fg.grad.zero_()
+        gws = self._buf("dec_bws", lib.gic_decode_bwd_workspace_floats(B, L, V, E, H, layers))
+        dfeat = self._buf("dfeat", B * E).view(B, E)
+        _lib.check(lib.gic_decode_sample_bwd(
+            mode, P(dlogits), None, P(ids), P(dec.embed.weight), _lib.ptr_array(W_ih), _lib.ptr_array(W_hh),
+            P(dec.linear.weight), 1.0, 1, B, L, V, E, H, layers, P(dsaved), P(gws), P(gg(dec.embed.weight)),
+            _lib.ptr_array([gg(w) for w in W_ih]), _lib.ptr_array([gg(w) for w in W_hh]),
+            _lib.ptr_array([gg(w) for w in b_ih]), _lib.ptr_array([gg(w) for w in b_hh]), P(gg(dec.linear.weight)),
+            P(gg(dec.linear.bias)), P(dfeat), 0, stream), "gic_decode_sample_bwd")
+        if self.cgan:
+            enc = self.gen.encoder
+            _lib.check(lib.gic_encoder_bwd(mode, P(dfeat), P(pooled), P(lin), P(mean), P(rstd), P(enc.linear.weight),
+                                           P(enc.bn.weight), B, pooled.shape[1], E, P(self._buf("enc_dlin", B * E)),
+                                           P(gg(enc.linear.weight)), P(gg(enc.linear.bias)), P(gg(enc.bn.weight)),
+                                           P(gg(enc.bn.bias)), 0, stream), "gic_encoder_bwd")
+        else:
+            gg(dec.embed.weight)[1] += dfeat.sum(0)
+        parallel.allreduce_sum_(fg.grad)
+        # pretrain_opt is its own Adam instance in the reference (:24-26): separate moments and step count
+        if not hasattr(fg, "m_pre"):
+            fg.m_pre, fg.v_pre, fg.step_pre = torch.zeros_like(fg.m), torch.zeros_like(fg.v), 0
+        sq = torch.zeros(1, device=dev)
+        _lib.check(lib.gic_grad_sqnorm(P(fg.grad), fg.n, P(sq), stream), "gic_grad_sqnorm")
+        if update:
+            fg.step_pre += 1
+            _lib.check(lib.gic_clip_adam(P(fg.flat), P(fg.grad), P(fg.m_pre), P(fg.v_pre), fg.n, P(sq),
+                                         float(a.clip_norm), 1.0 / self.world, fg.step_pre, float(a.pretrain_lr), 0.9,
+                                         0.999, 1e-8, stream), "gic_clip_adam")
+        self.pretrain_steps += 1
+        return dict(loss=loss[0], ids=ids, logits=logits, sqnorm=sq)
+
+    # ---- discriminator step on hard captions (real vs generated ids): D pre-training sweep (BASELINE configs[4]) and
+    #      the D half of the policy-gradient step.  F.one_hot is never materialised (column gather, src/training.py:158).
+    @torch.no_grad()
+    def disc_step(self, real_ids, fake_ids, keep=None, update=True):
+        _lib.require_cuda()
+        lib = _lib.lib()
+        a, dev = self.args, self.device
+        mode = gic_b200.get_gemm_mode()
+        self._ensure_flat()
+        fd, disc = self._flat_d, self.disc
+        real_ids = real_ids.to(dev).long().contiguous()
+        fake_ids = fake_ids.to(dev).long().contiguous()
+        B, L = real_ids.shape
+        V, De, R, Fd = a.vocab_size, a.disc_embed_dim, a.disc_num_rep, sum(a.disc_num_filters)
+        fsz, nfl = list(a.disc_filter_sizes), list(a.disc_num_filters)
+        stream = _lib.stream()
+        P = _lib.ptr
+        cw = [c.weight for c in disc.convs]
+        cb = [c.bias for c in disc.convs]
+        dW = (disc.embeddings.weight, cw, cb, disc.highway.weight, disc.highway.bias, disc.feature2out.weight,
+              disc.feature2out.bias, disc.out2logits.weight, disc.out2logits.bias)
+        drop_p = disc.dropout.p
+        if keep is None:
+            keep = torch.rand(2, B * R, Fd, device=dev) >= drop_p
+        keep = keep.to(dev).to(torch.uint8).contiguous()
+        (d_real,), saved_r = disc_fwd_raw(lib, mode, None, real_ids, B, L, V, De, R, fsz, nfl, *dW, [keep[0]], drop_p, dev)
+        (d_fake,), saved_f = disc_fwd_raw(lib, mode, None, fake_ids, B, L, V, De, R, fsz, nfl, *dW, [keep[1]], drop_p, dev)
+        nn_ = B * R
+        losses = torch.empty(2, device=dev)
+        seeds = self._buf("seeds", 3 * nn_).view(3, nn_)
+        _lib.check(lib.gic_gan_loss_fwd_bwd(_lib.LOSS_TYPES["standard"], P(d_real), P(d_fake), P(d_fake), nn_, P(losses),
+                                            P(seeds[0]), P(seeds[1]), P(seeds[2]), stream), "gic_gan_loss_fwd_bwd")
+        bws = self._buf("disc_bws", lib.gic_disc_bwd_workspace_floats(B, L, De, R, Fd))
+        g = fd.g
+        dcw, dcb = [g(c.weight) for c in disc.convs], [g(c.bias) for c in disc.convs]
+        for seed, kp, idz, saved, acc in ((seeds[0], keep[0], real_ids, saved_r, 0), (seeds[1], keep[1], fake_ids, saved_f, 1)):
+            _lib.check(lib.gic_disc_bwd(mode, P(seed), P(kp), drop_p, None, P(idz), B, L, V, De, R, len(fsz),
+                                        _lib.int_array(fsz), _lib.int_array(nfl), P(disc.embeddings.weight),
+                                        _lib.ptr_array(cw), _lib.ptr_array(cb), P(disc.highway.weight),
+                                        P(disc.feature2out.weight), P(disc.feature2out.bias),
+                                        disc.feature2out.weight.shape[0], P(disc.out2logits.weight),
+                                        P(disc.out2logits.bias), P(saved), P(bws), P(g(disc.embeddings.weight)),
+                                        _lib.ptr_array(dcw), _lib.ptr_array(dcb), P(g(disc.highway.weight)),
+                                        P(g(disc.highway.bias)), P(g(disc.feature2out.weight)),
+                                        P(g(disc.feature2out.bias)), P(g(disc.out2logits.weight)),
+                                        P(g(disc.out2logits.bias)), None, 1, acc, stream), "gic_disc_bwd")
+        parallel.allreduce_sum_(fd.grad)
+        return dict(d_loss=losses[1], d_real=d_real, d_fake=d_fake, d_sqnorm=self._clip_adam(fd, a.disc_lr, update, 1))
+
     # ---- EXTENSION: SeqGAN-style policy-gradient step (north-star stages 2-4; not in the reference) -------------
     @torch.no_grad()
     def pg_step(self, captions, pooled=None, u=None, u_roll=None, keep=None, n_roll=16, baseline_mode=1, update=True,
@@ -549,36 +671,8 @@ class GANInstructor:
             parallel.allreduce_sum_(fg.grad)
         out["g_sqnorm"] = self._clip_adam(fg, a.gen_lr, update, 3)
         if d_update:
-            # -- discriminator step on hard captions: real vs sampled ('standard' BCE), two dropout masks
-            if keep is None:
-                keep = torch.rand(2, B * R, Fd, device=dev) >= drop_p
-            keep = keep.to(dev).to(torch.uint8).contiguous()
-            (d_real,), saved_r = disc_fwd_raw(lib, mode, None, captions, B, L, V, De, R, fsz, nfl, *dW, [keep[0]], drop_p, dev)
-            (d_fake,), saved_f = disc_fwd_raw(lib, mode, None, ids, B, L, V, De, R, fsz, nfl, *dW, [keep[1]], drop_p, dev)
-            nn_ = B * R
-            losses = torch.empty(2, device=dev)
-            seeds = self._buf("seeds", 3 * nn_).view(3, nn_)
-            _lib.check(lib.gic_gan_loss_fwd_bwd(_lib.LOSS_TYPES["standard"], P(d_real), P(d_fake), P(d_fake), nn_,
-                                                P(losses), P(seeds[0]), P(seeds[1]), P(seeds[2]), stream),
-                       "gic_gan_loss_fwd_bwd")
-            bws = self._buf("disc_bws", lib.gic_disc_bwd_workspace_floats(B, L, De, R, Fd))
-            g = fd.g
-            dcw, dcb = [g(c.weight) for c in disc.convs], [g(c.bias) for c in disc.convs]
-            for seed, kp, idz, saved, acc in ((seeds[0], keep[0], captions, saved_r, 0), (seeds[1], keep[1], ids, saved_f, 1)):
-                _lib.check(lib.gic_disc_bwd(mode, P(seed), P(kp), drop_p, None, P(idz), B, L, V, De, R, len(fsz),
-                                            _lib.int_array(fsz), _lib.int_array(nfl), P(disc.embeddings.weight),
-                                            _lib.ptr_array(cw), _lib.ptr_array(cb), P(disc.highway.weight),
-                                            P(disc.feature2out.weight), P(disc.feature2out.bias),
-                                            disc.feature2out.weight.shape[0], P(disc.out2logits.weight),
-                                            P(disc.out2logits.bias), P(saved), P(bws), P(g(disc.embeddings.weight)),
-                                            _lib.ptr_array(dcw), _lib.ptr_array(dcb), P(g(disc.highway.weight)),
-                                            P(g(disc.highway.bias)), P(g(disc.feature2out.weight)),
-                                            P(g(disc.feature2out.bias)), P(g(disc.out2logits.weight)),
-                                            P(g(disc.out2logits.bias)), None, 1, acc, stream), "gic_disc_bwd")
-            if self.world > 1:
-                parallel.allreduce_sum_(fd.grad)
-            out["d_loss"] = losses[1]
-            out["d_sqnorm"] = self._clip_adam(fd, a.disc_lr, update, 1)
+            d = self.disc_step(captions, ids, keep=keep, update=update)
+            out["d_loss"], out["d_sqnorm"] = d["d_loss"], d["d_sqnorm"]
         return out
 
     def adv_loop(self, what, batches, total_batches=None, graph=False):

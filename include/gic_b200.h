@@ -62,8 +62,10 @@ unsigned long long gic_launch_count(void);
 /* Optional per-kernel-class device timing for bench.py's roofline: between gic_prof_begin() and gic_prof_end()
  * every launch of a profiled class is bracketed by CUDA events on its own stream.  gic_prof_end (call after the
  * stream is synchronised) fills ms[k], work[k] (algorithmic flops for k=0 GEMM, bytes otherwise) and calls[k] for
- * the GIC_PROF_KINDS classes: 0 GEMM, 1 sample step, 2 conv+pool fwd, 3 softmax bwd, 4 clip+Adam, 5 head fwd. */
-#define GIC_PROF_KINDS 6
+ * the GIC_PROF_KINDS classes: 0 GEMM (all other contractions), 1 sample step, 2 conv+pool fwd, 3 softmax bwd, 4 clip+Adam,
+ * 5 head fwd, 6 the discriminator's [N*R, F] x [F, F] contractions (highway forward, dx, dW_h: the FLOP-dominant kernel),
+ * 7 decode-step contractions (fused LSTM step, vocab projection). */
+#define GIC_PROF_KINDS 8
 void gic_prof_begin(void);
 void gic_prof_end(double* ms, double* work, unsigned long long* calls);
 
@@ -174,6 +176,12 @@ int gic_gan_loss_fwd_bwd(int loss_type, const float* d_out_real, const float* d_
 int gic_grad_sqnorm(const float* g, size_t n, float* sqnorm, gic_stream_t stream);
 int gic_clip_adam(float* p, const float* g, float* m, float* v, size_t n, const float* sqnorm, float max_norm,
                   float grad_scale, int step, float lr, float beta1, float beta2, float eps, gic_stream_t stream);
+
+/* ---- generator pre-training loss (src/training.py:81-83): nn.CrossEntropyLoss() over ALL B*L positions, PAD
+ * included (no ignore_index), of the raw logits Decoder.sample(pretrain=True) returns, with its
+ * backward seed dlogits = (softmax(logits) - onehot(target)) / (B L).  Feed dlogits to gic_decode_sample_bwd(pretrain=1). */
+int gic_ce_loss_fwd_bwd(const float* logits /*[B,L,V]*/, const int64_t* targets /*[B,L]*/, int B, int L, int V,
+                        float* loss /*[1]*/, float* dlogits /*[B,L,V] or NULL*/, gic_stream_t stream);
 
 /* ==== EXTENSIONS beyond the reference (north-star stages 2-4).  The reference has no
  * rollouts, no inverse-CDF sampler and no policy-gradient loss: these entry points are defined by

@@ -8,7 +8,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start o
     --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launch_$TAG.log 2>&1
 for pat in "lstm_step|sample_step" "conv_pool|head_fwd|head_bwd|softmax_bwd|clip_adam" "gemm_p_kernel|gemm_tf32_kernel"; do
   name=$(echo "$pat" | tr -c 'a-zA-Z0-9' '_' | cut -c1-24)
-  ncu --set full --clock-control none --import-source on --profile-from-start off -k "regex:$pat" -c 24 \
+  ncu --set full --clock-control none --import-source on --profile-from-start off -k "regex:$pat" -c 9 \
       -f -o gpurun_out/prof_${TAG}_$name $CMD > gpurun_out/ncu_full_${TAG}_$name.log 2>&1
 done
 ls -la gpurun_out/*.ncu-rep

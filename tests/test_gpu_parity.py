@@ -580,3 +580,37 @@ def test_graph_replay_matches_eager_steps():
         close(f"graph/disc/{k}", pg, pe.detach().cpu(), rtol=1e-5, atol=len(temps) * ADAM_ATOL)   # atomics order differs run to run
     for (k, pe), (_, pg) in zip(eager.gen.named_parameters(), graphed.gen.named_parameters()):
         close(f"graph/gen/{k}", pg, pe.detach().cpu(), rtol=1e-5, atol=len(temps) * ADAM_ATOL)
+
+
+@pytest.mark.parametrize("cfg_name", ["c0", "c1"])
+def test_pretrain_step_vs_oracle(cfg_name):
+    """Generator pre-training step (src/training.py:53-95): free-running greedy decode, CrossEntropyLoss over all
+    positions (PAD included), gradients of every generator parameter vs autograd on the oracle."""
+    import torch.nn.functional as F
+    from gic_b200.training import GANInstructor
+    inp = rp.make_inputs(rp.CONFIGS[cfg_name])
+    a = inp["args"]
+    gp = {k: v.clone().requires_grad_(True) for k, v in inp["gen"].items()}
+    B, L = inp["captions"].shape
+    feats = rp.encoder_project(gp, inp["pooled"]) if a.conditional_gan else rp.start_features(gp, B)
+    logits, ids, _ = rp.decoder_sample(gp, feats, None, 1.0, L, layers=a.gen_num_layers, pretrain=True)
+    loss = F.cross_entropy(logits.reshape(-1, logits.shape[-1]), inp["captions"].reshape(-1))      # :81-83
+    names = [k for k in gp]
+    grads = torch.autograd.grad(loss, [gp[k] for k in names], allow_unused=True)
+    a.device = "cuda"
+    inst = GANInstructor(a, device="cuda:0")
+    sd = inst.gen.state_dict(); sd.update({k: v.clone() for k, v in inp["gen"].items()}); inst.gen.load_state_dict(sd)
+    inst.gen.train()
+    out = inst.pretrain_step(inp["captions"], pooled=inp["pooled"], update=False)
+    torch.cuda.synchronize()
+    assert torch.equal(out["ids"].cpu(), ids)
+    close(f"pretrain/{cfg_name}/loss", out["loss"], loss.detach())
+    close(f"pretrain/{cfg_name}/logits", out["logits"], logits.detach())
+    fg = inst._flat_g
+    ref = {k: g for k, g in zip(names, grads) if g is not None}
+    for k, p in inst.gen.named_parameters():
+        if k in ref:
+            close(f"pretrain/{cfg_name}/grad/{k}", fg.g(p), ref[k], **GRAD)
+    w0 = inst.gen.decoder.linear.weight.detach().clone()
+    inst.pretrain_step(inp["captions"], pooled=inp["pooled"])
+    assert not torch.equal(w0, inst.gen.decoder.linear.weight.detach())
