@@ -42,8 +42,9 @@ WORKLOADS = {
     # BASELINE.json configs[4]: discriminator-only step, 4096 real + 4096 fake captions of length 32 (--workload c5)
     "c5": dict(B=4096, L=32, V=10000, E=512, H=512, layers=1, feat=0, filters=[300, 300, 300]),
 }
-MODES = {"fp32": 0, "tf32": 1, "tf32x3": 2}
-DTYPE_NAME = {"fp32": "f32", "tf32": "tf32 (fp32 accumulate)", "tf32x3": "f32 (3xTF32 tensor-core split, fp32 accumulate)"}
+MODES = {"fp32": 0, "tf32": 1, "tf32x3": 2, "bf16": 3}
+DTYPE_NAME = {"fp32": "f32", "tf32": "tf32 (fp32 accumulate)", "tf32x3": "f32 (3xTF32 tensor-core split, fp32 accumulate)",
+              "bf16": "bf16 operands on the discriminator's highway/dx/dW_h contractions, tf32 on the others (fp32 accumulate)"}
 
 
 def load_peaks():
@@ -308,10 +309,11 @@ def run_ours(args):
         flops_launch = g["work_per_step"] / g["calls_per_step"]
         us_launch = g["ms_per_step"] * 1e3 / g["calls_per_step"]
         ach = flops_launch / (us_launch * 1e-6) / 1e12
-        roofline = {"kernel": ("gemm_p_kernel (tcgen05 kind::tf32, persistent): discriminator highway / dx / dW_h, "
+        roofline = {"kernel": (f"gemm_p_kernel (tcgen05 kind::{'f16 bf16 operands' if args.mode == 'bf16' else 'tf32'}, persistent): discriminator highway / dx / dW_h, "
                                f"{B * R}x{Fd}x{Fd}") if args.mode != "fp32" else "sgemm_kernel (fp32 FFMA)",
                     "bound": "tensor", "achieved": ach, "peak": peaks["tf"], "unit": "TFLOP/s", "frac": ach / peaks["tf"],
-                    "traffic": traffic, "peak_source": peaks["src"] + ", sustained bf16 dense (TF32 runs at half that rate)",
+                    "traffic": traffic if args.mode == "tf32" else None,
+                    "peak_source": peaks["src"] + ", sustained bf16 dense (TF32 runs at half that rate)",
                     "share_of_step": g["ms_per_step"] / ms_step, "launches_per_step": g["calls_per_step"],
                     "algorithmic_flops_per_launch": flops_launch, "us_per_launch": us_launch}
     tensor_classes = {}

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libgic_b200.so")
 HEADER = os.path.join(os.path.dirname(HERE), "include", "gic_b200.h")
 
-GEMM_FP32, GEMM_TF32, GEMM_TF32X3 = 0, 1, 2
+GEMM_FP32, GEMM_TF32, GEMM_TF32X3, GEMM_BF16 = 0, 1, 2, 3
 LOSS_TYPES = {"standard": 0, "JS": 1, "KL": 2, "hinge": 3, "tv": 4, "rsgan": 5}
 
 _lib = None
@@ -69,6 +69,7 @@ def _declare(L):
     L.gic_prof_end.restype = None
     L.gic_prof_end.argtypes = [P, P, P]
     L.gic_gemm.argtypes = [I, I, I, I, I, I, F, P, I, P, I, F, P, I, P, P]
+    L.gic_gemm_bf16.argtypes = [I, I, I, I, I, F, P, I, P, I, F, P, I, P, P]
     L.gic_encoder_fwd.argtypes = [I, P, I, I, I, P, P, P, P, F, P, P, P, P, P]
     L.gic_encoder_bwd.argtypes = [I, P, P, P, P, P, P, P, I, I, I, P, P, P, P, P, I, P]
     L.gic_sample_step.argtypes = [I, P, P, F, I, I, I, I, P, P, P, P, I, P, P]

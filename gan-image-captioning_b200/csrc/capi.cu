@@ -148,7 +148,7 @@ static int decode_fwd(int mode, const float* features, const float* W_emb, const
       float* h_new = saved + sv.hs(l) + (size_t)(t + 1) * BH;
       float* htop = (l == layers - 1) ? saved + sv.htop : nullptr;
       bool fused = false;
-      if (mode == GEMM_TF32)   // tensor-core mode: both contractions + the cell update in one tcgen05 kernel
+      if (mode == GEMM_TF32 || mode == GEMM_BF16)   // tensor-core modes: both contractions + the cell update in one tcgen05 kernel
         GIC_TRY(lstm_step_tc(xin, In, hprev, W_ih[l], W_hh[l], b_ih[l], b_hh[l], c_prev, B, H, acts_t, c_new, h_new,
                              htop, L, t, s, &fused));
       if (!fused) {
@@ -165,7 +165,7 @@ static int decode_fwd(int mode, const float* features, const float* W_emb, const
       GIC_TRY(sample_cdf_step(logits, u + (size_t)t * B, B, V, L, t, L, out, ids, logp, forced, W_emb, E, x_next, s));
     else
       GIC_TRY(sample_step(pretrain != 0, logits, pretrain ? nullptr : u + (size_t)t * B * V, T, B, V, L, t, out, ids,
-                          forced, W_emb, E, x_next, s, /*fast_math=*/mode == GEMM_TF32));
+                            forced, W_emb, E, x_next, s, /*fast_math=*/mode == GEMM_TF32 || mode == GEMM_BF16));
   }
   return GIC_OK;
 }
@@ -349,7 +349,7 @@ static int decode_rollouts(int mode, const float* saved, const int64_t* main_ids
     const int M = (int)((size_t)t * G);                       // live rows
     float* hn = hbuf[cur ^ 1];
     bool fused = false;
-    if (mode == GEMM_TF32)
+    if (mode == GEMM_TF32 || mode == GEMM_BF16)
       GIC_TRY(lstm_step_tc(x, E, hbuf[cur], W_ih, W_hh, b_ih, b_hh, c, M, H, nullptr, c, hn, nullptr, L, t, s, &fused));
     if (!fused) {
       float* gates = ws + w.gates;
@@ -400,6 +400,12 @@ int gic_gemm(int mode, int transA, int transB, int M, int N, int K, float alpha,
              const float* B, int ldb, float beta, float* C, int ldc, const float* bias, gic_stream_t stream) {
   GIC_TRY(require_device());
   return gemm(mode, transA != 0, transB != 0, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, S(stream));
+}
+
+int gic_gemm_bf16(int transA, int transB, int M, int N, int K, float alpha, const void* A, int lda, const void* B,
+                  int ldb, float beta, float* C, int ldc, const float* bias, gic_stream_t stream) {
+  GIC_TRY(require_device());
+  return gemm_bf16(transA != 0, transB != 0, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, S(stream));
 }
 
 int gic_encoder_fwd(int mode, const float* pooled, int B, int Fin, int E, const float* W, const float* b,
@@ -525,7 +531,9 @@ int gic_decode_sample_bwd_factored(int mode, const float* demb, const float* emb
 size_t gic_disc_bwd_demb_offset_floats(int N, int L, int De, int R, int F) {
   (void)L; (void)De;
   const size_t rows = (size_t)N * R;
-  return a4((size_t)F + 1) + 2 * a4(rows * F) + 2 * a4(F);
+  const size_t Fp = (size_t)((F + 63) / 64) * 64;
+  const size_t dh = a4(rows * F) > a4(rows * Fp / 2) ? a4(rows * F) : a4(rows * Fp / 2);
+  return a4((size_t)F + 1) + dh + a4(rows * F) + 2 * a4(F);
 }
 
 int gic_decode_sample_cdf_fwd(int mode, const float* features, const float* W_emb, const float* const* W_ih,

@@ -8,6 +8,13 @@ namespace gic {
 
 constexpr int MAX_GROUPS = 8;
 
+// fp32 -> bf16, round to nearest even (finite inputs)
+__device__ __forceinline__ unsigned short f2bf(float x) {
+  unsigned int u = __float_as_uint(x);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (unsigned short)(u >> 16);
+}
+
 struct ConvGroups {
   const float* w[MAX_GROUPS];   // [n, 1, f, es] contiguous == [n][f*es]
   const float* b[MAX_GROUPS];   // [n]
@@ -103,7 +110,8 @@ __device__ __forceinline__ void conv_item_es1(const float* emb_s, const float* w
 template <bool ES1>
 __global__ void __launch_bounds__(256)
 conv_pool_fwd_kernel(const float* __restrict__ emb, int L, int De, int R, int es, ConvGroups g, int cs,
-                     float* __restrict__ pooled, uint8_t* __restrict__ arg) {
+                     float* __restrict__ pooled, uint8_t* __restrict__ arg, unsigned short* __restrict__ pooled_bf,
+                     int Fp) {
   extern __shared__ __align__(16) float sm[];
   const int F = g.F, kmax = g.kmax;
   const int c_lo = blockIdx.y * cs, c_hi = min(F, c_lo + cs), CW = c_hi - c_lo;
@@ -145,6 +153,10 @@ conv_pool_fwd_kernel(const float* __restrict__ emb, int L, int De, int R, int es
       pooled[(row + 1) * F + c] = best.y; arg[(row + 1) * F + c] = (uint8_t)a[1];
       pooled[(row + 2) * F + c] = best.z; arg[(row + 2) * F + c] = (uint8_t)a[2];
       pooled[(row + 3) * F + c] = best.w; arg[(row + 3) * F + c] = (uint8_t)a[3];
+      if (pooled_bf) {           // bf16 copy (pitch Fp) for the tensor-core contractions of GIC_GEMM_BF16
+        pooled_bf[(row + 0) * Fp + c] = f2bf(best.x); pooled_bf[(row + 1) * Fp + c] = f2bf(best.y);
+        pooled_bf[(row + 2) * Fp + c] = f2bf(best.z); pooled_bf[(row + 3) * Fp + c] = f2bf(best.w);
+      }
     }
   } else {
     for (int item = threadIdx.x; item < CW * R; item += blockDim.x) {
@@ -163,6 +175,7 @@ conv_pool_fwd_kernel(const float* __restrict__ emb, int L, int De, int R, int es
       if (!(best > 0.f)) { best = 0.f; a = ARG_DEAD; }
       pooled[((size_t)n * R + r) * F + c] = best;
       arg[((size_t)n * R + r) * F + c] = (uint8_t)a;
+      if (pooled_bf) pooled_bf[((size_t)n * R + r) * Fp + c] = f2bf(best);
     }
   }
 }
@@ -186,8 +199,8 @@ constexpr int BWD_KMAX = 8;      // f * es <= 8 on the register path
 // VEC requires F % 4 == 0 and every filter group a multiple of 4 columns wide (a float4 never straddles groups).
 template <bool ES1, bool VEC>
 __global__ void __launch_bounds__(256)
-conv_pool_bwd_demb_kernel(const uint8_t* __restrict__ arg, const float* __restrict__ dx, int rows /*N*R*/, int L,
-                          int De, int R, int es, ConvGroups g, float* __restrict__ demb) {
+conv_pool_bwd_demb_kernel(const uint8_t* __restrict__ arg, const float* __restrict__ dx, const float* __restrict__ dx2,
+                          int rows /*N*R*/, int L, int De, int R, int es, ConvGroups g, float* __restrict__ demb) {
   extern __shared__ __align__(16) float sm[];
   const int F = g.F, kmax = g.kmax;
   const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -211,17 +224,21 @@ conv_pool_bwd_demb_kernel(const uint8_t* __restrict__ arg, const float* __restri
     if (VEC) {
       const int F4 = F >> 2;
       const float4* dx4 = reinterpret_cast<const float4*>(dx + base);
+      const float4* dy4 = reinterpret_cast<const float4*>(dx2 + base);
       const uint32_t* a4 = reinterpret_cast<const uint32_t*>(arg + base);
       for (int q0 = 0; q0 < F4; q0 += 128) {   // 4 float4 groups per lane in flight
-        float4 gv[4];
+        float4 gv[4], hv[4];
         uint32_t av[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int q = q0 + j * 32 + lane;
           const bool ok = q < F4;
           gv[j] = ok ? dx4[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+          hv[j] = ok ? dy4[q] : make_float4(0.f, 0.f, 0.f, 0.f);
           av[j] = ok ? __ldg(a4 + q) : 0xffffffffu;
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { gv[j].x += hv[j].x; gv[j].y += hv[j].y; gv[j].z += hv[j].z; gv[j].w += hv[j].w; }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int q = q0 + j * 32 + lane;
@@ -256,7 +273,7 @@ conv_pool_bwd_demb_kernel(const uint8_t* __restrict__ arg, const float* __restri
         for (int j = 0; j < 4; ++j) {
           const int c = c0 + j * 32 + lane;
           const bool ok = c < F;
-          gv[j] = ok ? dx[base + c] : 0.f;
+          gv[j] = ok ? dx[base + c] + dx2[base + c] : 0.f;
           av[j] = ok ? (int)arg[base + c] : ARG_DEAD;
         }
 #pragma unroll
@@ -293,7 +310,8 @@ constexpr int DW_RC = 8;
 template <bool ES1>
 __global__ void __launch_bounds__(256)
 conv_pool_bwd_dw_kernel(const float* __restrict__ emb, const uint8_t* __restrict__ arg, const float* __restrict__ dx,
-                        int rows, int L, int De, int R, int es, ConvGroups g, int rows_per_cta) {
+                        const float* __restrict__ dx2, int rows, int L, int De, int R, int es, ConvGroups g,
+                        int rows_per_cta) {
   extern __shared__ __align__(16) float sm[];   // [DW_RC][L*es]
   const int F = g.F, LE = L * es;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -322,7 +340,7 @@ conv_pool_bwd_dw_kernel(const float* __restrict__ emb, const uint8_t* __restrict
       const int row = rb + j;
       const bool ok = active && row < r1;
       const size_t i = (size_t)row * F + c;
-      gv[j] = ok ? dx[i] : 0.f;
+      gv[j] = ok ? dx[i] + dx2[i] : 0.f;
       av[j] = ok ? (int)arg[i] : ARG_DEAD;
     }
     __syncthreads();
@@ -465,11 +483,13 @@ head_fwd_vec_kernel(const float* __restrict__ hpre, const float* __restrict__ po
 
 // float4 variant of head_bwd_kernel (F % 4 == 0): thread = 4 consecutive feature columns, CTA = row chunk, 4 rows of
 // loads in flight per thread.
+// DH_BF16: dh is written as bf16 with row pitch Fp (it is only read by tensor-core contractions in GIC_GEMM_BF16 mode)
+template <bool DH_BF16>
 __global__ void __launch_bounds__(256)
 head_bwd_vec_kernel(const float* __restrict__ dlogit, const uint8_t* __restrict__ keep, float drop_scale,
                     const float* __restrict__ hpre, const float* __restrict__ pooled, int rows, int F,
                     const float* __restrict__ weff, int rows_per_cta, float* __restrict__ dh,
-                    float* __restrict__ dx, float* __restrict__ s_acc, float* __restrict__ dbh_acc) {
+                    float* __restrict__ dx, float* __restrict__ s_acc, float* __restrict__ dbh_acc, int Fp) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;      // float4 column group
   const int F4 = F >> 2;
   if (q >= F4) return;
@@ -514,7 +534,14 @@ head_bwd_vec_kernel(const float* __restrict__ dlogit, const uint8_t* __restrict_
         sb[e] += dhv[e];
       }
       const size_t i = (size_t)r * F4 + q;
-      reinterpret_cast<float4*>(dh)[i] = make_float4(dhv[0], dhv[1], dhv[2], dhv[3]);
+      if (DH_BF16) {
+        uint2 pk;
+        pk.x = (unsigned int)f2bf(dhv[0]) | ((unsigned int)f2bf(dhv[1]) << 16);
+        pk.y = (unsigned int)f2bf(dhv[2]) | ((unsigned int)f2bf(dhv[3]) << 16);
+        *reinterpret_cast<uint2*>(reinterpret_cast<unsigned short*>(dh) + (size_t)r * Fp + 4 * q) = pk;
+      } else {
+        reinterpret_cast<float4*>(dh)[i] = make_float4(dhv[0], dhv[1], dhv[2], dhv[3]);
+      }
       reinterpret_cast<float4*>(dx)[i] = make_float4(dxv[0], dxv[1], dxv[2], dxv[3]);
     }
   }
@@ -617,16 +644,25 @@ struct DiscDims {
 static size_t align4(size_t x) { return (x + 3) & ~(size_t)3; }
 
 // saved-for-backward layout (floats): emb[N*L*De] | pooled[N*R*F] | hpre[N*R*F] | arg(u8)[N*R*F]
+// pitch (elements) of the bf16 copies used by GIC_GEMM_BF16: rows of 128-byte multiples (TMA fetches whole lines)
+static inline int bf_pitch(int F) { return ((F + 63) / 64) * 64; }
+
+// saved-for-backward layout (floats): emb[N*L*De] | pooled[N*R*F] | hpre[N*R*F] | arg(u8)[N*R*F] | pooled_bf(bf16)[N*R*Fp]
 size_t disc_saved_floats(int N, int L, int De, int R, int F) {
   const size_t rows = (size_t)N * R;
-  return align4((size_t)N * L * De) + 2 * align4(rows * F) + align4((rows * F + 3) / 4);
+  return align4((size_t)N * L * De) + 2 * align4(rows * F) + align4((rows * F + 3) / 4) + align4(rows * bf_pitch(F) / 2);
 }
 // forward workspace: weff[F+1]
-size_t disc_fwd_workspace_floats(int F) { return align4((size_t)F + 1); }
+// forward workspace: weff[F+1] | W_h_bf(bf16)[F*Fp]
+size_t disc_fwd_workspace_floats(int F) { return align4((size_t)F + 1) + align4((size_t)F * bf_pitch(F) / 2); }
 // backward workspace: weff[F+1] | dh[rows*F] | dx[rows*F] | s[F] | dbh[F] | demb[N*L*De]
 size_t disc_bwd_workspace_floats(int N, int L, int De, int R, int F) {
   const size_t rows = (size_t)N * R;
-  return align4((size_t)F + 1) + 2 * align4(rows * F) + 2 * align4(F) + align4((size_t)N * L * De);
+  // weff | dh (fp32 [rows,F], or bf16 [rows,Fp] in GIC_GEMM_BF16 mode) | dx | s | dbh | demb | W_h_bf(bf16)[F*Fp]
+  const size_t dh = align4(rows * F) > align4(rows * bf_pitch(F) / 2) ? align4(rows * F) : align4(rows * bf_pitch(F) / 2);
+  // ... | W_h_bf | dxg[rows*F] (dh W_h, written with beta = 0; the consumers add it to the direct term in dx)
+  return align4((size_t)F + 1) + dh + align4(rows * F) + 2 * align4(F) + align4((size_t)N * L * De) +
+         align4((size_t)F * bf_pitch(F) / 2) + align4(rows * F);
 }
 
 int disc_fill_groups(ConvGroups& g, int ngroups, const int* fs, const int* nf, const float* const* cw,
@@ -654,7 +690,11 @@ int disc_forward(int mode, const float* inp_soft, const int64_t* ids, const Disc
   float* pooled = emb + align4((size_t)d.N * d.L * d.De);
   float* hpre = pooled + align4(rows * d.F);
   uint8_t* arg = reinterpret_cast<uint8_t*>(hpre + align4(rows * d.F));
+  const bool bf = (mode == GEMM_BF16) && (d.F % 4 == 0);
+  const int Fp = bf_pitch(d.F);
+  unsigned short* pooled_bf = reinterpret_cast<unsigned short*>(reinterpret_cast<float*>(arg) + align4((rows * d.F + 3) / 4));
   float* weff = ws;
+  unsigned short* W_h_bf = reinterpret_cast<unsigned short*>(ws + align4((size_t)d.F + 1));
   if (d.N == 0) return GIC_OK;
   // 1. embedding
   if (inp_soft) {
@@ -682,12 +722,19 @@ int disc_forward(int mode, const float* inp_soft, const int64_t* ids, const Disc
       cudaFuncSetAttribute(conv_pool_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       attr = true;
     }
-    if (es1) conv_pool_fwd_kernel<true><<<dim3(d.N, slices), 256, smem, s>>>(emb, d.L, d.De, d.R, d.es, g, cs, pooled, arg);
-    else conv_pool_fwd_kernel<false><<<dim3(d.N, slices), 256, smem, s>>>(emb, d.L, d.De, d.R, d.es, g, cs, pooled, arg);
+    unsigned short* pbf = bf ? pooled_bf : nullptr;
+    if (es1) conv_pool_fwd_kernel<true><<<dim3(d.N, slices), 256, smem, s>>>(emb, d.L, d.De, d.R, d.es, g, cs, pooled, arg, pbf, Fp);
+    else conv_pool_fwd_kernel<false><<<dim3(d.N, slices), 256, smem, s>>>(emb, d.L, d.De, d.R, d.es, g, cs, pooled, arg, pbf, Fp);
     GIC_TRY(check_launch("conv_pool_fwd_kernel"));
   }
   // 3. highway pre-activation
-  GIC_TRY(gemm(mode, false, true, (int)rows, d.F, d.F, 1.f, pooled, d.F, W_h, d.F, 0.f, hpre, d.F, b_h, s, PROF_GEMM_D));
+  if (bf) {
+    // bf16 operands: pooled_bf written by the conv kernel, W_h converted here (1.6 MB); fp32 accumulate / output
+    GIC_TRY(f32_to_bf16(W_h, d.F, d.F, d.F, W_h_bf, Fp, s));
+    GIC_TRY(gemm_bf16(false, true, (int)rows, d.F, d.F, 1.f, pooled_bf, Fp, W_h_bf, Fp, 0.f, hpre, d.F, b_h, s, PROF_GEMM_D));
+  } else {
+    GIC_TRY(gemm(mode, false, true, (int)rows, d.F, d.F, 1.f, pooled, d.F, W_h, d.F, 0.f, hpre, d.F, b_h, s, PROF_GEMM_D));
+  }
   // 4. collapsed head
   head_collapse_kernel<<<cdiv(d.F + 1, 256), 256, 0, s>>>(W_f, b_f, W_o, b_o, d.F, d.Hd, weff);
   GIC_TRY(check_launch("head_collapse_kernel"));
@@ -724,12 +771,19 @@ int disc_backward(int mode, const float* dlogit, const uint8_t* keep, float drop
   const float* pooled = emb + align4((size_t)d.N * d.L * d.De);
   const float* hpre = pooled + align4(rows * d.F);
   const uint8_t* arg = reinterpret_cast<const uint8_t*>(hpre + align4(rows * d.F));
+  const bool bf = (mode == GEMM_BF16) && (d.F % 4 == 0) && (!keep || (reinterpret_cast<uintptr_t>(keep) & 3u) == 0);
+  const int Fp = bf_pitch(d.F);
+  const unsigned short* pooled_bf =
+      reinterpret_cast<const unsigned short*>(reinterpret_cast<const float*>(arg) + align4((rows * d.F + 3) / 4));
   float* weff = ws;
   float* dh = weff + align4((size_t)d.F + 1);
-  float* dx = dh + align4(rows * d.F);
+  const size_t dh_floats = align4(rows * d.F) > align4(rows * Fp / 2) ? align4(rows * d.F) : align4(rows * Fp / 2);
+  float* dx = dh + dh_floats;
   float* sacc = dx + align4(rows * d.F);
   float* dbh = sacc + align4(d.F);
   float* demb = dbh + align4(d.F);
+  unsigned short* W_h_bf = reinterpret_cast<unsigned short*>(demb + align4((size_t)d.N * d.L * d.De));
+  float* dxg = reinterpret_cast<float*>(W_h_bf) + align4((size_t)d.F * Fp / 2);
   const float beta = accumulate ? 1.f : 0.f;
 
   head_collapse_kernel<<<cdiv(d.F + 1, 256), 256, 0, s>>>(W_f, b_f, W_o, b_o, d.F, d.Hd, weff);
@@ -741,8 +795,12 @@ int disc_backward(int mode, const float* dlogit, const uint8_t* keep, float drop
     int rpc = cdiv((long long)rows, chunks);
     rpc = (rpc + 3) & ~3;
     chunks = cdiv((long long)rows, rpc);
-    head_bwd_vec_kernel<<<dim3(colb, chunks), 256, 0, s>>>(dlogit, keep, 1.f / (1.f - drop_p), hpre, pooled, (int)rows,
-                                                          d.F, weff, rpc, dh, dx, sacc, dbh);
+    if (bf)
+      head_bwd_vec_kernel<true><<<dim3(colb, chunks), 256, 0, s>>>(dlogit, keep, 1.f / (1.f - drop_p), hpre, pooled,
+                                                                  (int)rows, d.F, weff, rpc, dh, dx, sacc, dbh, Fp);
+    else
+      head_bwd_vec_kernel<false><<<dim3(colb, chunks), 256, 0, s>>>(dlogit, keep, 1.f / (1.f - drop_p), hpre, pooled,
+                                                                   (int)rows, d.F, weff, rpc, dh, dx, sacc, dbh, Fp);
     GIC_TRY(check_launch("head_bwd_vec_kernel"));
   } else {
     const int colb = cdiv(d.F, 256);
@@ -758,10 +816,20 @@ int disc_backward(int mode, const float* dlogit, const uint8_t* keep, float drop
                                                 db_f, dW_o, db_o, db_h);
     GIC_TRY(check_launch("head_param_grads_kernel"));
     // dW_h[F,F] (+)= dh^T [F, rows] * pooled [rows, F]
-    GIC_TRY(gemm(mode, true, false, d.F, d.F, (int)rows, 1.f, dh, d.F, pooled, d.F, beta, dW_h, d.F, nullptr, s, PROF_GEMM_D));
+    if (bf)
+      GIC_TRY(gemm_bf16(true, false, d.F, d.F, (int)rows, 1.f, dh, Fp, pooled_bf, Fp, beta, dW_h, d.F, nullptr, s, PROF_GEMM_D));
+    else
+      GIC_TRY(gemm(mode, true, false, d.F, d.F, (int)rows, 1.f, dh, d.F, pooled, d.F, beta, dW_h, d.F, nullptr, s, PROF_GEMM_D));
   }
-  // dx += dh * W_h        ([rows,F] x [F,F], W_h is [out,in] so this is the non-transposed product)
-  GIC_TRY(gemm(mode, false, false, (int)rows, d.F, d.F, 1.f, dh, d.F, W_h, d.F, 1.f, dx, d.F, nullptr, s, PROF_GEMM_D));
+  // dxg = dh * W_h        ([rows,F] x [F,F], W_h is [out,in] so this is the non-transposed product).  Written with
+  // beta = 0 (TMA-store epilogue); the conv/pool backward kernels read dx + dxg: a beta = 1 epilogue has to pull the C
+  // tile through the LSU and measured 97 us vs 45 us (profiles/README.md).
+  if (bf) {
+    GIC_TRY(f32_to_bf16(W_h, d.F, d.F, d.F, W_h_bf, Fp, s));
+    GIC_TRY(gemm_bf16(false, false, (int)rows, d.F, d.F, 1.f, dh, Fp, W_h_bf, Fp, 0.f, dxg, d.F, nullptr, s, PROF_GEMM_D));
+  } else {
+    GIC_TRY(gemm(mode, false, false, (int)rows, d.F, d.F, 1.f, dh, d.F, W_h, d.F, 0.f, dxg, d.F, nullptr, s, PROF_GEMM_D));
+  }
   // conv / pool backward
   {
     GIC_REQUIRE(g.kmax <= BWD_KMAX, GIC_ERR_SHAPE, "disc bwd: filter_size*emb_dim_single <= %d supported", BWD_KMAX);
@@ -780,7 +848,7 @@ int disc_backward(int mode, const float* dlogit, const uint8_t* keep, float drop
       const size_t smem = fixed + nwarps * per_warp;
       GIC_REQUIRE(smem <= 200 * 1024, GIC_ERR_SHAPE, "disc bwd: L*emb_dim_single too large for shared memory");
       const int grid = min(cdiv((long long)rows, nwarps), 4 * num_sms());
-      bool vec = (d.F % 4 == 0) && aligned16(dx) && ((reinterpret_cast<uintptr_t>(arg) & 3u) == 0);
+      bool vec = (d.F % 4 == 0) && aligned16(dx) && aligned16(dxg) && ((reinterpret_cast<uintptr_t>(arg) & 3u) == 0);
       for (int i = 0; i < g.ngroups; ++i) vec = vec && (g.n[i] % 4 == 0);
       static bool attr = false;
       if (!attr) {
@@ -790,7 +858,7 @@ int disc_backward(int mode, const float* dlogit, const uint8_t* keep, float drop
         cudaFuncSetAttribute(conv_pool_bwd_demb_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr = true;
       }
-#define GIC_DEMB(ES1_, VEC_) conv_pool_bwd_demb_kernel<ES1_, VEC_><<<grid, nwarps * 32, smem, s>>>(arg, dx, (int)rows, d.L, d.De, d.R, d.es, g, demb)
+#define GIC_DEMB(ES1_, VEC_) conv_pool_bwd_demb_kernel<ES1_, VEC_><<<grid, nwarps * 32, smem, s>>>(arg, dx, dxg, (int)rows, d.L, d.De, d.R, d.es, g, demb)
       if (d.es == 1) { if (vec) GIC_DEMB(true, true); else GIC_DEMB(true, false); }
       else { if (vec) GIC_DEMB(false, true); else GIC_DEMB(false, false); }
 #undef GIC_DEMB
@@ -806,9 +874,9 @@ int disc_backward(int mode, const float* dlogit, const uint8_t* keep, float drop
       const size_t smem = (size_t)DW_RC * d.L * d.es * 4;
       GIC_REQUIRE(smem <= 48 * 1024, GIC_ERR_SHAPE, "disc bwd: L*emb_dim_single too large for shared memory");
       if (d.es == 1)
-        conv_pool_bwd_dw_kernel<true><<<dim3(colb, chunks), 256, smem, s>>>(emb, arg, dx, (int)rows, d.L, d.De, d.R, d.es, g, rpc);
+        conv_pool_bwd_dw_kernel<true><<<dim3(colb, chunks), 256, smem, s>>>(emb, arg, dx, dxg, (int)rows, d.L, d.De, d.R, d.es, g, rpc);
       else
-        conv_pool_bwd_dw_kernel<false><<<dim3(colb, chunks), 256, smem, s>>>(emb, arg, dx, (int)rows, d.L, d.De, d.R, d.es, g, rpc);
+        conv_pool_bwd_dw_kernel<false><<<dim3(colb, chunks), 256, smem, s>>>(emb, arg, dx, dxg, (int)rows, d.L, d.De, d.R, d.es, g, rpc);
       GIC_TRY(check_launch("conv_pool_bwd_dw_kernel"));
     }
   }

@@ -57,9 +57,40 @@ int gemm_dz(int mode, int M, int N, int K, const float* demb, int lda, const flo
                             handled);
 }
 
+int gemm_tc_bf16(bool transA, bool transB, int M, int N, int K, float alpha, const void* A, int lda, const void* B,
+                 int ldb, float beta, float* C, int ldc, const float* bias, cudaStream_t stream, bool* handled);
+
+int gemm_bf16(bool transA, bool transB, int M, int N, int K, float alpha, const void* A, int lda, const void* B, int ldb,
+              float beta, float* C, int ldc, const float* bias, cudaStream_t stream, int prof_kind) {
+  ProfScope prof(prof_kind, 2.0 * M * N * K, stream);
+  bool handled = false;
+  GIC_TRY(gemm_tc_bf16(transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, stream, &handled));
+  GIC_REQUIRE(handled, GIC_ERR_UNSUPPORTED, "gemm_bf16: operands must be 16-byte aligned with leading dimensions %% 8 == 0");
+  return GIC_OK;
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, int rows, int cols, int ld_src,
+                                   unsigned short* __restrict__ dst, int ld_dst) {
+  const size_t n = (size_t)rows * cols;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    const float x = src[(size_t)r * ld_src + c];
+    unsigned int u = __float_as_uint(x);
+    u += 0x7fffu + ((u >> 16) & 1u);                 // round to nearest even (inputs are finite)
+    dst[(size_t)r * ld_dst + c] = (unsigned short)(u >> 16);
+  }
+}
+int f32_to_bf16(const float* src, int rows, int cols, int ld_src, void* dst, int ld_dst, cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0) return GIC_OK;
+  const int grid = min(cdiv((long long)rows * cols, 256), 8 * num_sms());
+  f32_to_bf16_kernel<<<grid, 256, 0, stream>>>(src, rows, cols, ld_src, reinterpret_cast<unsigned short*>(dst), ld_dst);
+  return check_launch("f32_to_bf16_kernel");
+}
+
 int gemm(int mode, bool transA, bool transB, int M, int N, int K, float alpha, const float* A, int lda,
          const float* B, int ldb, float beta, float* C, int ldc, const float* bias, cudaStream_t stream, int prof_kind) {
   ProfScope prof(prof_kind, 2.0 * M * N * K, stream);
+  if (mode == GEMM_BF16) mode = GEMM_TF32;      // only the discriminator's big contractions have bf16 operands
   if (mode != GEMM_FP32) {
     bool handled = false;
     int rc = GIC_OK;

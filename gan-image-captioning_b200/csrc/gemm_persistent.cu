@@ -82,7 +82,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
+// DT: 0 = fp32 operands fed as TF32 (k-block = 32 elements), 1 = bf16 operands (k-block = 64 elements); both are 128-byte
+// rows in shared memory, so tile sizes, the ring and the K-major descriptors are identical.
+template <int BN, bool A_MN, bool B_MN, int EPI, int DT = 0>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
               const __grid_constant__ CUtensorMap tmC, int M, int N, int K, int tiles_n, int tiles, int dp_tiles,
@@ -98,7 +100,10 @@ gemm_p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nkb = (K + BK - 1) / BK;
+  constexpr int BKE = DT ? 64 : 32;            // elements per k-block (128 bytes)
+  constexpr int SLAB = DT ? 64 : 32;           // MN elements per 128-byte row of an MN-major slab
+  constexpr int SLAB_BYTES = BKE * 128;        // one slab = BKE k-rows of 128 bytes
+  const int nkb = (K + BKE - 1) / BKE;
   // one segment per CTA (tiles <= grid, no stream-K): a single accumulator is enough
   const bool single = (dp_tiles == tiles) && (tiles <= (int)gridDim.x);
   constexpr uint32_t COLS1 = (BN <= 32) ? 32 : (BN <= 64) ? 64 : (BN <= 128) ? 128 : 256;
@@ -135,16 +140,16 @@ gemm_p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           uint8_t* sa = smem + s * S::STAGE;
           uint8_t* sb = sa + S::A_BYTES;
           mbar_expect_tx(&full[s], S::STAGE);
-          const int k0 = kb * BK;
+          const int k0 = kb * BKE;
           if (A_MN) {
 #pragma unroll
-            for (int j = 0; j < BM / 32; ++j) tma_load_2d(sa + j * (BK * 128), &tmA, &full[s], m0 + 32 * j, k0);
+            for (int j = 0; j < BM / SLAB; ++j) tma_load_2d(sa + j * SLAB_BYTES, &tmA, &full[s], m0 + SLAB * j, k0);
           } else {
             tma_load_2d(sa, &tmA, &full[s], k0, m0);
           }
           if (B_MN) {
 #pragma unroll
-            for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + j * (BK * 128), &tmB, &full[s], n0 + 32 * j, k0);
+            for (int j = 0; j < BN / SLAB; ++j) tma_load_2d(sb + j * SLAB_BYTES, &tmB, &full[s], n0 + SLAB * j, k0);
           } else {
             tma_load_2d(sb, &tmB, &full[s], k0, n0);
           }
@@ -154,7 +159,7 @@ gemm_p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(A_MN ? 1 : 0, B_MN ? 1 : 0, BN);
+      constexpr uint32_t idesc = DT ? make_idesc_bf16(A_MN ? 1 : 0, B_MN ? 1 : 0, BN) : make_idesc(A_MN ? 1 : 0, B_MN ? 1 : 0, BN);
       Sched sch(tiles, tiles_n, nkb, dp_tiles);
       int tile, kb_lo, kb_hi;
       uint32_t it = 0, seg = 0;
@@ -171,10 +176,15 @@ gemm_p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           const uint32_t sa = smem_u32(smem + s * S::STAGE);
           const uint32_t sb = sa + S::A_BYTES;
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t da = A_MN ? make_desc(sa + k * 1024, BK * 128, 512, 1) : make_desc(sa + k * 32, 16, 1024, 2);
-            const uint64_t db = B_MN ? make_desc(sb + k * 1024, BK * 128, 512, 1) : make_desc(sb + k * 32, 16, 1024, 2);
-            umma_tf32(d_tmem, da, db, idesc, (kb > kb_lo || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {          // 4 MMAs of 32 bytes of K per k-block
+            // MN-major: tf32 uses SWIZZLE_128B_BASE32B (atoms of 4 k-rows, 512 B), bf16 plain SWIZZLE_128B (atoms of
+            // 8 k-rows, 1024 B); one MMA consumes 8 resp. 16 k-rows = 1024 resp. 2048 bytes
+            const uint64_t da = A_MN ? (DT ? make_desc(sa + k * 2048, SLAB_BYTES, 1024, 2) : make_desc(sa + k * 1024, SLAB_BYTES, 512, 1))
+                                     : make_desc(sa + k * 32, 16, 1024, 2);
+            const uint64_t db = B_MN ? (DT ? make_desc(sb + k * 2048, SLAB_BYTES, 1024, 2) : make_desc(sb + k * 1024, SLAB_BYTES, 512, 1))
+                                     : make_desc(sb + k * 32, 16, 1024, 2);
+            if (DT) umma_bf16(d_tmem, da, db, idesc, (kb > kb_lo || k > 0) ? 1u : 0u);
+            else umma_tf32(d_tmem, da, db, idesc, (kb > kb_lo || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty[s]);
         }
@@ -353,16 +363,16 @@ gemm_p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
+template <int BN, bool A_MN, bool B_MN, int EPI, int DT = 0>
 static int launch_p(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm, int M, int N, int K, int tiles_n, int tiles,
                     int dp_tiles, int grid, const EpiArgs& ea, cudaStream_t s) {
   using S = PCfg<BN>;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(gemm_p_kernel<BN, A_MN, B_MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    cudaFuncSetAttribute(gemm_p_kernel<BN, A_MN, B_MN, EPI, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
     attr = true;
   }
-  gemm_p_kernel<BN, A_MN, B_MN, EPI><<<grid, NTHREADS, S::TOTAL, s>>>(ta, tb, tcm, M, N, K, tiles_n, tiles, dp_tiles, ea);
+  gemm_p_kernel<BN, A_MN, B_MN, EPI, DT><<<grid, NTHREADS, S::TOTAL, s>>>(ta, tb, tcm, M, N, K, tiles_n, tiles, dp_tiles, ea);
   return check_launch("gemm_p_kernel");
 }
 
@@ -487,6 +497,80 @@ int gemm_tc_persistent(bool transA, bool transB, int M, int N, int K, float alph
     }
   }
 #undef GIC_P
+  if (rc == GIC_OK) *handled = true;
+  return rc;
+}
+
+// bf16 operands (kind::f16), fp32 accumulate and fp32 output: the discriminator's [N*R, F] x [F, F] contractions in
+// GIC_GEMM_BF16 mode.  A / B are bf16 with leading dimensions in elements (multiples of 8); layouts as gemm().
+int gemm_tc_bf16(bool transA, bool transB, int M, int N, int K, float alpha, const void* A, int lda, const void* B,
+                 int ldb, float beta, float* C, int ldc, const float* bias, cudaStream_t stream, bool* handled) {
+  using namespace tc;
+  *handled = false;
+  if (M <= 0 || N <= 0 || K <= 0) return GIC_OK;
+  if (!aligned16(A) || !aligned16(B) || (lda % 8) || (ldb % 8)) return GIC_OK;
+  const bool a_mn = transA, b_mn = !transB;
+  const bool allow_sk = (beta == 0.f || beta == 1.f);
+  const int G = num_sms();
+  // tile width: as choose_bn with 64-element k-blocks; MN-major B needs BN % 64 == 0
+  int BN = 256;
+  {
+    static const int kBN[4] = {64, 128, 192, 256};
+    double best = -1.0;
+    const int nkb = cdiv(K, 64);
+    for (int i = 0; i < 4; ++i) {
+      const int bn = kBN[i];
+      if (b_mn && (bn % 64)) continue;
+      const long long tiles = (long long)cdiv(N, bn) * cdiv(M, BM);
+      const double t_kb = fmax(1.0 * bn, (16384.0 + 128.0 * bn) / 48.0);
+      double iters, epis;
+      if (allow_sk && tiles * 2 <= G) { iters = fmax(1.0, (double)tiles * nkb / G); epis = 6.0; }
+      else { iters = (double)cdiv(tiles, G) * nkb; epis = (double)cdiv(tiles, G); }
+      const double cost = iters * t_kb + epis * 13.0 * bn;
+      if (best < 0 || cost < best) { best = cost; BN = bn; }
+    }
+  }
+  CUtensorMap ta, tb;
+  bool ok;
+  if (a_mn) ok = make_map_bf16(&ta, A, K, M, lda, 64, 64);
+  else      ok = make_map_bf16(&ta, A, M, K, lda, 64, BM);
+  if (ok) {
+    if (b_mn) ok = make_map_bf16(&tb, B, K, N, ldb, 64, 64);
+    else      ok = make_map_bf16(&tb, B, N, K, ldb, 64, BN);
+  }
+  if (!ok) return GIC_OK;
+  const int tiles_n = cdiv(N, BN), tiles_m = cdiv(M, BM), tiles = tiles_n * tiles_m, nkb = cdiv(K, 64);
+  int dp_tiles = tiles;
+  if (allow_sk && tiles * 2 <= G && (long long)tiles * nkb >= 4LL * G) dp_tiles = 0;
+  const int grid = (dp_tiles < tiles) ? G : min(tiles, G);
+  if (dp_tiles < tiles && beta == 0.f) {
+    cudaError_t e = cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, stream);
+    if (e != cudaSuccess) { set_error("memset2D: %s", cudaGetErrorString(e)); return GIC_ERR_CUDA; }
+  }
+  EpiArgs ea;
+  ea.alpha = alpha; ea.beta = beta; ea.C = C; ea.ldc = ldc; ea.bias = bias; ea.aux = nullptr; ea.rowv = nullptr;
+  ea.scalar = 0.f; ea.scalar_dev = nullptr; ea.dbg = 0;
+  ea.vec_red = (aligned16(C) && (ldc % 4) == 0 && (!bias || aligned16(bias))) ? 1 : 0;
+  CUtensorMap tcm;
+  ea.tma_store = 0;
+  if (beta == 0.f && aligned16(C) && (ldc % 4) == 0 && (!bias || aligned16(bias)))
+    ea.tma_store = make_map(&tcm, C, M, N, ldc, 32, 32, false, false) ? 1 : 0;
+  if (!ea.tma_store) tcm = ta;
+  int rc = GIC_OK;
+#define GIC_PB(BN_)                                                                                                  \
+  do {                                                                                                              \
+    if (!a_mn && !b_mn) rc = launch_p<BN_, false, false, EPI_STORE, 1>(ta, tb, tcm, M, N, K, tiles_n, tiles, dp_tiles, grid, ea, stream); \
+    else if (a_mn && !b_mn) rc = launch_p<BN_, true, false, EPI_STORE, 1>(ta, tb, tcm, M, N, K, tiles_n, tiles, dp_tiles, grid, ea, stream); \
+    else if (!a_mn) rc = launch_p<BN_, false, true, EPI_STORE, 1>(ta, tb, tcm, M, N, K, tiles_n, tiles, dp_tiles, grid, ea, stream); \
+    else rc = launch_p<BN_, true, true, EPI_STORE, 1>(ta, tb, tcm, M, N, K, tiles_n, tiles, dp_tiles, grid, ea, stream); \
+  } while (0)
+  switch (BN) {
+    case 64: GIC_PB(64); break;
+    case 128: GIC_PB(128); break;
+    case 192: GIC_PB(192); break;
+    default: GIC_PB(256); break;
+  }
+#undef GIC_PB
   if (rc == GIC_OK) *handled = true;
   return rc;
 }

@@ -56,8 +56,15 @@ int gemm_f32(bool transA, bool transB, int M, int N, int K, float alpha, const f
 enum GemmMode : int {
   GEMM_FP32 = 0,     // CUDA-core FFMA, exact fp32 (parity mode)
   GEMM_TF32 = 1,     // tcgen05 kind::tf32, single pass (throughput mode)
-  GEMM_TF32X3 = 2    // tcgen05 kind::tf32, 3-pass split (fp32-equivalent on tensor cores)
+  GEMM_TF32X3 = 2,   // tcgen05 kind::tf32, 3-pass split (fp32-equivalent on tensor cores)
+  GEMM_BF16 = 3      // as GEMM_TF32, with the discriminator's [N*R,F] x [F,F] contractions on bf16 operands (kind::f16)
 };
+
+// bf16-operand GEMM (fp32 accumulate / output); A, B are bf16 with leading dimensions in elements.
+int gemm_bf16(bool transA, bool transB, int M, int N, int K, float alpha, const void* A, int lda, const void* B,
+              int ldb, float beta, float* C, int ldc, const float* bias, cudaStream_t stream, int prof_kind = PROF_GEMM);
+// dst[r, c] = bf16(src[r, c]) for c < cols (pitches in elements)
+int f32_to_bf16(const float* src, int rows, int cols, int ld_src, void* dst, int ld_dst, cudaStream_t stream);
 
 // Dispatching GEMM used by the path: routes to tcgen05 when the mode/shape allow, else FFMA.
 int gemm(int mode, bool transA, bool transB, int M, int N, int K, float alpha, const float* A,

@@ -44,6 +44,8 @@ typedef void* gic_stream_t; /* cudaStream_t */
 #define GIC_GEMM_FP32 0   /* CUDA-core FFMA, exact fp32                                   */
 #define GIC_GEMM_TF32 1   /* tcgen05 kind::tf32, one pass, fp32 accumulate in TMEM         */
 #define GIC_GEMM_TF32X3 2 /* tcgen05 kind::tf32, 3-pass hi/lo split: fp32-equivalent       */
+#define GIC_GEMM_BF16 3   /* as TF32, with the discriminator's [N*R,F]x[F,F] contractions (highway forward, dx, dW_h) on
+                             bf16 operands (tcgen05 kind::f16, fp32 accumulate): "bf16 GEMM inputs, stated separately" */
 
 /* adversarial loss types, src/utils.py:14-50 */
 #define GIC_LOSS_STANDARD 0
@@ -73,6 +75,11 @@ void gic_prof_end(double* ms, double* work, unsigned long long* calls);
  * C[M,N] = alpha * op(A) * op(B) + beta * C + bias[N];  transA: A stored [K,M]; transB: B stored [N,K]. */
 int gic_gemm(int mode, int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
              const float* B, int ldb, float beta, float* C, int ldc, const float* bias, gic_stream_t stream);
+
+/* same contraction with bf16 operands (A, B: bf16, leading dimensions in elements, multiples of 8; 16-byte aligned),
+ * fp32 accumulation in TMEM and fp32 C. */
+int gic_gemm_bf16(int transA, int transB, int M, int N, int K, float alpha, const void* A, int lda, const void* B,
+                  int ldb, float beta, float* C, int ldc, const float* bias, gic_stream_t stream);
 
 /* ---- Encoder.linear + Encoder.bn, train-mode batch statistics (src/generator.py:15-16,23-24) ---- */
 int gic_encoder_fwd(int mode, const float* pooled /*[B,Fin]*/, int B, int Fin, int E, const float* W /*[E,Fin]*/,

@@ -70,3 +70,46 @@ def test_gemm_tf32_unaligned_falls_back_to_exact_kernel():
     # lda = 37 is not TMA-addressable: the dispatcher must use the exact-fp32 kernel (still CUDA, still ours)
     err, scale = run_gemm(1, 0, 1, 70, 90, 37, seed=3)
     assert err <= 1e-5 * scale
+
+
+# ---- bf16 operands (tcgen05 kind::f16, fp32 accumulate): GIC_GEMM_BF16 mode's contraction ----------------------
+def run_gemm_bf16(tA, tB, M, N, K, alpha=1.0, beta=0.0, use_bias=False, seed=0, pad=0):
+    """Operands are rounded to bf16 first, so the fp64 product of the rounded operands is the exact target and the
+    only error left is the fp32 accumulation order."""
+    from gic_b200 import _lib as L
+    L.require_cuda()
+    g = torch.Generator().manual_seed(seed + M * 7 + N * 3 + K + tA * 2 + tB)
+    ra, ca = ((K, M) if tA else (M, K))
+    rb, cb = ((N, K) if tB else (K, N))
+    lda, ldb = ((ca + 7) // 8) * 8 + pad, ((cb + 7) // 8) * 8 + pad
+    A = torch.zeros(ra, lda, dtype=torch.bfloat16); A[:, :ca] = torch.randn(ra, ca, generator=g).to(torch.bfloat16)
+    B = torch.zeros(rb, ldb, dtype=torch.bfloat16); B[:, :cb] = torch.randn(rb, cb, generator=g).to(torch.bfloat16)
+    C0 = torch.randn(M, N, generator=g)
+    bias = torch.randn(N, generator=g) if use_bias else None
+    Ad, Bd, Cd = A.to(dev()), B.to(dev()), C0.clone().to(dev())
+    bd = bias.to(dev()) if use_bias else None
+    Aop = (A[:, :ca].double().t() if tA else A[:, :ca].double())
+    Bop = (B[:, :cb].double().t() if tB else B[:, :cb].double())
+    want = alpha * (Aop @ Bop) + beta * C0.double()
+    if use_bias:
+        want = want + bias.double()
+    L.check(L.lib().gic_gemm_bf16(tA, tB, M, N, K, alpha, L.ptr(Ad), lda, L.ptr(Bd), ldb, beta, L.ptr(Cd), N, L.ptr(bd),
+                                  L.stream()), "gic_gemm_bf16")
+    torch.cuda.synchronize()
+    scale = float(want.abs().max())
+    err = float((Cd.double().cpu() - want).abs().max())
+    return err, scale
+
+
+@pytest.mark.parametrize("tA,tB", [(0, 1), (0, 0), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 128), (300, 900, 900), (16384, 900, 900), (900, 900, 4096),
+                                   (130, 100, 72), (2048, 512, 5120)])
+def test_gemm_bf16_vs_fp64(tA, tB, M, N, K):
+    err, scale = run_gemm_bf16(tA, tB, M, N, K, seed=4)
+    REPORT[f"bf16/{M}x{N}x{K}/tA{tA}tB{tB}"] = dict(err=err, scale=scale, rel=err / scale)
+    assert err <= 2e-5 * scale, f"rel err {err / scale:.3e}"          # exact bf16 products, fp32 accumulation
+
+
+def test_gemm_bf16_alpha_beta_bias_padded_pitch():
+    err, scale = run_gemm_bf16(0, 1, 384, 900, 900, alpha=0.75, beta=1.0, use_bias=True, seed=5, pad=56)
+    assert err <= 2e-5 * scale
