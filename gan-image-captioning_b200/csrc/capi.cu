@@ -15,6 +15,8 @@ int sample_cdf_step(const float*, const float*, int, int, int, int, long long, f
 int rollout_init(const float*, const float*, const int64_t*, const float*, int, int, int, int, int, int, int, float*,
                  float*, float*, int64_t*, cudaStream_t);
 int softmax_bwd_dot(const float*, const float*, const float*, float, int, int, float*, cudaStream_t);
+int softmax_bwd_dot_bf16(const float*, const float*, const float*, float, int, int, void*, int, cudaStream_t);
+int colsum_bf16(const void*, int, int, int, bool, float*, cudaStream_t);
 int embed_scatter(const float*, const int64_t*, int, int, int, int, float*, float*, cudaStream_t);
 int bn_fwd(const float*, int, int, const float*, const float*, float, float*, float*, float*, cudaStream_t);
 int bn_bwd(const float*, const float*, int, int, const float*, const float*, const float*, float*, float*, float*,
@@ -172,9 +174,10 @@ static int decode_fwd(int mode, const float* features, const float* W_emb, const
 
 // backward workspace (floats):
 //   dlogits[B*L*V] | dHtop[B*L*H] | dG[layers][L][B][4H] | dh_rec[layers][B][H] | dc_rec[layers][B][H]
-//   | dxin[B][H] | dX[L][B][E] | dot[B*L]
+//   | dxin[B][H] | dX[L][B][E] | dot[B*L] | bf16 copies for GIC_GEMM_BF16: dz[B*L][Vp], htop[B*L][H], W_out[V][H]
 struct DecodeBwdWs {
-  size_t dlogits, dhtop, dG, dhrec, dcrec, dxin, dX, dot, total;
+  size_t dlogits, dhtop, dG, dhrec, dcrec, dxin, dX, dot, dz_bf, htop_bf, wout_bf, total;
+  int Vp;
   DecodeBwdWs(int B, int L, int V, int E, int H, int layers) {
     const size_t BH = (size_t)B * H;
     dlogits = 0;
@@ -185,7 +188,11 @@ struct DecodeBwdWs {
     dxin = dcrec + (size_t)layers * a4(BH);
     dX = dxin + a4(BH);
     dot = dX + a4((size_t)L * B * E);
-    total = dot + a4((size_t)B * L);
+    Vp = ((V + 63) / 64) * 64;
+    dz_bf = dot + a4((size_t)B * L);
+    htop_bf = dz_bf + a4((size_t)B * L * Vp / 2);
+    wout_bf = htop_bf + a4(((size_t)B * L * H + 1) / 2);
+    total = wout_bf + a4(((size_t)V * H + 1) / 2);
   }
 };
 
@@ -220,6 +227,7 @@ static int decode_bwd(int mode, const float* dout, const float* demb, const floa
   const size_t dG_stride = a4((size_t)L * BH * 4);
 
   // 1. through the tempered softmax (the Gumbel add is a constant)
+  bool vocab_done = false;          // GIC_GEMM_BF16: step 2 already done on bf16 operands
   const float* dlogits = dout;
   if (dout == nullptr) {
     GIC_REQUIRE(!pretrain, GIC_ERR_UNSUPPORTED, "decode_sample_bwd: factored dout is the adversarial path only");
@@ -231,9 +239,25 @@ static int decode_bwd(int mode, const float* dout, const float* demb, const floa
       GIC_TRY(softmax_bwd(out, ws + w.dlogits, T, BL, V, ws + w.dlogits, s));
     } else {
       GIC_TRY(rowdot(demb, emb, BL, De, ws + w.dot, s));
+      if (mode == GEMM_BF16 && (V % 4 == 0) && (H % 8 == 0)) {
+        // bf16 operands for the two 52-GF contractions of the vocab projection's backward: dz is written once as bf16
+        // (it is read by nothing else), htop and W_out are converted (2.6 M + 5.1 M elements)
+        void* dz_bf = ws + w.dz_bf;
+        void* htop_bf = ws + w.htop_bf;
+        void* wout_bf = ws + w.wout_bf;
+        GIC_TRY(gemm(mode, false, false, BL, V, De, 1.f, demb, De, W_e, V, 0.f, ws + w.dlogits, V, nullptr, s));
+        GIC_TRY(softmax_bwd_dot_bf16(out, ws + w.dlogits, ws + w.dot, T, BL, V, dz_bf, w.Vp, s));
+        GIC_TRY(colsum_bf16(dz_bf, BL, V, w.Vp, accumulate != 0, db_out, s));
+        GIC_TRY(f32_to_bf16(saved + sv.htop, BL, H, H, htop_bf, H, s));
+        GIC_TRY(f32_to_bf16(W_out, V, H, H, wout_bf, H, s));
+        GIC_TRY(gemm_bf16(true, false, V, H, BL, 1.f, dz_bf, w.Vp, htop_bf, H, beta, dW_out, H, nullptr, s));
+        GIC_TRY(gemm_bf16(false, false, BL, H, V, 1.f, dz_bf, w.Vp, wout_bf, H, 0.f, ws + w.dhtop, H, nullptr, s));
+        vocab_done = true;
+      }
       bool fused = false;
+      if (!vocab_done)
       GIC_TRY(gemm_dz(mode, BL, V, De, demb, De, W_e, V, out, ws + w.dot, T, ws + w.dlogits, V, s, &fused));
-      if (!fused) {
+      if (!fused && !vocab_done) {
         GIC_TRY(gemm(mode, false, false, BL, V, De, 1.f, demb, De, W_e, V, 0.f, ws + w.dlogits, V, nullptr, s));
         GIC_TRY(softmax_bwd_dot(out, ws + w.dlogits, ws + w.dot, T, BL, V, ws + w.dlogits, s));
       }
@@ -244,9 +268,11 @@ static int decode_bwd(int mode, const float* dout, const float* demb, const floa
     dlogits = ws + w.dlogits;
   }
   // 2. vocab projection: db_out, dW_out[V,H] = dlogits^T htop, dHtop[B*L,H] = dlogits W_out
-  GIC_TRY(colsum_f32(dlogits, BL, V, V, 1.f, accumulate != 0, db_out, s));
-  GIC_TRY(gemm(mode, true, false, V, H, BL, 1.f, dlogits, V, saved + sv.htop, H, beta, dW_out, H, nullptr, s));
-  GIC_TRY(gemm(mode, false, false, BL, H, V, 1.f, dlogits, V, W_out, H, 0.f, ws + w.dhtop, H, nullptr, s));
+  if (!vocab_done) {
+    GIC_TRY(colsum_f32(dlogits, BL, V, V, 1.f, accumulate != 0, db_out, s));
+    GIC_TRY(gemm(mode, true, false, V, H, BL, 1.f, dlogits, V, saved + sv.htop, H, beta, dW_out, H, nullptr, s));
+    GIC_TRY(gemm(mode, false, false, BL, H, V, 1.f, dlogits, V, W_out, H, 0.f, ws + w.dhtop, H, nullptr, s));
+  }
   // 3. BPTT through (h, c)
   cudaMemsetAsync(ws + w.dhrec, 0, (size_t)2 * layers * a4(BH) * sizeof(float), s);   // dh_rec and dc_rec
   for (int t = L - 1; t >= 0; --t) {

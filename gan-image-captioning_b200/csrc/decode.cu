@@ -550,6 +550,52 @@ int softmax_bwd_dot(const float* p, const float* dp, const float* dot, float tem
   return check_launch("softmax_bwd_dot_kernel");
 }
 
+// bf16-output variant (GIC_GEMM_BF16): dz is only read by tensor-core contractions, so it is written once as bf16 with
+// row pitch Vp (8 B per 4 elements instead of 16): 10 B of HBM traffic per element.
+__global__ void __launch_bounds__(256)
+softmax_bwd_dot_bf16_kernel(const float4* __restrict__ p, const float4* __restrict__ dp, const float* __restrict__ dot,
+                            float temperature_v, const float* __restrict__ t_dev, int V4, int Vp, size_t n4,
+                            unsigned short* __restrict__ dz) {
+  const float temperature = pick_t(temperature_v, t_dev);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i0 < n4; i0 += 4 * stride) {
+    float4 pv[4], dv[4];
+    float dt[4];
+    size_t row[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const size_t i = i0 + j * stride;
+      if (i < n4) { pv[j] = p[i]; dv[j] = dp[i]; row[j] = i / V4; dt[j] = dot[row[j]]; }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const size_t i = i0 + j * stride;
+      if (i < n4) {
+        const float z0 = temperature * pv[j].x * (dv[j].x - dt[j]), z1 = temperature * pv[j].y * (dv[j].y - dt[j]);
+        const float z2 = temperature * pv[j].z * (dv[j].z - dt[j]), z3 = temperature * pv[j].w * (dv[j].w - dt[j]);
+        auto bf = [](float x) { unsigned int u = __float_as_uint(x); u += 0x7fffu + ((u >> 16) & 1u); return u >> 16; };
+        uint2 pk;
+        pk.x = bf(z0) | (bf(z1) << 16);
+        pk.y = bf(z2) | (bf(z3) << 16);
+        const size_t c4 = i - row[j] * V4;
+        *reinterpret_cast<uint2*>(dz + row[j] * Vp + 4 * c4) = pk;
+      }
+    }
+  }
+}
+int softmax_bwd_dot_bf16(const float* p, const float* dp, const float* dot, float temperature, int rows, int V, void* dz,
+                         int Vp, cudaStream_t s) {
+  if (rows == 0) return GIC_OK;
+  GIC_REQUIRE((V % 4 == 0) && (Vp % 4 == 0) && aligned16(p) && aligned16(dp) && aligned16(dz), GIC_ERR_SHAPE,
+              "softmax_bwd_dot_bf16: V %% 4 != 0 or misaligned operands");
+  ProfScope prof(PROF_SOFTMAX_BWD, 10.0 * rows * V, s);
+  const size_t n4 = (size_t)rows * V / 4;
+  const int grid = (int)min((size_t)num_sms() * 8, (n4 + 1023) / 1024);
+  softmax_bwd_dot_bf16_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(p), reinterpret_cast<const float4*>(dp), dot,
+                                                  temperature, g_t_dev, V / 4, Vp, n4, reinterpret_cast<unsigned short*>(dz));
+  return check_launch("softmax_bwd_dot_bf16_kernel");
+}
+
 // dot[row] = <a[row, :n], b[row, :n]>, one warp per row.  With a = d(emb), b = emb = p W_e^T of the discriminator's
 // soft-caption embedding this is sum_v p[row,v] * d(p)[row,v] of the softmax backward without the dense d(p).
 __global__ void rowdot_kernel(const float* __restrict__ a, const float* __restrict__ b, int rows, int n,

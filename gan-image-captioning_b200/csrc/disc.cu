@@ -8,6 +8,21 @@ namespace gic {
 
 constexpr int MAX_GROUPS = 8;
 
+// packed fp32 pair helpers for fma.rn.f32x2 (Blackwell packed FP32 pipe)
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
 // fp32 -> bf16, round to nearest even (finite inputs)
 __device__ __forceinline__ unsigned short f2bf(float x) {
   unsigned int u = __float_as_uint(x);
@@ -84,14 +99,17 @@ __device__ __forceinline__ void conv_item_es1(const float* emb_s, const float* w
 #pragma unroll 4
   for (int t = 0; t < T; ++t) {
     win[FK - 1] = e4[(t + FK - 1) * RS];
-    float4 acc = make_float4(bias, bias, bias, bias);
+    // packed fp32 FMAs (fma.rn.f32x2, sm_100): two representations per instruction, same rounding as fmaf
+    unsigned long long a01 = pack2(bias, bias), a23 = a01;
 #pragma unroll
     for (int k = 0; k < FK; ++k) {
-      acc.x = fmaf(w[k], win[k].x, acc.x);
-      acc.y = fmaf(w[k], win[k].y, acc.y);
-      acc.z = fmaf(w[k], win[k].z, acc.z);
-      acc.w = fmaf(w[k], win[k].w, acc.w);
+      const unsigned long long ww = pack2(w[k], w[k]);
+      a01 = ffma2(ww, pack2(win[k].x, win[k].y), a01);
+      a23 = ffma2(ww, pack2(win[k].z, win[k].w), a23);
     }
+    float4 acc;
+    unpack2(a01, acc.x, acc.y);
+    unpack2(a23, acc.z, acc.w);
     if (acc.x > best.x) { best.x = acc.x; a[0] = t; }
     if (acc.y > best.y) { best.y = acc.y; a[1] = t; }
     if (acc.z > best.z) { best.z = acc.z; a[2] = t; }

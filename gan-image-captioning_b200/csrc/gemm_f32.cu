@@ -243,6 +243,30 @@ colsum_kernel(const float* __restrict__ A, int M, int N, int lda, float scale, i
   }
 }
 
+// column sums of a bf16 matrix (fp32 accumulation): bias gradients in GIC_GEMM_BF16 mode
+__global__ void __launch_bounds__(1024)
+colsum_bf16_kernel(const unsigned short* __restrict__ A, int M, int N, int lda, int accumulate, float* __restrict__ out) {
+  __shared__ float part[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + tx;
+  float s = 0.f;
+  if (n < N)
+    for (int m = ty; m < M; m += 32) s += __uint_as_float((unsigned int)A[(size_t)m * lda + n] << 16);
+  part[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) t += part[i][tx];
+    if (n < N) out[n] = (accumulate ? out[n] : 0.f) + t;
+  }
+}
+int colsum_bf16(const void* A, int M, int N, int lda, bool accumulate, float* out, cudaStream_t s) {
+  if (N == 0) return GIC_OK;
+  colsum_bf16_kernel<<<cdiv(N, 32), 1024, 0, s>>>(reinterpret_cast<const unsigned short*>(A), M, N, lda, accumulate ? 1 : 0, out);
+  return check_launch("colsum_bf16_kernel");
+}
+
 int colsum_f32(const float* A, int M, int N, int lda, float scale, bool accumulate, float* out,
                cudaStream_t s) {
   if (N == 0) return GIC_OK;
