@@ -291,7 +291,7 @@ def run_ours(args):
 
     # roofline of the dominant kernel class: instrumented steps (events around every launch of the class)
     peaks = load_peaks()
-    NK = 8
+    NK = 9
     K = C.c_double * NK
     ms_k, work_k, calls_k = K(), K(), (C.c_ulonglong * NK)()
     use_graph = False          # events around individual launches need the eager path
@@ -302,7 +302,8 @@ def run_ours(args):
         step_resident(i)
     torch.cuda.synchronize()
     lib.gic_prof_end(ms_k, work_k, calls_k)
-    names = ["gemm_other", "sample_step", "conv_pool_fwd", "softmax_bwd", "clip_adam", "head_fwd", "gemm_disc", "gemm_decode"]
+    names = ["gemm_other", "sample_step", "conv_pool_fwd", "softmax_bwd", "clip_adam", "head_fwd", "gemm_disc", "gemm_decode",
+             "vocab_sample_fused"]
     classes = {}
     for k, nm in enumerate(names):
         if calls_k[k]:
@@ -336,7 +337,13 @@ def run_ours(args):
             tensor_classes[nm] = {"achieved_TFLOPs": tf, "frac_of_bf16_peak": tf / peaks["tf"], "ms_per_step": c["ms_per_step"],
                                   "launches_per_step": c["calls_per_step"]}
     hbm = {}
-    for nm in ("sample_step", "conv_pool_fwd", "softmax_bwd", "clip_adam", "head_fwd"):
+    c = classes.get("vocab_sample_fused")
+    if c:
+        # the fused projection + Gumbel-softmax + sample kernel is both: 2*B*V*H flop and 8*B*V HBM bytes per launch
+        tf = c["calls_per_step"] * 2.0 * B * V * cfg["H"] / (c["ms_per_step"] * 1e-3) / 1e12
+        tensor_classes["vocab_sample_fused"] = {"achieved_TFLOPs": tf, "frac_of_bf16_peak": tf / peaks["tf"],
+                                                "ms_per_step": c["ms_per_step"], "launches_per_step": c["calls_per_step"]}
+    for nm in ("sample_step", "vocab_sample_fused", "conv_pool_fwd", "softmax_bwd", "clip_adam", "head_fwd"):
         c = classes.get(nm)
         if c:
             gbs = c["work_per_step"] / (c["ms_per_step"] * 1e-3) / 1e9

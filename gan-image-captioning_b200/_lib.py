@@ -113,6 +113,11 @@ def _declare(L):
     L.gic_pg_loss_fwd_bwd.argtypes = [P, P, P, I, I, I, I, P, P, P, P]
     L.gic_set_temperature_device.restype = None
     L.gic_set_temperature_device.argtypes = [P]
+    L.gic_disc_prepared_floats.restype = Z
+    L.gic_disc_prepared_floats.argtypes = [I]
+    L.gic_disc_prepare.argtypes = [I, P, P, P, I, P, P, I, P, P]
+    L.gic_disc_set_prepared.restype = None
+    L.gic_disc_set_prepared.argtypes = [P]
     for name in header_symbols():      # every declared entry point must be exported
         getattr(L, name)
 

@@ -47,6 +47,10 @@ int pg_loss(const float*, const int64_t*, const float*, int, int, int, int, floa
 int clip_adam(float*, const float*, float*, float*, size_t, const float*, float, float, int, float, float, float,
               float, const float*, cudaStream_t);
 void set_temperature_device(const float*);
+const float* temperature_device();
+void disc_set_prepared(const float*);
+int disc_prepare(int, const float*, const float*, const float*, int, const float*, const float*, int, float*, cudaStream_t);
+size_t disc_fwd_workspace_floats(int);
 const char* last_error();
 unsigned long long launch_count();
 void prof_begin();
@@ -116,6 +120,7 @@ static int decode_fwd(int mode, const float* features, const float* W_emb, const
   const size_t BH = (size_t)B * H, BE = (size_t)B * E;
   float* gates = ws;                         // [B,4H]
   float* logits = ws + a4(4 * BH);           // [B,V]
+  float* vs_scratch = logits + a4((size_t)B * V);   // fused projection + sampler: barrier counters + row statistics
   cudaMemcpyAsync(saved + sv.xs, features, BE * sizeof(float), cudaMemcpyDeviceToDevice, s);
   for (int l = 0; l < layers; ++l) {
     cudaMemsetAsync(saved + sv.hs(l), 0, BH * sizeof(float), s);
@@ -161,8 +166,18 @@ static int decode_fwd(int mode, const float* features, const float* W_emb, const
       }
     }
     const float* htop_t = saved + sv.hs(layers - 1) + (size_t)(t + 1) * BH;
-    GIC_TRY(gemm(mode, false, true, B, V, H, 1.f, htop_t, H, W_out, H, 0.f, logits, V, b_out, s, PROF_GEMM_DECODE));   // :64,68
     float* x_next = (t + 1 < L) ? saved + sv.xs + (size_t)(t + 1) * BE : nullptr;
+    if (pretrain == 0 && (mode == GEMM_TF32 || mode == GEMM_BF16)) {
+      // tensor-core modes: projection + Gumbel-softmax + sample + next-token gather in ONE kernel (logits stay on chip)
+      bool fused_vs = false;
+      {
+        ProfScope prof(PROF_VOCAB_SAMPLE, 8.0 * B * V, s);
+        GIC_TRY(vocab_sample_tc(htop_t, H, W_out, b_out, u + (size_t)t * B * V, T, temperature_device(), B, V, H, L, t, out,
+                                ids, forced, W_emb, E, x_next, vs_scratch, s, &fused_vs));
+      }
+      if (fused_vs) continue;
+    }
+    GIC_TRY(gemm(mode, false, true, B, V, H, 1.f, htop_t, H, W_out, H, 0.f, logits, V, b_out, s, PROF_GEMM_DECODE));   // :64,68
     if (pretrain == 2)
       GIC_TRY(sample_cdf_step(logits, u + (size_t)t * B, B, V, L, t, L, out, ids, logp, forced, W_emb, E, x_next, s));
     else
@@ -513,7 +528,9 @@ int gic_sample_cdf_step(const float* logits, const float* u, int B, int V, int L
 }
 
 size_t gic_decode_saved_floats(int B, int L, int E, int H, int layers) { return DecodeSaved(B, L, E, H, layers).total; }
-size_t gic_decode_fwd_workspace_floats(int B, int V, int H) { return a4((size_t)4 * B * H) + a4((size_t)B * V); }
+size_t gic_decode_fwd_workspace_floats(int B, int V, int H) {
+  return a4((size_t)4 * B * H) + a4((size_t)B * V) + a4(vocab_sample_scratch_floats(B, V));
+}
 size_t gic_decode_bwd_workspace_floats(int B, int L, int V, int E, int H, int layers) {
   return DecodeBwdWs(B, L, V, E, H, layers).total;
 }
@@ -659,5 +676,13 @@ int gic_clip_adam_dyn(float* p, const float* g, float* m, float* v, size_t n, co
 }
 
 void gic_set_temperature_device(const float* t_dev) { set_temperature_device(t_dev); }
+
+size_t gic_disc_prepared_floats(int F) { return disc_fwd_workspace_floats(F); }
+int gic_disc_prepare(int mode, const float* W_h, const float* W_f, const float* b_f, int Hd, const float* W_o,
+                     const float* b_o, int F, float* prepared, gic_stream_t stream) {
+  GIC_TRY(require_device());
+  return disc_prepare(mode, W_h, W_f, b_f, Hd, W_o, b_o, F, prepared, S(stream));
+}
+void gic_disc_set_prepared(const float* prepared) { disc_set_prepared(prepared); }
 
 }  // extern "C"

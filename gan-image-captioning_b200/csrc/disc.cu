@@ -385,18 +385,29 @@ conv_pool_bwd_dw_kernel(const float* __restrict__ emb, const uint8_t* __restrict
 // (src/discriminator.py:58-60), so logits = yd . w_eff + b_eff with
 //   w_eff[j] = sum_k w_o[k] W_f[k, j],  b_eff = sum_k w_o[k] b_f[k] + b_o.
 // ---------------------------------------------------------------------------------------
-__global__ void head_collapse_kernel(const float* __restrict__ W_f, const float* __restrict__ b_f,
-                                     const float* __restrict__ w_o, const float* __restrict__ b_o, int F,
-                                     int Hd, float* __restrict__ weff /*[F+1]*/) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+// grid = ceil((F+1)/32) CTAs of 256 threads: lane = column, the 8 warps split the Hd rows (coalesced 128-byte reads of
+// W_f rows, 8 x fewer dependent FMAs per thread than one thread per column), fixed-order reduction in shared memory.
+__global__ void __launch_bounds__(256)
+head_collapse_kernel(const float* __restrict__ W_f, const float* __restrict__ b_f,
+                     const float* __restrict__ w_o, const float* __restrict__ b_o, int F,
+                     int Hd, float* __restrict__ weff /*[F+1]*/) {
+  __shared__ float part[8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + lane;
+  float s = 0.f;
   if (j < F) {
-    float s = 0.f;
-    for (int k = 0; k < Hd; ++k) s = fmaf(w_o[k], W_f[(size_t)k * F + j], s);
-    weff[j] = s;
+#pragma unroll 4
+    for (int k = w; k < Hd; k += 8) s = fmaf(w_o[k], W_f[(size_t)k * F + j], s);
   } else if (j == F) {
-    float s = b_o[0];
-    for (int k = 0; k < Hd; ++k) s = fmaf(w_o[k], b_f[k], s);
-    weff[F] = s;
+    for (int k = w; k < Hd; k += 8) s = fmaf(w_o[k], b_f[k], s);
+  }
+  part[w][lane] = s;
+  __syncthreads();
+  if (w == 0 && j <= F) {
+    float t = (j == F) ? b_o[0] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += part[i][lane];
+    weff[j] = t;
   }
 }
 
@@ -699,6 +710,26 @@ int disc_fill_groups(ConvGroups& g, int ngroups, const int* fs, const int* nf, c
   return GIC_OK;
 }
 
+// Derived weights shared by every discriminator call of one step (collapsed head, bf16 copy of highway.weight):
+// layout = the forward workspace, weff[F+1] | W_h_bf(bf16)[F*Fp].  While a prepared blob is registered the forward /
+// backward read it instead of recomputing (one adversarial step makes 2 forward and 3 backward calls on the same
+// pre-update weights).
+static const float* g_prepared = nullptr;
+void disc_set_prepared(const float* prep) { g_prepared = prep; }
+
+int disc_prepare(int mode, const float* W_h, const float* W_f, const float* b_f, int Hd, const float* W_o,
+                 const float* b_o, int F, float* prep, cudaStream_t s) {
+  GIC_REQUIRE(W_h && W_f && b_f && W_o && b_o && prep, GIC_ERR_NULL, "disc_prepare: NULL pointer");
+  GIC_REQUIRE(F >= 1 && Hd >= 1, GIC_ERR_SHAPE, "disc_prepare: bad shape");
+  head_collapse_kernel<<<cdiv(F + 1, 32), 256, 0, s>>>(W_f, b_f, W_o, b_o, F, Hd, prep);
+  GIC_TRY(check_launch("head_collapse_kernel"));
+  if (mode == GEMM_BF16 && (F % 4 == 0)) {
+    unsigned short* W_h_bf = reinterpret_cast<unsigned short*>(prep + align4((size_t)F + 1));
+    GIC_TRY(f32_to_bf16(W_h, F, F, F, W_h_bf, bf_pitch(F), s));
+  }
+  return GIC_OK;
+}
+
 int disc_forward(int mode, const float* inp_soft, const int64_t* ids, const DiscDims& d, const ConvGroups& g,
                  const float* W_e, const float* W_h, const float* b_h, const float* W_f, const float* b_f,
                  const float* W_o, const float* b_o, int n_heads, const uint8_t* const* keep, float drop_p,
@@ -711,8 +742,9 @@ int disc_forward(int mode, const float* inp_soft, const int64_t* ids, const Disc
   const bool bf = (mode == GEMM_BF16) && (d.F % 4 == 0);
   const int Fp = bf_pitch(d.F);
   unsigned short* pooled_bf = reinterpret_cast<unsigned short*>(reinterpret_cast<float*>(arg) + align4((rows * d.F + 3) / 4));
-  float* weff = ws;
-  unsigned short* W_h_bf = reinterpret_cast<unsigned short*>(ws + align4((size_t)d.F + 1));
+  const float* prep = g_prepared;
+  const float* weff = prep ? prep : ws;
+  const unsigned short* W_h_bf = reinterpret_cast<const unsigned short*>(weff + align4((size_t)d.F + 1));
   if (d.N == 0) return GIC_OK;
   // 1. embedding
   if (inp_soft) {
@@ -748,14 +780,16 @@ int disc_forward(int mode, const float* inp_soft, const int64_t* ids, const Disc
   // 3. highway pre-activation
   if (bf) {
     // bf16 operands: pooled_bf written by the conv kernel, W_h converted here (1.6 MB); fp32 accumulate / output
-    GIC_TRY(f32_to_bf16(W_h, d.F, d.F, d.F, W_h_bf, Fp, s));
+    if (!prep) GIC_TRY(f32_to_bf16(W_h, d.F, d.F, d.F, const_cast<unsigned short*>(W_h_bf), Fp, s));
     GIC_TRY(gemm_bf16(false, true, (int)rows, d.F, d.F, 1.f, pooled_bf, Fp, W_h_bf, Fp, 0.f, hpre, d.F, b_h, s, PROF_GEMM_D));
   } else {
     GIC_TRY(gemm(mode, false, true, (int)rows, d.F, d.F, 1.f, pooled, d.F, W_h, d.F, 0.f, hpre, d.F, b_h, s, PROF_GEMM_D));
   }
   // 4. collapsed head
-  head_collapse_kernel<<<cdiv(d.F + 1, 256), 256, 0, s>>>(W_f, b_f, W_o, b_o, d.F, d.Hd, weff);
-  GIC_TRY(check_launch("head_collapse_kernel"));
+  if (!prep) {
+    head_collapse_kernel<<<cdiv(d.F + 1, 32), 256, 0, s>>>(W_f, b_f, W_o, b_o, d.F, d.Hd, ws);
+    GIC_TRY(check_launch("head_collapse_kernel"));
+  }
   HeadPtrs hp;
   hp.n = n_heads;
   for (int m = 0; m < MAX_HEADS; ++m) {
@@ -793,19 +827,23 @@ int disc_backward(int mode, const float* dlogit, const uint8_t* keep, float drop
   const int Fp = bf_pitch(d.F);
   const unsigned short* pooled_bf =
       reinterpret_cast<const unsigned short*>(reinterpret_cast<const float*>(arg) + align4((rows * d.F + 3) / 4));
-  float* weff = ws;
-  float* dh = weff + align4((size_t)d.F + 1);
+  const float* prep = g_prepared;
+  const float* weff = prep ? prep : ws;
+  float* dh = ws + align4((size_t)d.F + 1);
   const size_t dh_floats = align4(rows * d.F) > align4(rows * Fp / 2) ? align4(rows * d.F) : align4(rows * Fp / 2);
   float* dx = dh + dh_floats;
   float* sacc = dx + align4(rows * d.F);
   float* dbh = sacc + align4(d.F);
   float* demb = dbh + align4(d.F);
-  unsigned short* W_h_bf = reinterpret_cast<unsigned short*>(demb + align4((size_t)d.N * d.L * d.De));
-  float* dxg = reinterpret_cast<float*>(W_h_bf) + align4((size_t)d.F * Fp / 2);
+  unsigned short* W_h_bf_ws = reinterpret_cast<unsigned short*>(demb + align4((size_t)d.N * d.L * d.De));
+  const unsigned short* W_h_bf = prep ? reinterpret_cast<const unsigned short*>(prep + align4((size_t)d.F + 1)) : W_h_bf_ws;
+  float* dxg = reinterpret_cast<float*>(W_h_bf_ws) + align4((size_t)d.F * Fp / 2);
   const float beta = accumulate ? 1.f : 0.f;
 
-  head_collapse_kernel<<<cdiv(d.F + 1, 256), 256, 0, s>>>(W_f, b_f, W_o, b_o, d.F, d.Hd, weff);
-  GIC_TRY(check_launch("head_collapse_kernel"));
+  if (!prep) {
+    head_collapse_kernel<<<cdiv(d.F + 1, 32), 256, 0, s>>>(W_f, b_f, W_o, b_o, d.F, d.Hd, ws);
+    GIC_TRY(check_launch("head_collapse_kernel"));
+  }
   cudaMemsetAsync(sacc, 0, 2 * align4(d.F) * sizeof(float), s);
   if ((d.F % 4 == 0) && (!keep || (reinterpret_cast<uintptr_t>(keep) & 3u) == 0)) {
     const int colb = cdiv(d.F / 4, 256);
@@ -843,7 +881,7 @@ int disc_backward(int mode, const float* dlogit, const uint8_t* keep, float drop
   // beta = 0 (TMA-store epilogue); the conv/pool backward kernels read dx + dxg: a beta = 1 epilogue has to pull the C
   // tile through the LSU and measured 97 us vs 45 us (profiles/README.md).
   if (bf) {
-    GIC_TRY(f32_to_bf16(W_h, d.F, d.F, d.F, W_h_bf, Fp, s));
+    if (!prep) GIC_TRY(f32_to_bf16(W_h, d.F, d.F, d.F, W_h_bf_ws, Fp, s));
     GIC_TRY(gemm_bf16(false, false, (int)rows, d.F, d.F, 1.f, dh, Fp, W_h_bf, Fp, 0.f, dxg, d.F, nullptr, s, PROF_GEMM_D));
   } else {
     GIC_TRY(gemm(mode, false, false, (int)rows, d.F, d.F, 1.f, dh, d.F, W_h, d.F, 0.f, dxg, d.F, nullptr, s, PROF_GEMM_D));

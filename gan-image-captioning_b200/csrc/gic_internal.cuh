@@ -34,7 +34,7 @@ int num_sms();
 
 // ---- optional per-kernel-class device timing (bench.py roofline): CUDA events on the launching stream ----
 enum ProfKind : int { PROF_GEMM = 0, PROF_SAMPLE = 1, PROF_CONVPOOL = 2, PROF_SOFTMAX_BWD = 3, PROF_ADAM = 4,
-                      PROF_HEAD = 5, PROF_GEMM_D = 6, PROF_GEMM_DECODE = 7, PROF_KINDS = 8 };
+                      PROF_HEAD = 5, PROF_GEMM_D = 6, PROF_GEMM_DECODE = 7, PROF_VOCAB_SAMPLE = 8, PROF_KINDS = 9 };
 bool prof_enabled();
 void prof_open(int kind, double work, cudaStream_t s);    // work = algorithmic flops (GEMM) or bytes
 void prof_close(cudaStream_t s);
@@ -70,6 +70,12 @@ int f32_to_bf16(const float* src, int rows, int cols, int ld_src, void* dst, int
 int gemm(int mode, bool transA, bool transB, int M, int N, int K, float alpha, const float* A,
          int lda, const float* B, int ldb, float beta, float* C, int ldc, const float* bias,
          cudaStream_t stream, int prof_kind = PROF_GEMM);
+
+// Fused vocab projection + Gumbel-softmax + sample of one decode step (vocab_sample_tcgen05.cu).
+size_t vocab_sample_scratch_floats(int B, int V);
+int vocab_sample_tc(const float* htop, int lda, const float* W_out, const float* b_out, const float* u_t, float T,
+                    const float* T_dev, int B, int V, int H, int L, int t, float* out, int64_t* ids, const int64_t* forced,
+                    const float* embed, int E, float* x_next, float* scratch, cudaStream_t stream, bool* handled);
 
 // out[N] (+)= scale * sum_rows A[M,N]
 int colsum_f32(const float* A, int M, int N, int lda, float scale, bool accumulate, float* out,

@@ -1,6 +1,10 @@
 // GAN losses with their backward seeds (src/utils.py:10-53) and the optimizer step
 // (clip_grad_norm_ + Adam, src/training.py:194-199 with the Adam ctor at :24-26).
+#include <cooperative_groups.h>
+
 #include "gic_internal.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace gic {
 
@@ -9,7 +13,9 @@ enum LossType : int { LOSS_STANDARD = 0, LOSS_JS = 1, LOSS_KL = 2, LOSS_HINGE = 
 // BCEWithLogits(x, y) = max(x,0) - x*y + log1p(exp(-|x|))
 __device__ __forceinline__ float bce(float x, float y) { return fmaxf(x, 0.f) - x * y + log1pf(expf(-fabsf(x))); }
 
-// One CTA.  losses[0] = g_loss, losses[1] = d_loss (get_losses returns g first, utils.py:53).
+// One thread-block cluster (1 or 8 CTAs): every CTA reduces its slice, the partial sums meet in CTA 0's shared memory
+// over DSMEM and are added in rank order, so the result does not depend on scheduling (no atomics, no scratch buffer).
+// losses[0] = g_loss, losses[1] = d_loss (get_losses returns g first, utils.py:53).
 // Seeds: dd_real = d d_loss / d d_out_real, dd_fake = d d_loss / d d_out_fake,
 //        dg_out = d g_loss / d g_out.  (rsgan: g_loss only sees detached D outputs -> dg_out = 0.)
 __global__ void __launch_bounds__(1024)
@@ -17,9 +23,12 @@ gan_loss_kernel(int type, const float* __restrict__ d_real, const float* __restr
                 const float* __restrict__ g_out, int n, float* __restrict__ losses,
                 float* __restrict__ dd_real, float* __restrict__ dd_fake, float* __restrict__ dg_out) {
   __shared__ float red[32];
+  __shared__ float cpart[2][8];
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned crank = cluster.block_rank(), csize = cluster.num_blocks();
   const float inv = 1.0f / (float)n;
   float sd = 0.f, sg = 0.f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  for (int i = crank * blockDim.x + threadIdx.x; i < n; i += csize * blockDim.x) {
     const float r = d_real[i], f = d_fake[i], g = g_out[i];
     float gr = 0.f, gf = 0.f, gg = 0.f;
     switch (type) {
@@ -63,7 +72,21 @@ gan_loss_kernel(int type, const float* __restrict__ d_real, const float* __restr
   }
   sd = block_sum(sd, red);
   sg = block_sum(sg, red);
-  if (threadIdx.x == 0) { losses[0] = sg * inv; losses[1] = sd * inv; }
+  if (csize == 1) {
+    if (threadIdx.x == 0) { losses[0] = sg * inv; losses[1] = sd * inv; }
+    return;
+  }
+  if (threadIdx.x == 0) {
+    float* dst = cluster.map_shared_rank(&cpart[0][0], 0);
+    dst[crank] = sg;
+    dst[8 + crank] = sd;
+  }
+  cluster.sync();
+  if (crank == 0 && threadIdx.x == 0) {
+    float tg = 0.f, td = 0.f;
+    for (unsigned i = 0; i < csize; ++i) { tg += cpart[0][i]; td += cpart[1][i]; }
+    losses[0] = tg * inv; losses[1] = td * inv;
+  }
 }
 
 int gan_loss(int type, const float* d_real, const float* d_fake, const float* g_out, int n, float* losses,
@@ -71,7 +94,19 @@ int gan_loss(int type, const float* d_real, const float* d_fake, const float* g_
   GIC_REQUIRE(type >= 0 && type <= LOSS_RSGAN, GIC_ERR_UNSUPPORTED, "Divergence type %d is not implemented", type);
   GIC_REQUIRE(n > 0, GIC_ERR_SHAPE, "gan_loss: empty batch");
   GIC_REQUIRE(d_real && d_fake && g_out && losses, GIC_ERR_NULL, "gan_loss: NULL operand");
-  gan_loss_kernel<<<1, 1024, 0, s>>>(type, d_real, d_fake, g_out, n, losses, dd_real, dd_fake, dg_out);
+  const int csize = (n >= 4096) ? 8 : 1;
+  const int threads = (n >= 8192) ? 1024 : 256;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(csize);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gan_loss_kernel, type, d_real, d_fake, g_out, n, losses, dd_real, dd_fake, dg_out);
+  if (e != cudaSuccess) { set_error("gan_loss_kernel launch: %s", cudaGetErrorString(e)); return GIC_ERR_CUDA; }
   return check_launch("gan_loss_kernel");
 }
 

@@ -1,0 +1,469 @@
+// Fused vocab projection + Gumbel-softmax + sample for ONE decode step (sm_100a only):
+//   logits = h_t W_out^T + b_out                                     (src/generator.py:64,68)
+//   z      = (logits - log(-log(u + eps) + eps)) * T                 (add_gumbel, :84-96; :69)
+//   p      = softmax(z)          -> written in place to out[b, t, :] (:69-70, no torch.stack copy)
+//   tok    = first index of max p -> ids[b, t]; x_{t+1} = embed[tok] (:73-76)
+// The logits never leave the chip: every CTA owns one 128 x BN tile of the [B, V] logits, accumulated by tcgen05.mma
+// (kind::tf32) in TMEM from a TMA-fed shared-memory ring, while a second TMA stream prefetches the matching tile of
+// the uniform draws u_t into 128-byte-swizzled shared memory underneath the main loop.  The row statistics of the
+// softmax span all column tiles, so the tiles of one 128-row block meet at a counter barrier in global memory (the
+// whole grid is co-resident: tiles <= SMs, one CTA per SM):
+//   pass 1  TMEM -> registers (lane = row), perturb with the Gumbel noise, running max m and sum s of exp(z - m)
+//           (online rescaling, one row per thread: no shuffles needed); e = exp(z - m_running) replaces u in shared memory
+//   publish (m, s) per row and tile; barrier over the tiles_n CTAs of the row block
+//   combine M = max m_j, S = sum s_j exp(m_j - M), winner tile = first j with m_j == M
+//   pass 2  p = e * exp(m_running - M) / S in shared memory, TMA store to out[b, t, n0:n0+BN]; the winner tile finds the
+//           first column with p == max p (the reference's first-max tie rule), writes ids and gathers embed[tok]
+// HBM traffic per step: read u (4 B V bytes), write p (4 B V bytes); W_out streams from L2.
+// Warp roles (576 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..17 = epilogue: four
+// warps per TMEM lane quarter split the tile's columns in 16-column units; they turn u into the Gumbel term while the
+// main loop runs (pass 0), so only the exp / normalise passes remain after the last MMA.
+#include "tcgen05_common.cuh"
+
+namespace gic {
+namespace tc {
+
+template <int BN>
+struct VSCfg {
+  static constexpr int A_BYTES = BM * BK * 4;          // 16 KB
+  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int STAGE = A_BYTES + B_BYTES;
+  static constexpr int NBOX = BN / 32;                 // 32-column boxes of the u / p tile
+  static constexpr int BOX_BYTES = BM * 128;           // 128 rows x 128 bytes
+  static constexpr int U_BYTES = NBOX * BOX_BYTES;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int AVAIL = 227 * 1024 - 1024 - U_BYTES - BAR_BYTES;
+  static constexpr int STAGES = (AVAIL / STAGE) > 6 ? 6 : (AVAIL / STAGE);
+  static constexpr int TOTAL = STAGES * STAGE + U_BYTES + BAR_BYTES + 1024;
+  static constexpr uint32_t TMEM_COLS = (BN <= 128) ? 128 : 256;
+  static_assert(STAGES >= 2, "vocab_sample: shared memory ring too small");
+  static_assert(BN % 32 == 0 && BN <= 256, "vocab_sample: BN must be a multiple of 32, <= 256");
+};
+
+struct VSArgs {
+  int M, N, K, tiles_n, Mpad;
+  const float* bias;          // [N]
+  float T;
+  const float* T_dev;         // temperature read at run time when non-null (CUDA-graph replay)
+  float2* part;               // [tiles_n][Mpad] (m, s) per row and column tile
+  unsigned int* counters;     // [tiles_m] arrival counters, zeroed before step 0
+  unsigned int target;        // tiles_n * (t + 1)
+  int64_t* ids;               // [M, L]
+  const int64_t* forced;      // [M, L] or null: token fed to the next step instead of the sampled one
+  int L, t;
+  const float* embed;         // [V, E]
+  int E;
+  float* x_next;              // [M, E] or null
+};
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+constexpr int VS_G = 4;                              // epilogue warps per TMEM lane quarter (they split the tile's columns)
+constexpr int VS_EPI_THREADS = 128 * VS_G;
+constexpr int VS_THREADS = 64 + VS_EPI_THREADS;      // warp 0 = TMA producer, warp 1 = MMA issuer, 16 epilogue warps
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(VS_EPI_THREADS) : "memory"); }
+
+template <int BN>
+__global__ void __launch_bounds__(VS_THREADS, 1)
+vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmP, VSArgs a) {
+  using S = VSCfg<BN>;
+  constexpr int NUNIT = BN / 16;                     // 16-column units, dealt round-robin to the VS_G warps of a quarter
+  constexpr int MAXU = (NUNIT + VS_G - 1) / VS_G;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* ubox = smem + S::STAGES * S::STAGE;                    // NBOX boxes of [128 rows][128 B], 128B-swizzled
+  uint64_t* full = reinterpret_cast<uint64_t*>(ubox + S::U_BYTES);
+  uint64_t* empty = full + S::STAGES;
+  uint64_t* tmem_full = empty + S::STAGES;
+  uint64_t* u_full = tmem_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(u_full + 1);
+  // small exchange buffers of the epilogue live in stage 0 of the operand ring, which is dead once tmem_full fires
+  float2 (*s_part)[BM] = reinterpret_cast<float2 (*)[BM]>(smem);              // [VS_G][BM] row statistics of pass 1
+  float4* s_row = reinterpret_cast<float4*>(smem + VS_G * BM * 8);            // [VS_G][BM] (M, S, first tile, -) per group
+  int* s_hit = reinterpret_cast<int*>(smem + VS_G * BM * 8 + VS_G * BM * 16); // first column holding the row maximum
+  static_assert(VS_G * BM * 8 + VS_G * BM * 16 + BM * 4 <= S::STAGE, "vocab_sample: exchange buffers exceed one stage");
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = (a.K + BK - 1) / BK;
+  const int mtile = blockIdx.x / a.tiles_n, ntile = blockIdx.x % a.tiles_n;
+  const int m0 = mtile * BM, n0 = ntile * BN;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmU) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmP) : "memory");
+    for (int s = 0; s < S::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    mbar_init(u_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(S::TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer: the u tile first (the epilogue warps turn it into Gumbel noise underneath the main loop),
+    //       then the operand ring =====
+    if (lane == 0) {
+      mbar_expect_tx(u_full, S::U_BYTES);
+#pragma unroll
+      for (int c = 0; c < S::NBOX; ++c) tma_load_2d(ubox + c * S::BOX_BYTES, &tmU, u_full, n0 + 32 * c, m0);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % S::STAGES;
+        const uint32_t ph = (kb / S::STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* sa = smem + s * S::STAGE;
+        mbar_expect_tx(&full[s], S::STAGE);
+        tma_load_2d(sa, &tmA, &full[s], kb * BK, m0);
+        tma_load_2d(sa + S::A_BYTES, &tmB, &full[s], kb * BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(0, 0, BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % S::STAGES;
+        const uint32_t ph = (kb / S::STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        tcgen05_fence_after();
+        const uint32_t sa = smem_u32(smem + s * S::STAGE);
+        const uint32_t sb = sa + S::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t da = make_desc(sa + k * 32, 16, 1024, 2);
+          const uint64_t db = make_desc(sb + k * 32, 16, 1024, 2);
+          umma_tf32(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    // ===== epilogue warps: thread = (row, column group g); unit = 16 columns =====
+    const int q = warp & 3;                          // TMEM lane quarter this warp may access
+    const int g = (warp - 2) >> 2;                   // column group 0..VS_G-1
+    const int row = q * 32 + lane;                   // row inside the tile
+    const int m = m0 + row;
+    const int etid = threadIdx.x - 64;
+    const float T = a.T_dev ? __ldg(a.T_dev) : a.T;
+    const float eps = 1e-10f;
+    uint8_t* urow = ubox + row * 128;
+    const int sw = row & 7;
+    // unit j (16 columns) = box j/2, 16-byte chunks 4*(j&1) .. 4*(j&1)+3
+#define VS_CHUNK(j, k) (urow + ((j) >> 1) * S::BOX_BYTES + (((4 * ((j) & 1) + (k)) ^ sw) << 4))
+
+    // ---- pass 0 (under the main loop): u -> log2(-log(u + eps) + eps), the Gumbel term subtracted from the logits
+    mbar_wait(u_full, 0);
+#pragma unroll
+    for (int i = 0; i < MAXU; ++i) {
+      const int j = g + i * VS_G;
+      if (j < NUNIT && n0 + 16 * j < a.N) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float4* sp = reinterpret_cast<float4*>(VS_CHUNK(j, k));
+          float4 u4 = *sp;
+          // log2 of the inner term: the ln 2 factor is applied in pass 1 inside the same fused multiply-subtract the
+          // separate sampler kernel compiles to (logit - lg2 * ln2), so both paths round identically
+          u4.x = __log2f(-logf(u4.x + eps) + eps); u4.y = __log2f(-logf(u4.y + eps) + eps);
+          u4.z = __log2f(-logf(u4.z + eps) + eps); u4.w = __log2f(-logf(u4.w + eps) + eps);
+          *sp = u4;
+        }
+      }
+    }
+
+    // ---- pass 1: z = (acc + b - noise) * T, online (max, sum); e = exp(z - running max) replaces the noise
+    mbar_wait(tmem_full, 0);
+    tcgen05_fence_after();
+    const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    float m_run = -INFINITY, s_run = 0.f;
+    float mrun_u[MAXU];
+#pragma unroll
+    for (int i = 0; i < MAXU; ++i) {
+      const int j = g + i * VS_G;
+      mrun_u[i] = -INFINITY;
+      if (j < NUNIT) {                                 // warp-uniform
+        uint32_t r[16];
+        tmem_ld16(t_addr + 16 * j, r);
+        float z[16];
+        float cm = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int n = n0 + 16 * j + 4 * k;
+          if (n < a.N) {                               // N % 4 == 0: a float4 is entirely inside or outside
+            const float4 ng = *reinterpret_cast<const float4*>(VS_CHUNK(j, k));
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + n));
+            constexpr float LN2 = 0.693147182f;
+            z[4 * k + 0] = (__uint_as_float(r[4 * k + 0]) + b4.x - ng.x * LN2) * T;
+            z[4 * k + 1] = (__uint_as_float(r[4 * k + 1]) + b4.y - ng.y * LN2) * T;
+            z[4 * k + 2] = (__uint_as_float(r[4 * k + 2]) + b4.z - ng.z * LN2) * T;
+            z[4 * k + 3] = (__uint_as_float(r[4 * k + 3]) + b4.w - ng.w * LN2) * T;
+          } else {
+            z[4 * k + 0] = z[4 * k + 1] = z[4 * k + 2] = z[4 * k + 3] = -INFINITY;
+          }
+          cm = fmaxf(cm, fmaxf(fmaxf(z[4 * k + 0], z[4 * k + 1]), fmaxf(z[4 * k + 2], z[4 * k + 3])));
+        }
+        if (cm > -INFINITY) {
+          const float m_new = fmaxf(m_run, cm);
+          s_run *= (m_run > -INFINITY) ? __expf(m_run - m_new) : 0.f;
+          m_run = m_new;
+          float cs = 0.f;
+#pragma unroll
+          for (int e = 0; e < 16; ++e) { z[e] = __expf(z[e] - m_new); cs += z[e]; }
+          s_run += cs;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) z[e] = 0.f;
+        }
+        mrun_u[i] = m_run;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          *reinterpret_cast<float4*>(VS_CHUNK(j, k)) = make_float4(z[4 * k + 0], z[4 * k + 1], z[4 * k + 2], z[4 * k + 3]);
+      }
+    }
+    s_part[g][row] = make_float2(m_run, s_run);
+    if (g == 0) s_hit[row] = 0x7fffffff;
+    epi_bar();
+
+    // ---- the tile's row statistics (column groups combined in group order), published for the other column tiles
+    if (g == 0) {
+      float Mt = -INFINITY, St = 0.f;
+#pragma unroll
+      for (int i = 0; i < VS_G; ++i) {
+        const float2 v = s_part[i][row];
+        if (v.x > Mt) { St = St * ((Mt > -INFINITY) ? __expf(Mt - v.x) : 0.f) + v.y; Mt = v.x; }
+        else if (v.x > -INFINITY) St += v.y * __expf(v.x - Mt);
+      }
+      a.part[(size_t)ntile * a.Mpad + m] = make_float2(Mt, St);
+      __threadfence();
+    }
+    epi_bar();
+    if (etid == 0) {
+      unsigned int* ctr = a.counters + mtile;
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+      const unsigned long long t0 = globaltimer_ns();
+      for (;;) {
+        unsigned int v;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+        if (v >= a.target) break;
+        __nanosleep(32);
+        if (globaltimer_ns() - t0 > 4000000000ull) __trap();     // a protocol bug traps instead of hanging the GPU
+      }
+    }
+    epi_bar();
+
+    // ---- combine over the column tiles: M, S, winner tile (first tile holding the row maximum).  The four column
+    //      groups of a row each take every fourth tile (loads issued in batches of 8 before any use: the partials come
+    //      from L2 and a dependent chain of ~tiles_n round trips would cost more than the whole main loop), then the
+    //      four partial results meet in shared memory and every thread folds them in group order.
+    {
+      float Mg = -INFINITY, Sg = 0.f;
+      int jb = 0x7fffffff;
+      const float2* pp = a.part + m;
+      for (int j0 = g; j0 < a.tiles_n; j0 += 8 * VS_G) {
+        float2 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int j = j0 + i * VS_G;
+          v[i] = (j < a.tiles_n) ? __ldcg(pp + (size_t)j * a.Mpad) : make_float2(-INFINITY, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (v[i].x > Mg) {
+            Sg = Sg * ((Mg > -INFINITY) ? __expf(Mg - v[i].x) : 0.f) + v[i].y;
+            Mg = v[i].x; jb = j0 + i * VS_G;
+          } else if (v[i].x > -INFINITY) {
+            Sg += v[i].y * __expf(v[i].x - Mg);
+          }
+        }
+      }
+      s_row[g * BM + row] = make_float4(Mg, Sg, __int_as_float(jb), 0.f);
+    }
+    epi_bar();
+    float M = -INFINITY, Ssum = 0.f;
+    int jbest = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < VS_G; ++i) {
+      const float4 v = s_row[i * BM + row];
+      const int jv = __float_as_int(v.z);
+      if (v.x > M) {
+        Ssum = Ssum * ((M > -INFINITY) ? __expf(M - v.x) : 0.f) + v.y;
+        M = v.x; jbest = jv;
+      } else if (v.x > -INFINITY) {
+        Ssum += v.y * __expf(v.x - M);
+        if (v.x == M && jv < jbest) jbest = jv;
+      }
+    }
+    if (jbest == 0x7fffffff) jbest = 0;
+    const float inv = 1.0f / Ssum;
+    const bool winner = (jbest == ntile);
+
+    // ---- pass 2: p = e * exp(m_running - M) / S in shared memory; first-max column in the winner tile
+    int hit = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < MAXU; ++i) {
+      const int j = g + i * VS_G;
+      if (j < NUNIT && n0 + 16 * j < a.N) {
+        const float f = __expf(mrun_u[i] - M) * inv;
+        const bool may_hit = winner && (mrun_u[i] == M) && (hit == 0x7fffffff);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float4* sp = reinterpret_cast<float4*>(VS_CHUNK(j, k));
+          float4 e = *sp;
+          if (may_hit && hit == 0x7fffffff) {
+            if (e.x == 1.0f) hit = 16 * j + 4 * k;
+            else if (e.y == 1.0f) hit = 16 * j + 4 * k + 1;
+            else if (e.z == 1.0f) hit = 16 * j + 4 * k + 2;
+            else if (e.w == 1.0f) hit = 16 * j + 4 * k + 3;
+          }
+          e.x *= f; e.y *= f; e.z *= f; e.w *= f;
+          *sp = e;
+        }
+      }
+    }
+    if (hit != 0x7fffffff) atomicMin(&s_hit[row], hit);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    epi_bar();
+
+    // ---- TMA stores of the finished tile (one 32 x 32 box per quarter and column box), token id, next-step input
+    if (g == 0) {
+      if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < S::NBOX; ++c) {
+          if (n0 + 32 * c < a.N)
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                         ::"l"(&tmP), "r"(smem_u32(ubox + c * S::BOX_BYTES + q * 4096)), "r"(n0 + 32 * c), "r"(m0 + q * 32)
+                         : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      int fed = -1;
+      const bool m_ok = m < a.M;
+      if (winner && m_ok) {
+        const int h = s_hit[row];
+        int tok = n0 + (h == 0x7fffffff ? 0 : h);
+        if (tok >= a.N) tok = a.N - 1;
+        a.ids[(size_t)m * a.L + a.t] = tok;
+        fed = tok;
+      }
+      if (a.forced != nullptr) {
+        fed = -1;
+        if (ntile == 0 && m_ok) {
+          const int64_t fz = a.forced[(size_t)m * a.L + a.t];
+          fed = (fz >= 0 && fz < a.N) ? (int)fz : 0;
+        }
+      }
+      if (a.x_next != nullptr) {
+        unsigned mask = __ballot_sync(0xffffffffu, fed >= 0);
+        const bool vec = ((a.E & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.embed) & 15u) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(a.x_next) & 15u) == 0);
+        while (mask) {
+          const int src = __ffs(mask) - 1;
+          mask &= mask - 1;
+          const int tok = __shfl_sync(0xffffffffu, fed, src);
+          const float* er = a.embed + (size_t)tok * a.E;
+          float* xr = a.x_next + (size_t)(m0 + q * 32 + src) * a.E;
+          if (vec) {
+            for (int i = lane; i < (a.E >> 2); i += 32) reinterpret_cast<float4*>(xr)[i] = __ldg(reinterpret_cast<const float4*>(er) + i);
+          } else {
+            for (int i = lane; i < a.E; i += 32) xr[i] = __ldg(er + i);
+          }
+        }
+      }
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+#undef VS_CHUNK
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(S::TMEM_COLS));
+  }
+}
+
+template <int BN>
+static int launch_vs(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tu, const CUtensorMap& tp, const VSArgs& a,
+                     int grid, cudaStream_t s) {
+  using S = VSCfg<BN>;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(vocab_sample_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    attr = true;
+  }
+  vocab_sample_kernel<BN><<<grid, VS_THREADS, S::TOTAL, s>>>(ta, tb, tu, tp, a);
+  return check_launch("vocab_sample_kernel");
+}
+
+}  // namespace tc
+
+// scratch (floats) for B rows and V columns: counters[64 uints] | part[tiles_n][Mpad] float2 (sized for the narrowest tile)
+size_t vocab_sample_scratch_floats(int B, int V) {
+  const size_t Mpad = (size_t)cdiv(B, tc::BM) * tc::BM;
+  return 64 + 2 * Mpad * (size_t)cdiv(V, 128);
+}
+
+// One fused decode step on the tensor cores.  handled = false (nothing launched) when the shape does not fit the
+// co-resident grid or TMA's alignment rules; the caller then runs the separate projection + sampler kernels.
+int vocab_sample_tc(const float* htop, int lda, const float* W_out, const float* b_out, const float* u_t, float T,
+                    const float* T_dev, int B, int V, int H, int L, int t, float* out, int64_t* ids, const int64_t* forced,
+                    const float* embed, int E, float* x_next, float* scratch, cudaStream_t stream, bool* handled) {
+  using namespace tc;
+  *handled = false;
+  { const char* e = getenv("GIC_FUSED_SAMPLE"); if (e && e[0] == '0') return GIC_OK; }   // read per call: tests toggle it
+  if (B <= 0 || V <= 0 || H <= 0) return GIC_OK;
+  if ((V % 4) || (H % 4) || (lda % 4) || !aligned16(htop) || !aligned16(W_out) || !aligned16(b_out) || !aligned16(u_t) ||
+      !aligned16(out) || (((size_t)L * V) % 4))
+    return GIC_OK;
+  const int tiles_m = cdiv(B, BM);
+  if (tiles_m > 64) return GIC_OK;
+  const int G = num_sms();
+  static const int kBN[6] = {128, 160, 192, 224, 256, 0};
+  int BN = 0;
+  for (int i = 0; kBN[i]; ++i)
+    if ((long long)tiles_m * cdiv(V, kBN[i]) <= G) { BN = kBN[i]; break; }
+  if (!BN) return GIC_OK;
+  const int tiles_n = cdiv(V, BN);
+  const bool rn = tf32_round_in_tma();
+  CUtensorMap ta, tb, tu, tp;
+  bool ok = make_map(&ta, htop, B, H, lda, BK, BM, rn, false) && make_map(&tb, W_out, V, H, H, BK, BN, rn, false) &&
+            make_map(&tu, u_t, B, V, V, 32, BM, false, false) &&
+            make_map(&tp, out + (size_t)t * V, B, V, L * V, 32, 32, false, false);
+  if (!ok) return GIC_OK;
+  VSArgs a;
+  a.M = B; a.N = V; a.K = H; a.tiles_n = tiles_n; a.Mpad = tiles_m * BM;
+  a.bias = b_out; a.T = T; a.T_dev = T_dev;
+  a.counters = reinterpret_cast<unsigned int*>(scratch);
+  a.part = reinterpret_cast<float2*>(scratch + 64);
+  a.target = (unsigned int)tiles_n * (unsigned int)(t + 1);
+  a.ids = ids; a.forced = forced; a.L = L; a.t = t; a.embed = embed; a.E = E; a.x_next = x_next;
+  if (t == 0) {
+    cudaError_t e = cudaMemsetAsync(scratch, 0, 64 * sizeof(float), stream);
+    if (e != cudaSuccess) { set_error("vocab_sample memset: %s", cudaGetErrorString(e)); return GIC_ERR_CUDA; }
+  }
+  int rc;
+  const int grid = tiles_m * tiles_n;
+  switch (BN) {
+    case 128: rc = launch_vs<128>(ta, tb, tu, tp, a, grid, stream); break;
+    case 160: rc = launch_vs<160>(ta, tb, tu, tp, a, grid, stream); break;
+    case 192: rc = launch_vs<192>(ta, tb, tu, tp, a, grid, stream); break;
+    case 224: rc = launch_vs<224>(ta, tb, tu, tp, a, grid, stream); break;
+    default: rc = launch_vs<256>(ta, tb, tu, tp, a, grid, stream); break;
+  }
+  if (rc == GIC_OK) *handled = true;
+  return rc;
+}
+
+}  // namespace gic

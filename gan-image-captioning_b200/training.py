@@ -167,7 +167,33 @@ class GANInstructor:
         P = _lib.ptr
         if self._in_graph:
             lib.gic_set_temperature_device(P(self._dyn[0:1]))
+        # derived D weights (collapsed head, bf16 highway.weight) once per step: all six D calls below see the same
+        # pre-update weights (Q1)
+        prep = self._buf("disc_prep", lib.gic_disc_prepared_floats(Fd))
+        _lib.check(lib.gic_disc_prepare(mode, P(disc.highway.weight), P(disc.feature2out.weight), P(disc.feature2out.bias),
+                                        disc.feature2out.weight.shape[0], P(disc.out2logits.weight),
+                                        P(disc.out2logits.bias), Fd, P(prep), stream), "gic_disc_prepare")
+        lib.gic_disc_set_prepared(P(prep))
+        try:
+            return self._adv_step_body(captions, pooled, u, keep, train, forced_ids, loss_type, update, grid, prep)
+        finally:
+            lib.gic_disc_set_prepared(None)
+            if self._in_graph:
+                lib.gic_set_temperature_device(None)
 
+    def _adv_step_body(self, captions, pooled, u, keep, train, forced_ids, loss_type, update, grid, prep):
+        lib = _lib.lib()
+        a, dev = self.args, self.device
+        mode = gic_b200.get_gemm_mode()
+        fg, fd = self._flat_g, self._flat_d
+        dec, disc = self.gen.decoder, self.disc
+        B, L = captions.shape
+        V, E, H, layers = a.vocab_size, a.gen_embed_dim, a.gen_hidden_dim, a.gen_num_layers
+        De, R, Fd = a.disc_embed_dim, a.disc_num_rep, sum(a.disc_num_filters)
+        fsz, nfl = list(a.disc_filter_sizes), list(a.disc_num_filters)
+        T = float(dec.temperature)
+        stream = _lib.stream()
+        P = _lib.ptr
         # -- discriminator on the real captions (hard tokens, :158,162): independent of the decode, so it runs on a
         #    side stream underneath the latency-bound autoregressive loop
         if train:
@@ -350,8 +376,6 @@ class GANInstructor:
             if g_has_grad:
                 out["g_sqnorm"] = self._clip_adam(fg, a.gen_lr, update, 3)
         out["g_has_grad"] = g_has_grad
-        if self._in_graph:
-            lib.gic_set_temperature_device(None)
         return out
 
     def _clip_adam(self, fp: FlatParams, lr: float, update: bool, dyn_slot: int = 1):

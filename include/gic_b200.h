@@ -66,8 +66,9 @@ unsigned long long gic_launch_count(void);
  * stream is synchronised) fills ms[k], work[k] (algorithmic flops for k=0 GEMM, bytes otherwise) and calls[k] for
  * the GIC_PROF_KINDS classes: 0 GEMM (all other contractions), 1 sample step, 2 conv+pool fwd, 3 softmax bwd, 4 clip+Adam,
  * 5 head fwd, 6 the discriminator's [N*R, F] x [F, F] contractions (highway forward, dx, dW_h: the FLOP-dominant kernel),
- * 7 decode-step contractions (fused LSTM step, vocab projection). */
-#define GIC_PROF_KINDS 8
+ * 7 decode-step contractions (fused LSTM step, vocab projection), 8 the fused vocab projection + Gumbel-softmax +
+ * sample kernel (work = its HBM bytes, 8 B V: read u, write probs). */
+#define GIC_PROF_KINDS 9
 void gic_prof_begin(void);
 void gic_prof_end(double* ms, double* work, unsigned long long* calls);
 
@@ -277,6 +278,19 @@ void gic_set_temperature_device(const float* t_dev);
 int gic_clip_adam_dyn(float* p, const float* g, float* m, float* v, size_t n, const float* sqnorm, float max_norm,
                       float grad_scale, const float* bias_corr_dev, float beta1, float beta2, float eps,
                       gic_stream_t stream);
+
+/* ---- per-step derived discriminator weights ----
+ * One adversarial step calls Discriminator.forward three times and backpropagates through it three times
+ * (src/training.py:162-169) on the SAME pre-update weights.  The quantities derived from the weights
+ * alone -- the collapsed score head w_eff = out2logits.weight * feature2out.weight (src/discriminator.py:58-60) and, in
+ * GIC_GEMM_BF16 mode, the bf16 copy of highway.weight -- can therefore be computed once:
+ * gic_disc_prepare fills prepared[gic_disc_prepared_floats(F)] from the current weights; while
+ * gic_disc_set_prepared(prepared) is non-NULL (process-wide, NULL switches back) gic_disc_fwd / gic_disc_bwd read it
+ * instead of recomputing.  The caller must clear it (or prepare again) before the weights change. */
+size_t gic_disc_prepared_floats(int F);
+int gic_disc_prepare(int mode, const float* W_h /*[F,F]*/, const float* W_f /*[Hd,F]*/, const float* b_f, int Hd,
+                     const float* W_o, const float* b_o, int F, float* prepared, gic_stream_t stream);
+void gic_disc_set_prepared(const float* prepared);
 
 #ifdef __cplusplus
 }

@@ -113,3 +113,56 @@ def test_gemm_bf16_vs_fp64(tA, tB, M, N, K):
 def test_gemm_bf16_alpha_beta_bias_padded_pitch():
     err, scale = run_gemm_bf16(0, 1, 384, 900, 900, alpha=0.75, beta=1.0, use_bias=True, seed=5, pad=56)
     assert err <= 2e-5 * scale
+
+
+# ---- fused vocab projection + Gumbel-softmax + sample (vocab_sample_tcgen05.cu) vs the separate kernels ----------------
+def _decode_pair(B, L, V, E, H, T, forced=False, seed=0):
+    """Decoder.sample in TF32 mode with the fused kernel and with GIC_FUSED_SAMPLE=0 (projection GEMM + sampler kernel):
+    both read the same TF32 accumulators, so the sampled ids must be IDENTICAL and the probabilities equal up to the
+    different summation order of the softmax normaliser."""
+    import gic_b200
+    import gic_b200.generator as G
+    from gic_b200.args import default_args
+    a = default_args(vocab_size=V, gen_embed_dim=E, gen_hidden_dim=H, gen_num_layers=1, conditional_gan=0, device="cuda")
+    torch.manual_seed(seed)
+    gen = G.Generator(a).to("cuda:0")
+    gen.train()
+    gen.decoder.temperature = T
+    g = torch.Generator(device="cuda:0").manual_seed(seed + 1)
+    u = torch.rand(L, B, V, generator=g, device="cuda:0")
+    feats = torch.randn(B, E, generator=g, device="cuda:0") * 0.05
+    fz = torch.randint(0, V, (B, L), generator=g, device="cuda:0") if forced else None
+    old = gic_b200.get_gemm_mode()
+    gic_b200.set_gemm_mode(gic_b200.GEMM_TF32)
+    res = []
+    try:
+        for flag in ("1", "0"):
+            os.environ["GIC_FUSED_SAMPLE"] = flag
+            with torch.no_grad():
+                p, ids = gen.decoder.sample(feats, max_caption_len=L, u=u, forced_ids=fz)
+            torch.cuda.synchronize()
+            res.append((p.clone(), ids.clone()))
+    finally:
+        os.environ.pop("GIC_FUSED_SAMPLE", None)
+        gic_b200.set_gemm_mode(old)
+    return res
+
+
+@pytest.mark.parametrize("B,L,V,E,H,T,forced", [
+    (8, 6, 1000, 32, 512, 1.0, False),        # c1-like: one row block, 8 column tiles, rows padded to 128
+    (8, 6, 1000, 32, 512, 100.0, True),       # saturated softmax (first-max tie rule), teacher forcing
+    (256, 4, 10000, 512, 512, 1.0, False),    # c2 shape: 2 x 63 tiles of 128 x 160
+    (200, 3, 10000, 64, 256, 5.0, False),     # ragged last row block
+    (130, 3, 4004, 64, 128, 1.0, True),       # V not a multiple of the tile width
+])
+def test_fused_vocab_sample_matches_unfused(B, L, V, E, H, T, forced):
+    (p1, i1), (p0, i0) = _decode_pair(B, L, V, E, H, T, forced)
+    nm = f"vocab_sample/B{B}V{V}T{T}"
+    mism = int((i1 != i0).sum())
+    REPORT[nm + "/id_mismatches"] = dict(err=float(mism), scale=float(i0.numel()), rel=mism / i0.numel())
+    assert mism == 0, f"{mism} of {i0.numel()} sampled ids differ between the fused and the separate kernels"
+    err = float((p1 - p0).abs().max())
+    REPORT[nm + "/probs"] = dict(err=err, scale=float(p0.max()), rel=err / float(p0.max()))
+    assert err <= 1e-5 * float(p0.max()) + 1e-12
+    rs = p1.sum(-1)
+    assert float((rs - 1).abs().max()) < 1e-4
