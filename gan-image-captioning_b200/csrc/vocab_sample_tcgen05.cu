@@ -6,11 +6,11 @@
 // The logits never leave the chip: every CTA owns one 128 x BN tile of the [B, V] logits, accumulated by tcgen05.mma
 // (kind::tf32) in TMEM from a TMA-fed shared-memory ring, while a second TMA stream prefetches the matching tile of
 // the uniform draws u_t into 128-byte-swizzled shared memory underneath the main loop.  The row statistics of the
-// softmax span all column tiles, so the tiles of one 128-row block meet at a counter barrier in global memory (the
-// whole grid is co-resident: tiles <= SMs, one CTA per SM):
+// softmax span all column tiles, so the tiles of one 128-row block exchange their row statistics through global
+// memory (L2) and wait for each other there (the whole grid is co-resident: tiles <= SMs, one CTA per SM):
 //   pass 1  TMEM -> registers (lane = row), perturb with the Gumbel noise, running max m and sum s of exp(z - m)
 //           (online rescaling, one row per thread: no shuffles needed); e = exp(z - m_running) replaces u in shared memory
-//   publish (m, s) per row and tile; barrier over the tiles_n CTAs of the row block
+//   publish (m, s) per row and tile as one 8-byte store whose s != 0 is the ready flag; poll the other tiles' entries
 //   combine M = max m_j, S = sum s_j exp(m_j - M), winner tile = first j with m_j == M
 //   pass 2  p = e * exp(m_running - M) / S in shared memory, TMA store to out[b, t, n0:n0+BN]; the winner tile finds the
 //           first column with p == max p (the reference's first-max tie rule), writes ids and gathers embed[tok]
@@ -21,6 +21,7 @@
 #include "tcgen05_common.cuh"
 
 namespace gic {
+long long* vs_stamps_buffer();
 namespace tc {
 
 template <int BN>
@@ -31,7 +32,7 @@ struct VSCfg {
   static constexpr int NBOX = BN / 32;                 // 32-column boxes of the u / p tile
   static constexpr int BOX_BYTES = BM * 128;           // 128 rows x 128 bytes
   static constexpr int U_BYTES = NBOX * BOX_BYTES;
-  static constexpr int BAR_BYTES = 256;
+  static constexpr int BAR_BYTES = 256 + 1024;          // mbarriers + TMEM slot | bias tile (BN floats)
   static constexpr int AVAIL = 227 * 1024 - 1024 - U_BYTES - BAR_BYTES;
   static constexpr int STAGES = (AVAIL / STAGE) > 6 ? 6 : (AVAIL / STAGE);
   static constexpr int TOTAL = STAGES * STAGE + U_BYTES + BAR_BYTES + 1024;
@@ -45,16 +46,27 @@ struct VSArgs {
   const float* bias;          // [N]
   float T;
   const float* T_dev;         // temperature read at run time when non-null (CUDA-graph replay)
-  float2* part;               // [tiles_n][Mpad] (m, s) per row and column tile
-  unsigned int* counters;     // [tiles_m] arrival counters, zeroed before step 0
-  unsigned int target;        // tiles_n * (t + 1)
+  float2* part;               // [tiles_n][Mpad] (m, s) per row and column tile of THIS step; s != 0 doubles as the ready flag
+  float2* part_next;          // the other buffer: every CTA clears its own entries for the next step
   int64_t* ids;               // [M, L]
   const int64_t* forced;      // [M, L] or null: token fed to the next step instead of the sampled one
   int L, t;
   const float* embed;         // [V, E]
   int E;
   float* x_next;              // [M, E] or null
+  long long* stamps;          // debug (GIC_VS_STAMPS=1): 16 clock64 stamps per CTA, else null
 };
+
+#define VS_STAMP(i) do { if (a.stamps) a.stamps[blockIdx.x * 16 + (i)] = (long long)globaltimer_ns(); } while (0)
+
+__device__ __forceinline__ float2 ld_relaxed_f2(const float2* p) {
+  float2 v;
+  asm volatile("ld.relaxed.gpu.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_f2(float2* p, float2 v) {
+  asm volatile("st.relaxed.gpu.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
@@ -114,12 +126,10 @@ vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer: the u tile first (the epilogue warps turn it into Gumbel noise underneath the main loop),
-    //       then the operand ring =====
+    // ===== TMA producer: operand ring; the u tile is queued once the ring is primed (the epilogue warps turn it into
+    //       Gumbel noise underneath the rest of the main loop) =====
     if (lane == 0) {
-      mbar_expect_tx(u_full, S::U_BYTES);
-#pragma unroll
-      for (int c = 0; c < S::NBOX; ++c) tma_load_2d(ubox + c * S::BOX_BYTES, &tmU, u_full, n0 + 32 * c, m0);
+      VS_STAMP(0);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % S::STAGES;
         const uint32_t ph = (kb / S::STAGES) & 1;
@@ -128,7 +138,13 @@ vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_expect_tx(&full[s], S::STAGE);
         tma_load_2d(sa, &tmA, &full[s], kb * BK, m0);
         tma_load_2d(sa + S::A_BYTES, &tmB, &full[s], kb * BK, n0);
+        if (kb == min(nkb, S::STAGES) - 1) {             // ring primed: now the u tile (comes from HBM)
+          mbar_expect_tx(u_full, S::U_BYTES);
+#pragma unroll
+          for (int c = 0; c < S::NBOX; ++c) tma_load_2d(ubox + c * S::BOX_BYTES, &tmU, u_full, n0 + 32 * c, m0);
+        }
       }
+      VS_STAMP(1);
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
@@ -138,6 +154,7 @@ vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int s = kb % S::STAGES;
         const uint32_t ph = (kb / S::STAGES) & 1;
         mbar_wait(&full[s], ph);
+        if (kb == 0) VS_STAMP(2);
         tcgen05_fence_after();
         const uint32_t sa = smem_u32(smem + s * S::STAGE);
         const uint32_t sb = sa + S::A_BYTES;
@@ -150,6 +167,7 @@ vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         umma_commit(&empty[s]);
       }
       umma_commit(tmem_full);
+      VS_STAMP(3);
     }
   } else {
     // ===== epilogue warps: thread = (row, column group g); unit = 16 columns =====
@@ -165,8 +183,17 @@ vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // unit j (16 columns) = box j/2, 16-byte chunks 4*(j&1) .. 4*(j&1)+3
 #define VS_CHUNK(j, k) (urow + ((j) >> 1) * S::BOX_BYTES + (((4 * ((j) & 1) + (k)) ^ sw) << 4))
 
+    // ---- housekeeping under the main loop: clear this CTA's entries of the other statistics buffer (read again in
+    //      the step after next), stage the bias tile in shared memory
+    float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 256);
+    if (g == VS_G - 1) st_relaxed_f2(a.part_next + (size_t)ntile * a.Mpad + m, make_float2(0.f, 0.f));
+    if (etid < BN / 4) {
+      const int n = n0 + 4 * etid;
+      reinterpret_cast<float4*>(s_bias)[etid] = (n < a.N) ? __ldg(reinterpret_cast<const float4*>(a.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     // ---- pass 0 (under the main loop): u -> log2(-log(u + eps) + eps), the Gumbel term subtracted from the logits
     mbar_wait(u_full, 0);
+    if (etid == 0) VS_STAMP(4);
 #pragma unroll
     for (int i = 0; i < MAXU; ++i) {
       const int j = g + i * VS_G;
@@ -185,7 +212,10 @@ vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
 
     // ---- pass 1: z = (acc + b - noise) * T, online (max, sum); e = exp(z - running max) replaces the noise
+    if (etid == 0) VS_STAMP(5);
+    epi_bar();                                         // bias tile visible to all epilogue warps
     mbar_wait(tmem_full, 0);
+    if (etid == 0) VS_STAMP(6);
     tcgen05_fence_after();
     const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     float m_run = -INFINITY, s_run = 0.f;
@@ -204,7 +234,7 @@ vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int n = n0 + 16 * j + 4 * k;
           if (n < a.N) {                               // N % 4 == 0: a float4 is entirely inside or outside
             const float4 ng = *reinterpret_cast<const float4*>(VS_CHUNK(j, k));
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + n));
+            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + 16 * j + 4 * k);
             constexpr float LN2 = 0.693147182f;
             z[4 * k + 0] = (__uint_as_float(r[4 * k + 0]) + b4.x - ng.x * LN2) * T;
             z[4 * k + 1] = (__uint_as_float(r[4 * k + 1]) + b4.y - ng.y * LN2) * T;
@@ -235,9 +265,12 @@ vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     s_part[g][row] = make_float2(m_run, s_run);
     if (g == 0) s_hit[row] = 0x7fffffff;
+    if (etid == 0) VS_STAMP(7);
     epi_bar();
 
-    // ---- the tile's row statistics (column groups combined in group order), published for the other column tiles
+    // ---- the tile's row statistics (column groups combined in group order), published for the other column tiles.
+    //      (m, s) is ONE 8-byte relaxed store and s != 0 is its own ready flag (the buffer was cleared two steps ago),
+    //      so no counter, fence or second round trip is needed: consumers poll the data itself.
     if (g == 0) {
       float Mt = -INFINITY, St = 0.f;
 #pragma unroll
@@ -246,41 +279,38 @@ vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (v.x > Mt) { St = St * ((Mt > -INFINITY) ? __expf(Mt - v.x) : 0.f) + v.y; Mt = v.x; }
         else if (v.x > -INFINITY) St += v.y * __expf(v.x - Mt);
       }
-      a.part[(size_t)ntile * a.Mpad + m] = make_float2(Mt, St);
-      __threadfence();
+      if (St == 0.f) St = 1e-37f;                      // keep the flag set for a degenerate (all -inf) row
+      st_relaxed_f2(a.part + (size_t)ntile * a.Mpad + m, make_float2(Mt, St));
+      if (etid == 0) VS_STAMP(8);
     }
-    epi_bar();
-    if (etid == 0) {
-      unsigned int* ctr = a.counters + mtile;
-      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
-      const unsigned long long t0 = globaltimer_ns();
-      for (;;) {
-        unsigned int v;
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-        if (v >= a.target) break;
-        __nanosleep(32);
-        if (globaltimer_ns() - t0 > 4000000000ull) __trap();     // a protocol bug traps instead of hanging the GPU
-      }
-    }
-    epi_bar();
 
     // ---- combine over the column tiles: M, S, winner tile (first tile holding the row maximum).  The four column
-    //      groups of a row each take every fourth tile (loads issued in batches of 8 before any use: the partials come
-    //      from L2 and a dependent chain of ~tiles_n round trips would cost more than the whole main loop), then the
-    //      four partial results meet in shared memory and every thread folds them in group order.
+    //      groups of a row each take every fourth tile, polled in batches of 8 (all loads of a batch in flight: the
+    //      partials live in L2 and a dependent chain of ~tiles_n round trips would cost more than the main loop);
+    //      the four partial results then meet in shared memory and every thread folds them in group order.
     {
       float Mg = -INFINITY, Sg = 0.f;
       int jb = 0x7fffffff;
       const float2* pp = a.part + m;
+      const unsigned long long t0 = globaltimer_ns();
       for (int j0 = g; j0 < a.tiles_n; j0 += 8 * VS_G) {
         float2 v[8];
+        for (;;) {
+          bool ready = true;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int j = j0 + i * VS_G;
-          v[i] = (j < a.tiles_n) ? __ldcg(pp + (size_t)j * a.Mpad) : make_float2(-INFINITY, 0.f);
+          for (int i = 0; i < 8; ++i) {
+            const int j = j0 + i * VS_G;
+            v[i] = (j < a.tiles_n) ? ld_relaxed_f2(pp + (size_t)j * a.Mpad) : make_float2(-INFINITY, 1.f);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ready = ready && (__float_as_uint(v[i].y) != 0u);
+          if (ready) break;
+          __nanosleep(20);
+          if (globaltimer_ns() - t0 > 4000000000ull) __trap();   // a protocol bug traps instead of hanging the GPU
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
+          if (j0 + i * VS_G >= a.tiles_n) continue;
           if (v[i].x > Mg) {
             Sg = Sg * ((Mg > -INFINITY) ? __expf(Mg - v[i].x) : 0.f) + v[i].y;
             Mg = v[i].x; jb = j0 + i * VS_G;
@@ -289,6 +319,7 @@ vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
       }
+      if (etid == 0) VS_STAMP(9);
       s_row[g * BM + row] = make_float4(Mg, Sg, __int_as_float(jb), 0.f);
     }
     epi_bar();
@@ -309,6 +340,7 @@ vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (jbest == 0x7fffffff) jbest = 0;
     const float inv = 1.0f / Ssum;
     const bool winner = (jbest == ntile);
+    if (etid == 0) VS_STAMP(10);
 
     // ---- pass 2: p = e * exp(m_running - M) / S in shared memory; first-max column in the winner tile
     int hit = 0x7fffffff;
@@ -335,6 +367,7 @@ vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     if (hit != 0x7fffffff) atomicMin(&s_hit[row], hit);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (etid == 0) VS_STAMP(11);
     epi_bar();
 
     // ---- TMA stores of the finished tile (one 32 x 32 box per quarter and column box), token id, next-step input
@@ -382,7 +415,8 @@ vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
       }
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem may be released; the writes land by grid end
+      if (etid == 0) VS_STAMP(12);
     }
 #undef VS_CHUNK
   }
@@ -409,11 +443,45 @@ static int launch_vs(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
 
 }  // namespace tc
 
-// scratch (floats) for B rows and V columns: counters[64 uints] | part[tiles_n][Mpad] float2 (sized for the narrowest tile)
-size_t vocab_sample_scratch_floats(int B, int V) {
-  const size_t Mpad = (size_t)cdiv(B, tc::BM) * tc::BM;
-  return 64 + 2 * Mpad * (size_t)cdiv(V, 128);
+// debug timeline (GIC_VS_STAMPS=1): a static device buffer of 16 clock64 stamps per CTA, printed by gic_vs_stamps_dump()
+static long long* g_stamps = nullptr;
+long long* vs_stamps_buffer() {
+  const char* e = getenv("GIC_VS_STAMPS");
+  if (!(e && e[0] == '1')) return nullptr;
+  if (!g_stamps) { cudaMalloc(&g_stamps, 256 * 16 * sizeof(long long)); cudaMemset(g_stamps, 0, 256 * 16 * sizeof(long long)); }
+  return g_stamps;
 }
+extern "C" void gic_vs_stamps_dump(int cta) {
+  if (!g_stamps) return;
+  long long h[16];
+  cudaDeviceSynchronize();
+  cudaMemcpy(h, g_stamps + cta * 16, sizeof(h), cudaMemcpyDeviceToHost);
+  static const char* nm[13] = {"producer start", "last load issued", "first operands landed", "last mma issued", "u tile landed",
+                               "pass0 done", "tmem_full", "pass1 done", "barrier in", "barrier out", "combine done", "pass2 done", "end"};
+  for (int i = 0; i < 13; ++i) printf("  cta %3d  %-22s %8lld ns\n", cta, nm[i], h[i] ? h[i] - h[0] : -1);
+}
+extern "C" void gic_vs_stamps_table(int ncta) {
+  if (!g_stamps) return;
+  static long long h[256 * 16];
+  cudaDeviceSynchronize();
+  cudaMemcpy(h, g_stamps, sizeof(h), cudaMemcpyDeviceToHost);
+  long long t0 = h[0];
+  for (int c = 0; c < ncta; ++c) if (h[c * 16] && h[c * 16] < t0) t0 = h[c * 16];
+  printf("cta start first_ops u_landed pass0 tmem_full pass1 publish polled combine pass2 end (ns since the earliest CTA start)\n");
+  for (int c = 0; c < ncta; ++c) {
+    const long long* r = h + c * 16;
+    printf("%3d %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld\n", c, r[0] - t0, r[2] - t0, r[4] - t0, r[5] - t0,
+           r[6] - t0, r[7] - t0, r[8] - t0, r[9] - t0, r[10] - t0, r[11] - t0, r[12] - t0);
+  }
+}
+
+// scratch (floats) for B rows and V columns: two buffers part[tiles_n][Mpad] float2 (sized for the narrowest tile) that
+// alternate between steps
+static size_t vs_part_floats(int B, int V) {
+  const size_t Mpad = (size_t)cdiv(B, tc::BM) * tc::BM;
+  return 2 * Mpad * (size_t)cdiv(V, 128);
+}
+size_t vocab_sample_scratch_floats(int B, int V) { return 2 * vs_part_floats(B, V); }
 
 // One fused decode step on the tensor cores.  handled = false (nothing launched) when the shape does not fit the
 // co-resident grid or TMA's alignment rules; the caller then runs the separate projection + sampler kernels.
@@ -445,12 +513,13 @@ int vocab_sample_tc(const float* htop, int lda, const float* W_out, const float*
   VSArgs a;
   a.M = B; a.N = V; a.K = H; a.tiles_n = tiles_n; a.Mpad = tiles_m * BM;
   a.bias = b_out; a.T = T; a.T_dev = T_dev;
-  a.counters = reinterpret_cast<unsigned int*>(scratch);
-  a.part = reinterpret_cast<float2*>(scratch + 64);
-  a.target = (unsigned int)tiles_n * (unsigned int)(t + 1);
+  const size_t pf = vs_part_floats(B, V);
+  a.part = reinterpret_cast<float2*>(scratch + (size_t)(t & 1) * pf);
+  a.part_next = reinterpret_cast<float2*>(scratch + (size_t)((t + 1) & 1) * pf);
   a.ids = ids; a.forced = forced; a.L = L; a.t = t; a.embed = embed; a.E = E; a.x_next = x_next;
+  a.stamps = vs_stamps_buffer();
   if (t == 0) {
-    cudaError_t e = cudaMemsetAsync(scratch, 0, 64 * sizeof(float), stream);
+    cudaError_t e = cudaMemsetAsync(scratch, 0, 2 * pf * sizeof(float), stream);   // both statistics buffers "not ready"
     if (e != cudaSuccess) { set_error("vocab_sample memset: %s", cudaGetErrorString(e)); return GIC_ERR_CUDA; }
   }
   int rc;
