@@ -260,9 +260,18 @@ static int decode_bwd(int mode, const float* dout, const float* demb, const floa
         void* dz_bf = ws + w.dz_bf;
         void* htop_bf = ws + w.htop_bf;
         void* wout_bf = ws + w.wout_bf;
-        GIC_TRY(gemm(mode, false, false, BL, V, De, 1.f, demb, De, W_e, V, 0.f, ws + w.dlogits, V, nullptr, s));
-        GIC_TRY(softmax_bwd_dot_bf16(out, ws + w.dlogits, ws + w.dot, T, BL, V, dz_bf, w.Vp, s));
-        GIC_TRY(colsum_bf16(dz_bf, BL, V, w.Vp, accumulate != 0, db_out, s));
+        // one streaming kernel: d(probs) tile in TMEM -> dz (bf16) + db_out; the separate kernels are the fallback
+        bool dz_done = false;
+        {
+          ProfScope prof(PROF_SOFTMAX_BWD, 6.0 * BL * V, s);        // algorithmic HBM bytes: read p (4), write dz (2)
+          GIC_TRY(dz_fused_tc(demb, De, W_e, out, ws + w.dot, T, temperature_device(), BL, V, dz_bf, w.Vp, db_out,
+                              accumulate, s, &dz_done));
+        }
+        if (!dz_done) {
+          GIC_TRY(gemm(mode, false, false, BL, V, De, 1.f, demb, De, W_e, V, 0.f, ws + w.dlogits, V, nullptr, s));
+          GIC_TRY(softmax_bwd_dot_bf16(out, ws + w.dlogits, ws + w.dot, T, BL, V, dz_bf, w.Vp, s));
+          GIC_TRY(colsum_bf16(dz_bf, BL, V, w.Vp, accumulate != 0, db_out, s));
+        }
         GIC_TRY(f32_to_bf16(saved + sv.htop, BL, H, H, htop_bf, H, s));
         GIC_TRY(f32_to_bf16(W_out, V, H, H, wout_bf, H, s));
         GIC_TRY(gemm_bf16(true, false, V, H, BL, 1.f, dz_bf, w.Vp, htop_bf, H, beta, dW_out, H, nullptr, s));

@@ -77,6 +77,10 @@ int vocab_sample_tc(const float* htop, int lda, const float* W_out, const float*
                     const float* T_dev, int B, int V, int H, int L, int t, float* out, int64_t* ids, const int64_t* forced,
                     const float* embed, int E, float* x_next, float* scratch, cudaStream_t stream, bool* handled);
 
+// dz (bf16) = T p (demb W_e - dot) and db_out = colsum(dz) in one streaming tcgen05 kernel (dz_fused_tcgen05.cu)
+int dz_fused_tc(const float* demb, int K, const float* W_e, const float* p, const float* dot, float T, const float* T_dev,
+                int M, int V, void* dz_bf, int Vp, float* db_out, int accumulate, cudaStream_t stream, bool* handled);
+
 // out[N] (+)= scale * sum_rows A[M,N]
 int colsum_f32(const float* A, int M, int N, int lda, float scale, bool accumulate, float* out,
                cudaStream_t stream);

@@ -166,3 +166,46 @@ def test_fused_vocab_sample_matches_unfused(B, L, V, E, H, T, forced):
     assert err <= 1e-5 * float(p0.max()) + 1e-12
     rs = p1.sum(-1)
     assert float((rs - 1).abs().max()) < 1e-4
+
+
+# ---- fused dz kernel (dz_fused_tcgen05.cu): D-embedding input gradient + tempered-softmax backward + db_out ------------
+def _adv_grads(fused_dz, B, L, V, E, H, T=1.0):
+    import gic_b200
+    from gic_b200.args import default_args
+    from gic_b200.training import GANInstructor
+    a = default_args(vocab_size=V, gen_embed_dim=E, gen_hidden_dim=H, gen_num_layers=1, conditional_gan=0, device="cuda")
+    torch.manual_seed(3)
+    inst = GANInstructor(a, device="cuda:0")
+    inst.gen.train(); inst.disc.train(); inst.gen.decoder.temperature = T
+    g = torch.Generator(device="cuda:0").manual_seed(11)
+    caps = torch.randint(4, V, (B, L), generator=g, device="cuda:0")
+    u = torch.rand(L, B, V, generator=g, device="cuda:0")
+    keep = (torch.rand(3, B * 64, 900, generator=g, device="cuda:0") >= 0.2).to(torch.uint8)
+    os.environ["GIC_FUSED_DZ_BF16"] = "1" if fused_dz else "0"
+    try:
+        inst.adv_step(caps, u=u, keep=keep, update=False)
+        torch.cuda.synchronize()
+    finally:
+        os.environ.pop("GIC_FUSED_DZ_BF16", None)
+    return {k: inst._flat_g.g(p).clone() for k, p in inst.gen.named_parameters() if id(p) in inst._flat_g._index}
+
+
+@pytest.mark.parametrize("B,L,V,E,H,T", [(24, 10, 1000, 64, 64, 1.0), (64, 12, 4000, 128, 256, 3.0)])
+def test_fused_dz_matches_separate_kernels(B, L, V, E, H, T):
+    """GIC_GEMM_BF16: the streaming dz kernel against GEMM + softmax-backward + column-sum kernels.  Both round the same
+    fp32 dz to bf16, so every generator gradient agrees to summation order; db_out is summed from the fp32 values in the
+    fused kernel (from the bf16 copy in the separate one) and agrees to bf16 rounding."""
+    import gic_b200
+    old = gic_b200.get_gemm_mode()
+    gic_b200.set_gemm_mode(gic_b200.GEMM_BF16)
+    try:
+        g1 = _adv_grads(True, B, L, V, E, H, T)
+        g0 = _adv_grads(False, B, L, V, E, H, T)
+    finally:
+        gic_b200.set_gemm_mode(old)
+    for k in g0:
+        scale = float(g0[k].abs().max())
+        err = float((g1[k] - g0[k]).abs().max())
+        REPORT[f"dz_fused/B{B}V{V}/{k}"] = dict(err=err, scale=scale, rel=err / max(scale, 1e-30))
+        tol = 2e-2 if k.endswith("linear.bias") else 5e-3     # bf16 rounding flips of dz where dp - dot cancels
+        assert err <= tol * scale + 1e-12, f"{k}: err {err:.3e} scale {scale:.3e}"
