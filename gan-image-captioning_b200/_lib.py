@@ -116,6 +116,8 @@ def _declare(L):
     L.gic_disc_prepared_floats.restype = Z
     L.gic_disc_prepared_floats.argtypes = [I]
     L.gic_disc_prepare.argtypes = [I, P, P, P, I, P, P, I, P, P]
+    L.gic_set_vocab_grads_event.restype = None
+    L.gic_set_vocab_grads_event.argtypes = [P]
     L.gic_disc_set_prepared.restype = None
     L.gic_disc_set_prepared.argtypes = [P]
     for name in header_symbols():      # every declared entry point must be exported

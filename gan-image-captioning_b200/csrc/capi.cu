@@ -213,6 +213,17 @@ struct DecodeBwdWs {
 
 // dout source: dense dout[B,L,V], or (dout == nullptr) the factored form d(emb)[B*L,De] x W_e[De,V] coming out of the
 // discriminator's embedding layer, with emb[B*L,De] = out W_e^T saved by its forward.
+//
+// Data-parallel hook: dW_out / db_out (40 % of the generator's gradient bytes at c2) are final long before the serial
+// BPTT tail.  When the caller registered an event (gic_set_vocab_grads_event) it is recorded on the stream right after
+// those two buffers are complete, so their all-reduce can run on another stream underneath the rest of the backward.
+static cudaEvent_t g_vocab_grads_event = nullptr;
+static int record_vocab_grads_event(cudaStream_t s) {
+  if (!g_vocab_grads_event) return GIC_OK;
+  cudaError_t e = cudaEventRecord(g_vocab_grads_event, s);
+  if (e != cudaSuccess) { set_error("cudaEventRecord(vocab grads): %s", cudaGetErrorString(e)); return GIC_ERR_CUDA; }
+  return GIC_OK;
+}
 static int decode_bwd(int mode, const float* dout, const float* demb, const float* emb, const float* W_e, int De,
                       const float* out, const int64_t* fed, const float* W_emb,
                       const float* const* W_ih, const float* const* W_hh, const float* W_out, float T, int pretrain,
@@ -275,6 +286,7 @@ static int decode_bwd(int mode, const float* dout, const float* demb, const floa
         GIC_TRY(f32_to_bf16(saved + sv.htop, BL, H, H, htop_bf, H, s));
         GIC_TRY(f32_to_bf16(W_out, V, H, H, wout_bf, H, s));
         GIC_TRY(gemm_bf16(true, false, V, H, BL, 1.f, dz_bf, w.Vp, htop_bf, H, beta, dW_out, H, nullptr, s));
+        GIC_TRY(record_vocab_grads_event(s));
         GIC_TRY(gemm_bf16(false, false, BL, H, V, 1.f, dz_bf, w.Vp, wout_bf, H, 0.f, ws + w.dhtop, H, nullptr, s));
         vocab_done = true;
       }
@@ -295,6 +307,7 @@ static int decode_bwd(int mode, const float* dout, const float* demb, const floa
   if (!vocab_done) {
     GIC_TRY(colsum_f32(dlogits, BL, V, V, 1.f, accumulate != 0, db_out, s));
     GIC_TRY(gemm(mode, true, false, V, H, BL, 1.f, dlogits, V, saved + sv.htop, H, beta, dW_out, H, nullptr, s));
+    GIC_TRY(record_vocab_grads_event(s));
     GIC_TRY(gemm(mode, false, false, BL, H, V, 1.f, dlogits, V, W_out, H, 0.f, ws + w.dhtop, H, nullptr, s));
   }
   // 3. BPTT through (h, c)
@@ -693,5 +706,6 @@ int gic_disc_prepare(int mode, const float* W_h, const float* W_f, const float* 
   return disc_prepare(mode, W_h, W_f, b_f, Hd, W_o, b_o, F, prepared, S(stream));
 }
 void gic_disc_set_prepared(const float* prepared) { disc_set_prepared(prepared); }
+void gic_set_vocab_grads_event(void* cuda_event) { g_vocab_grads_event = reinterpret_cast<cudaEvent_t>(cuda_event); }
 
 }  // extern "C"

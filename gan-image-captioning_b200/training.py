@@ -75,6 +75,9 @@ class GANInstructor:
         self._dyn_host = None
         self._in_graph = False
         self._side = None
+        self._comm = None
+        self._vocab_ev = None
+        self.bucketed = os.environ.get("GIC_NO_BUCKET", "0") != "1"
         self.overlap = os.environ.get("GIC_NO_OVERLAP", "0") != "1"
         self.world = 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
@@ -97,10 +100,53 @@ class GANInstructor:
             self._side = torch.cuda.Stream(device=self.device)
         return self._side
 
+    def _comm_stream(self):
+        if self._comm is None:
+            self._comm = torch.cuda.Stream(device=self.device)
+        return self._comm
+
+    def _gen_backward_early_bucket(self, run_backward):
+        """Data parallel, phase 1: generator backward with the C library's hook event registered; the
+        [linear.weight | linear.bias] bucket (final before the BPTT tail) is all-reduced on a third stream as soon as
+        the event fires.  Returns True when phase 2 (_gen_allreduce_rest) must follow."""
+        fg = self._flat_g
+        if self.world <= 1 or not self.bucketed or fg.n_early <= 0 or fg.n_early >= fg.n:
+            run_backward()
+            return False
+        lib = _lib.lib()
+        cur = torch.cuda.current_stream()
+        if self._vocab_ev is None:
+            self._vocab_ev = torch.cuda.Event()
+            self._vocab_ev.record(cur)                  # materialises the cudaEvent_t handle
+        ev = self._vocab_ev
+        lib.gic_set_vocab_grads_event(ev.cuda_event)
+        try:
+            run_backward()
+        finally:
+            lib.gic_set_vocab_grads_event(None)
+        comm = self._comm_stream()
+        comm.wait_event(ev)
+        with torch.cuda.stream(comm):
+            parallel.allreduce_sum_(fg.grad[:fg.n_early])
+        return True
+
+    def _gen_allreduce_rest(self, bucketed):
+        """Phase 2 (issued after the discriminator's all-reduce so that NCCL's queue order is early bucket, D, rest)."""
+        fg = self._flat_g
+        if self.world <= 1:
+            return
+        if bucketed:
+            parallel.allreduce_sum_(fg.grad[fg.n_early:])
+            torch.cuda.current_stream().wait_stream(self._comm_stream())
+        else:
+            parallel.allreduce_sum_(fg.grad)
+
     # ---- flat buffers ---------------------------------------------------------------------------
     def _gen_params(self):
         dec = self.gen.decoder
-        ps = [dec.embed.weight, *dec.lstm_params(), dec.linear.weight, dec.linear.bias]
+        # the vocab projection comes first: its gradients are final before the BPTT tail, so data-parallel runs all-reduce
+        # that contiguous bucket early (n_early) underneath the rest of the backward
+        ps = [dec.linear.weight, dec.linear.bias, dec.embed.weight, *dec.lstm_params()]
         if dec.attention:
             ps += dec.attn_params()
         if self.cgan:
@@ -120,6 +166,7 @@ class GANInstructor:
     def _ensure_flat(self):
         if self._flat_g is None or not self._flat_g.homed():
             self._flat_g = FlatParams(self._gen_params(), self.device)
+            self._flat_g.n_early = self._flat_g.offsets[2]          # [linear.weight | linear.bias]
         if self._flat_d is None or not self._flat_d.homed():
             self._flat_d = FlatParams(self._disc_params(), self.device)
 
@@ -349,16 +396,19 @@ class GANInstructor:
             bws2 = self._buf("disc_bws2", lib.gic_disc_bwd_workspace_floats(B, L, De, R, Fd))
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                gen_chain(bws2, side.cuda_stream)
                 gen_done = torch.cuda.Event()
-                gen_done.record(side)
-                if self.world > 1:
-                    parallel.allreduce_sum_(fg.grad)
-                out["g_sqnorm"] = self._clip_adam(fg, a.gen_lr, update, 3)
+
+                def _bwd():
+                    gen_chain(bws2, side.cuda_stream)
+                    gen_done.record(side)
+                g_bucketed = self._gen_backward_early_bucket(_bwd)
             disc_bwd(seeds[0], k0, None, captions, saved_r, 1, 0, None, bws, stream)
             disc_bwd(seeds[1], k1, probs, None, saved_f, 1, 1, None, bws, stream)
             if self.world > 1:
                 parallel.allreduce_sum_(fd.grad)
+            with torch.cuda.stream(side):
+                self._gen_allreduce_rest(g_bucketed)
+                out["g_sqnorm"] = self._clip_adam(fg, a.gen_lr, update, 3)
             main.wait_event(gen_done)
             out["d_sqnorm"] = self._clip_adam(fd, a.disc_lr, update, 1)
             main.wait_stream(side)

@@ -292,6 +292,13 @@ int gic_disc_prepare(int mode, const float* W_h /*[F,F]*/, const float* W_f /*[H
                      const float* W_o, const float* b_o, int F, float* prepared, gic_stream_t stream);
 void gic_disc_set_prepared(const float* prepared);
 
+/* ---- data-parallel overlap hook ----
+ * gic_set_vocab_grads_event(ev): while ev (a cudaEvent_t, NULL to clear; process-wide) is registered,
+ * gic_decode_sample_bwd / _bwd_factored / _bwd_attn record it on their stream as soon as dW_out and db_out are final
+ * -- before the serial BPTT tail -- so the caller can all-reduce that bucket on another stream underneath the rest of
+ * the backward (the reference is single-GPU). */
+void gic_set_vocab_grads_event(void* cuda_event);
+
 #ifdef __cplusplus
 }
 #endif
