@@ -317,15 +317,16 @@ def run_ours(args):
         traffic = None
         tp = os.path.join(ROOT, "profiles", "r1", "traffic.json")
         if args.workload == "c2" and os.path.exists(tp):
-            tj = json.load(open(tp))
-            traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
+            tj = json.load(open(tp)).get(args.mode)
+            if tj:
+                traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
         flops_launch = g["work_per_step"] / g["calls_per_step"]
         us_launch = g["ms_per_step"] * 1e3 / g["calls_per_step"]
         ach = flops_launch / (us_launch * 1e-6) / 1e12
         roofline = {"kernel": (f"gemm_p_kernel (tcgen05 kind::{'f16 bf16 operands' if args.mode == 'bf16' else 'tf32'}, persistent): discriminator highway / dx / dW_h, "
                                f"{B * R}x{Fd}x{Fd}") if args.mode != "fp32" else "sgemm_kernel (fp32 FFMA)",
                     "bound": "tensor", "achieved": ach, "peak": peaks["tf"], "unit": "TFLOP/s", "frac": ach / peaks["tf"],
-                    "traffic": traffic if args.mode == "tf32" else None,
+                    "traffic": traffic,
                     "peak_source": peaks["src"] + ", sustained bf16 dense (TF32 runs at half that rate)",
                     "share_of_step": g["ms_per_step"] / ms_step, "launches_per_step": g["calls_per_step"],
                     "algorithmic_flops_per_launch": flops_launch, "us_per_launch": us_launch}

@@ -166,6 +166,7 @@ int lstm_step_tc(const float* x, int In, const float* h_prev, const float* W_ih,
   int U = 32;
   if ((H % 32) || (H / 32) * mt * 4 < 3 * num_sms()) U = 16;
   if (U == 16 && ((H % 16) || (H / 16) * mt * 4 < 3 * num_sms())) U = 8;
+  { const char* e = getenv("GIC_LSTM_U"); if (e) { const int u = atoi(e); if ((u == 8 || u == 16 || u == 32) && H % u == 0) U = u; } }   // tuning experiments
   const bool rn = tf32_round_in_tma();
   CUtensorMap tx, th, twi, twh;
   bool ok = make_map(&tx, x, B, In, In, BK, BM, rn, false) && make_map(&th, h_prev, B, H, H, BK, BM, rn, false) &&
