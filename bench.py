@@ -39,6 +39,8 @@ WORKLOADS = {
     "c1": dict(B=8, L=16, V=1000, E=32, H=512, layers=1, feat=2048, filters=[300, 300, 300]),
     # BASELINE.json configs[2]: SeqGAN-style reward, 128 captions x 16 rollouts per prefix (secondary line: --workload c3)
     "c3": dict(B=128, L=20, V=10000, E=512, H=512, layers=1, feat=0, filters=[300, 300, 300], n_roll=16),
+    # BASELINE.json configs[3]: scaled decoder (hidden 1024, vocab 30k, global batch 1024 over 8 GPUs = 128 rows per GPU; --workload c4)
+    "c4": dict(B=128, L=20, V=30000, E=512, H=1024, layers=1, feat=2048, filters=[300, 300, 300]),
     # BASELINE.json configs[4]: discriminator-only step, 4096 real + 4096 fake captions of length 32 (--workload c5)
     "c5": dict(B=4096, L=32, V=10000, E=512, H=512, layers=1, feat=0, filters=[300, 300, 300]),
 }
