@@ -116,6 +116,7 @@ def _declare(L):
     L.gic_disc_prepared_floats.restype = Z
     L.gic_disc_prepared_floats.argtypes = [I]
     L.gic_disc_prepare.argtypes = [I, P, P, P, I, P, P, I, P, P]
+    L.gic_pack_captions.argtypes = [P, P, I, I, P, P, P]
     L.gic_set_vocab_grads_event.restype = None
     L.gic_set_vocab_grads_event.argtypes = [P]
     L.gic_disc_set_prepared.restype = None

@@ -47,6 +47,7 @@ int pg_loss(const float*, const int64_t*, const float*, int, int, int, int, floa
 int clip_adam(float*, const float*, float*, float*, size_t, const float*, float, float, int, float, float, float,
               float, const float*, cudaStream_t);
 void set_temperature_device(const float*);
+int pack_captions(const int32_t*, const int32_t*, int, int, int64_t*, int32_t*, cudaStream_t);
 const float* temperature_device();
 void disc_set_prepared(const float*);
 int disc_prepare(int, const float*, const float*, const float*, int, const float*, const float*, int, float*, cudaStream_t);
@@ -706,6 +707,11 @@ int gic_disc_prepare(int mode, const float* W_h, const float* W_f, const float* 
   return disc_prepare(mode, W_h, W_f, b_f, Hd, W_o, b_o, F, prepared, S(stream));
 }
 void gic_disc_set_prepared(const float* prepared) { disc_set_prepared(prepared); }
+int gic_pack_captions(const int32_t* tokens, const int32_t* offsets, int B, int max_caption_len, int64_t* captions,
+                      int32_t* lengths, gic_stream_t stream) {
+  GIC_TRY(require_device());
+  return pack_captions(tokens, offsets, B, max_caption_len, captions, lengths, S(stream));
+}
 void gic_set_vocab_grads_event(void* cuda_event) { g_vocab_grads_event = reinterpret_cast<cudaEvent_t>(cuda_event); }
 
 }  // extern "C"

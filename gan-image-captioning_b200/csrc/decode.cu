@@ -14,6 +14,36 @@ const float* temperature_device() { return g_t_dev; }
 __device__ __forceinline__ float pick_t(float by_value, const float* t_dev) { return t_dev ? __ldg(t_dev) : by_value; }
 
 // ---------------------------------------------------------------------------------------
+// batch contract (collate_fn, src/tasks.py:138-158): ragged token lists arrive as ONE flat int32 array + B+1 offsets
+// (sum(len) + B + 1 ints over PCIe instead of a padded [B, Lm] int64 tensor) and are packed on the device into
+// captions[B, Lm] = <S>=1, tokens, <E>=2, <PAD>=0 ... and lengths[b] = len + 2.  Thread = one (caption, position).
+// ---------------------------------------------------------------------------------------
+__global__ void pack_captions_kernel(const int32_t* __restrict__ tokens, const int32_t* __restrict__ offsets, int B,
+                                     int Lm, int64_t* __restrict__ captions, int32_t* __restrict__ lengths) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * Lm) return;
+  const int b = idx / Lm, pos = idx - b * Lm;
+  const int o = offsets[b];
+  int len = offsets[b + 1] - o;
+  if (len > Lm - 2) len = Lm - 2;                    // the host shim rejects this case; stay in bounds regardless
+  int64_t v = 0;                                     // <PAD>
+  if (pos == 0) v = 1;                               // <S>
+  else if (pos <= len) v = tokens[o + pos - 1];
+  else if (pos == len + 1) v = 2;                    // <E>
+  captions[idx] = v;
+  if (pos == 0 && lengths) lengths[b] = len + 2;
+}
+
+int pack_captions(const int32_t* tokens, const int32_t* offsets, int B, int Lm, int64_t* captions, int32_t* lengths,
+                  cudaStream_t s) {
+  GIC_REQUIRE(B >= 0 && Lm >= 2, GIC_ERR_SHAPE, "pack_captions: bad shape B=%d max_caption_len=%d", B, Lm);
+  if (B == 0) return GIC_OK;
+  GIC_REQUIRE(offsets && captions, GIC_ERR_NULL, "pack_captions: NULL pointer");
+  pack_captions_kernel<<<cdiv((long long)B * Lm, 256), 256, 0, s>>>(tokens, offsets, B, Lm, captions, lengths);
+  return check_launch("pack_captions_kernel");
+}
+
+// ---------------------------------------------------------------------------------------
 // row gather: out[i, :] = table[ids[i], :]     (nn.Embedding lookup, src/generator.py:75)
 // ---------------------------------------------------------------------------------------
 __global__ void gather_rows_kernel(const float* __restrict__ table, const int64_t* __restrict__ ids,

@@ -749,6 +749,81 @@ class GANInstructor:
             out["d_loss"], out["d_sqnorm"] = d["d_loss"], d["d_sqnorm"]
         return out
 
+    # ---- checkpoints (src/training.py:116-119 pretrained_model.ckpt, :223-227 adv_model.ckpt) -----
+    # The reference only ever SAVES (plain state_dict dumps) and has no load / resume.  The files written here keep its
+    # formats -- a reference-side torch.load(...)["generator"] keeps working -- and add one extra key with what a
+    # resumed run needs: Adam moments and step counts (per parameter NAME, so the flat layout may change), temperature,
+    # epoch / step counters.
+    def _named_flat(self, fp, module):
+        names = {id(p): n for n, p in module.named_parameters()}
+        return [(names[id(p)], o, n) for p, o, n in zip(fp.params, fp.offsets, fp.sizes)]
+
+    def _optim_state(self):
+        self._ensure_flat()
+        out = {}
+        for tag, fp, mod in (("gen", self._flat_g, self.gen), ("disc", self._flat_d, self.disc)):
+            st = {"step": int(fp.step), "m": {}, "v": {}}
+            for name, o, n in self._named_flat(fp, mod):
+                st["m"][name] = fp.m[o:o + n].detach().cpu().clone()
+                st["v"][name] = fp.v[o:o + n].detach().cpu().clone()
+            if hasattr(fp, "m_pre"):
+                st["step_pre"] = int(fp.step_pre)
+                st["m_pre"] = {name: fp.m_pre[o:o + n].detach().cpu().clone() for name, o, n in self._named_flat(fp, mod)}
+                st["v_pre"] = {name: fp.v_pre[o:o + n].detach().cpu().clone() for name, o, n in self._named_flat(fp, mod)}
+            out[tag] = st
+        return out
+
+    def save_pretrained(self, path):
+        """pretrained_model.ckpt: the generator's state_dict, exactly as src/training.py:118."""
+        torch.save(self.gen.state_dict(), path)
+
+    def save_checkpoint(self, path, resume_state=True):
+        """adv_model.ckpt: {"generator": ..., "discriminator": ...} as src/training.py:225-226 (+ "gic_resume")."""
+        blob = {"generator": self.gen.state_dict(), "discriminator": self.disc.state_dict()}
+        if resume_state:
+            blob["gic_resume"] = {"optim": self._optim_state(), "temperature": float(self.gen.decoder.temperature),
+                                  "adv_epoch": int(self.adv_epoch), "pretrain_steps": int(self.pretrain_steps),
+                                  "gen_steps": int(self.gen_steps), "disc_steps": int(self.disc_steps), "format": 1}
+        torch.save(blob, path)
+
+    def load_checkpoint(self, path, strict=True):
+        """Loads either file format (a bare generator state_dict, or the generator/discriminator dict) and, when the
+        file carries it, the resume state.  Parameters stay views of the flat buffers (load_state_dict copies in place),
+        captured CUDA graphs stay valid.  Returns True when optimizer / schedule state was restored."""
+        blob = torch.load(path, map_location="cpu", weights_only=False)
+        if not isinstance(blob, dict):
+            raise ValueError("%s: not a checkpoint written by this code or the reference" % path)
+        if "generator" in blob or "discriminator" in blob:
+            if "generator" in blob:
+                self.gen.load_state_dict(blob["generator"], strict=strict)
+            if "discriminator" in blob:
+                self.disc.load_state_dict(blob["discriminator"], strict=strict)
+        else:
+            self.gen.load_state_dict(blob, strict=strict)              # pretrained_model.ckpt
+        rs = blob.get("gic_resume") if isinstance(blob.get("gic_resume", None), dict) else None
+        if rs is None:
+            return False
+        self._ensure_flat()
+        for tag, fp, mod in (("gen", self._flat_g, self.gen), ("disc", self._flat_d, self.disc)):
+            st = rs["optim"][tag]
+            fp.step = int(st["step"])
+            for name, o, n in self._named_flat(fp, mod):
+                if name not in st["m"]:
+                    if strict:
+                        raise KeyError("checkpoint has no Adam state for %s.%s" % (tag, name))
+                    continue
+                fp.m[o:o + n].copy_(st["m"][name].reshape(-1))
+                fp.v[o:o + n].copy_(st["v"][name].reshape(-1))
+            if "m_pre" in st:
+                fp.m_pre, fp.v_pre, fp.step_pre = torch.zeros_like(fp.m), torch.zeros_like(fp.v), int(st["step_pre"])
+                for name, o, n in self._named_flat(fp, mod):
+                    fp.m_pre[o:o + n].copy_(st["m_pre"][name].reshape(-1))
+                    fp.v_pre[o:o + n].copy_(st["v_pre"][name].reshape(-1))
+        self.gen.decoder.temperature = rs["temperature"]
+        self.adv_epoch, self.pretrain_steps = rs["adv_epoch"], rs["pretrain_steps"]
+        self.gen_steps, self.disc_steps = rs["gen_steps"], rs["disc_steps"]
+        return True
+
     def adv_loop(self, what, batches, total_batches=None, graph=False):
         """Body of the reference's adv_loop over an iterable of (pooled_or_None, captions) batches."""
         gen_loss, disc_loss = [], []

@@ -292,6 +292,14 @@ int gic_disc_prepare(int mode, const float* W_h /*[F,F]*/, const float* W_f /*[H
                      const float* W_o, const float* b_o, int F, float* prepared, gic_stream_t stream);
 void gic_disc_set_prepared(const float* prepared);
 
+/* ---- batch contract: collate_fn (src/tasks.py:138-158), the step immediately before the path ----
+ * The ragged token lists of a batch arrive as tokens[sum(len)] (int32, caption after caption) and offsets[B+1] (int32,
+ * offsets[b] = start of caption b); captions[B, max_caption_len] int64 = <S>=1, tokens, <E>=2, <PAD>=0 ... and
+ * lengths[B] int32 = len + 2 (may be NULL) are written on the device.  max_caption_len = longest caption + 2 is the
+ * host's to compute (the reference returns it as a Python int, src/tasks.py:147,158). */
+int gic_pack_captions(const int32_t* tokens, const int32_t* offsets, int B, int max_caption_len, int64_t* captions,
+                      int32_t* lengths, gic_stream_t stream);
+
 /* ---- data-parallel overlap hook ----
  * gic_set_vocab_grads_event(ev): while ev (a cudaEvent_t, NULL to clear; process-wide) is registered,
  * gic_decode_sample_bwd / _bwd_factored / _bwd_attn record it on their stream as soon as dW_out and db_out are final

@@ -371,3 +371,22 @@ def adversarial_step(inp: dict, temperature: float, loss_type: str = "standard",
             new_g[k] = w
         out["new_disc"], out["new_gen"] = new_d, new_g
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# batch contract: collate_fn (src/tasks.py:138-158) -- the step immediately before the hot path
+# ------------------------------------------------------------------------------------------------
+def collate_captions(token_lists):
+    """captions[B, max_len + 2] int64 = <S>=1, tokens, <E>=2, <PAD>=0 ...; lengths[B] int32 = len + 2; max_caption_len
+    (src/tasks.py:143-156).  Plain loops, as the reference writes them."""
+    max_caption_len = 0
+    for toks in token_lists:                                    # :143-146
+        max_caption_len = max(max_caption_len, len(toks))
+    max_caption_len += 2
+    captions = torch.zeros(len(token_lists), max_caption_len, dtype=torch.long)       # :149
+    lengths = torch.zeros(len(token_lists), dtype=torch.int32)                        # :150
+    for i, toks in enumerate(token_lists):                      # :152-155
+        row = [1] + [int(t) for t in toks] + [2] + [0] * (max_caption_len - len(toks) - 2)
+        captions[i] = torch.tensor(row, dtype=torch.long)
+        lengths[i] = len(toks) + 2
+    return captions, lengths, max_caption_len

@@ -113,3 +113,48 @@ def test_flat_params_views(built):
         assert torch.equal(p.detach(), 2 * v)          # params are views of the flat buffer
     fp.g(ps[1]).fill_(1.0)
     assert float(fp.grad.sum()) == 7.0
+
+
+def test_checkpoint_formats_and_resume_state_roundtrip(tmp_path):
+    """src/training.py:118 (pretrained_model.ckpt = generator state_dict) and :225-226 (adv_model.ckpt =
+    {"generator", "discriminator"}) keep their formats; the extra "gic_resume" key restores Adam moments per parameter
+    name, step counts, temperature and counters.  Host logic only (no kernels run)."""
+    import torch
+    from gic_b200.args import default_args
+    from gic_b200.training import GANInstructor
+    a = default_args(vocab_size=50, gen_embed_dim=8, gen_hidden_dim=16, disc_num_filters=[4, 4, 4], conditional_gan=1,
+                     feature_dim=12, device="cpu")
+    torch.manual_seed(0)
+    inst = GANInstructor(a, device="cpu")
+    inst._ensure_flat()
+    for fp in (inst._flat_g, inst._flat_d):
+        fp.m.uniform_(-1, 1); fp.v.uniform_(0, 1); fp.step = 7
+    inst._flat_g.m_pre, inst._flat_g.v_pre, inst._flat_g.step_pre = torch.rand_like(inst._flat_g.m), torch.rand_like(inst._flat_g.v), 3
+    inst.gen.decoder.temperature, inst.adv_epoch, inst.gen_steps, inst.disc_steps, inst.pretrain_steps = 12.5, 4, 40, 41, 2
+    adv, pre = str(tmp_path / "adv_model.ckpt"), str(tmp_path / "pretrained_model.ckpt")
+    inst.save_checkpoint(adv); inst.save_pretrained(pre)
+    # reference-side readers: plain dicts of tensors with the reference's keys
+    blob = torch.load(adv, map_location="cpu", weights_only=False)
+    assert set(blob) == {"generator", "discriminator", "gic_resume"}
+    assert "decoder.lstm.weight_ih_l0" in blob["generator"] and "highway.weight" in blob["discriminator"]
+    assert "decoder.embed.weight" in torch.load(pre, map_location="cpu", weights_only=False)
+    torch.manual_seed(1)
+    other = GANInstructor(a, device="cpu")
+    assert other.load_checkpoint(adv) is True
+    for k, v in inst.gen.state_dict().items():
+        assert torch.equal(other.gen.state_dict()[k], v), k
+    for k, v in inst.disc.state_dict().items():
+        assert torch.equal(other.disc.state_dict()[k], v), k
+    assert other._flat_g.homed() and other._flat_d.homed()            # parameters are still views of the flat buffers
+    for f0, f1 in ((inst._flat_g, other._flat_g), (inst._flat_d, other._flat_d)):
+        assert f0.step == f1.step == 7
+        for o, n in zip(f0.offsets, f0.sizes):                         # (the 16-byte alignment gaps between tensors carry no state)
+            assert torch.equal(f0.m[o:o + n], f1.m[o:o + n]) and torch.equal(f0.v[o:o + n], f1.v[o:o + n])
+            assert torch.equal(f0.flat[o:o + n], f1.flat[o:o + n])
+    for o, n in zip(inst._flat_g.offsets, inst._flat_g.sizes):
+        assert torch.equal(inst._flat_g.m_pre[o:o + n], other._flat_g.m_pre[o:o + n])
+    assert other._flat_g.step_pre == 3
+    assert other.gen.decoder.temperature == 12.5 and (other.adv_epoch, other.gen_steps, other.disc_steps, other.pretrain_steps) == (4, 40, 41, 2)
+    third = GANInstructor(a, device="cpu")
+    assert third.load_checkpoint(pre) is False                       # weights only: no optimizer state in that format
+    assert torch.equal(third.gen.state_dict()["decoder.linear.weight"], inst.gen.state_dict()["decoder.linear.weight"])

@@ -446,6 +446,39 @@ def test_two_steps_adam_state_carries():
             close(f"two_steps/gen/{k}", p, r2["new_gen"][k], rtol=1e-5, atol=2 * ADAM_ATOL)
 
 
+def test_checkpoint_resume_continues_training(tmp_path):
+    """save_checkpoint after two steps, load into a fresh instructor, take the third step on both: same parameters
+    (the resumed run has the Adam moments, step counts and temperature of the original one)."""
+    from gic_b200.training import GANInstructor
+    inp = rp.make_inputs(rp.CONFIGS["c0"])
+    a = inp["args"]; a.device = "cuda"
+
+    def fresh(seed):
+        torch.manual_seed(seed)
+        inst = GANInstructor(a, device="cuda:0")
+        inst.gen.train(); inst.disc.train()
+        return inst
+    inst = fresh(1)
+    sd = inst.gen.state_dict(); sd.update({k: v.clone() for k, v in inp["gen"].items()}); inst.gen.load_state_dict(sd)
+    inst.disc.load_state_dict({k: v.clone() for k, v in inp["disc"].items()})
+    inst.gen.decoder.temperature = 3.0
+    forced = inp["captions"]
+    for _ in range(2):
+        inst.adv_step(inp["captions"], u=inp["u"], keep=inp["keep"], forced_ids=forced)
+    path = str(tmp_path / "adv_model.ckpt")
+    inst.save_checkpoint(path)
+    other = fresh(2)
+    assert other.load_checkpoint(path) is True
+    assert other.gen.decoder.temperature == 3.0 and other._flat_d.step == 2 and other._flat_g.step == 2
+    inst.adv_step(inp["captions"], u=inp["u"], keep=inp["keep"], forced_ids=forced)
+    other.adv_step(inp["captions"], u=inp["u"], keep=inp["keep"], forced_ids=forced)
+    torch.cuda.synchronize()
+    for (k, p), (_, q) in zip(inst.gen.named_parameters(), other.gen.named_parameters()):
+        close(f"resume/gen/{k}", q, p, rtol=1e-6, atol=ADAM_ATOL)
+    for (k, p), (_, q) in zip(inst.disc.named_parameters(), other.disc.named_parameters()):
+        close(f"resume/disc/{k}", q, p, rtol=1e-6, atol=ADAM_ATOL)
+
+
 def test_reference_style_loop_with_torch_optimizers():
     """Drop-in use exactly as src/training.py:144-169 writes it (Q1-fixed order), torch.optim.Adam on
     our modules' parameters, autograd driving our kernels."""
