@@ -70,6 +70,7 @@ class GANInstructor:
         self._flat_g: Optional[FlatParams] = None
         self._flat_d: Optional[FlatParams] = None
         self._cache = {}
+        self._retired = []
         self._graphs = {}
         self._dyn = None          # device scalars of the captured step: [T, D lr/bc1, D 1/sqrt(bc2), G lr/bc1, G 1/sqrt(bc2)]
         self._dyn_host = None
@@ -173,9 +174,11 @@ class GANInstructor:
     def _buf(self, key, numel, dtype=torch.float32):
         t = self._cache.get(key)
         if t is None or t.numel() < numel or t.dtype != dtype:
+            if t is not None and self._graphs:
+                self._retired.append(t)      # a captured graph may still replay on the old buffer: keep it alive
             t = torch.empty(int(numel), dtype=dtype, device=self.device)
             self._cache[key] = t
-        return t
+        return t[:int(numel)]            # a smaller batch after a larger one reuses the front of the cached buffer
 
     # ---- the fused adversarial step ---------------------------------------------------------------
     @torch.no_grad()
