@@ -117,6 +117,10 @@ def _declare(L):
     L.gic_disc_prepared_floats.argtypes = [I]
     L.gic_disc_prepare.argtypes = [I, P, P, P, I, P, P, I, P, P]
     L.gic_pack_captions.argtypes = [P, P, I, I, P, P, P]
+    L.gic_encoder_fwd_stats.argtypes = [I, P, I, I, I, P, P, P, P, P]
+    L.gic_encoder_fwd_apply.argtypes = [P, I, I, P, P, F, P, F, P, P, P, P]
+    L.gic_encoder_bwd_stats.argtypes = [P, P, P, P, I, I, P, P]
+    L.gic_encoder_bwd_apply.argtypes = [I, P, P, P, P, P, P, I, I, I, P, F, F, P, P, P, P, P, P]
     L.gic_set_vocab_grads_event.restype = None
     L.gic_set_vocab_grads_event.argtypes = [P]
     L.gic_disc_set_prepared.restype = None

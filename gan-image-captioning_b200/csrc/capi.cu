@@ -47,6 +47,11 @@ int pg_loss(const float*, const int64_t*, const float*, int, int, int, int, floa
 int clip_adam(float*, const float*, float*, float*, size_t, const float*, float, float, int, float, float, float,
               float, const float*, cudaStream_t);
 void set_temperature_device(const float*);
+int bn_stats(const float*, int, int, float*, cudaStream_t);
+int bn_apply(const float*, int, int, const float*, const float*, float, const float*, float, float*, float*, float*, cudaStream_t);
+int bn_bwd_stats(const float*, const float*, int, int, const float*, const float*, float*, cudaStream_t);
+int bn_bwd_apply(const float*, const float*, int, int, const float*, const float*, const float*, const float*, float, float,
+                 float*, float*, float*, cudaStream_t);
 int pack_captions(const int32_t*, const int32_t*, int, int, int64_t*, int32_t*, cudaStream_t);
 const float* temperature_device();
 void disc_set_prepared(const float*);
@@ -494,6 +499,44 @@ int gic_encoder_bwd(int mode, const float* dfeatures, const float* pooled, const
   GIC_REQUIRE(!accumulate, GIC_ERR_UNSUPPORTED, "encoder_bwd: accumulate is not supported");
   (void)W;
   GIC_TRY(bn_bwd(lin_out, dfeatures, B, E, gamma, save_mean, save_rstd, dlin_ws, dgamma, dbeta, S(stream)));
+  GIC_TRY(gemm(mode, true, false, E, Fin, B, 1.f, dlin_ws, E, pooled, Fin, 0.f, dW, Fin, nullptr, S(stream)));
+  return colsum_f32(dlin_ws, B, E, E, 1.f, false, db, S(stream));
+}
+
+// ---- synchronised-BatchNorm variant of the encoder projection (data parallel; see decode.cu) ----
+int gic_encoder_fwd_stats(int mode, const float* pooled, int B, int Fin, int E, const float* W, const float* b,
+                          float* lin_out, float* stats, gic_stream_t stream) {
+  GIC_TRY(require_device());
+  GIC_REQUIRE(B >= 1 && Fin >= 1 && E >= 1, GIC_ERR_SHAPE, "encoder_fwd_stats: bad shape");
+  GIC_REQUIRE(pooled && W && b && lin_out && stats, GIC_ERR_NULL, "encoder_fwd_stats: NULL pointer");
+  GIC_TRY(gemm(mode, false, true, B, E, Fin, 1.f, pooled, Fin, W, Fin, 0.f, lin_out, E, b, S(stream)));
+  return bn_stats(lin_out, B, E, stats, S(stream));
+}
+int gic_encoder_fwd_apply(const float* lin_out, int B, int E, const float* gamma, const float* beta, float eps,
+                          const float* stats, float count, float* save_mean, float* save_rstd, float* features,
+                          gic_stream_t stream) {
+  GIC_TRY(require_device());
+  GIC_REQUIRE(B >= 1 && E >= 1 && count >= 1.f, GIC_ERR_SHAPE, "encoder_fwd_apply: bad shape");
+  GIC_REQUIRE(lin_out && gamma && beta && stats && save_mean && save_rstd && features, GIC_ERR_NULL, "encoder_fwd_apply: NULL pointer");
+  return bn_apply(lin_out, B, E, gamma, beta, eps, stats, count, features, save_mean, save_rstd, S(stream));
+}
+int gic_encoder_bwd_stats(const float* dfeatures, const float* lin_out, const float* save_mean, const float* save_rstd,
+                          int B, int E, float* stats, gic_stream_t stream) {
+  GIC_TRY(require_device());
+  GIC_REQUIRE(B >= 1 && E >= 1, GIC_ERR_SHAPE, "encoder_bwd_stats: bad shape");
+  GIC_REQUIRE(dfeatures && lin_out && save_mean && save_rstd && stats, GIC_ERR_NULL, "encoder_bwd_stats: NULL pointer");
+  return bn_bwd_stats(lin_out, dfeatures, B, E, save_mean, save_rstd, stats, S(stream));
+}
+int gic_encoder_bwd_apply(int mode, const float* dfeatures, const float* pooled, const float* lin_out,
+                          const float* save_mean, const float* save_rstd, const float* gamma, int B, int Fin, int E,
+                          const float* stats, float count, float grad_share, float* dlin_ws, float* dW, float* db,
+                          float* dgamma, float* dbeta, gic_stream_t stream) {
+  GIC_TRY(require_device());
+  GIC_REQUIRE(B >= 1 && Fin >= 1 && E >= 1 && count >= 1.f, GIC_ERR_SHAPE, "encoder_bwd_apply: bad shape");
+  GIC_REQUIRE(dfeatures && pooled && lin_out && save_mean && save_rstd && gamma && stats && dlin_ws && dW && db && dgamma && dbeta,
+              GIC_ERR_NULL, "encoder_bwd_apply: NULL pointer");
+  GIC_TRY(bn_bwd_apply(lin_out, dfeatures, B, E, gamma, save_mean, save_rstd, stats, count, grad_share, dlin_ws, dgamma, dbeta,
+                       S(stream)));
   GIC_TRY(gemm(mode, true, false, E, Fin, B, 1.f, dlin_ws, E, pooled, Fin, 0.f, dW, Fin, nullptr, S(stream)));
   return colsum_f32(dlin_ws, B, E, E, 1.f, false, db, S(stream));
 }

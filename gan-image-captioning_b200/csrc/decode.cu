@@ -718,6 +718,87 @@ __global__ void bn_bwd_kernel(const float* __restrict__ y, const float* __restri
   if (lane == 0) { dgamma[j] = sdx; dbeta[j] = sd; }
 }
 
+// ---- synchronised BatchNorm (data parallel): the batch statistics are sums over ALL ranks' rows, so each half of the
+// BN forward / backward is split into "local sums" and "apply with the all-reduced sums" (the one
+// op of the path that is not row-local).  stats = [2][E]; count = global number of rows.
+__global__ void bn_stats_kernel(const float* __restrict__ y, int B, int E, float* __restrict__ stats) {
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= E) return;
+  float s = 0.f, q = 0.f;
+  for (int b = lane; b < B; b += 32) { const float v = y[(size_t)b * E + j]; s += v; q = fmaf(v, v, q); }
+  s = warp_sum(s); q = warp_sum(q);
+  if (lane == 0) { stats[j] = s; stats[E + j] = q; }
+}
+__global__ void bn_apply_kernel(const float* __restrict__ y, int B, int E, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, float eps, const float* __restrict__ stats, float count,
+                                float* __restrict__ out, float* __restrict__ save_mean, float* __restrict__ save_rstd) {
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= E) return;
+  const float mu = stats[j] / count;
+  const float var = fmaxf(stats[E + j] / count - mu * mu, 0.f);        // biased variance, as BatchNorm1d in training mode
+  const float rstd = 1.0f / sqrtf(var + eps);
+  for (int b = lane; b < B; b += 32)
+    out[(size_t)b * E + j] = (y[(size_t)b * E + j] - mu) * rstd * gamma[j] + beta[j];
+  if (lane == 0) { save_mean[j] = mu; save_rstd[j] = rstd; }
+}
+__global__ void bn_bwd_stats_kernel(const float* __restrict__ y, const float* __restrict__ dout, int B, int E,
+                                    const float* __restrict__ save_mean, const float* __restrict__ save_rstd,
+                                    float* __restrict__ stats) {
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= E) return;
+  const float mu = save_mean[j], rstd = save_rstd[j];
+  float sd = 0.f, sdx = 0.f;
+  for (int b = lane; b < B; b += 32) {
+    const float d = dout[(size_t)b * E + j];
+    sd += d; sdx = fmaf(d, (y[(size_t)b * E + j] - mu) * rstd, sdx);
+  }
+  sd = warp_sum(sd); sdx = warp_sum(sdx);
+  if (lane == 0) { stats[j] = sd; stats[E + j] = sdx; }
+}
+// dgamma / dbeta are written as (global sum) * grad_share so that the later all-reduce(sum) of the flat gradient buffers
+// (every rank holds the same value) followed by the 1/world factor of the optimizer gives the global-batch gradient.
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ y, const float* __restrict__ dout, int B, int E,
+                                    const float* __restrict__ gamma, const float* __restrict__ save_mean,
+                                    const float* __restrict__ save_rstd, const float* __restrict__ stats, float count,
+                                    float grad_share, float* __restrict__ dy, float* __restrict__ dgamma,
+                                    float* __restrict__ dbeta) {
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= E) return;
+  const float mu = save_mean[j], rstd = save_rstd[j], g = gamma[j];
+  const float sd = stats[j], sdx = stats[E + j];
+  for (int b = lane; b < B; b += 32) {
+    const float d = dout[(size_t)b * E + j];
+    const float xh = (y[(size_t)b * E + j] - mu) * rstd;
+    dy[(size_t)b * E + j] = g * rstd * (d - sd / count - xh * sdx / count);
+  }
+  if (lane == 0) { dgamma[j] = sdx * grad_share; dbeta[j] = sd * grad_share; }
+}
+int bn_stats(const float* y, int B, int E, float* stats, cudaStream_t s) {
+  bn_stats_kernel<<<cdiv(E, 4), 128, 0, s>>>(y, B, E, stats);
+  return check_launch("bn_stats_kernel");
+}
+int bn_apply(const float* y, int B, int E, const float* gamma, const float* beta, float eps, const float* stats,
+             float count, float* out, float* save_mean, float* save_rstd, cudaStream_t s) {
+  bn_apply_kernel<<<cdiv(E, 4), 128, 0, s>>>(y, B, E, gamma, beta, eps, stats, count, out, save_mean, save_rstd);
+  return check_launch("bn_apply_kernel");
+}
+int bn_bwd_stats(const float* y, const float* dout, int B, int E, const float* save_mean, const float* save_rstd,
+                 float* stats, cudaStream_t s) {
+  bn_bwd_stats_kernel<<<cdiv(E, 4), 128, 0, s>>>(y, dout, B, E, save_mean, save_rstd, stats);
+  return check_launch("bn_bwd_stats_kernel");
+}
+int bn_bwd_apply(const float* y, const float* dout, int B, int E, const float* gamma, const float* save_mean,
+                 const float* save_rstd, const float* stats, float count, float grad_share, float* dy, float* dgamma,
+                 float* dbeta, cudaStream_t s) {
+  bn_bwd_apply_kernel<<<cdiv(E, 4), 128, 0, s>>>(y, dout, B, E, gamma, save_mean, save_rstd, stats, count, grad_share, dy,
+                                                 dgamma, dbeta);
+  return check_launch("bn_bwd_apply_kernel");
+}
+
 int bn_fwd(const float* y, int B, int E, const float* gamma, const float* beta, float eps, float* out,
            float* save_mean, float* save_rstd, cudaStream_t s) {
   bn_fwd_kernel<<<cdiv(E, 4), 128, 0, s>>>(y, B, E, gamma, beta, eps, out, save_mean, save_rstd);

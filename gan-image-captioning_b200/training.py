@@ -79,6 +79,9 @@ class GANInstructor:
         self._comm = None
         self._vocab_ev = None
         self.bucketed = os.environ.get("GIC_NO_BUCKET", "0") != "1"
+        # data parallel: Encoder.bn over the GLOBAL batch (two [2, E] all-reduces per step) instead of per shard;
+        # opt-in (args.sync_bn / GIC_SYNC_BN=1): the reference is single-GPU, per-shard statistics are the documented default
+        self.sync_bn = bool(getattr(args, "sync_bn", 0)) or os.environ.get("GIC_SYNC_BN", "0") == "1"
         self.overlap = os.environ.get("GIC_NO_OVERLAP", "0") != "1"
         self.world = 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
@@ -141,6 +144,43 @@ class GANInstructor:
             torch.cuda.current_stream().wait_stream(self._comm_stream())
         else:
             parallel.allreduce_sum_(fg.grad)
+
+    # ---- Encoder.linear + Encoder.bn (src/generator.py:15-16,23-24), per-shard or synchronised statistics ------------
+    def _sync_bn_on(self):
+        return self.sync_bn and self.world > 1
+
+    def _encoder_fwd(self, mode, pooled, B, Fin, E, lin, mean, rstd, feats, stream):
+        lib, P, enc = _lib.lib(), _lib.ptr, self.gen.encoder
+        if not self._sync_bn_on():
+            _lib.check(lib.gic_encoder_fwd(mode, P(pooled), B, Fin, E, P(enc.linear.weight), P(enc.linear.bias),
+                                           P(enc.bn.weight), P(enc.bn.bias), enc.bn.eps, P(lin), P(mean), P(rstd),
+                                           P(feats), stream), "gic_encoder_fwd")
+            return
+        # SyncBN: local sums -> all-reduce of [2, E] -> normalise with the global-batch statistics
+        stats = self._buf("enc_stats", 2 * E)
+        _lib.check(lib.gic_encoder_fwd_stats(mode, P(pooled), B, Fin, E, P(enc.linear.weight), P(enc.linear.bias), P(lin),
+                                             P(stats), stream), "gic_encoder_fwd_stats")
+        parallel.allreduce_sum_(stats)
+        _lib.check(lib.gic_encoder_fwd_apply(P(lin), B, E, P(enc.bn.weight), P(enc.bn.bias), enc.bn.eps, P(stats),
+                                             float(B * self.world), P(mean), P(rstd), P(feats), stream), "gic_encoder_fwd_apply")
+
+    def _encoder_bwd(self, mode, dfeat, pooled, lin, mean, rstd, B, E, stream):
+        lib, P, enc = _lib.lib(), _lib.ptr, self.gen.encoder
+        gg = self._flat_g.g
+        dlin = self._buf("enc_dlin", B * E)
+        if not self._sync_bn_on():
+            _lib.check(lib.gic_encoder_bwd(mode, P(dfeat), P(pooled), P(lin), P(mean), P(rstd), P(enc.linear.weight),
+                                           P(enc.bn.weight), B, pooled.shape[1], E, P(dlin), P(gg(enc.linear.weight)),
+                                           P(gg(enc.linear.bias)), P(gg(enc.bn.weight)), P(gg(enc.bn.bias)), 0, stream),
+                       "gic_encoder_bwd")
+            return
+        stats = self._buf("enc_bstats", 2 * E)
+        _lib.check(lib.gic_encoder_bwd_stats(P(dfeat), P(lin), P(mean), P(rstd), B, E, P(stats), stream), "gic_encoder_bwd_stats")
+        parallel.allreduce_sum_(stats)
+        _lib.check(lib.gic_encoder_bwd_apply(mode, P(dfeat), P(pooled), P(lin), P(mean), P(rstd), P(enc.bn.weight), B,
+                                             pooled.shape[1], E, P(stats), float(B * self.world), 1.0 / self.world, P(dlin),
+                                             P(gg(enc.linear.weight)), P(gg(enc.linear.bias)), P(gg(enc.bn.weight)),
+                                             P(gg(enc.bn.bias)), stream), "gic_encoder_bwd_apply")
 
     # ---- flat buffers ---------------------------------------------------------------------------
     def _gen_params(self):
@@ -285,9 +325,7 @@ class GANInstructor:
             Fin = pooled.shape[1]
             lin, mean, rstd = self._buf("enc_lin", B * E).view(B, E), self._buf("enc_mean", E), self._buf("enc_rstd", E)
             feats = self._buf("feats", B * E).view(B, E)
-            _lib.check(lib.gic_encoder_fwd(mode, P(pooled), B, Fin, E, P(enc.linear.weight), P(enc.linear.bias),
-                                           P(enc.bn.weight), P(enc.bn.bias), enc.bn.eps, P(lin), P(mean), P(rstd),
-                                           P(feats), stream), "gic_encoder_fwd")
+            self._encoder_fwd(mode, pooled, B, Fin, E, lin, mean, rstd, feats, stream)
         else:
             feats = dec.embed.weight[1].expand(B, E).contiguous()
         # -- Decoder.sample (:150)
@@ -382,12 +420,7 @@ class GANInstructor:
                     _lib.ptr_array([gg(w) for w in b_hh]), P(gg(dec.linear.weight)), P(gg(dec.linear.bias)), P(dfeat), 0,
                     st), "gic_decode_sample_bwd_factored")
             if self.cgan:
-                enc = self.gen.encoder
-                _lib.check(lib.gic_encoder_bwd(mode, P(dfeat), P(pooled), P(lin), P(mean), P(rstd),
-                                               P(enc.linear.weight), P(enc.bn.weight), B, pooled.shape[1], E,
-                                               P(self._buf("enc_dlin", B * E)), P(gg(enc.linear.weight)),
-                                               P(gg(enc.linear.bias)), P(gg(enc.bn.weight)), P(gg(enc.bn.bias)), 0,
-                                               st), "gic_encoder_bwd")
+                self._encoder_bwd(mode, dfeat, pooled, lin, mean, rstd, B, E, st)
             else:
                 gg(dec.embed.weight)[1] += dfeat.sum(0)      # features = embed(<S>) for every row (:147)
 

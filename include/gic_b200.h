@@ -292,6 +292,28 @@ int gic_disc_prepare(int mode, const float* W_h /*[F,F]*/, const float* W_f /*[H
                      const float* W_o, const float* b_o, int F, float* prepared, gic_stream_t stream);
 void gic_disc_set_prepared(const float* prepared);
 
+/* ---- synchronised BatchNorm for the encoder projection under data parallelism ----
+ * Encoder.bn (src/generator.py:16,24) is the one op of the path that is not row-local: its training-mode statistics run
+ * over the whole batch.  With the batch sharded over ranks each half of gic_encoder_fwd / gic_encoder_bwd is split in
+ * two, with an all-reduce(sum) of stats[2*E] by the caller in between; count = rows of the GLOBAL batch.
+ *   fwd_stats : lin_out = pooled W^T + b;  stats = [sum_b y | sum_b y^2]                  (local rows)
+ *   fwd_apply : mean = s1/count, var = s2/count - mean^2 (biased), features = (y - mean) rstd gamma + beta
+ *   bwd_stats : stats = [sum_b dout | sum_b dout * xhat]                                  (local rows)
+ *   bwd_apply : dlin = gamma rstd (dout - s1/count - xhat s2/count); dW, db from the local rows; dgamma / dbeta =
+ *               (global sums) * grad_share, grad_share = 1/world: every rank holds the same value, so the all-reduce(sum)
+ *               of the flat gradients followed by the optimizer's 1/world factor yields the global-batch gradient. */
+int gic_encoder_fwd_stats(int mode, const float* pooled, int B, int Fin, int E, const float* W, const float* b,
+                          float* lin_out, float* stats, gic_stream_t stream);
+int gic_encoder_fwd_apply(const float* lin_out, int B, int E, const float* gamma, const float* beta, float eps,
+                          const float* stats, float count, float* save_mean, float* save_rstd, float* features,
+                          gic_stream_t stream);
+int gic_encoder_bwd_stats(const float* dfeatures, const float* lin_out, const float* save_mean, const float* save_rstd,
+                          int B, int E, float* stats, gic_stream_t stream);
+int gic_encoder_bwd_apply(int mode, const float* dfeatures, const float* pooled, const float* lin_out,
+                          const float* save_mean, const float* save_rstd, const float* gamma, int B, int Fin, int E,
+                          const float* stats, float count, float grad_share, float* dlin_ws, float* dW, float* db,
+                          float* dgamma, float* dbeta, gic_stream_t stream);
+
 /* ---- batch contract: collate_fn (src/tasks.py:138-158), the step immediately before the path ----
  * The ragged token lists of a batch arrive as tokens[sum(len)] (int32, caption after caption) and offsets[B+1] (int32,
  * offsets[b] = start of caption b); captions[B, max_caption_len] int64 = <S>=1, tokens, <E>=2, <PAD>=0 ... and

@@ -39,6 +39,53 @@ def run(bucketed, graph, steps=4):
     return torch.cat([inst._flat_g.flat.clone(), inst._flat_d.flat.clone()]), losses
 
 
+def sync_bn_check():
+    """Sharded step with synchronised Encoder.bn statistics == the same step on the full batch in one process."""
+    import gic_b200
+    from gic_b200.args import default_args
+    from gic_b200.training import GANInstructor
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+    B, L, V = 32 * world, 10, 2000
+    a = default_args(vocab_size=V, gen_embed_dim=64, gen_hidden_dim=128, gen_num_layers=1, conditional_gan=1,
+                     feature_dim=256, device="cuda")
+    g = torch.Generator(device=dev).manual_seed(123)                 # the same global batch on every rank
+    caps = torch.randint(4, V, (B, L), generator=g, device=dev)
+    pooled = torch.randn(B, 256, generator=g, device=dev) * 2 + 0.5
+    u = torch.rand(L, B, V, generator=g, device=dev)
+    keep = (torch.rand(3, B * 64, 900, generator=g, device=dev) >= 0.2).to(torch.uint8)
+
+    def build(world_, sync):
+        torch.manual_seed(1008)
+        inst = GANInstructor(a, device=dev)
+        inst.world, inst.sync_bn = world_, sync
+        inst.gen.train(); inst.disc.train(); inst.gen.decoder.temperature = 1.0
+        return inst
+    full = build(1, False)
+    r = full.adv_step(caps, pooled=pooled, u=u, keep=keep, update=False)
+    ids, feats_full = r["ids"].clone(), r["features"].clone()
+    gfull, dfull = full._flat_g.grad.clone(), full._flat_d.grad.clone()
+    per = B // world
+    sl = slice(rank * per, (rank + 1) * per)
+    kp = keep.view(3, B, 64, 900)[:, sl].reshape(3, per * 64, 900).contiguous()
+    res = {}
+    for sync in (True, False):
+        sh = build(world, sync)
+        r = sh.adv_step(caps[sl], pooled=pooled[sl], u=u[:, sl].contiguous(), keep=kp, update=False, forced_ids=ids[sl])
+        torch.cuda.synchronize()
+        gs, ds = sh._flat_g.grad / world, sh._flat_d.grad / world
+        fe = float((r["features"] - feats_full[sl]).abs().max()) / float(feats_full.abs().max())
+        ge = float((gs - gfull).abs().max()) / float(gfull.abs().max())
+        de = float((ds - dfull).abs().max()) / float(dfull.abs().max())
+        res[sync] = (fe, ge, de)
+        if rank == 0:
+            print(f"sync_bn={sync}: features rel err {fe:.2e}  G grads {ge:.2e}  D grads {de:.2e}  (vs the full batch in one process)", flush=True)
+    ok = res[True][0] < 1e-3 and res[True][1] < 2e-2 and res[True][2] < 2e-2 and res[False][0] > 10 * res[True][0]
+    t = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(t.item() > 0.5)
+
+
 def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -58,6 +105,7 @@ def main():
         # the step is not bit-reproducible run to run (fp32 atomics of the stream-K GEMMs; a max-over-time tie can re-route a
         # gradient, DESIGN.md "Ties"), and Adam normalises: bound = a fraction of lr * steps
         ok = ok and same and err <= 0.5 * 1e-4 * 4 and abs(l[-1] - l0[-1]) <= 1e-4 * abs(l0[-1])
+    ok = sync_bn_check() and ok
     if dist.get_rank() == 0:
         print("DP_CHECK", "OK" if ok else "FAILED", flush=True)
     torch.cuda.synchronize(); dist.barrier()
