@@ -60,6 +60,9 @@ F = C.c_float
 Z = C.c_size_t
 
 
+RNG_TAG_GUMBEL, RNG_TAG_DROPOUT = 0x47, 0x44
+
+
 def _declare(L):
     L.gic_version.restype = I
     L.gic_last_error.restype = C.c_char_p
@@ -117,6 +120,10 @@ def _declare(L):
     L.gic_disc_prepared_floats.argtypes = [I]
     L.gic_disc_prepare.argtypes = [I, P, P, P, I, P, P, I, P, P]
     L.gic_pack_captions.argtypes = [P, P, I, I, P, P, P]
+    L.gic_set_rng.restype = None
+    L.gic_set_rng.argtypes = [C.c_ulonglong, C.c_ulonglong, P]
+    L.gic_philox_uniform.argtypes = [C.c_uint, Z, P, P]
+    L.gic_philox_keep_mask.argtypes = [C.c_uint, Z, F, P, P]
     L.gic_encoder_fwd_stats.argtypes = [I, P, I, I, I, P, P, P, P, P]
     L.gic_encoder_fwd_apply.argtypes = [P, I, I, P, P, F, P, F, P, P, P, P]
     L.gic_encoder_bwd_stats.argtypes = [P, P, P, P, I, I, P, P]

@@ -47,6 +47,9 @@ int pg_loss(const float*, const int64_t*, const float*, int, int, int, int, floa
 int clip_adam(float*, const float*, float*, float*, size_t, const float*, float, float, int, float, float, float,
               float, const float*, cudaStream_t);
 void set_temperature_device(const float*);
+void set_rng(unsigned long long, unsigned long long, const unsigned long long*);
+int philox_uniform(uint32_t, unsigned long long, size_t, float*, cudaStream_t);
+int philox_keep_mask(uint32_t, size_t, float, uint8_t*, cudaStream_t);
 int bn_stats(const float*, int, int, float*, cudaStream_t);
 int bn_apply(const float*, int, int, const float*, const float*, float, const float*, float, float*, float*, float*, cudaStream_t);
 int bn_bwd_stats(const float*, const float*, int, int, const float*, const float*, float*, cudaStream_t);
@@ -121,12 +124,15 @@ static int decode_fwd(int mode, const float* features, const float* W_emb, const
   if (B == 0) return GIC_OK;
   GIC_REQUIRE(features && W_emb && W_ih && W_hh && b_ih && b_hh && W_out && b_out && (out || pretrain == 2) && ids &&
                   saved && ws, GIC_ERR_NULL, "decode_sample_fwd: NULL pointer");
-  GIC_REQUIRE(pretrain == 1 || u, GIC_ERR_NULL, "decode_sample_fwd: uniforms required when sampling");
+  GIC_REQUIRE(pretrain != 2 || u, GIC_ERR_NULL, "decode_sample_cdf_fwd: uniforms required");
+  // pretrain == 0 with u == NULL: the Gumbel uniforms are drawn by the library (Philox state of gic_set_rng; the fused
+  // kernel draws its tile on the fly, the separate sampler reads a [B,V] slice filled by the same generator)
   const DecodeSaved sv(B, L, E, H, layers);
   const size_t BH = (size_t)B * H, BE = (size_t)B * E;
   float* gates = ws;                         // [B,4H]
   float* logits = ws + a4(4 * BH);           // [B,V]
   float* vs_scratch = logits + a4((size_t)B * V);   // fused projection + sampler: barrier counters + row statistics
+  float* u_slice = vs_scratch + a4(vocab_sample_scratch_floats(B, V));   // [B,V] uniforms of one step (u == NULL, unfused path)
   cudaMemcpyAsync(saved + sv.xs, features, BE * sizeof(float), cudaMemcpyDeviceToDevice, s);
   for (int l = 0; l < layers; ++l) {
     cudaMemsetAsync(saved + sv.hs(l), 0, BH * sizeof(float), s);
@@ -178,7 +184,7 @@ static int decode_fwd(int mode, const float* features, const float* W_emb, const
       bool fused_vs = false;
       {
         ProfScope prof(PROF_VOCAB_SAMPLE, 8.0 * B * V, s);
-        GIC_TRY(vocab_sample_tc(htop_t, H, W_out, b_out, u + (size_t)t * B * V, T, temperature_device(), B, V, H, L, t, out,
+        GIC_TRY(vocab_sample_tc(htop_t, H, W_out, b_out, u ? u + (size_t)t * B * V : nullptr, T, temperature_device(), B, V, H, L, t, out,
                                 ids, forced, W_emb, E, x_next, vs_scratch, s, &fused_vs));
       }
       if (fused_vs) continue;
@@ -186,9 +192,15 @@ static int decode_fwd(int mode, const float* features, const float* W_emb, const
     GIC_TRY(gemm(mode, false, true, B, V, H, 1.f, htop_t, H, W_out, H, 0.f, logits, V, b_out, s, PROF_GEMM_DECODE));   // :64,68
     if (pretrain == 2)
       GIC_TRY(sample_cdf_step(logits, u + (size_t)t * B, B, V, L, t, L, out, ids, logp, forced, W_emb, E, x_next, s));
-    else
-      GIC_TRY(sample_step(pretrain != 0, logits, pretrain ? nullptr : u + (size_t)t * B * V, T, B, V, L, t, out, ids,
+    else {
+      const float* u_t = nullptr;
+      if (!pretrain) {
+        if (u) u_t = u + (size_t)t * B * V;
+        else { GIC_TRY(philox_uniform(0x47u /*RNG_TAG_GUMBEL*/, (unsigned long long)t * B * V, (size_t)B * V, u_slice, s)); u_t = u_slice; }
+      }
+      GIC_TRY(sample_step(pretrain != 0, logits, u_t, T, B, V, L, t, out, ids,
                             forced, W_emb, E, x_next, s, /*fast_math=*/mode == GEMM_TF32 || mode == GEMM_BF16));
+    }
   }
   return GIC_OK;
 }
@@ -595,7 +607,7 @@ int gic_sample_cdf_step(const float* logits, const float* u, int B, int V, int L
 
 size_t gic_decode_saved_floats(int B, int L, int E, int H, int layers) { return DecodeSaved(B, L, E, H, layers).total; }
 size_t gic_decode_fwd_workspace_floats(int B, int V, int H) {
-  return a4((size_t)4 * B * H) + a4((size_t)B * V) + a4(vocab_sample_scratch_floats(B, V));
+  return a4((size_t)4 * B * H) + 2 * a4((size_t)B * V) + a4(vocab_sample_scratch_floats(B, V));
 }
 size_t gic_decode_bwd_workspace_floats(int B, int L, int V, int E, int H, int layers) {
   return DecodeBwdWs(B, L, V, E, H, layers).total;
@@ -754,6 +766,17 @@ int gic_pack_captions(const int32_t* tokens, const int32_t* offsets, int B, int 
                       int32_t* lengths, gic_stream_t stream) {
   GIC_TRY(require_device());
   return pack_captions(tokens, offsets, B, max_caption_len, captions, lengths, S(stream));
+}
+void gic_set_rng(unsigned long long seed, unsigned long long offset, const unsigned long long* state_dev) {
+  set_rng(seed, offset, state_dev);
+}
+int gic_philox_uniform(unsigned int tag, size_t n, float* out, gic_stream_t stream) {
+  GIC_TRY(require_device());
+  return philox_uniform(tag, 0ull, n, out, S(stream));
+}
+int gic_philox_keep_mask(unsigned int tag, size_t n, float p, uint8_t* out, gic_stream_t stream) {
+  GIC_TRY(require_device());
+  return philox_keep_mask(tag, n, p, out, S(stream));
 }
 void gic_set_vocab_grads_event(void* cuda_event) { g_vocab_grads_event = reinterpret_cast<cudaEvent_t>(cuda_event); }
 

@@ -3,6 +3,7 @@
 // backward of that graph.  Encoder.linear + Encoder.bn
 // (src/generator.py:15-16,23-24) is here too because it feeds step 0 of the decode.
 #include "gic_internal.cuh"
+#include "philox.cuh"
 
 namespace gic {
 
@@ -12,6 +13,67 @@ static const float* g_t_dev = nullptr;
 void set_temperature_device(const float* p) { g_t_dev = p; }
 const float* temperature_device() { return g_t_dev; }
 __device__ __forceinline__ float pick_t(float by_value, const float* t_dev) { return t_dev ? __ldg(t_dev) : by_value; }
+
+// ---------------------------------------------------------------------------------------
+// shim-side random draws (caller passed no uniforms / no dropout masks): Philox4x32-10, see philox.cuh
+// ---------------------------------------------------------------------------------------
+static RngState g_rng = {0ull, 0ull, nullptr};
+void set_rng(unsigned long long seed, unsigned long long offset, const unsigned long long* state_dev) {
+  g_rng.seed = seed; g_rng.offset = offset; g_rng.dev = state_dev;
+}
+RngState rng_state() { return g_rng; }
+
+__global__ void philox_uniform_kernel(RngState st, uint32_t tag, unsigned long long base, size_t n, float* __restrict__ out) {
+  unsigned long long seed, offset;
+  rng_load(st, seed, offset);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  // thread = one Philox group (4 consecutive logical elements); base may start inside a group
+  const unsigned long long g0 = base >> 2, g1 = (base + n + 3) >> 2;
+  for (unsigned long long gi = g0 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; gi < g1; gi += stride) {
+    const float4 u = philox_uniform4(seed, offset, tag, gi);
+    const float v[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const unsigned long long i = 4 * gi + e;
+      if (i >= base && i < base + n) out[i - base] = v[e];
+    }
+  }
+}
+int philox_uniform(uint32_t tag, unsigned long long base, size_t n, float* out, cudaStream_t s) {
+  if (n == 0) return GIC_OK;
+  GIC_REQUIRE(out, GIC_ERR_NULL, "philox_uniform: NULL output");
+  const int grid = (int)min((size_t)num_sms() * 16, (n / 4 + 255) / 256 + 1);
+  philox_uniform_kernel<<<grid, 256, 0, s>>>(g_rng, tag, base, n, out);
+  return check_launch("philox_uniform_kernel");
+}
+
+// keep[i] = (u_i >= p) as uint8, four per thread (n % 4 == 0 and a 4-byte aligned output take the packed store)
+__global__ void philox_keep_mask_kernel(RngState st, uint32_t tag, size_t n, float p, uint8_t* __restrict__ out, int packed) {
+  unsigned long long seed, offset;
+  rng_load(st, seed, offset);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t groups = (n + 3) >> 2;
+  for (size_t gi = blockIdx.x * (size_t)blockDim.x + threadIdx.x; gi < groups; gi += stride) {
+    const float4 u = philox_uniform4(seed, offset, tag, gi);
+    const uint32_t k0 = u.x >= p, k1 = u.y >= p, k2 = u.z >= p, k3 = u.w >= p;
+    if (packed) {
+      reinterpret_cast<uint32_t*>(out)[gi] = k0 | (k1 << 8) | (k2 << 16) | (k3 << 24);
+    } else {
+      const uint32_t kk[4] = {k0, k1, k2, k3};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) if (4 * gi + e < n) out[4 * gi + e] = (uint8_t)kk[e];
+    }
+  }
+}
+int philox_keep_mask(uint32_t tag, size_t n, float p, uint8_t* out, cudaStream_t s) {
+  if (n == 0) return GIC_OK;
+  GIC_REQUIRE(out, GIC_ERR_NULL, "philox_keep_mask: NULL output");
+  GIC_REQUIRE(p >= 0.f && p < 1.f, GIC_ERR_SHAPE, "philox_keep_mask: dropout p in [0,1)");
+  const int packed = ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 3u) == 0) ? 1 : 0;
+  const int grid = (int)min((size_t)num_sms() * 16, (n / 4 + 255) / 256 + 1);
+  philox_keep_mask_kernel<<<grid, 256, 0, s>>>(g_rng, tag, n, p, out, packed);
+  return check_launch("philox_keep_mask_kernel");
+}
 
 // ---------------------------------------------------------------------------------------
 // batch contract (collate_fn, src/tasks.py:138-158): ragged token lists arrive as ONE flat int32 array + B+1 offsets

@@ -19,6 +19,7 @@
 // warps per TMEM lane quarter split the tile's columns in 16-column units; they turn u into the Gumbel term while the
 // main loop runs (pass 0), so only the exp / normalise passes remain after the last MMA.
 #include "tcgen05_common.cuh"
+#include "philox.cuh"
 
 namespace gic {
 long long* vs_stamps_buffer();
@@ -55,6 +56,8 @@ struct VSArgs {
   int E;
   float* x_next;              // [M, E] or null
   long long* stamps;          // debug (GIC_VS_STAMPS=1): 16 clock64 stamps per CTA, else null
+  int use_rng;                // no uniforms supplied: draw u[t, m, n] in the kernel (Philox, same numbers as gic_philox_uniform)
+  RngState rng;
 };
 
 #define VS_STAMP(i) do { if (a.stamps) a.stamps[blockIdx.x * 16 + (i)] = (long long)globaltimer_ns(); } while (0)
@@ -138,7 +141,7 @@ vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_expect_tx(&full[s], S::STAGE);
         tma_load_2d(sa, &tmA, &full[s], kb * BK, m0);
         tma_load_2d(sa + S::A_BYTES, &tmB, &full[s], kb * BK, n0);
-        if (kb == min(nkb, S::STAGES) - 1) {             // ring primed: now the u tile (comes from HBM)
+        if (!a.use_rng && kb == min(nkb, S::STAGES) - 1) {   // ring primed: now the u tile (comes from HBM)
           mbar_expect_tx(u_full, S::U_BYTES);
 #pragma unroll
           for (int c = 0; c < S::NBOX; ++c) tma_load_2d(ubox + c * S::BOX_BYTES, &tmU, u_full, n0 + 32 * c, m0);
@@ -192,7 +195,8 @@ vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       reinterpret_cast<float4*>(s_bias)[etid] = (n < a.N) ? __ldg(reinterpret_cast<const float4*>(a.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     // ---- pass 0 (under the main loop): u -> log2(-log(u + eps) + eps), the Gumbel term subtracted from the logits
-    mbar_wait(u_full, 0);
+    unsigned long long rseed = 0ull, roff = 0ull;
+    if (a.use_rng) rng_load(a.rng, rseed, roff); else mbar_wait(u_full, 0);
     if (etid == 0) VS_STAMP(4);
 #pragma unroll
     for (int i = 0; i < MAXU; ++i) {
@@ -201,7 +205,15 @@ vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           float4* sp = reinterpret_cast<float4*>(VS_CHUNK(j, k));
-          float4 u4 = *sp;
+          float4 u4;
+          if (a.use_rng) {
+            // element (t, m, n) of the logical u[L, M, N]; a float4 chunk is one Philox group (N % 4 == 0)
+            const int n = n0 + 16 * j + 4 * k;
+            const unsigned long long e = ((unsigned long long)a.t * a.M + (unsigned long long)min(m, a.M - 1)) * a.N + min(n, a.N - 4);
+            u4 = philox_uniform4(rseed, roff, RNG_TAG_GUMBEL, e >> 2);
+          } else {
+            u4 = *sp;
+          }
           // log2 of the inner term: the ln 2 factor is applied in pass 1 inside the same fused multiply-subtract the
           // separate sampler kernel compiles to (logit - lg2 * ln2), so both paths round identically
           u4.x = __log2f(-logf(u4.x + eps) + eps); u4.y = __log2f(-logf(u4.y + eps) + eps);
@@ -488,11 +500,12 @@ size_t vocab_sample_scratch_floats(int B, int V) { return 2 * vs_part_floats(B, 
 int vocab_sample_tc(const float* htop, int lda, const float* W_out, const float* b_out, const float* u_t, float T,
                     const float* T_dev, int B, int V, int H, int L, int t, float* out, int64_t* ids, const int64_t* forced,
                     const float* embed, int E, float* x_next, float* scratch, cudaStream_t stream, bool* handled) {
+  extern RngState rng_state();
   using namespace tc;
   *handled = false;
   { const char* e = getenv("GIC_FUSED_SAMPLE"); if (e && e[0] == '0') return GIC_OK; }   // read per call: tests toggle it
   if (B <= 0 || V <= 0 || H <= 0) return GIC_OK;
-  if ((V % 4) || (H % 4) || (lda % 4) || !aligned16(htop) || !aligned16(W_out) || !aligned16(b_out) || !aligned16(u_t) ||
+  if ((V % 4) || (H % 4) || (lda % 4) || !aligned16(htop) || !aligned16(W_out) || !aligned16(b_out) || (u_t && !aligned16(u_t)) ||
       !aligned16(out) || (((size_t)L * V) % 4))
     return GIC_OK;
   const int tiles_m = cdiv(B, BM);
@@ -507,7 +520,7 @@ int vocab_sample_tc(const float* htop, int lda, const float* W_out, const float*
   const bool rn = tf32_round_in_tma();
   CUtensorMap ta, tb, tu, tp;
   bool ok = make_map(&ta, htop, B, H, lda, BK, BM, rn, false) && make_map(&tb, W_out, V, H, H, BK, BN, rn, false) &&
-            make_map(&tu, u_t, B, V, V, 32, BM, false, false) &&
+            make_map(&tu, u_t ? u_t : out, B, V, V, 32, BM, false, false) &&
             make_map(&tp, out + (size_t)t * V, B, V, L * V, 32, 32, false, false);
   if (!ok) return GIC_OK;
   VSArgs a;
@@ -518,6 +531,8 @@ int vocab_sample_tc(const float* htop, int lda, const float* W_out, const float*
   a.part_next = reinterpret_cast<float2*>(scratch + (size_t)((t + 1) & 1) * pf);
   a.ids = ids; a.forced = forced; a.L = L; a.t = t; a.embed = embed; a.E = E; a.x_next = x_next;
   a.stamps = vs_stamps_buffer();
+  a.use_rng = (u_t == nullptr) ? 1 : 0;
+  a.rng = rng_state();
   if (t == 0) {
     cudaError_t e = cudaMemsetAsync(scratch, 0, 2 * pf * sizeof(float), stream);   // both statistics buffers "not ready"
     if (e != cudaSuccess) { set_error("vocab_sample memset: %s", cudaGetErrorString(e)); return GIC_ERR_CUDA; }

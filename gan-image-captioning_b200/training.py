@@ -77,6 +77,9 @@ class GANInstructor:
         self._in_graph = False
         self._side = None
         self._comm = None
+        self._rng_seed = None        # Philox state of the library-side draws (u / dropout masks not supplied by the caller)
+        self._rng_offset = 0
+        self._rng_dyn = None
         self._vocab_ev = None
         self.bucketed = os.environ.get("GIC_NO_BUCKET", "0") != "1"
         # data parallel: Encoder.bn over the GLOBAL batch (two [2, E] all-reduces per step) instead of per shard;
@@ -268,6 +271,7 @@ class GANInstructor:
             return self._adv_step_body(captions, pooled, u, keep, train, forced_ids, loss_type, update, grid, prep)
         finally:
             lib.gic_disc_set_prepared(None)
+            lib.gic_set_rng(0, 0, None)
             if self._in_graph:
                 lib.gic_set_temperature_device(None)
 
@@ -286,9 +290,21 @@ class GANInstructor:
         P = _lib.ptr
         # -- discriminator on the real captions (hard tokens, :158,162): independent of the decode, so it runs on a
         #    side stream underneath the latency-bound autoregressive loop
+        if u is None or (train and keep is None):
+            # draws not supplied: Philox inside the library (the Gumbel uniforms are generated in the fused decode kernel
+            # itself; the reference draws with uniform_ / nn.Dropout, src/generator.py:86-90, src/discriminator.py:30)
+            if self._rng_seed is None:
+                self._rng_seed = int(torch.initial_seed()) & ((1 << 63) - 1)
+            if self._in_graph:
+                lib.gic_set_rng(0, 0, P(self._rng_dyn))
+            else:
+                self._rng_offset += 1
+                lib.gic_set_rng(self._rng_seed, self._rng_offset, None)
         if train:
             if keep is None:
-                keep = torch.rand(3, B * R, Fd, device=dev) >= disc.dropout.p
+                keep = self._buf("keep_u8", 3 * B * R * Fd, dtype=torch.uint8).view(3, B * R, Fd)
+                _lib.check(lib.gic_philox_keep_mask(_lib.RNG_TAG_DROPOUT, keep.numel(), float(disc.dropout.p), P(keep),
+                                                    stream), "gic_philox_keep_mask")
             keep = keep.to(dev).to(torch.uint8).contiguous()
             k0, k1, k2 = keep[0], keep[1], keep[2]
         else:
@@ -329,9 +345,8 @@ class GANInstructor:
         else:
             feats = dec.embed.weight[1].expand(B, E).contiguous()
         # -- Decoder.sample (:150)
-        if u is None:
-            u = torch.rand(L, B, V, device=dev)
-        u = u.to(dev).float().contiguous()
+        if u is not None:
+            u = u.to(dev).float().contiguous()
         probs = self._buf("probs", B * L * V).view(B, L, V)
         ids = torch.empty(B, L, dtype=torch.int64, device=dev)
         dsaved = self._buf("dec_saved", lib.gic_decode_saved_floats(B, L, E, H, layers))
@@ -499,6 +514,8 @@ class GANInstructor:
             self._dyn_host = [torch.zeros(8).pin_memory() for _ in range(16)]
             self._dyn_ev = [None] * 16
             self._dyn_i = 0
+            self._rng_dyn = torch.zeros(2, dtype=torch.int64, device=dev)
+            self._rng_host = [torch.zeros(2, dtype=torch.int64).pin_memory() for _ in range(16)]
         if st is None and static:
             st = dict(captions=captions, pooled=pooled, u=u, keep=keep)
             self._graphs[key] = st
@@ -532,6 +549,13 @@ class GANInstructor:
                 h[slot] = lr / (1.0 - 0.9 ** t)
                 h[slot + 1] = 1.0 / (1.0 - 0.999 ** t) ** 0.5
             self._dyn.copy_(h, non_blocking=True)
+            if self._rng_seed is None:
+                self._rng_seed = int(torch.initial_seed()) & ((1 << 63) - 1)
+            self._rng_offset += 1
+            hr = self._rng_host[i]
+            hr[0] = self._rng_seed
+            hr[1] = self._rng_offset
+            self._rng_dyn.copy_(hr, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()
             self._dyn_ev[i] = ev

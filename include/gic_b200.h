@@ -292,6 +292,22 @@ int gic_disc_prepare(int mode, const float* W_h /*[F,F]*/, const float* W_f /*[H
                      const float* W_o, const float* b_o, int F, float* prepared, gic_stream_t stream);
 void gic_disc_set_prepared(const float* prepared);
 
+/* ---- random draws made by the library when the caller supplies none ----
+ * The reference draws fresh uniforms every decode step (Tensor.uniform_, src/generator.py:86-90) and fresh dropout masks
+ * (nn.Dropout, src/discriminator.py:30,58).  Parity runs pass them in (u[L,B,V], keep masks); a production step passes
+ * u = NULL to gic_decode_sample_fwd and the uniforms are then generated INSIDE the fused decode kernel (Philox4x32-10,
+ * counter = element index of the logical u[L,B,V], no 4*L*B*V-byte tensor is written or read).
+ * gic_set_rng(seed, offset, state_dev): generator state for the calls that follow (process-wide).  state_dev != NULL:
+ *   {seed, offset} are read from device memory when the kernels run (CUDA-graph replay with a fresh offset per step).
+ * gic_philox_uniform(tag, n, out): the first n elements of the logical stream `tag` (GIC_RNG_TAG_GUMBEL: exactly the
+ *   uniforms the decode uses for u = NULL, so out[L*B*V] passed back in as `u` reproduces that decode bit for bit).
+ * gic_philox_keep_mask(tag, n, p, out): uint8 keep masks out[i] = (u_i >= p) for nn.Dropout(p) (GIC_RNG_TAG_DROPOUT). */
+#define GIC_RNG_TAG_GUMBEL 0x47u
+#define GIC_RNG_TAG_DROPOUT 0x44u
+void gic_set_rng(unsigned long long seed, unsigned long long offset, const unsigned long long* state_dev);
+int gic_philox_uniform(unsigned int tag, size_t n, float* out, gic_stream_t stream);
+int gic_philox_keep_mask(unsigned int tag, size_t n, float p, uint8_t* out, gic_stream_t stream);
+
 /* ---- synchronised BatchNorm for the encoder projection under data parallelism ----
  * Encoder.bn (src/generator.py:16,24) is the one op of the path that is not row-local: its training-mode statistics run
  * over the whole batch.  With the batch sharded over ranks each half of gic_encoder_fwd / gic_encoder_bwd is split in

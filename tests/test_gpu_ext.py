@@ -338,3 +338,105 @@ def test_adv_step_with_attention_grid_runs_and_trains_attention_params():
     torch.cuda.synchronize()
     for b0, p in zip(before, inst.gen.decoder.attn_params()):
         assert not torch.equal(b0, p.detach())
+
+
+# ---- library-side random draws (Philox4x32-10): production steps pass no uniforms / masks ---------------------------------
+def test_philox_uniform_statistics_and_determinism():
+    from gic_b200 import _lib as L
+    L.require_cuda(); lib = L.lib()
+    n = 4_000_003                                                   # not a multiple of 4: the tail group is clipped
+    a, b, c = (torch.empty(n, device="cuda:0") for _ in range(3))
+    lib.gic_set_rng(1008, 7, None); L.check(lib.gic_philox_uniform(L.RNG_TAG_GUMBEL, n, L.ptr(a), L.stream()), "u")
+    lib.gic_set_rng(1008, 7, None); L.check(lib.gic_philox_uniform(L.RNG_TAG_GUMBEL, n, L.ptr(b), L.stream()), "u")
+    lib.gic_set_rng(1008, 8, None); L.check(lib.gic_philox_uniform(L.RNG_TAG_GUMBEL, n, L.ptr(c), L.stream()), "u")
+    lib.gic_set_rng(0, 0, None)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    assert float(a.min()) >= 0.0 and float(a.max()) < 1.0
+    assert abs(float(a.double().mean()) - 0.5) < 1e-3 and abs(float(a.double().var()) - 1 / 12) < 1e-3
+    hist = torch.histc(a, bins=64, min=0.0, max=1.0)
+    assert float((hist / n - 1 / 64).abs().max()) < 5e-4               # 64 equiprobable bins, 62 500 expected each
+    assert abs(float(torch.corrcoef(torch.stack([a[:-1], a[1:]]))[0, 1])) < 2e-3     # neighbouring draws uncorrelated
+    # the state can also live in device memory (CUDA-graph replay)
+    st = torch.tensor([1008, 7], dtype=torch.int64, device="cuda:0")
+    lib.gic_set_rng(0, 0, L.ptr(st)); L.check(lib.gic_philox_uniform(L.RNG_TAG_GUMBEL, n, L.ptr(c), L.stream()), "u")
+    lib.gic_set_rng(0, 0, None)
+    assert torch.equal(a, c)
+    # keep masks: the same stream thresholded at p
+    k = torch.empty(n - 3, dtype=torch.uint8, device="cuda:0")
+    u = torch.empty(n - 3, device="cuda:0")
+    lib.gic_set_rng(5, 1, None)
+    L.check(lib.gic_philox_keep_mask(L.RNG_TAG_DROPOUT, n - 3, 0.2, L.ptr(k), L.stream()), "k")
+    L.check(lib.gic_philox_uniform(L.RNG_TAG_DROPOUT, n - 3, L.ptr(u), L.stream()), "u")
+    lib.gic_set_rng(0, 0, None)
+    assert torch.equal(k.bool(), u >= 0.2) and abs(float(k.float().mean()) - 0.8) < 1e-3
+
+
+@pytest.mark.parametrize("mode_name", ["GEMM_BF16", "GEMM_FP32"])
+def test_step_with_library_draws_equals_step_with_the_same_draws_supplied(mode_name):
+    """adv_step(u=None, keep=None) -- uniforms generated inside the fused decode kernel (tensor-core modes) or slice by
+    slice (exact-fp32 mode), masks by gic_philox_keep_mask -- against the same step with exactly those draws passed in."""
+    import gic_b200
+    from gic_b200 import _lib as L
+    from gic_b200.args import default_args
+    from gic_b200.training import GANInstructor
+    B, Lc, V = 40, 7, 1200
+    a = default_args(vocab_size=V, gen_embed_dim=64, gen_hidden_dim=128, gen_num_layers=1, conditional_gan=0, device="cuda")
+    old = gic_b200.get_gemm_mode()
+    gic_b200.set_gemm_mode(getattr(gic_b200, mode_name))
+    try:
+        def build():
+            torch.manual_seed(3)
+            inst = GANInstructor(a, device="cuda:0")
+            inst.gen.train(); inst.disc.train(); inst.gen.decoder.temperature = 2.0
+            return inst
+        g = torch.Generator(device="cuda:0").manual_seed(9)
+        caps = torch.randint(4, V, (B, Lc), generator=g, device="cuda:0")
+        lib = L.lib()
+        seed, off = 424242, 17
+        U = torch.empty(Lc, B, V, device="cuda:0")
+        K = torch.empty(3, B * 64, 900, dtype=torch.uint8, device="cuda:0")
+        lib.gic_set_rng(seed, off, None)
+        L.check(lib.gic_philox_uniform(L.RNG_TAG_GUMBEL, U.numel(), L.ptr(U), L.stream()), "u")
+        L.check(lib.gic_philox_keep_mask(L.RNG_TAG_DROPOUT, K.numel(), 0.2, L.ptr(K), L.stream()), "k")
+        lib.gic_set_rng(0, 0, None)
+        i1 = build(); i1._rng_seed, i1._rng_offset = seed, off - 1
+        r1 = i1.adv_step(caps, update=False)
+        ids1, p1, g1 = r1["ids"].clone(), r1["probs"].clone(), i1._flat_g.grad.clone()
+        i2 = build()
+        r2 = i2.adv_step(caps, u=U, keep=K, update=False)
+        torch.cuda.synchronize()
+        assert torch.equal(ids1, r2["ids"])
+        assert torch.equal(p1, r2["probs"])                           # same uniforms -> bit-identical soft captions
+        close(f"philox/{mode_name}/d_loss", r1["d_loss"], r2["d_loss"], rtol=1e-6)
+        close(f"philox/{mode_name}/g_grad", g1, i2._flat_g.grad, rtol=2e-2, atol=1e-12)     # run-to-run noise of the step (atomics, pool ties)
+        # the next step draws a different stream
+        r3 = i1.adv_step(caps, update=False)
+        assert not torch.equal(r3["ids"], ids1)
+    finally:
+        gic_b200.set_gemm_mode(old)
+
+
+def test_graph_replay_with_library_draws_advances_the_stream():
+    import gic_b200
+    from gic_b200.args import default_args
+    from gic_b200.training import GANInstructor
+    B, Lc, V = 32, 6, 1000
+    a = default_args(vocab_size=V, gen_embed_dim=32, gen_hidden_dim=64, gen_num_layers=1, conditional_gan=0, device="cuda")
+    old = gic_b200.get_gemm_mode()
+    gic_b200.set_gemm_mode(gic_b200.GEMM_BF16)
+    try:
+        torch.manual_seed(3)
+        inst = GANInstructor(a, device="cuda:0")
+        inst.gen.train(); inst.disc.train()
+        caps = torch.randint(4, V, (B, Lc), device="cuda:0")
+        seen = []
+        for _ in range(4):                                          # step 1 eager + capture, steps 2-4 replayed
+            r = inst.adv_step(caps, graph=True)
+            torch.cuda.synchronize()
+            seen.append(r["ids"].clone())
+        assert not torch.equal(seen[1], seen[2]) and not torch.equal(seen[2], seen[3])
+        assert all(int(s.min()) >= 0 and int(s.max()) < V for s in seen)
+        assert inst._rng_offset >= 4
+    finally:
+        gic_b200.set_gemm_mode(old)
