@@ -77,6 +77,7 @@ class GANInstructor:
         self._in_graph = False
         self._side = None
         self._comm = None
+        self.timeline = None         # list of (name, timing event) when a profiling script asks for markers
         self._rng_seed = None        # Philox state of the library-side draws (u / dropout masks not supplied by the caller)
         self._rng_offset = 0
         self._rng_dyn = None
@@ -101,6 +102,15 @@ class GANInstructor:
         if model is not None:
             torch.nn.utils.clip_grad_norm_(model.parameters(), self.args.clip_norm)
         opt.step()
+
+    def _mark(self, name):
+        """Timeline marker (profiles/step_timeline.py): a timing event on the current stream, also inside graph capture."""
+        if self.timeline is None:
+            return
+        # external=True: captured as an event-record NODE, so the event can be timed after every replay
+        ev = torch.cuda.Event(enable_timing=True, external=True)
+        ev.record(torch.cuda.current_stream())
+        self.timeline.append((name, ev))
 
     def _side_stream(self):
         if self._side is None:
@@ -316,11 +326,47 @@ class GANInstructor:
         drop_p = disc.dropout.p
         main = torch.cuda.current_stream()
         side = self._side_stream() if (train and self.overlap) else None
+        self._mark("start (masks drawn)")
+        # -- backward helper: D parameter gradients from (real, fake); generator gradients through D(gen) (:168-169, Q1)
+        bws = self._buf("disc_bws", lib.gic_disc_bwd_workspace_floats(B, L, De, R, Fd))
+        g = fd.g
+        dcw, dcb = [g(c.weight) for c in disc.convs], [g(c.bias) for c in disc.convs]
+
+        def disc_bwd(seed, kp, inp, idz, saved, want_param, acc, dinp, bws, stream):
+            _lib.check(lib.gic_disc_bwd(mode, P(seed), P(kp), drop_p, P(inp), P(idz), B, L, V, De, R, len(fsz),
+                                        _lib.int_array(fsz), _lib.int_array(nfl), P(disc.embeddings.weight),
+                                        _lib.ptr_array(cw), _lib.ptr_array(cb), P(disc.highway.weight),
+                                        P(disc.feature2out.weight), P(disc.feature2out.bias),
+                                        disc.feature2out.weight.shape[0], P(disc.out2logits.weight),
+                                        P(disc.out2logits.bias), P(saved), P(bws), P(g(disc.embeddings.weight)),
+                                        _lib.ptr_array(dcw), _lib.ptr_array(dcb), P(g(disc.highway.weight)),
+                                        P(g(disc.highway.bias)), P(g(disc.feature2out.weight)),
+                                        P(g(disc.feature2out.bias)), P(g(disc.out2logits.weight)),
+                                        P(g(disc.out2logits.bias)), P(dinp), want_param, acc, stream), "gic_disc_bwd")
+
+        # The seed of d_loss w.r.t. D(real) does not depend on D(fake) (every divergence except rsgan), and neither does
+        # anything else in backward(real), so it CAN run on the side stream right behind forward(real), underneath the
+        # decode loop.  Measured (profiles/step_timeline.py): the decode kernels need nearly every SM (126-128 CTAs of
+        # ~200 KB shared memory), so whatever runs beside them stalls them almost one for one: decode 989 -> 1232 us, the
+        # phase after the losses 1346 -> 1150 us, step 2.62 -> 2.67 ms.  Opt-in only (GIC_EARLY_REAL=1).
+        early_real = train and self.overlap and loss_type != "rsgan" and os.environ.get("GIC_EARLY_REAL", "0") == "1"
+        real_bwd_done = None
         if side is not None:
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 (d_real,), saved_r = disc_fwd_raw(lib, mode, None, captions, B, L, V, De, R, fsz, nfl, *dW, [k0], drop_p,
                                                   dev)
+                self._mark("side: D(real) forward done")
+                if early_real:
+                    nR = B * R
+                    seed_real = self._buf("seed_real", nR)
+                    _lib.check(lib.gic_gan_loss_fwd_bwd(_lib.LOSS_TYPES[loss_type], P(d_real), P(d_real), P(d_real), nR,
+                                                        P(self._buf("loss_scratch", 2)), P(seed_real), None, None,
+                                                        side.cuda_stream), "gic_gan_loss_fwd_bwd")
+                    disc_bwd(seed_real, k0, None, captions, saved_r, 1, 0, None, bws, side.cuda_stream)
+                    real_bwd_done = torch.cuda.Event()
+                    real_bwd_done.record(side)
+                    self._mark("side: D backward(real) done")
         else:
             (d_real,), saved_r = disc_fwd_raw(lib, mode, None, captions, B, L, V, De, R, fsz, nfl, *dW, [k0], drop_p, dev)
         # -- step-0 input (:144-147)
@@ -368,9 +414,11 @@ class GANInstructor:
                                                  P(dec.linear.weight), P(dec.linear.bias), P(u), T, 0, P(forced_ids), B,
                                                  L, V, E, H, layers, P(probs), P(ids), P(dsaved), P(dws), stream),
                        "gic_decode_sample_fwd")
+        self._mark("main: decode done")
         # -- discriminator on the generated captions: fake / gen share one trunk, two dropout masks (:163-164)
         (d_fake, g_out), saved_f = disc_fwd_raw(lib, mode, probs, None, B, L, V, De, R, fsz, nfl, *dW, [k1, k2],
                                                 drop_p, dev)
+        self._mark("main: D(fake/gen) forward done")
         if side is not None:
             main.wait_stream(side)
         # -- losses + seeds (:165)
@@ -379,27 +427,11 @@ class GANInstructor:
         seeds = self._buf("seeds", 3 * n).view(3, n)
         _lib.check(lib.gic_gan_loss_fwd_bwd(_lib.LOSS_TYPES[loss_type], P(d_real), P(d_fake), P(g_out), n, P(losses),
                                             P(seeds[0]), P(seeds[1]), P(seeds[2]), stream), "gic_gan_loss_fwd_bwd")
+        self._mark("main: losses done")
         out = dict(g_loss=losses[0], d_loss=losses[1], ids=ids, probs=probs, d_real=d_real, d_fake=d_fake,
                    g_out=g_out, features=feats)
         if not train:
             return out
-
-        # -- backward: D parameter gradients from (real, fake); generator gradients through D(gen) (:168-169, Q1)
-        bws = self._buf("disc_bws", lib.gic_disc_bwd_workspace_floats(B, L, De, R, Fd))
-        g = fd.g
-        dcw, dcb = [g(c.weight) for c in disc.convs], [g(c.bias) for c in disc.convs]
-
-        def disc_bwd(seed, kp, inp, idz, saved, want_param, acc, dinp, bws, stream):
-            _lib.check(lib.gic_disc_bwd(mode, P(seed), P(kp), drop_p, P(inp), P(idz), B, L, V, De, R, len(fsz),
-                                        _lib.int_array(fsz), _lib.int_array(nfl), P(disc.embeddings.weight),
-                                        _lib.ptr_array(cw), _lib.ptr_array(cb), P(disc.highway.weight),
-                                        P(disc.feature2out.weight), P(disc.feature2out.bias),
-                                        disc.feature2out.weight.shape[0], P(disc.out2logits.weight),
-                                        P(disc.out2logits.bias), P(saved), P(bws), P(g(disc.embeddings.weight)),
-                                        _lib.ptr_array(dcw), _lib.ptr_array(dcb), P(g(disc.highway.weight)),
-                                        P(g(disc.highway.bias)), P(g(disc.feature2out.weight)),
-                                        P(g(disc.feature2out.bias)), P(g(disc.out2logits.weight)),
-                                        P(g(disc.out2logits.bias)), P(dinp), want_param, acc, stream), "gic_disc_bwd")
 
         g_has_grad = loss_type != "rsgan"          # A14: rsgan's g_loss only sees detached D outputs
 
@@ -407,6 +439,7 @@ class GANInstructor:
             # D's input gradient stays factored (demb x W_e): the dense d(probs)[B,L,V] is never written; the
             # decoder backward fuses demb W_e with the tempered-softmax backward (gic_decode_sample_bwd_factored)
             disc_bwd(seeds[2], k2, probs, None, saved_f, 0, 0, None, ws_d, st)
+            self._mark("G chain: D input gradient (demb) done")
             off = lib.gic_disc_bwd_demb_offset_floats(B, L, De, R, Fd)
             demb = ws_d[off:off + B * L * De]
             emb = saved_f[:B * L * De]
@@ -434,6 +467,7 @@ class GANInstructor:
                     _lib.ptr_array([gg(w) for w in W_hh]), _lib.ptr_array([gg(w) for w in b_ih]),
                     _lib.ptr_array([gg(w) for w in b_hh]), P(gg(dec.linear.weight)), P(gg(dec.linear.bias)), P(dfeat), 0,
                     st), "gic_decode_sample_bwd_factored")
+            self._mark("G chain: decoder backward done")
             if self.cgan:
                 self._encoder_bwd(mode, dfeat, pooled, lin, mean, rstd, B, E, st)
             else:
@@ -453,16 +487,24 @@ class GANInstructor:
                     gen_chain(bws2, side.cuda_stream)
                     gen_done.record(side)
                 g_bucketed = self._gen_backward_early_bucket(_bwd)
-            disc_bwd(seeds[0], k0, None, captions, saved_r, 1, 0, None, bws, stream)
+            if real_bwd_done is None:
+                disc_bwd(seeds[0], k0, None, captions, saved_r, 1, 0, None, bws, stream)
+                self._mark("D chain: backward(real) done")
+            else:
+                main.wait_event(real_bwd_done)         # fake accumulates onto real's parameter gradients
             disc_bwd(seeds[1], k1, probs, None, saved_f, 1, 1, None, bws, stream)
+            self._mark("D chain: backward(fake) done")
             if self.world > 1:
                 parallel.allreduce_sum_(fd.grad)
             with torch.cuda.stream(side):
                 self._gen_allreduce_rest(g_bucketed)
                 out["g_sqnorm"] = self._clip_adam(fg, a.gen_lr, update, 3)
+                self._mark("G chain: clip + Adam done")
             main.wait_event(gen_done)
             out["d_sqnorm"] = self._clip_adam(fd, a.disc_lr, update, 1)
+            self._mark("D chain: clip + Adam done")
             main.wait_stream(side)
+            self._mark("end")
         else:
             disc_bwd(seeds[0], k0, None, captions, saved_r, 1, 0, None, bws, stream)
             disc_bwd(seeds[1], k1, probs, None, saved_f, 1, 1, None, bws, stream)
