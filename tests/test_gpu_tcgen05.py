@@ -209,3 +209,40 @@ def test_fused_dz_matches_separate_kernels(B, L, V, E, H, T):
         REPORT[f"dz_fused/B{B}V{V}/{k}"] = dict(err=err, scale=scale, rel=err / max(scale, 1e-30))
         tol = 2e-2 if k.endswith("linear.bias") else 5e-3     # bf16 rounding flips of dz where dp - dot cancels
         assert err <= tol * scale + 1e-12, f"{k}: err {err:.3e} scale {scale:.3e}"
+
+
+# ---- split-K LSTM step over 4-CTA clusters (lstm_tcgen05.cu) vs the one-CTA-per-tile kernel ---------------------------
+@pytest.mark.parametrize("B,L,V,E,H", [(256, 4, 2000, 512, 512), (200, 3, 1000, 256, 1024), (130, 3, 1000, 512, 512)])
+def test_lstm_splitk_cluster_matches_single_cta_kernel(B, L, V, E, H):
+    """Same decode with GIC_LSTM_SPLITK=1 (four partial accumulators added over distributed shared memory, in rank
+    order) and =0: the only difference is the association of the K sum, so h/c/probabilities agree to fp32 round-off."""
+    import gic_b200
+    import gic_b200.generator as G
+    from gic_b200.args import default_args
+    a = default_args(vocab_size=V, gen_embed_dim=E, gen_hidden_dim=H, gen_num_layers=1, conditional_gan=0, device="cuda")
+    torch.manual_seed(5)
+    gen = G.Generator(a).to("cuda:0"); gen.train(); gen.decoder.temperature = 1.0
+    g = torch.Generator(device="cuda:0").manual_seed(6)
+    u = torch.rand(L, B, V, generator=g, device="cuda:0")
+    feats = torch.randn(B, E, generator=g, device="cuda:0") * 0.5
+    fz = torch.randint(0, V, (B, L), generator=g, device="cuda:0")
+    old = gic_b200.get_gemm_mode()
+    gic_b200.set_gemm_mode(gic_b200.GEMM_TF32)
+    res = []
+    try:
+        for flag in ("1", "0"):
+            os.environ["GIC_LSTM_SPLITK"] = flag
+            with torch.no_grad():
+                p, ids = gen.decoder.sample(feats, max_caption_len=L, u=u, forced_ids=fz)
+            torch.cuda.synchronize()
+            res.append((p.clone(), ids.clone()))
+    finally:
+        os.environ.pop("GIC_LSTM_SPLITK", None)
+        gic_b200.set_gemm_mode(old)
+    (p1, i1), (p0, i0) = res
+    err = float((p1 - p0).abs().max()); scale = float(p0.max())
+    mism = int((i1 != i0).sum())
+    REPORT[f"lstm_splitk/B{B}H{H}"] = dict(err=err, scale=scale, rel=err / scale, id_mismatches=mism)
+    assert err <= 2e-5 * scale, f"probs differ by {err:.3e} (scale {scale:.3e})"
+    assert mism <= 1
+    assert float((p1.sum(-1) - 1).abs().max()) < 1e-4
