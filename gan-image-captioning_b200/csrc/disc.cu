@@ -2,6 +2,8 @@
 // column gather), fused conv + bias + ReLU + max-over-time emitting [N*R, F] directly, highway
 // mix, dropout and the collapsed 900->100->1 score head, plus the backward of all of it.
 // Replaces Discriminator.forward (src/discriminator.py:34-62) and its autograd backward.
+#include <stdlib.h>
+
 #include "gic_internal.cuh"
 
 namespace gic {
@@ -194,6 +196,217 @@ conv_pool_fwd_kernel(const float* __restrict__ emb, int L, int De, int R, int es
       pooled[((size_t)n * R + r) * F + c] = best;
       arg[((size_t)n * R + r) * F + c] = (uint8_t)a;
       if (pooled_bf) pooled_bf[((size_t)n * R + r) * Fp + c] = f2bf(best);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Tensor-core variant of conv_pool_fwd_kernel for the tensor-core GEMM modes (ES1 layout, f <= 5).
+// The conv over time is a tiny contraction out[c, t, r] = sum_k w[c, k] emb[t + k, r] (k < f): one warp-level
+// mma.sync.m16n8k16 (bf16 operands, fp32 accumulate) per 16 channels x 8 representations x 1 time step, and the max /
+// first arg-max over t is a per-register compare on the accumulator fragment -- the 250 M conv outputs of a c2 call never
+// leave registers.  The CUDA-core kernel spends ~10 instructions per output (ncu), this one ~3.5.
+// Precision: both operands are split x = hi + lo with hi, lo in bf16 (round to nearest), and the three significant
+// products share the K = 16 slots of ONE instruction:
+//     k = 0..4   w_hi[k]    * x_hi[t + k]
+//     k = 5..9   w_hi[k-5]  * x_lo[t + k - 5]
+//     k = 10..14 w_lo[k-10] * x_hi[t + k - 10]            (k = 15 unused; the dropped lo * lo term is 2^-16 relative)
+// so the result carries ~16 mantissa bits per operand: 30 x finer than the TF32 contraction that produced emb in these
+// modes.  The pooled value itself is stored with its low 5 mantissa bits cleared (see the arg-max trick in the loop).  (Three TF32 m16n8k8 MMAs per step reach fp32 accuracy but measured SLOWER than the CUDA-core kernel, 131 vs
+// 121 us: the legacy tensor path issues one HMMA per ~12 cycles and sub-partition.  A tcgen05/TMEM formulation was
+// rejected: TMEM reads back at 64 B/clk/SM, and all outputs would have to come back through it, ~55 us.)
+// grid = (captions, slices of channel blocks); a channel block = 16 channels of ONE filter group (groups padded to 16).
+// smem: XB[T_max][4 (tg)][68] uint2 = the two B-fragment registers of lane (tg, r) at time t, ready-made
+//       | WA[blocks][16][12] uint32 (bf16 pairs, A fragment order) | bias[blocks][16] | meta[blocks] int4
+// ---------------------------------------------------------------------------------------
+constexpr int CM_XS = 68;     // uint2 row pitch of one (t, tg) row: the 8-byte loads of a half-warp hit 32 distinct banks
+constexpr int CM_WS = 12;     // 32-bit row pitch of a weight block: the four A-fragment loads are conflict-free
+constexpr int CM_FMAX = 5;    // taps per part: 3 parts x 5 taps fill the 16 K slots
+
+__device__ __forceinline__ void mma_bf16_16x8x16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float bf2f(unsigned short h) { return __uint_as_float((uint32_t)h << 16); }
+__device__ __forceinline__ float fmax3(float a, float b, float c) {       // 3-input maximum (sm_100: one FMNMX3)
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned short cvt_bf16(float x) {     // round to nearest even, one instruction
+  unsigned short h;
+  asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(h) : "f"(x));
+  return h;
+}
+// number of 16-channel blocks over all groups
+static inline int conv_mma_blocks(const ConvGroups& g) {
+  int nb = 0;
+  for (int i = 0; i < g.ngroups; ++i) nb += (g.n[i] + 15) / 16;
+  return nb;
+}
+
+template <int NBLK>
+__device__ __forceinline__ void conv_mma_unit(const uint2* __restrict__ xs, const uint32_t* __restrict__ wa,
+                                              const float* __restrict__ bias_s, const int4* __restrict__ meta, int b0,
+                                              int T, int gq, int tg, size_t row0, int F, float* __restrict__ pooled,
+                                              uint8_t* __restrict__ arg, unsigned short* __restrict__ pooled_bf, int Fp) {
+  uint32_t af[NBLK][4];
+  float bs[NBLK][2], best[NBLK][4];
+  uint32_t tinv = 31u;
+#pragma unroll
+  for (int i = 0; i < NBLK; ++i) {
+    const uint32_t* w = wa + (size_t)(b0 + i) * 16 * CM_WS;
+    af[i][0] = w[gq * CM_WS + tg];
+    af[i][1] = w[(gq + 8) * CM_WS + tg];
+    af[i][2] = w[gq * CM_WS + tg + 4];
+    af[i][3] = w[(gq + 8) * CM_WS + tg + 4];
+    bs[i][0] = bias_s[(b0 + i) * 16 + gq];
+    bs[i][1] = bias_s[(b0 + i) * 16 + gq + 8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) best[i][e] = -INFINITY;
+  }
+  // (max, first arg-max) in ONE maximum: the low 5 mantissa bits of a candidate are replaced by 31 - t, so that among
+  // candidates equal in the upper 27 bits the earliest step wins and the winner's step can be read back from the maximum
+  // itself.  Compare / select instructions run on the half-rate ALU pipe and were the bound of this kernel (FSETP + FSEL +
+  // SEL per output: ncu ALU pipe 68 %, math-pipe throttle); this is one LOP3 per output and one 3-input FMNMX per two.
+  // The 2^-19 truncation is below the 2^-16 of the bf16 split; only positive maxima are used (ReLU), where float
+  // order = bit order.
+  int t = 0;
+#pragma unroll 2
+  for (; t + 1 < T; t += 2) {
+    const uint2 q0 = xs[(size_t)t * 4 * CM_XS], q1 = xs[(size_t)(t + 1) * 4 * CM_XS];
+#pragma unroll
+    for (int i = 0; i < NBLK; ++i) {
+      float c0[4] = {bs[i][0], bs[i][0], bs[i][1], bs[i][1]};
+      float c1[4] = {bs[i][0], bs[i][0], bs[i][1], bs[i][1]};
+      mma_bf16_16x8x16(c0, af[i], q0.x, q0.y);
+      mma_bf16_16x8x16(c1, af[i], q1.x, q1.y);
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        best[i][e] = fmax3(best[i][e], __uint_as_float((__float_as_uint(c0[e]) & 0xffffffe0u) | tinv),
+                           __uint_as_float((__float_as_uint(c1[e]) & 0xffffffe0u) | (tinv - 1u)));
+    }
+    tinv -= 2u;
+  }
+  if (t < T) {
+    const uint2 q = xs[(size_t)t * 4 * CM_XS];
+#pragma unroll
+    for (int i = 0; i < NBLK; ++i) {
+      float c[4] = {bs[i][0], bs[i][0], bs[i][1], bs[i][1]};
+      mma_bf16_16x8x16(c, af[i], q.x, q.y);
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        best[i][e] = fmaxf(best[i][e], __uint_as_float((__float_as_uint(c[e]) & 0xffffffe0u) | tinv));
+    }
+  }
+  // ReLU hoisted out of the max; outputs: channels (gq, gq + 8) x representations (2 tg, 2 tg + 1)
+#pragma unroll
+  for (int i = 0; i < NBLK; ++i) {
+    const int4 m = meta[b0 + i];                   // x = first global column of the block, y = valid channels
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int ch = gq + ((e >> 1) << 3), rr = 2 * tg + (e & 1);
+      if (ch < m.y) {
+        const uint32_t kb = __float_as_uint(best[i][e]);
+        float v = __uint_as_float(kb & 0xffffffe0u);
+        int a = 31 - (int)(kb & 31u);
+        if (!(v > 0.f)) { v = 0.f; a = ARG_DEAD; }
+        const size_t o = (row0 + rr) * F + m.x + ch;
+        pooled[o] = v;
+        arg[o] = (uint8_t)a;
+        if (pooled_bf) pooled_bf[(row0 + rr) * Fp + m.x + ch] = cvt_bf16(v);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+conv_pool_fwd_mma_kernel(const float* __restrict__ emb, int L, int R, ConvGroups g, int bps /*blocks per slice*/,
+                         int nblocks, int Tmax, float* __restrict__ pooled, uint8_t* __restrict__ arg,
+                         unsigned short* __restrict__ pooled_bf, int Fp) {
+  extern __shared__ __align__(16) float sm[];
+  const int F = g.F;
+  const int n = blockIdx.x;
+  const int blk_lo = blockIdx.y * bps, nb = min(bps, nblocks - blk_lo);
+  uint2* xb = reinterpret_cast<uint2*>(sm);                                     // [Tmax][4][CM_XS]
+  uint32_t* wa = reinterpret_cast<uint32_t*>(sm + (size_t)Tmax * 4 * CM_XS * 2);  // [bps][16][CM_WS]
+  float* bias_s = reinterpret_cast<float*>(wa + (size_t)bps * 16 * CM_WS);      // [bps][16]
+  int4* meta = reinterpret_cast<int4*>(bias_s + (size_t)bps * 16);              // [bps]: first column, valid channels, f, -
+  // stage 1: hl[t][r] = bf16 hi | bf16 lo << 16 of the caption's embedding rows (rows past the end are zero; their
+  // weights are zero as well).  hl aliases the tail of the dynamic shared memory (after meta).
+  uint32_t* hl = reinterpret_cast<uint32_t*>(meta + bps);                       // [(Tmax + 4)][R]
+  const float* en = emb + (size_t)n * L * R;
+  for (int i = threadIdx.x; i < (Tmax + 4) * R; i += blockDim.x) {
+    const int t = i / R;
+    uint32_t v = 0;
+    if (t < L) {
+      const float x = en[i];
+      const unsigned short h = cvt_bf16(x);
+      v = (uint32_t)h | ((uint32_t)cvt_bf16(x - bf2f(h)) << 16);
+    }
+    hl[i] = v;
+  }
+  __syncthreads();
+  // stage 2: B fragments.  Lane (tg, gq) needs K rows 2 tg, 2 tg + 1 (register 0) and 2 tg + 8, 2 tg + 9 (register 1)
+  // of column r0 + gq at every time step; with the slot map above (H = hi, L = lo of the embedding row):
+  //   tg 0: H[t] H[t+1] | L[t+3] L[t+4]      tg 1: H[t+2] H[t+3] | H[t] H[t+1]
+  //   tg 2: H[t+4] L[t] | H[t+2] H[t+3]      tg 3: L[t+1] L[t+2] | H[t+4] 0
+  for (int i = threadIdx.x; i < Tmax * R; i += blockDim.x) {
+    const int r = i % R, t = i / R;
+    const uint32_t* c = hl + (size_t)t * R + r;
+    const uint32_t e0 = c[0], e1 = c[R], e2 = c[2 * R], e3 = c[3 * R], e4 = c[4 * R];
+    const uint32_t H01 = __byte_perm(e0, e1, 0x5410), H23 = __byte_perm(e2, e3, 0x5410);    // lo halves = hi parts
+    const uint32_t L34 = __byte_perm(e3, e4, 0x7632), L12 = __byte_perm(e1, e2, 0x7632);    // hi halves = lo parts
+    const uint32_t H4L0 = __byte_perm(e4, e0, 0x7610), H4Z = e4 & 0xffffu;
+    uint2* o = xb + (size_t)t * 4 * CM_XS + r;
+    o[0 * CM_XS] = make_uint2(H01, L34);
+    o[1 * CM_XS] = make_uint2(H23, H01);
+    o[2 * CM_XS] = make_uint2(H4L0, H23);
+    o[3 * CM_XS] = make_uint2(L12, H4Z);
+  }
+  // A fragments of this slice's weight blocks: one thread per (block, channel row) splits the row's f <= 5 taps once and
+  // writes the 16 K slots [hi(5) | hi(5) | lo(5) | 0] as 8 bf16 pairs (channels past the group's end and taps past f
+  // are zero)
+  for (int i = threadIdx.x; i < nb * 16; i += blockDim.x) {
+    const int bl = i >> 4, row = i & 15;
+    int b = blk_lo + bl, gi = 0;
+    while (gi + 1 < g.ngroups && b >= (g.n[gi] + 15) / 16) { b -= (g.n[gi] + 15) / 16; ++gi; }
+    const int ch = b * 16 + row, f = g.f[gi];
+    const bool live = ch < g.n[gi];
+    uint32_t hi[CM_FMAX + 1], lo[CM_FMAX + 1];
+#pragma unroll
+    for (int k = 0; k < CM_FMAX; ++k) {
+      const float w = (live && k < f) ? g.w[gi][ch * f + k] : 0.f;
+      const unsigned short h = cvt_bf16(w);
+      hi[k] = h;
+      lo[k] = cvt_bf16(w - bf2f(h));
+    }
+    hi[CM_FMAX] = lo[CM_FMAX] = 0;
+    uint32_t* o = wa + (size_t)(bl * 16 + row) * CM_WS;
+    o[0] = hi[0] | (hi[1] << 16); o[1] = hi[2] | (hi[3] << 16); o[2] = hi[4] | (hi[0] << 16); o[3] = hi[1] | (hi[2] << 16);
+    o[4] = hi[3] | (hi[4] << 16); o[5] = lo[0] | (lo[1] << 16); o[6] = lo[2] | (lo[3] << 16); o[7] = lo[4];
+    bias_s[bl * 16 + row] = live ? g.b[gi][ch] : 0.f;
+    if (row == 0) meta[bl] = make_int4(g.col0[gi] + b * 16, min(16, g.n[gi] - b * 16), f, 0);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int gq = lane >> 2, tg = lane & 3;
+  // work units: (representation block of 8, pair of channel blocks with the same filter size)
+  for (int rb = warp; rb < R / 8; rb += nwarps) {
+    const uint2* xs = xb + (size_t)tg * CM_XS + rb * 8 + gq;
+    const size_t row0 = (size_t)n * R + rb * 8;
+    int b = 0;
+    while (b < nb) {
+      const int f = meta[b].z;
+      const int T = L - f + 1;
+      if (b + 1 < nb && meta[b + 1].z == f) {
+        conv_mma_unit<2>(xs, wa, bias_s, meta, b, T, gq, tg, row0, F, pooled, arg, pooled_bf, Fp);
+        b += 2;
+      } else {
+        conv_mma_unit<1>(xs, wa, bias_s, meta, b, T, gq, tg, row0, F, pooled, arg, pooled_bf, Fp);
+        b += 1;
+      }
     }
   }
 }
@@ -773,7 +986,35 @@ int disc_forward(int mode, const float* inp_soft, const int64_t* ids, const Disc
       attr = true;
     }
     unsigned short* pbf = bf ? pooled_bf : nullptr;
-    if (es1) conv_pool_fwd_kernel<true><<<dim3(d.N, slices), 256, smem, s>>>(emb, d.L, d.De, d.R, d.es, g, cs, pooled, arg, pbf, Fp);
+    // tensor-core modes: mma.sync formulation (bf16 hi/lo split along K, one HMMA per step); GIC_CONV_MMA=0 keeps the
+    // CUDA-core kernel
+    int fmin = g.kmax;
+    for (int i = 0; i < g.ngroups; ++i) fmin = min(fmin, g.f[i]);
+    bool use_mma = (mode == GEMM_TF32 || mode == GEMM_BF16) && d.es == 1 && d.De == d.R && (d.R % 8 == 0) && g.kmax <= CM_FMAX &&
+                   d.L >= g.kmax && d.L - fmin + 1 <= 32;
+    { const char* e = getenv("GIC_CONV_MMA"); if (e && e[0] == '0') use_mma = false; }
+    if (use_mma) {
+      const int nblocks = conv_mma_blocks(g);
+      const int Tmax = d.L - fmin + 1;
+      // slices: enough CTAs to balance the SMs, and at least two so that a CTA's weight fragments leave room for a second
+      // resident CTA next to the B-fragment table (measured: c5 shape 3.09 ms with one slice, 2.63 ms with two)
+      int sl = max(1, min(max(2, cdiv(4 * num_sms(), d.N)), nblocks));
+      { const char* e = getenv("GIC_CONV_MMA_SLICES"); if (e && atoi(e) > 0) sl = min(atoi(e), nblocks); }   // tuning
+      const int bps = cdiv(nblocks, sl);
+      sl = cdiv(nblocks, bps);
+      const size_t msmem = (size_t)Tmax * 4 * CM_XS * 8 + (size_t)bps * 16 * CM_WS * 4 + (size_t)bps * 16 * 4 + (size_t)bps * 16 +
+                           (size_t)(Tmax + 4) * d.R * 4;
+      if (msmem <= 200 * 1024) {
+        static bool mattr = false;
+        if (!mattr) { cudaFuncSetAttribute(conv_pool_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); mattr = true; }
+        conv_pool_fwd_mma_kernel<<<dim3(d.N, sl), 256, msmem, s>>>(emb, d.L, d.R, g, bps, nblocks, Tmax, pooled, arg, pbf, Fp);
+        GIC_TRY(check_launch("conv_pool_fwd_mma_kernel"));
+      } else {
+        use_mma = false;
+      }
+    }
+    if (use_mma) {}
+    else if (es1) conv_pool_fwd_kernel<true><<<dim3(d.N, slices), 256, smem, s>>>(emb, d.L, d.De, d.R, d.es, g, cs, pooled, arg, pbf, Fp);
     else conv_pool_fwd_kernel<false><<<dim3(d.N, slices), 256, smem, s>>>(emb, d.L, d.De, d.R, d.es, g, cs, pooled, arg, pbf, Fp);
     GIC_TRY(check_launch("conv_pool_fwd_kernel"));
   }

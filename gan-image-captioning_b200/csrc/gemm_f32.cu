@@ -2,6 +2,7 @@
 // fallback for shapes the tcgen05 kernels do not take; the tensor-core path lives in
 // gemm_tcgen05.cu.  Replaces the reference's nn.Linear / cuBLAS calls
 // (src/generator.py:61,64,68; src/discriminator.py:40,53,58,60) and their autograd backward.
+#include <stdlib.h>
 #include <stdarg.h>
 #include <string.h>
 
@@ -44,6 +45,11 @@ int num_sms() {
     if (n <= 0) n = 148;
   }
   return n;
+}
+
+bool pdl_enabled() {
+  const char* e = getenv("GIC_PDL");
+  return !(e && e[0] == '0');
 }
 
 // ---------------------------------------------------------------------------------------

@@ -85,6 +85,34 @@ int dz_fused_tc(const float* demb, int K, const float* W_e, const float* p, cons
 int colsum_f32(const float* A, int M, int N, int lda, float scale, bool accumulate, float* out,
                cudaStream_t stream);
 
+// ---- programmatic dependent launch (serial kernel chains: decode steps, BPTT) ---------------------------
+// A kernel that executes pdl_wait() before its first global-memory access may be launched with launch_pdl(): the
+// launch is processed while its predecessor in the stream still runs, so launch latency, barrier initialisation, TMEM
+// allocation and tensor-map prefetch overlap the predecessor's tail.  pdl_wait() returns once the predecessor grid has
+// completed and its writes are visible; pdl_trigger() (after the wait: a kernel two places down the chain must never
+// start before the one two places up has finished) lets the successor's launch begin.  Both are no-ops in a kernel
+// launched without the attribute.  ONLY kernels containing pdl_wait() may be launched through launch_pdl().
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();          // GIC_PDL=0 turns the attribute off (read per call: tests and A/B runs toggle it)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- device helpers ---------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -62,6 +62,8 @@ lstm_step_tf32_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                      // everything above overlapped the previous kernel of the decode chain
+  pdl_trigger();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -99,11 +101,29 @@ lstm_step_tf32_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     }
   } else {
     // ===== epilogue: LSTM cell on the accumulator tile =====
-    mbar_wait(tmem_full, 0);
-    tcgen05_fence_after();
     const int q = warp & 3;
     const int b = m0 + q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    // the first unit group's previous cell state and biases are fetched while the main loop runs
+    float cp0[8], bs0[4][8];
+    {
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      const bool ok = b < B;
+      *reinterpret_cast<float4*>(cp0) = ok ? *reinterpret_cast<const float4*>(c_prev + (size_t)b * H + j0) : z4;
+      *reinterpret_cast<float4*>(cp0 + 4) = ok ? *reinterpret_cast<const float4*>(c_prev + (size_t)b * H + j0 + 4) : z4;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+#pragma unroll
+        for (int h4 = 0; h4 < 2; ++h4) {
+          const float4 x = __ldg(reinterpret_cast<const float4*>(b_ih + g * H + j0) + h4);
+          const float4 y = __ldg(reinterpret_cast<const float4*>(b_hh + g * H + j0) + h4);
+          bs0[g][4 * h4 + 0] = x.x + y.x; bs0[g][4 * h4 + 1] = x.y + y.y;
+          bs0[g][4 * h4 + 2] = x.z + y.z; bs0[g][4 * h4 + 3] = x.w + y.w;
+        }
+      }
+    }
+    mbar_wait(tmem_full, 0);
+    tcgen05_fence_after();
 #pragma unroll 1
     for (int u0 = 0; u0 < U; u0 += 8) {
       uint32_t ri[8], rf[8], rg[8], ro[8];
@@ -113,15 +133,27 @@ lstm_step_tf32_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       tmem_ld8(lane_addr + 3 * U + u0, ro);
       if (b < B) {
         const int j = j0 + u0;
-        float cp[8], ai[8], af[8], ag[8], ao[8], cn[8], hn[8];
-        *reinterpret_cast<float4*>(cp) = *reinterpret_cast<const float4*>(c_prev + (size_t)b * H + j);
-        *reinterpret_cast<float4*>(cp + 4) = *reinterpret_cast<const float4*>(c_prev + (size_t)b * H + j + 4);
+        float cp[8], bs[4][8], ai[8], af[8], ag[8], ao[8], cn[8], hn[8];
+        if (u0 == 0) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            cp[e] = cp0[e];
+            bs[0][e] = bs0[0][e]; bs[1][e] = bs0[1][e]; bs[2][e] = bs0[2][e]; bs[3][e] = bs0[3][e];
+          }
+        } else {
+          *reinterpret_cast<float4*>(cp) = *reinterpret_cast<const float4*>(c_prev + (size_t)b * H + j);
+          *reinterpret_cast<float4*>(cp + 4) = *reinterpret_cast<const float4*>(c_prev + (size_t)b * H + j + 4);
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) bs[g][e] = b_ih[g * H + j + e] + b_hh[g * H + j + e];
+        }
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const float pi = __uint_as_float(ri[e]) + b_ih[0 * H + j + e] + b_hh[0 * H + j + e];
-          const float pf = __uint_as_float(rf[e]) + b_ih[1 * H + j + e] + b_hh[1 * H + j + e];
-          const float pg = __uint_as_float(rg[e]) + b_ih[2 * H + j + e] + b_hh[2 * H + j + e];
-          const float po = __uint_as_float(ro[e]) + b_ih[3 * H + j + e] + b_hh[3 * H + j + e];
+          const float pi = __uint_as_float(ri[e]) + bs[0][e];
+          const float pf = __uint_as_float(rf[e]) + bs[1][e];
+          const float pg = __uint_as_float(rg[e]) + bs[2][e];
+          const float po = __uint_as_float(ro[e]) + bs[3][e];
           ai[e] = sigmoidf_acc(pi); af[e] = sigmoidf_acc(pf); ag[e] = tanhf(pg); ao[e] = sigmoidf_acc(po);
           cn[e] = af[e] * cp[e] + ai[e] * ag[e];
           hn[e] = ao[e] * tanhf(cn[e]);
@@ -338,7 +370,7 @@ int lstm_step_tc(const float* x, int In, const float* h_prev, const float* W_ih,
   using namespace tc;
   *handled = false;
   if (B <= 0 || (H % 8) || (In % 4) || In < 4) return GIC_OK;
-  const void* ptrs[] = {x, h_prev, W_ih, W_hh, c_prev, acts ? acts : h_out, c_out, h_out, htop ? htop : h_out};
+  const void* ptrs[] = {x, h_prev, W_ih, W_hh, c_prev, acts ? acts : h_out, c_out, h_out, htop ? htop : h_out, b_ih, b_hh};
   for (const void* p : ptrs)
     if (!aligned16(p)) return GIC_OK;
   // units per CTA: the widest tile that still gives at least ~3/4 of the SMs a CTA
@@ -396,9 +428,11 @@ int lstm_step_tc(const float* x, int In, const float* h_prev, const float* W_ih,
     }
   }
   dim3 grid(H / U, mt);
-#define GIC_LSTM(U_) lstm_step_tf32_kernel<U_><<<grid, NTHREADS, LstmCfg<U_>::SMEM, stream>>>(tx, th, twi, twh, B, H, In, b_ih, b_hh, c_prev, acts, c_out, h_out, htop, L, t)
+  cudaError_t le;
+#define GIC_LSTM(U_) le = launch_pdl(lstm_step_tf32_kernel<U_>, grid, dim3(NTHREADS), LstmCfg<U_>::SMEM, stream, tx, th, twi, twh, B, H, In, b_ih, b_hh, c_prev, acts, c_out, h_out, htop, L, t)
   if (U == 32) GIC_LSTM(32); else if (U == 16) GIC_LSTM(16); else GIC_LSTM(8);
 #undef GIC_LSTM
+  if (le != cudaSuccess) { set_error("lstm_step_tf32_kernel launch: %s", cudaGetErrorString(le)); return GIC_ERR_CUDA; }
   int rc = check_launch("lstm_step_tf32_kernel");
   if (rc == GIC_OK) *handled = true;
   return rc;

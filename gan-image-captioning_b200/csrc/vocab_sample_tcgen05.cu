@@ -127,6 +127,8 @@ vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                      // the LSTM step that produced h_t has completed; the set-up above overlapped its tail
+  pdl_trigger();
 
   if (warp == 0) {
     // ===== TMA producer: operand ring; the u tile is queued once the ring is primed (the epilogue warps turn it into
@@ -449,7 +451,8 @@ static int launch_vs(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     cudaFuncSetAttribute(vocab_sample_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
     attr = true;
   }
-  vocab_sample_kernel<BN><<<grid, VS_THREADS, S::TOTAL, s>>>(ta, tb, tu, tp, a);
+  cudaError_t e = launch_pdl(vocab_sample_kernel<BN>, dim3(grid), dim3(VS_THREADS), S::TOTAL, s, ta, tb, tu, tp, a);
+  if (e != cudaSuccess) { set_error("vocab_sample_kernel launch: %s", cudaGetErrorString(e)); return GIC_ERR_CUDA; }
   return check_launch("vocab_sample_kernel");
 }
 

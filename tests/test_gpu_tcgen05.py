@@ -246,3 +246,65 @@ def test_lstm_splitk_cluster_matches_single_cta_kernel(B, L, V, E, H):
     assert err <= 2e-5 * scale, f"probs differ by {err:.3e} (scale {scale:.3e})"
     assert mism <= 1
     assert float((p1.sum(-1) - 1).abs().max()) < 1e-4
+
+
+# ---- mma.sync conv + ReLU + max-pool forward (disc.cu, tensor-core modes) vs the CUDA-core kernel --------------------
+def _a4(n):
+    return (n + 3) & ~3
+
+
+def _conv_pool_pair(N, L, V, fsz, nfl, seed=0, R=64):
+    """gic_disc_fwd on hard token ids (the embedding gather is exact in every mode) in TF32 mode, once with the mma.sync
+    conv kernel (bf16 hi/lo split) and once with GIC_CONV_MMA=0 (CUDA-core FFMA kernel): (pooled, arg, logits) of both."""
+    import gic_b200
+    from gic_b200 import _lib
+    from gic_b200.discriminator import disc_fwd_raw
+    d = dev()
+    lib = _lib.lib()
+    g = torch.Generator(device=d).manual_seed(seed)
+    De, Fd, Hd = R, sum(nfl), 100
+    u = lambda *s: (torch.rand(*s, generator=g, device=d) - 0.5) * 0.1
+    W_e = u(De, V) * 10          # embedding values of order 0.5: conv outputs of order 0.1
+    cw = [u(n, 1, f, 1).contiguous() for n, f in zip(nfl, fsz)]
+    cb = [u(n) for n in nfl]
+    W_h, b_h, W_f, b_f, W_o, b_o = u(Fd, Fd), u(Fd), u(Hd, Fd), u(Hd), u(1, Hd), u(1)
+    ids = torch.randint(0, V, (N, L), generator=g, device=d)
+    res = []
+    try:
+        for flag in ("1", "0"):
+            os.environ["GIC_CONV_MMA"] = flag
+            logits, saved = disc_fwd_raw(lib, gic_b200.GEMM_TF32, None, ids, N, L, V, De, R, fsz, nfl, W_e, cw, cb, W_h, b_h,
+                                         W_f, b_f, W_o, b_o, [None], 0.0, d)
+            torch.cuda.synchronize()
+            rows = N * R
+            o = _a4(N * L * De)
+            pooled = saved[o:o + rows * Fd].view(rows, Fd).clone()
+            o2 = o + 2 * _a4(rows * Fd)
+            arg = saved[o2:o2 + _a4((rows * Fd + 3) // 4)].view(torch.uint8)[:rows * Fd].view(rows, Fd).clone()
+            res.append((pooled, arg, logits[0].clone()))
+    finally:
+        os.environ.pop("GIC_CONV_MMA", None)
+    return res
+
+
+@pytest.mark.parametrize("N,L,V,fsz,nfl", [
+    (8, 16, 1000, [3, 4, 5], [300, 300, 300]),      # c1 discriminator
+    (64, 20, 2000, [3, 4, 5], [300, 300, 300]),     # c2 caption length, several captions per SM
+    (5, 32, 500, [2, 3, 4, 5], [100, 52, 300, 20]), # c5 length; groups that are not multiples of 16 channels
+    (3, 6, 200, [3, 5], [24, 40]),                  # short captions: T = 2 for the widest filter
+    (2, 8, 300, [5, 1], [16, 36]),                  # f = 5 (all taps of a part) and f = 1
+])
+def test_conv_pool_mma_matches_cuda_core_kernel(N, L, V, fsz, nfl):
+    (p1, a1, l1), (p0, a0, l0) = _conv_pool_pair(N, L, V, fsz, nfl)
+    scale = float(p0.max())
+    err = float((p1 - p0).abs().max())
+    mism = int((a1 != a0).sum())
+    nm = f"conv_pool_mma/N{N}L{L}F{sum(nfl)}"
+    REPORT[nm] = dict(err=err, scale=scale, rel=err / scale, arg_mismatches=mism, n=int(a0.numel()))
+    # bf16 hi/lo split of both operands: ~2^-16 relative per operand (the TF32 contractions of these modes carry 2^-11)
+    assert err <= 5e-5 * scale + 1e-7, f"pooled differs by {err:.3e} (scale {scale:.3e})"
+    # the arg-max (routing of the gradient) may differ only where two time steps tie at that level
+    assert mism <= max(2, int(1e-3 * a0.numel())), f"{mism} of {a0.numel()} arg-max indices differ"
+    assert bool(((a1 == 255) == (a0 == 255)).all() or mism > 0)
+    lerr = float((l1 - l0).abs().max())
+    assert lerr <= 2e-4 * float(l0.abs().max()) + 1e-6
