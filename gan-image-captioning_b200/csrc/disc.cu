@@ -1164,7 +1164,9 @@ int disc_backward(int mode, const float* dlogit, const uint8_t* keep, float drop
     // (b) conv weight / bias gradients
     if (want_param) {
       const int colb = cdiv(d.F, 256);
-      int chunks = max(1, (4 * num_sms()) / colb);
+      int per_sm = 4;
+      { const char* e = getenv("GIC_DW_CTAS_PER_SM"); if (e && atoi(e) > 0) per_sm = atoi(e); }   // tuning
+      int chunks = max(1, (per_sm * num_sms()) / colb);
       int rpc = cdiv((long long)rows, chunks);
       rpc = ((rpc + DW_RC - 1) / DW_RC) * DW_RC;
       chunks = cdiv((long long)rows, rpc);

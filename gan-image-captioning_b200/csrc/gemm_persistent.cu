@@ -501,6 +501,9 @@ int gemm_tc_persistent(bool transA, bool transB, int M, int N, int K, float alph
   return rc;
 }
 
+int gemm_tc_bf16_pair(bool b_mn, int M, int N, int K, float alpha, const void* A, int lda, const void* B, int ldb, float* C,
+                      int ldc, const float* bias, cudaStream_t stream, bool* handled);
+
 // bf16 operands (kind::f16), fp32 accumulate and fp32 output: the discriminator's [N*R, F] x [F, F] contractions in
 // GIC_GEMM_BF16 mode.  A / B are bf16 with leading dimensions in elements (multiples of 8); layouts as gemm().
 int gemm_tc_bf16(bool transA, bool transB, int M, int N, int K, float alpha, const void* A, int lda, const void* B,
@@ -510,6 +513,11 @@ int gemm_tc_bf16(bool transA, bool transB, int M, int N, int K, float alpha, con
   if (M <= 0 || N <= 0 || K <= 0) return GIC_OK;
   if (!aligned16(A) || !aligned16(B) || (lda % 8) || (ldb % 8)) return GIC_OK;
   const bool a_mn = transA, b_mn = !transB;
+  // whole-tile shapes with a K-major A and a plain-store epilogue: CTA pairs (gemm_pair_tcgen05.cu)
+  if (!a_mn && beta == 0.f) {
+    GIC_TRY(gemm_tc_bf16_pair(b_mn, M, N, K, alpha, A, lda, B, ldb, C, ldc, bias, stream, handled));
+    if (*handled) return GIC_OK;
+  }
   const bool allow_sk = (beta == 0.f || beta == 1.f);
   const int G = num_sms();
   // tile width: as choose_bn with 64-element k-blocks; MN-major B needs BN % 64 == 0

@@ -110,6 +110,22 @@ def test_gemm_bf16_vs_fp64(tA, tB, M, N, K):
     assert err <= 2e-5 * scale, f"rel err {err / scale:.3e}"          # exact bf16 products, fp32 accumulation
 
 
+@pytest.mark.parametrize("tB,M,N,K", [(1, 16384 + 130, 900, 900), (0, 4096 + 256 + 8, 900, 900), (1, 8192, 256, 512),
+                                      (0, 19200, 1024, 192)])
+def test_gemm_bf16_cta_pair_kernel_bias_ragged_rows(tB, M, N, K):
+    """Shapes that take the cta_group::2 kernel (gemm_pair_tcgen05.cu): rows that are not a multiple of the 256-row pair
+    tile, bias, alpha, padded pitches; and the same call with GIC_GEMM_2CTA=0 (one CTA per tile)."""
+    err, scale = run_gemm_bf16(0, tB, M, N, K, alpha=0.5, use_bias=True, seed=9, pad=8)
+    REPORT[f"bf16_pair/{M}x{N}x{K}/tB{tB}"] = dict(err=err, scale=scale, rel=err / scale)
+    assert err <= 2e-5 * scale, f"rel err {err / scale:.3e}"
+    os.environ["GIC_GEMM_2CTA"] = "0"
+    try:
+        err0, _ = run_gemm_bf16(0, tB, M, N, K, alpha=0.5, use_bias=True, seed=9, pad=8)
+    finally:
+        os.environ.pop("GIC_GEMM_2CTA", None)
+    assert err0 <= 2e-5 * scale
+
+
 def test_gemm_bf16_alpha_beta_bias_padded_pitch():
     err, scale = run_gemm_bf16(0, 1, 384, 900, 900, alpha=0.75, beta=1.0, use_bias=True, seed=5, pad=56)
     assert err <= 2e-5 * scale
