@@ -297,20 +297,37 @@ def run_ours(args):
     K = C.c_double * NK
     ms_k, work_k, calls_k = K(), K(), (C.c_ulonglong * NK)()
     use_graph = False          # events around individual launches need the eager path
-    step_resident(0); torch.cuda.synchronize()
     psteps = min(args.steps, 3)
-    lib.gic_prof_begin()
-    for i in range(psteps):
-        step_resident(i)
-    torch.cuda.synchronize()
-    lib.gic_prof_end(ms_k, work_k, calls_k)
     names = ["gemm_other", "sample_step", "conv_pool_fwd", "softmax_bwd", "clip_adam", "head_fwd", "gemm_disc", "gemm_decode",
              "vocab_sample_fused"]
-    classes = {}
-    for k, nm in enumerate(names):
-        if calls_k[k]:
-            classes[nm] = dict(ms_per_step=ms_k[k] / psteps, calls_per_step=calls_k[k] / psteps,
-                               work_per_step=work_k[k] / psteps)
+
+    def instrumented(overlap):
+        """psteps eager steps with CUDA events around every launch of each kernel class (on the launching stream).
+        overlap=True: the step's two streams run side by side as in the timed region, so a kernel's events also cover
+        the time it shares the SMs with the other chain's kernels.  overlap=False: one stream, every kernel alone on the
+        machine -- the duration that belongs to the kernel (and the one ncu's serialised launch list can be compared with)."""
+        prev = inst.overlap
+        inst.overlap = overlap
+        try:
+            step_resident(0); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            lib.gic_prof_begin()
+            e0.record()
+            for i in range(psteps):
+                step_resident(i)
+            e1.record()
+            torch.cuda.synchronize()
+            lib.gic_prof_end(ms_k, work_k, calls_k)
+        finally:
+            inst.overlap = prev
+        out = {}
+        for k, nm in enumerate(names):
+            if calls_k[k]:
+                out[nm] = dict(ms_per_step=ms_k[k] / psteps, calls_per_step=calls_k[k] / psteps, work_per_step=work_k[k] / psteps)
+        return out, e0.elapsed_time(e1) / psteps
+
+    classes_2s, _ = instrumented(True)
+    classes, ms_serial = instrumented(False)
     # dominant kernel: the discriminator's [B*R, F] x [F, F] contractions (highway forward, dx, dW_h): 7 launches of
     # 2*B*R*F*F flop each (SURVEY.md 8d: 2*R*F^2 per caption), the FLOP-dominant kernel of the step
     g = classes.get("gemm_disc")
@@ -325,13 +342,22 @@ def run_ours(args):
         flops_launch = g["work_per_step"] / g["calls_per_step"]
         us_launch = g["ms_per_step"] * 1e3 / g["calls_per_step"]
         ach = flops_launch / (us_launch * 1e-6) / 1e12
-        roofline = {"kernel": (f"gemm_p_kernel (tcgen05 kind::{'f16 bf16 operands' if args.mode == 'bf16' else 'tf32'}, persistent): discriminator highway / dx / dW_h, "
-                               f"{B * R}x{Fd}x{Fd}") if args.mode != "fp32" else "sgemm_kernel (fp32 FFMA)",
+        g2 = classes_2s.get("gemm_disc", g)
+        us_launch_2s = g2["ms_per_step"] * 1e3 / g2["calls_per_step"]
+        ach_2s = flops_launch / (us_launch_2s * 1e-6) / 1e12
+        kname = ("gemm_pair_kernel (tcgen05 cta_group::2, M = 256: highway forward, dx) + gemm_p_kernel (persistent, stream-K: dW_h), "
+                 "kind::f16 bf16 operands" if args.mode == "bf16" else "gemm_p_kernel (tcgen05 kind::tf32, persistent)")
+        roofline = {"kernel": (f"{kname}: discriminator highway / dx / dW_h, {B * R}x{Fd}x{Fd}") if args.mode != "fp32" else "sgemm_kernel (fp32 FFMA)",
                     "bound": "tensor", "achieved": ach, "peak": peaks["tf"], "unit": "TFLOP/s", "frac": ach / peaks["tf"],
                     "traffic": traffic,
                     "peak_source": peaks["src"] + ", sustained bf16 dense (TF32 runs at half that rate)",
-                    "share_of_step": g["ms_per_step"] / ms_step, "launches_per_step": g["calls_per_step"],
-                    "algorithmic_flops_per_launch": flops_launch, "us_per_launch": us_launch}
+                    "measured": "CUDA events around every launch of the class, eager steps on ONE stream (each kernel alone on the "
+                                "machine, warm L2); in_step = the same with the step's two streams side by side, as in the timed region",
+                    "share_of_step": g["ms_per_step"] / ms_serial, "serialised_step_ms": ms_serial,
+                    "launches_per_step": g["calls_per_step"],
+                    "algorithmic_flops_per_launch": flops_launch, "us_per_launch": us_launch,
+                    "in_step": {"achieved": ach_2s, "frac": ach_2s / peaks["tf"], "us_per_launch": us_launch_2s,
+                                "share_of_timed_step": g2["ms_per_step"] / ms_step}}
     tensor_classes = {}
     for nm in ("gemm_disc", "gemm_decode", "gemm_other"):
         c = classes.get(nm)
