@@ -34,6 +34,9 @@ int attn_fwd(const float*, const float*, const float*, const float*, int, int, i
 int attn_bwd(const float*, const float*, const float*, const float*, const float*, const float*, int, int, int, int,
              float*, float*, float*, float*, cudaStream_t);
 // lstm_tcgen05.cu
+int bptt_step_tc(const float* dG_t, const float* W_hh, const float* acts_prev, const float* c_prev, const float* c_cur,
+                 const float* dh_top, float* dc_rec, float* dG_out, int B, int H, int L, int t, cudaStream_t stream,
+                 bool* handled);
 int lstm_step_tc(const float*, int, const float*, const float*, const float*, const float*, const float*, const float*,
                  int, int, float*, float*, float*, float*, int, int, cudaStream_t, bool*);
 // disc.cu
@@ -354,6 +357,8 @@ static int decode_bwd(int mode, const float* dout, const float* demb, const floa
   }
   // 3. BPTT through (h, c)
   cudaMemsetAsync(ws + w.dhrec, 0, (size_t)2 * layers * a4(BH) * sizeof(float), s);   // dh_rec and dc_rec
+  const bool bptt_fusable = (mode == GEMM_TF32 || mode == GEMM_BF16) && layers == 1 && !at && !rec_bf;
+  bool bptt_fused_prev = false;
   for (int t = L - 1; t >= 0; --t) {
     for (int l = layers - 1; l >= 0; --l) {
       const bool top = (l == layers - 1);
@@ -363,12 +368,23 @@ static int decode_bwd(int mode, const float* dout, const float* demb, const floa
       float* dhrec = ws + w.dhrec + (size_t)l * a4(BH);
       float* dcrec = ws + w.dcrec + (size_t)l * a4(BH);
       void* dG_bf_t = rec_bf ? (void*)(reinterpret_cast<unsigned short*>(dG_bf) + (size_t)t * BH * 4) : nullptr;
-      GIC_TRY(lstm_cell_bwd(saved + sv.acts(l) + (size_t)t * BH * 4, saved + sv.cs(l) + (size_t)t * BH,
-                            saved + sv.cs(l) + (size_t)(t + 1) * BH, dh_in, stride, dhrec, dcrec, B, H, dG_lt, s, dG_bf_t));
+      if (!bptt_fused_prev)      // else dG of this step (and dc) came out of the fused kernel launched for step t + 1
+        GIC_TRY(lstm_cell_bwd(saved + sv.acts(l) + (size_t)t * BH * 4, saved + sv.cs(l) + (size_t)t * BH,
+                              saved + sv.cs(l) + (size_t)(t + 1) * BH, dh_in, stride, dhrec, dcrec, B, H, dG_lt, s, dG_bf_t));
+      bptt_fused_prev = false;
       // recurrent gradient for step t-1: dh_rec = dgates W_hh    ([B,4H] x [4H,H])
       if (t > 0) {
         if (rec_bf) GIC_TRY(gemm_bf16(false, false, B, H, 4 * H, 1.f, dG_bf_t, 4 * H, ws + w.whh_bf, H, 0.f, dhrec, H, nullptr, s));
-        else GIC_TRY(gemm(mode, false, false, B, H, 4 * H, 1.f, dG_lt, 4 * H, W_hh[l], H, 0.f, dhrec, H, nullptr, s));
+        else {
+          // tensor-core modes, one layer, no attention: contraction (split-K over a cluster, DSMEM reduction) and the cell
+          // backward of step t - 1 in ONE kernel (bptt_tcgen05.cu)
+          if (bptt_fusable)
+            GIC_TRY(bptt_step_tc(dG_lt, W_hh[0], saved + sv.acts(0) + (size_t)(t - 1) * BH * 4, saved + sv.cs(0) + (size_t)(t - 1) * BH,
+                                 saved + sv.cs(0) + (size_t)t * BH, ws + w.dhtop, dcrec, ws + w.dG + (size_t)(t - 1) * BH * 4, B, H, L, t,
+                                 s, &bptt_fused_prev));
+          if (!bptt_fused_prev)
+            GIC_TRY(gemm(mode, false, false, B, H, 4 * H, 1.f, dG_lt, 4 * H, W_hh[l], H, 0.f, dhrec, H, nullptr, s));
+        }
       }
       if (at && l == 0) {
         // attention: dx'_t = dG_t W_ih (per step: dq_t feeds the recurrent gradient), then the attention backward

@@ -227,6 +227,31 @@ def test_fused_dz_matches_separate_kernels(B, L, V, E, H, T):
         assert err <= tol * scale + 1e-12, f"{k}: err {err:.3e} scale {scale:.3e}"
 
 
+# ---- fused BPTT step (bptt_tcgen05.cu): recurrent contraction over an 8-CTA cluster + cell backward in one kernel ------
+@pytest.mark.parametrize("B,L,V,E,H", [(256, 6, 1000, 512, 512), (200, 5, 1000, 64, 64), (130, 5, 1000, 128, 1024)])
+def test_fused_bptt_step_matches_gemm_plus_cell_kernel(B, L, V, E, H):
+    """TF32 mode with GIC_BPTT_FUSED=1 (split-K over a cluster, DSMEM reduction in rank order, cell backward in the
+    epilogue) and =0 (stream-K GEMM + lstm_cell_bwd_kernel): same TF32 products, different association of the K sum, so
+    every generator gradient agrees to fp32 round-off accumulated over the L steps."""
+    import gic_b200
+    old = gic_b200.get_gemm_mode()
+    gic_b200.set_gemm_mode(gic_b200.GEMM_TF32)
+    res = []
+    try:
+        for flag in ("1", "0"):
+            os.environ["GIC_BPTT_FUSED"] = flag
+            res.append(_adv_grads(True, B, L, V, E, H, 1.0))
+    finally:
+        os.environ.pop("GIC_BPTT_FUSED", None)
+        gic_b200.set_gemm_mode(old)
+    g1, g0 = res
+    for k in g0:
+        scale = float(g0[k].abs().max())
+        err = float((g1[k] - g0[k]).abs().max())
+        REPORT[f"bptt_fused/B{B}H{H}/{k}"] = dict(err=err, scale=scale, rel=err / max(scale, 1e-30))
+        assert err <= 2e-4 * scale + 1e-12, f"{k}: err {err:.3e} scale {scale:.3e}"
+
+
 # ---- split-K LSTM step over 4-CTA clusters (lstm_tcgen05.cu) vs the one-CTA-per-tile kernel ---------------------------
 @pytest.mark.parametrize("B,L,V,E,H", [(256, 4, 2000, 512, 512), (200, 3, 1000, 256, 1024), (130, 3, 1000, 512, 512)])
 def test_lstm_splitk_cluster_matches_single_cta_kernel(B, L, V, E, H):
