@@ -37,6 +37,8 @@ int attn_bwd(const float*, const float*, const float*, const float*, const float
 int bptt_step_tc(const float* dG_t, const float* W_hh, const float* acts_prev, const float* c_prev, const float* c_cur,
                  const float* dh_top, float* dc_rec, float* dG_out, int B, int H, int L, int t, cudaStream_t stream,
                  bool* handled);
+int bptt_persistent_tc(float* dG, const float* W_hh, const float* acts, const float* cs, const float* dh_top, const float* dc_in,
+                       unsigned int* counter, int B, int H, int L, cudaStream_t stream, bool* handled);
 int lstm_step_tc(const float*, int, const float*, const float*, const float*, const float*, const float*, const float*,
                  int, int, float*, float*, float*, float*, int, int, cudaStream_t, bool*);
 // disc.cu
@@ -359,7 +361,20 @@ static int decode_bwd(int mode, const float* dout, const float* demb, const floa
   cudaMemsetAsync(ws + w.dhrec, 0, (size_t)2 * layers * a4(BH) * sizeof(float), s);   // dh_rec and dc_rec
   const bool bptt_fusable = (mode == GEMM_TF32 || mode == GEMM_BF16) && layers == 1 && !at && !rec_bf;
   bool bptt_fused_prev = false;
-  for (int t = L - 1; t >= 0; --t) {
+  bool bptt_done = false;
+  if (bptt_fusable && L >= 2) {
+    // the whole recurrence as one persistent launch (bptt_tcgen05.cu): cell backward of the last step first, then
+    // dG[L-2 .. 0]; the zeroed dh_rec buffer (no longer needed after the first cell kernel) lends its first word to the
+    // grid-wide arrival counter
+    const int t = L - 1;
+    GIC_TRY(lstm_cell_bwd(saved + sv.acts(0) + (size_t)t * BH * 4, saved + sv.cs(0) + (size_t)t * BH,
+                          saved + sv.cs(0) + (size_t)(t + 1) * BH, ws + w.dhtop + (size_t)t * H, (long long)L * H, ws + w.dhrec,
+                          ws + w.dcrec, B, H, ws + w.dG + (size_t)t * BH * 4, s, nullptr));
+    GIC_TRY(bptt_persistent_tc(ws + w.dG, W_hh[0], saved + sv.acts(0), saved + sv.cs(0), ws + w.dhtop, ws + w.dcrec,
+                               reinterpret_cast<unsigned int*>(ws + w.dhrec), B, H, L, s, &bptt_done));
+    bptt_fused_prev = !bptt_done;      // not handled: the loop below continues from the cell backward already done
+  }
+  for (int t = bptt_done ? -1 : L - 1; t >= 0; --t) {
     for (int l = layers - 1; l >= 0; --l) {
       const bool top = (l == layers - 1);
       const float* dh_in = top ? ws + w.dhtop + (size_t)t * H : ws + w.dxin;

@@ -228,7 +228,7 @@ def test_fused_dz_matches_separate_kernels(B, L, V, E, H, T):
 
 
 # ---- fused BPTT step (bptt_tcgen05.cu): recurrent contraction over an 8-CTA cluster + cell backward in one kernel ------
-@pytest.mark.parametrize("B,L,V,E,H", [(256, 6, 1000, 512, 512), (200, 5, 1000, 64, 64), (130, 5, 1000, 128, 1024)])
+@pytest.mark.parametrize("B,L,V,E,H", [(256, 6, 1000, 512, 512), (200, 5, 1000, 64, 64), (130, 5, 1000, 128, 1024), (256, 20, 1000, 512, 512)])
 def test_fused_bptt_step_matches_gemm_plus_cell_kernel(B, L, V, E, H):
     """TF32 mode with GIC_BPTT_FUSED=1 (split-K over a cluster, DSMEM reduction in rank order, cell backward in the
     epilogue) and =0 (stream-K GEMM + lstm_cell_bwd_kernel): same TF32 products, different association of the K sum, so
@@ -238,18 +238,22 @@ def test_fused_bptt_step_matches_gemm_plus_cell_kernel(B, L, V, E, H):
     gic_b200.set_gemm_mode(gic_b200.GEMM_TF32)
     res = []
     try:
-        for flag in ("1", "0"):
-            os.environ["GIC_BPTT_FUSED"] = flag
+        # (persistent launch over all steps, per-step fused kernel) -> persistent / per-step fused / GEMM + cell kernel
+        for pers, fused in (("1", "1"), ("0", "1"), ("0", "0")):
+            os.environ["GIC_BPTT_PERSISTENT"] = pers
+            os.environ["GIC_BPTT_FUSED"] = fused
             res.append(_adv_grads(True, B, L, V, E, H, 1.0))
     finally:
         os.environ.pop("GIC_BPTT_FUSED", None)
+        os.environ.pop("GIC_BPTT_PERSISTENT", None)
         gic_b200.set_gemm_mode(old)
-    g1, g0 = res
-    for k in g0:
-        scale = float(g0[k].abs().max())
-        err = float((g1[k] - g0[k]).abs().max())
-        REPORT[f"bptt_fused/B{B}H{H}/{k}"] = dict(err=err, scale=scale, rel=err / max(scale, 1e-30))
-        assert err <= 2e-4 * scale + 1e-12, f"{k}: err {err:.3e} scale {scale:.3e}"
+    gp, g1, g0 = res
+    for nm, gx in (("persistent", gp), ("step", g1)):
+        for k in g0:
+            scale = float(g0[k].abs().max())
+            err = float((gx[k] - g0[k]).abs().max())
+            REPORT[f"bptt_{nm}/B{B}H{H}/{k}"] = dict(err=err, scale=scale, rel=err / max(scale, 1e-30))
+            assert err <= 2e-4 * scale + 1e-12, f"{nm} {k}: err {err:.3e} scale {scale:.3e}"
 
 
 # ---- split-K LSTM step over 4-CTA clusters (lstm_tcgen05.cu) vs the one-CTA-per-tile kernel ---------------------------
