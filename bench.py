@@ -369,7 +369,8 @@ def run_ours(args):
     c = classes.get("vocab_sample_fused")
     if c:
         # the fused projection + Gumbel-softmax + sample kernel is both: 2*B*V*H flop and 8*B*V HBM bytes per launch
-        tf = c["calls_per_step"] * 2.0 * B * V * cfg["H"] / (c["ms_per_step"] * 1e-3) / 1e12
+        # work_per_step = 8*B*V bytes per decoded step (one launch per step, or all L steps in the persistent launch)
+        tf = c["work_per_step"] / (8.0 * B * V) * 2.0 * B * V * cfg["H"] / (c["ms_per_step"] * 1e-3) / 1e12
         tensor_classes["vocab_sample_fused"] = {"achieved_TFLOPs": tf, "frac_of_bf16_peak": tf / peaks["tf"],
                                                 "ms_per_step": c["ms_per_step"], "launches_per_step": c["calls_per_step"]}
     for nm in ("sample_step", "vocab_sample_fused", "conv_pool_fwd", "softmax_bwd", "clip_adam", "head_fwd"):

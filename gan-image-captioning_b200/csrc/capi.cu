@@ -39,6 +39,10 @@ int bptt_step_tc(const float* dG_t, const float* W_hh, const float* acts_prev, c
                  bool* handled);
 int bptt_persistent_tc(float* dG, const float* W_hh, const float* acts, const float* cs, const float* dh_top, const float* dc_in,
                        unsigned int* counter, int B, int H, int L, cudaStream_t stream, bool* handled);
+int decode_persistent_tc(const float* W_ih, const float* W_hh, const float* b_ih, const float* b_hh, const float* W_out,
+                         const float* b_out, const float* u, float T, const float* T_dev, int B, int L, int V, int E, int H,
+                         float* out, int64_t* ids, const int64_t* forced, const float* embed, float* xs, float* hs, float* cs,
+                         float* acts, float* htop, float* scratch, cudaStream_t stream, bool* handled);
 int lstm_step_tc(const float*, int, const float*, const float*, const float*, const float*, const float*, const float*,
                  int, int, float*, float*, float*, float*, int, int, cudaStream_t, bool*);
 // disc.cu
@@ -154,6 +158,18 @@ static int decode_fwd(int mode, const float* features, const float* W_emb, const
                  at->Da, nullptr, s));
     GIC_TRY(gemm(mode, false, true, B * at->P, E, at->Cf, 1.f, at->grid, at->Cf, at->W_v, at->Cf, 0.f, at->saved + al.Av, E,
                  nullptr, s));
+  }
+  if (pretrain == 0 && !at && layers == 1 && (mode == GEMM_TF32 || mode == GEMM_BF16)) {
+    // tensor-core modes, one layer, Gumbel-softmax sampling: all L steps in ONE persistent launch (LSTM step and fused
+    // projection / sample as two phases of a resident grid, vocab_sample_tcgen05.cu)
+    bool persistent = false;
+    {
+      ProfScope prof(PROF_VOCAB_SAMPLE, 8.0 * B * V * L, s);
+      GIC_TRY(decode_persistent_tc(W_ih[0], W_hh[0], b_ih[0], b_hh[0], W_out, b_out, u, T, temperature_device(), B, L, V, E, H,
+                                   out, ids, forced, W_emb, saved + sv.xs, saved + sv.hs(0), saved + sv.cs(0), saved + sv.acts(0),
+                                   saved + sv.htop, vs_scratch, s, &persistent));
+    }
+    if (persistent) return GIC_OK;
   }
   for (int t = 0; t < L; ++t) {
     if (at) {

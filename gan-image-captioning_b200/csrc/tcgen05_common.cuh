@@ -141,6 +141,21 @@ inline bool make_map_bf16(CUtensorMap* m, const void* base, int rows, int cols, 
   return r == CUDA_SUCCESS;
 }
 
+// 3-D fp32 tensor [d2][d1][d0] (d0 contiguous; ld1, ld2 = element strides of d1, d2), box b0 x b1 x b2, 128B swizzle
+inline bool make_map_3d(CUtensorMap* m, const float* base, int d0, int d1, int d2, long long ld1, long long ld2, int b0, int b1,
+                        int b2) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+  cuuint64_t strides[2] = {(cuuint64_t)ld1 * sizeof(float), (cuuint64_t)ld2 * sizeof(float)};
+  cuuint32_t box[3] = {(cuuint32_t)b0, (cuuint32_t)b1, (cuuint32_t)b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 inline bool tf32_round_in_tma() {
   static int v = -1;
   if (v < 0) {

@@ -456,6 +456,496 @@ static int launch_vs(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   return check_launch("vocab_sample_kernel");
 }
 
+
+// =========================================================================================================
+// Persistent decode: ALL L steps of Decoder.sample (src/generator.py:55-81) in one launch.  The per-step kernels above
+// spend about as long on being kernels (launch, barrier / TMEM set-up, first-load latency, tear-down: ~8 us each, 40 of
+// them in a row at c2) as in their main loops.  Here the grid stays resident and every CTA owns one LSTM tile (128 rows x
+// U hidden units, as lstm_step_tf32_kernel) AND one projection tile (128 rows x BN vocabulary columns, as
+// vocab_sample_kernel); a step is
+//     phase L   gates = x_t W_ih^T + h_{t-1} W_hh^T (TMA ring -> tcgen05 -> TMEM columns 256..), cell update, h_t / c_t
+//     arrive + wait on the grid counter                      (every CTA's slice of h_t is visible)
+//     phase V   logits tile, Gumbel-softmax, row statistics exchanged between the column tiles, p TMA-stored in place,
+//               token id and the next step's input x_{t+1} = embed[tok] by the tile that holds the row maximum
+//     arrive + wait on the grid counter                      (x_{t+1} is visible)
+// Two monotonic counters, one per phase kind (a CTA without an LSTM tile arrives for phase L of step t+1 right after its
+// phase-V arrival of step t: on a shared counter that early arrival could stand in for a missing phase-V arrival of a
+// slower CTA); consumers are the TMA producer threads, which cross into the async proxy after the acquire.  The LSTM ring aliases the projection ring (the phases never overlap inside a CTA).
+// Requires the whole grid co-resident (grid <= SMs, one CTA per SM: the launch checks occupancy).
+// =========================================================================================================
+struct DPArgs {
+  VSArgs v;                      // projection phase (t, part, part_next, x_next are set per step in the kernel)
+  int B, H, In, U, l_tiles_n, tiles_l, tiles_v, L;
+  const float* b_ih;
+  const float* b_hh;
+  float* cs;                     // [(L+1)][B][H]  cs[t] = cell state entering step t
+  float* hs;                     // [(L+1)][B][H]
+  float* acts;                   // [L][B][4H] or null
+  float* htop;                   // [B][L][H]
+  float* xs;                     // [L][B][E]
+  float2* part0;                 // two statistics buffers, alternating by step parity
+  float2* part1;
+  unsigned int* counter;         // [2] zero on entry: LSTM-phase arrivals, projection-phase arrivals
+};
+
+__device__ __forceinline__ unsigned int dp_ld_acquire(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void dp_grid_wait(const unsigned int* ctr, unsigned int want) {
+  const long long t0 = clock64();
+  while (dp_ld_acquire(ctr) < want) {
+    __nanosleep(32);
+    if (clock64() - t0 > 4000000000ll) __trap();       // a protocol bug traps instead of hanging the GPU
+  }
+  asm volatile("fence.proxy.async;" ::: "memory");     // the data is read through TMA next
+}
+__device__ __forceinline__ void lstm_bar() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
+
+constexpr uint32_t DP_LCOL = 256;                       // first TMEM column of the LSTM accumulator
+constexpr int DP_LSTAGES = 6;
+
+template <int BN>
+__global__ void __launch_bounds__(VS_THREADS, 1)
+decode_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmH,
+                         const __grid_constant__ CUtensorMap tmWih, const __grid_constant__ CUtensorMap tmWhh,
+                         const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmU,
+                         const __grid_constant__ CUtensorMap tmP, DPArgs d) {
+  using S = VSCfg<BN>;
+  constexpr int NUNIT = BN / 16;
+  constexpr int MAXU = (NUNIT + VS_G - 1) / VS_G;
+  const VSArgs& a = d.v;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* ubox = smem + S::STAGES * S::STAGE;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ubox + S::U_BYTES);
+  uint64_t* empty = full + S::STAGES;
+  uint64_t* tmem_full = empty + S::STAGES;
+  uint64_t* u_full = tmem_full + 1;
+  uint64_t* lfull = u_full + 1;                        // [DP_LSTAGES]
+  uint64_t* lempty = lfull + DP_LSTAGES;               // [DP_LSTAGES]
+  uint64_t* ltmem_full = lempty + DP_LSTAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ltmem_full + 1);
+  static_assert((2 * 6 + 2 + 2 * DP_LSTAGES + 1) * 8 + 4 <= 256, "persistent decode: barrier block overflows");
+  float2 (*s_part)[BM] = reinterpret_cast<float2 (*)[BM]>(smem);
+  float4* s_row = reinterpret_cast<float4*>(smem + VS_G * BM * 8);
+  int* s_hit = reinterpret_cast<int*>(smem + VS_G * BM * 8 + VS_G * BM * 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = gridDim.x;
+  const bool has_l = (int)blockIdx.x < d.tiles_l, has_v = (int)blockIdx.x < d.tiles_v;
+  // projection tile
+  const int nkb = (a.K + BK - 1) / BK;
+  const int mtile = blockIdx.x / a.tiles_n, ntile = blockIdx.x % a.tiles_n;
+  const int m0 = mtile * BM, n0 = ntile * BN;
+  // LSTM tile
+  const int U = d.U, H = d.H;
+  const int lm0 = (blockIdx.x / d.l_tiles_n) * BM, j0 = (blockIdx.x % d.l_tiles_n) * U;
+  const int nkb1 = (d.In + BK - 1) / BK, nkb2 = (H + BK - 1) / BK, lnkb = nkb1 + nkb2;
+  const int LSTAGE = BM * BK * 4 + 4 * U * BK * 4;     // 16 KB + 4 gate slabs of U rows x 128 B
+  int lstages = (S::STAGES * S::STAGE) / LSTAGE;
+  if (lstages > DP_LSTAGES) lstages = DP_LSTAGES;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmH) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWih) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWhh) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmU) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmP) : "memory");
+    for (int s = 0; s < S::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < DP_LSTAGES; ++s) { mbar_init(&lfull[s], 1); mbar_init(&lempty[s], 1); }
+    mbar_init(tmem_full, 1);
+    mbar_init(u_full, 1);
+    mbar_init(ltmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  uint32_t itV = 0, itL = 0;                           // ring positions (producer and MMA threads count alike)
+  const int q = warp & 3;
+  const int g = (warp - 2) >> 2;
+  const int row = q * 32 + lane;
+  const int etid = threadIdx.x - 64;
+  const float eps = 1e-10f;
+  uint8_t* urow = ubox + row * 128;
+  const int sw = row & 7;
+#define VS_CHUNK(j, k) (urow + ((j) >> 1) * S::BOX_BYTES + (((4 * ((j) & 1) + (k)) ^ sw) << 4))
+  float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 256);
+  if (warp >= 2 && has_v && etid < BN / 4) {           // the bias tile does not change between steps
+    const int n = n0 + 4 * etid;
+    reinterpret_cast<float4*>(s_bias)[etid] = (n < a.N) ? __ldg(reinterpret_cast<const float4*>(a.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+
+  for (int t = 0; t < d.L; ++t) {
+    const size_t BH = (size_t)d.B * H;
+    // ======================================= phase L: LSTM step =======================================
+    if (warp == 0) {
+      if (lane == 0) {
+        if (t > 0) dp_grid_wait(d.counter + 1, (unsigned int)t * G);        // every projection phase of step t-1 has arrived: x_t complete
+        if (has_l) {
+          for (int kb = 0; kb < lnkb; ++kb, ++itL) {
+            const int s = itL % lstages;
+            const uint32_t ph = (itL / lstages) & 1;
+            mbar_wait(&lempty[s], ph ^ 1);
+            uint8_t* sa = smem + s * LSTAGE;
+            uint8_t* sb = sa + BM * BK * 4;
+            mbar_expect_tx(&lfull[s], LSTAGE);
+            const bool first = kb < nkb1;
+            const int k0 = (first ? kb : kb - nkb1) * BK;
+            tma_load_2d(sa, first ? &tmX : &tmH, &lfull[s], k0, t * d.B + lm0);
+            for (int gi = 0; gi < 4; ++gi) tma_load_2d(sb + gi * (U * 128), first ? &tmWih : &tmWhh, &lfull[s], k0, gi * H + j0);
+          }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0 && has_l) {
+        const uint32_t idesc = make_idesc(0, 0, 4 * U);
+        for (int kb = 0; kb < lnkb; ++kb, ++itL) {
+          const int s = itL % lstages;
+          const uint32_t ph = (itL / lstages) & 1;
+          mbar_wait(&lfull[s], ph);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + s * LSTAGE);
+          const uint32_t sb = sa + BM * BK * 4;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_tf32(tmem_base + DP_LCOL, make_desc(sa + k * 32, 16, 1024, 2), make_desc(sb + k * 32, 16, 1024, 2), idesc,
+                      (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&lempty[s]);
+        }
+        umma_commit(ltmem_full);
+      }
+    } else if (g == 0) {
+      // cell update on the accumulator tile: thread = batch row, 8 units at a time (as lstm_step_tf32_kernel)
+      if (has_l) {
+        const int b = lm0 + row;
+        const float* c_prev = d.cs + (size_t)t * BH;
+        float* c_out = d.cs + (size_t)(t + 1) * BH;
+        float* h_out = d.hs + (size_t)(t + 1) * BH;
+        mbar_wait(ltmem_full, (uint32_t)(t & 1));
+        tcgen05_fence_after();
+        const uint32_t lane_addr = tmem_base + DP_LCOL + ((uint32_t)(q * 32) << 16);
+        for (int u0 = 0; u0 < U; u0 += 8) {
+          uint32_t ri[8], rf[8], rg[8], ro[8];
+          tmem_ld8(lane_addr + 0 * U + u0, ri);
+          tmem_ld8(lane_addr + 1 * U + u0, rf);
+          tmem_ld8(lane_addr + 2 * U + u0, rg);
+          tmem_ld8(lane_addr + 3 * U + u0, ro);
+          if (b < d.B) {
+            const int j = j0 + u0;
+            float cp[8], ai[8], af[8], ag[8], ao[8], cn[8], hn[8];
+            *reinterpret_cast<float4*>(cp) = *reinterpret_cast<const float4*>(c_prev + (size_t)b * H + j);
+            *reinterpret_cast<float4*>(cp + 4) = *reinterpret_cast<const float4*>(c_prev + (size_t)b * H + j + 4);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float pi = __uint_as_float(ri[e]) + d.b_ih[0 * H + j + e] + d.b_hh[0 * H + j + e];
+              const float pf = __uint_as_float(rf[e]) + d.b_ih[1 * H + j + e] + d.b_hh[1 * H + j + e];
+              const float pg = __uint_as_float(rg[e]) + d.b_ih[2 * H + j + e] + d.b_hh[2 * H + j + e];
+              const float po = __uint_as_float(ro[e]) + d.b_ih[3 * H + j + e] + d.b_hh[3 * H + j + e];
+              ai[e] = sigmoidf_acc(pi); af[e] = sigmoidf_acc(pf); ag[e] = tanhf(pg); ao[e] = sigmoidf_acc(po);
+              cn[e] = af[e] * cp[e] + ai[e] * ag[e];
+              hn[e] = ao[e] * tanhf(cn[e]);
+            }
+            auto st8 = [](float* dst, const float* v) {
+              *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+              *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            };
+            if (d.acts) {
+              float* arow = d.acts + (size_t)t * BH * 4 + (size_t)b * 4 * H + j;
+              st8(arow, ai); st8(arow + H, af); st8(arow + 2 * H, ag); st8(arow + 3 * H, ao);
+            }
+            st8(c_out + (size_t)b * H + j, cn);
+            st8(h_out + (size_t)b * H + j, hn);
+            st8(d.htop + ((size_t)b * d.L + t) * H + j, hn);
+          }
+        }
+        tcgen05_fence_before();
+        __threadfence();                               // this thread's slice of h_t is visible device-wide
+      }
+      lstm_bar();                                      // the four cell warps
+      if (etid == 0) { __threadfence(); atomicAdd(d.counter, 1u); }   // LSTM-phase arrival of step t
+    }
+
+    // ======================================= phase V: projection + sample ==============================
+    float2* part = (t & 1) ? d.part1 : d.part0;
+    float2* part_next = (t & 1) ? d.part0 : d.part1;
+    float* x_next = (t + 1 < d.L) ? d.xs + (size_t)(t + 1) * d.B * a.E : nullptr;
+    if (warp == 0) {
+      if (lane == 0) {
+        dp_grid_wait(d.counter, (unsigned int)(t + 1) * G);                 // every LSTM phase of step t has arrived: h_t complete
+        if (has_v) {
+          for (int kb = 0; kb < nkb; ++kb, ++itV) {
+            const int s = itV % S::STAGES;
+            const uint32_t ph = (itV / S::STAGES) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            uint8_t* sa = smem + s * S::STAGE;
+            mbar_expect_tx(&full[s], S::STAGE);
+            tma_load_2d(sa, &tmH, &full[s], kb * BK, (t + 1) * d.B + m0);
+            tma_load_2d(sa + S::A_BYTES, &tmB, &full[s], kb * BK, n0);
+            if (!a.use_rng && kb == min(nkb, S::STAGES) - 1) {
+              mbar_expect_tx(u_full, S::U_BYTES);
+#pragma unroll
+              for (int c = 0; c < S::NBOX; ++c) tma_load_2d(ubox + c * S::BOX_BYTES, &tmU, u_full, n0 + 32 * c, t * d.B + m0);
+            }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0 && has_v) {
+        constexpr uint32_t idesc = make_idesc(0, 0, BN);
+        for (int kb = 0; kb < nkb; ++kb, ++itV) {
+          const int s = itV % S::STAGES;
+          const uint32_t ph = (itV / S::STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + s * S::STAGE);
+          const uint32_t sb = sa + S::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_tf32(tmem_base, make_desc(sa + k * 32, 16, 1024, 2), make_desc(sb + k * 32, 16, 1024, 2), idesc,
+                      (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty[s]);
+        }
+        umma_commit(tmem_full);
+      }
+    } else if (has_v) {
+      const int m = m0 + row;
+      const float T = a.T_dev ? __ldg(a.T_dev) : a.T;
+      if (g == VS_G - 1) st_relaxed_f2(part_next + (size_t)ntile * a.Mpad + m, make_float2(0.f, 0.f));
+      // ---- pass 0: u -> log2(-log(u + eps) + eps)
+      unsigned long long rseed = 0ull, roff = 0ull;
+      if (a.use_rng) rng_load(a.rng, rseed, roff); else mbar_wait(u_full, (uint32_t)(t & 1));
+#pragma unroll
+      for (int i = 0; i < MAXU; ++i) {
+        const int j = g + i * VS_G;
+        if (j < NUNIT && n0 + 16 * j < a.N) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float4* sp = reinterpret_cast<float4*>(VS_CHUNK(j, k));
+            float4 u4;
+            if (a.use_rng) {
+              const int n = n0 + 16 * j + 4 * k;
+              const unsigned long long e = ((unsigned long long)t * a.M + (unsigned long long)min(m, a.M - 1)) * a.N + min(n, a.N - 4);
+              u4 = philox_uniform4(rseed, roff, RNG_TAG_GUMBEL, e >> 2);
+            } else {
+              u4 = *sp;
+            }
+            u4.x = __log2f(-logf(u4.x + eps) + eps); u4.y = __log2f(-logf(u4.y + eps) + eps);
+            u4.z = __log2f(-logf(u4.z + eps) + eps); u4.w = __log2f(-logf(u4.w + eps) + eps);
+            *sp = u4;
+          }
+        }
+      }
+      // ---- pass 1
+      epi_bar();
+      mbar_wait(tmem_full, (uint32_t)(t & 1));
+      tcgen05_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+      float m_run = -INFINITY, s_run = 0.f;
+      float mrun_u[MAXU];
+#pragma unroll
+      for (int i = 0; i < MAXU; ++i) {
+        const int j = g + i * VS_G;
+        mrun_u[i] = -INFINITY;
+        if (j < NUNIT) {
+          uint32_t r[16];
+          tmem_ld16(t_addr + 16 * j, r);
+          float z[16];
+          float cm = -INFINITY;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int n = n0 + 16 * j + 4 * k;
+            if (n < a.N) {
+              const float4 ng = *reinterpret_cast<const float4*>(VS_CHUNK(j, k));
+              const float4 b4 = *reinterpret_cast<const float4*>(s_bias + 16 * j + 4 * k);
+              constexpr float LN2 = 0.693147182f;
+              z[4 * k + 0] = (__uint_as_float(r[4 * k + 0]) + b4.x - ng.x * LN2) * T;
+              z[4 * k + 1] = (__uint_as_float(r[4 * k + 1]) + b4.y - ng.y * LN2) * T;
+              z[4 * k + 2] = (__uint_as_float(r[4 * k + 2]) + b4.z - ng.z * LN2) * T;
+              z[4 * k + 3] = (__uint_as_float(r[4 * k + 3]) + b4.w - ng.w * LN2) * T;
+            } else {
+              z[4 * k + 0] = z[4 * k + 1] = z[4 * k + 2] = z[4 * k + 3] = -INFINITY;
+            }
+            cm = fmaxf(cm, fmaxf(fmaxf(z[4 * k + 0], z[4 * k + 1]), fmaxf(z[4 * k + 2], z[4 * k + 3])));
+          }
+          if (cm > -INFINITY) {
+            const float m_new = fmaxf(m_run, cm);
+            s_run *= (m_run > -INFINITY) ? __expf(m_run - m_new) : 0.f;
+            m_run = m_new;
+            float cs = 0.f;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) { z[e] = __expf(z[e] - m_new); cs += z[e]; }
+            s_run += cs;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) z[e] = 0.f;
+          }
+          mrun_u[i] = m_run;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            *reinterpret_cast<float4*>(VS_CHUNK(j, k)) = make_float4(z[4 * k + 0], z[4 * k + 1], z[4 * k + 2], z[4 * k + 3]);
+        }
+      }
+      tcgen05_fence_before();
+      s_part[g][row] = make_float2(m_run, s_run);
+      if (g == 0) s_hit[row] = 0x7fffffff;
+      epi_bar();
+      if (g == 0) {
+        float Mt = -INFINITY, St = 0.f;
+#pragma unroll
+        for (int i = 0; i < VS_G; ++i) {
+          const float2 v = s_part[i][row];
+          if (v.x > Mt) { St = St * ((Mt > -INFINITY) ? __expf(Mt - v.x) : 0.f) + v.y; Mt = v.x; }
+          else if (v.x > -INFINITY) St += v.y * __expf(v.x - Mt);
+        }
+        if (St == 0.f) St = 1e-37f;
+        st_relaxed_f2(part + (size_t)ntile * a.Mpad + m, make_float2(Mt, St));
+      }
+      {
+        float Mg = -INFINITY, Sg = 0.f;
+        int jb = 0x7fffffff;
+        const float2* pp = part + m;
+        const unsigned long long t0 = globaltimer_ns();
+        for (int jj0 = g; jj0 < a.tiles_n; jj0 += 8 * VS_G) {
+          float2 v[8];
+          for (;;) {
+            bool ready = true;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int j = jj0 + i * VS_G;
+              v[i] = (j < a.tiles_n) ? ld_relaxed_f2(pp + (size_t)j * a.Mpad) : make_float2(-INFINITY, 1.f);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ready = ready && (__float_as_uint(v[i].y) != 0u);
+            if (ready) break;
+            __nanosleep(20);
+            if (globaltimer_ns() - t0 > 4000000000ull) __trap();
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (jj0 + i * VS_G >= a.tiles_n) continue;
+            if (v[i].x > Mg) {
+              Sg = Sg * ((Mg > -INFINITY) ? __expf(Mg - v[i].x) : 0.f) + v[i].y;
+              Mg = v[i].x; jb = jj0 + i * VS_G;
+            } else if (v[i].x > -INFINITY) {
+              Sg += v[i].y * __expf(v[i].x - Mg);
+            }
+          }
+        }
+        s_row[g * BM + row] = make_float4(Mg, Sg, __int_as_float(jb), 0.f);
+      }
+      epi_bar();
+      float Mx = -INFINITY, Ssum = 0.f;
+      int jbest = 0x7fffffff;
+#pragma unroll
+      for (int i = 0; i < VS_G; ++i) {
+        const float4 v = s_row[i * BM + row];
+        const int jv = __float_as_int(v.z);
+        if (v.x > Mx) {
+          Ssum = Ssum * ((Mx > -INFINITY) ? __expf(Mx - v.x) : 0.f) + v.y;
+          Mx = v.x; jbest = jv;
+        } else if (v.x > -INFINITY) {
+          Ssum += v.y * __expf(v.x - Mx);
+          if (v.x == Mx && jv < jbest) jbest = jv;
+        }
+      }
+      if (jbest == 0x7fffffff) jbest = 0;
+      const float inv = 1.0f / Ssum;
+      const bool winner = (jbest == ntile);
+      int hit = 0x7fffffff;
+#pragma unroll
+      for (int i = 0; i < MAXU; ++i) {
+        const int j = g + i * VS_G;
+        if (j < NUNIT && n0 + 16 * j < a.N) {
+          const float f = __expf(mrun_u[i] - Mx) * inv;
+          const bool may_hit = winner && (mrun_u[i] == Mx) && (hit == 0x7fffffff);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float4* sp = reinterpret_cast<float4*>(VS_CHUNK(j, k));
+            float4 e = *sp;
+            if (may_hit && hit == 0x7fffffff) {
+              if (e.x == 1.0f) hit = 16 * j + 4 * k;
+              else if (e.y == 1.0f) hit = 16 * j + 4 * k + 1;
+              else if (e.z == 1.0f) hit = 16 * j + 4 * k + 2;
+              else if (e.w == 1.0f) hit = 16 * j + 4 * k + 3;
+            }
+            e.x *= f; e.y *= f; e.z *= f; e.w *= f;
+            *sp = e;
+          }
+        }
+      }
+      if (hit != 0x7fffffff) atomicMin(&s_hit[row], hit);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      epi_bar();
+      if (g == 0) {
+        if (lane == 0) {
+#pragma unroll
+          for (int c = 0; c < S::NBOX; ++c) {
+            if (n0 + 32 * c < a.N)
+              asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                           ::"l"(&tmP), "r"(smem_u32(ubox + c * S::BOX_BYTES + q * 4096)), "r"(n0 + 32 * c), "r"(t), "r"(m0 + q * 32)
+                           : "memory");
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        int fed = -1;
+        const bool m_ok = m < a.M;
+        if (winner && m_ok) {
+          const int h = s_hit[row];
+          int tok = n0 + (h == 0x7fffffff ? 0 : h);
+          if (tok >= a.N) tok = a.N - 1;
+          a.ids[(size_t)m * a.L + t] = tok;
+          fed = tok;
+        }
+        if (a.forced != nullptr) {
+          fed = -1;
+          if (ntile == 0 && m_ok) {
+            const int64_t fz = a.forced[(size_t)m * a.L + t];
+            fed = (fz >= 0 && fz < a.N) ? (int)fz : 0;
+          }
+        }
+        if (x_next != nullptr) {
+          unsigned mask = __ballot_sync(0xffffffffu, fed >= 0);
+          while (mask) {
+            const int src = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int tok = __shfl_sync(0xffffffffu, fed, src);
+            const float* er = a.embed + (size_t)tok * a.E;
+            float* xr = x_next + (size_t)(m0 + q * 32 + src) * a.E;
+            for (int i = lane; i < (a.E >> 2); i += 32) reinterpret_cast<float4*>(xr)[i] = __ldg(reinterpret_cast<const float4*>(er) + i);
+          }
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the p tile may be overwritten next step
+      }
+      __threadfence();                                 // ids / x_{t+1} / cleared statistics visible device-wide
+      epi_bar();
+      if (etid == 0) { __threadfence(); atomicAdd(d.counter + 1, 1u); }  // projection-phase arrival of step t
+    } else {
+      // CTA without a projection tile: its arrival only
+      if (etid == 0) atomicAdd(d.counter + 1, 1u);
+    }
+    __syncwarp();
+  }
+#undef VS_CHUNK
+  if (warp >= 2 && g == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
 }  // namespace tc
 
 // debug timeline (GIC_VS_STAMPS=1): a static device buffer of 16 clock64 stamps per CTA, printed by gic_vs_stamps_dump()
@@ -496,7 +986,7 @@ static size_t vs_part_floats(int B, int V) {
   const size_t Mpad = (size_t)cdiv(B, tc::BM) * tc::BM;
   return 2 * Mpad * (size_t)cdiv(V, 128);
 }
-size_t vocab_sample_scratch_floats(int B, int V) { return 2 * vs_part_floats(B, V); }
+size_t vocab_sample_scratch_floats(int B, int V) { return 2 * vs_part_floats(B, V) + 4; }   // + the persistent decode's grid counter
 
 // One fused decode step on the tensor cores.  handled = false (nothing launched) when the shape does not fit the
 // co-resident grid or TMA's alignment rules; the caller then runs the separate projection + sampler kernels.
@@ -551,6 +1041,98 @@ int vocab_sample_tc(const float* htop, int lda, const float* W_out, const float*
   }
   if (rc == GIC_OK) *handled = true;
   return rc;
+}
+
+template <int BN>
+static cudaError_t launch_dp(const CUtensorMap& tx, const CUtensorMap& th, const CUtensorMap& twi, const CUtensorMap& twh,
+                             const CUtensorMap& tb, const CUtensorMap& tu, const CUtensorMap& tp, const tc::DPArgs& d, int grid,
+                             cudaStream_t s, bool* fits) {
+  using namespace tc;
+  using S = VSCfg<BN>;
+  static int max_blocks = -1;
+  if (max_blocks < 0) {
+    cudaFuncSetAttribute(decode_persistent_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_persistent_kernel<BN>, VS_THREADS, S::TOTAL) != cudaSuccess) {
+      cudaGetLastError();
+      per_sm = 0;
+    }
+    max_blocks = per_sm * num_sms();
+  }
+  *fits = grid <= max_blocks;                 // the grid-wide barriers need every CTA resident
+  if (!*fits) return cudaSuccess;
+  decode_persistent_kernel<BN><<<grid, VS_THREADS, S::TOTAL, s>>>(tx, th, twi, twh, tb, tu, tp, d);
+  return cudaGetLastError();
+}
+
+// All L steps of Decoder.sample in one persistent launch (single layer, no attention, Gumbel-softmax mode).  xs / hs / cs /
+// acts / htop are the decode's saved-for-backward buffers (xs[0] = features, hs[0] = cs[0] = 0 on entry).  handled = false
+// (nothing launched) when the shape does not fit; the caller then runs the per-step kernels.
+int decode_persistent_tc(const float* W_ih, const float* W_hh, const float* b_ih, const float* b_hh, const float* W_out,
+                         const float* b_out, const float* u, float T, const float* T_dev, int B, int L, int V, int E, int H,
+                         float* out, int64_t* ids, const int64_t* forced, const float* embed, float* xs, float* hs, float* cs,
+                         float* acts, float* htop, float* scratch, cudaStream_t stream, bool* handled) {
+  extern RngState rng_state();
+  using namespace tc;
+  *handled = false;
+  // Measured at c2 (bench43_dp*.log): decode 0.891 ms against 0.759 ms for the 2 L per-step kernels, step 2.518 vs 2.425 ms.
+  // Replayed from a CUDA graph, a kernel boundary of the decode chain costs less than a grid-wide arrival / acquire round
+  // through L2 (two per step here, on top of the statistics exchange inside the projection phase), and the phases of a
+  // resident CTA cannot overlap the way consecutive kernels' tails and heads do.  Opt-in (GIC_DECODE_PERSISTENT=1); read
+  // per call so that the tests can toggle it.
+  { const char* e = getenv("GIC_DECODE_PERSISTENT"); if (!(e && e[0] == '1')) return GIC_OK; }
+  { const char* e = getenv("GIC_FUSED_SAMPLE"); if (e && e[0] == '0') return GIC_OK; }
+  { const char* e = getenv("GIC_LSTM_SPLITK"); if (e && e[0] == '1') return GIC_OK; }
+  if (B <= 0 || L < 1 || (V % 4) || (H % 32) || (E % 32) || (((size_t)L * V) % 4) || vs_stamps_buffer()) return GIC_OK;
+  const void* ptrs[] = {W_ih, W_hh, b_ih, b_hh, W_out, b_out, out, embed, xs, hs, cs, htop, acts ? acts : hs, u ? u : hs};
+  for (const void* p : ptrs)
+    if (!aligned16(p)) return GIC_OK;
+  const int G = num_sms();
+  const int tiles_m = cdiv(B, BM);
+  static const int kBN[6] = {128, 160, 192, 224, 256, 0};
+  int BN = 0;
+  for (int i = 0; kBN[i]; ++i)
+    if ((long long)tiles_m * cdiv(V, kBN[i]) <= G) { BN = kBN[i]; break; }
+  if (!BN) return GIC_OK;
+  int U = 8;
+  while (U <= 32 && ((H % U) || (long long)tiles_m * (H / U) > G)) U *= 2;
+  if (U > 32) return GIC_OK;
+  const int tiles_n = cdiv(V, BN), tiles_v = tiles_m * tiles_n, l_tiles_n = H / U, tiles_l = tiles_m * l_tiles_n;
+  const int grid = tiles_v > tiles_l ? tiles_v : tiles_l;
+  const bool rn = tf32_round_in_tma();
+  CUtensorMap tx, th, twi, twh, tb, tu, tp;
+  bool ok = make_map(&tx, xs, L * B, E, E, BK, BM, rn, false) && make_map(&th, hs, (L + 1) * B, H, H, BK, BM, rn, false) &&
+            make_map(&twi, W_ih, 4 * H, E, E, BK, U, rn, false) && make_map(&twh, W_hh, 4 * H, H, H, BK, U, rn, false) &&
+            make_map(&tb, W_out, V, H, H, BK, BN, rn, false) &&
+            make_map(&tu, u ? u : out, u ? L * B : B, V, V, 32, BM, false, false) &&
+            make_map_3d(&tp, out, V, L, B, V, (long long)L * V, 32, 1, 32);
+  if (!ok) return GIC_OK;
+  DPArgs d;
+  VSArgs& a = d.v;
+  a.M = B; a.N = V; a.K = H; a.tiles_n = tiles_n; a.Mpad = tiles_m * BM;
+  a.bias = b_out; a.T = T; a.T_dev = T_dev; a.part = nullptr; a.part_next = nullptr;
+  a.ids = ids; a.forced = forced; a.L = L; a.t = 0; a.embed = embed; a.E = E; a.x_next = nullptr; a.stamps = nullptr;
+  a.use_rng = (u == nullptr) ? 1 : 0;
+  a.rng = rng_state();
+  d.B = B; d.H = H; d.In = E; d.U = U; d.l_tiles_n = l_tiles_n; d.tiles_l = tiles_l; d.tiles_v = tiles_v; d.L = L;
+  d.b_ih = b_ih; d.b_hh = b_hh; d.cs = cs; d.hs = hs; d.acts = acts; d.htop = htop; d.xs = xs;
+  const size_t pf = vs_part_floats(B, V);
+  d.part0 = reinterpret_cast<float2*>(scratch);
+  d.part1 = reinterpret_cast<float2*>(scratch + pf);
+  d.counter = reinterpret_cast<unsigned int*>(scratch + 2 * pf);
+  cudaError_t e = cudaMemsetAsync(scratch, 0, (2 * pf + 4) * sizeof(float), stream);   // statistics "not ready", counter 0
+  if (e != cudaSuccess) { set_error("decode_persistent memset: %s", cudaGetErrorString(e)); return GIC_ERR_CUDA; }
+  bool fits = false;
+  switch (BN) {
+    case 128: e = launch_dp<128>(tx, th, twi, twh, tb, tu, tp, d, grid, stream, &fits); break;
+    case 160: e = launch_dp<160>(tx, th, twi, twh, tb, tu, tp, d, grid, stream, &fits); break;
+    case 192: e = launch_dp<192>(tx, th, twi, twh, tb, tu, tp, d, grid, stream, &fits); break;
+    case 224: e = launch_dp<224>(tx, th, twi, twh, tb, tu, tp, d, grid, stream, &fits); break;
+    default: e = launch_dp<256>(tx, th, twi, twh, tb, tu, tp, d, grid, stream, &fits); break;
+  }
+  if (e != cudaSuccess) { set_error("decode_persistent_kernel launch: %s", cudaGetErrorString(e)); return GIC_ERR_CUDA; }
+  if (fits) *handled = true;
+  return GIC_OK;
 }
 
 }  // namespace gic

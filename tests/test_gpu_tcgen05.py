@@ -184,6 +184,51 @@ def test_fused_vocab_sample_matches_unfused(B, L, V, E, H, T, forced):
     assert float((rs - 1).abs().max()) < 1e-4
 
 
+# ---- persistent decode (all L steps in one launch) vs the per-step kernels ---------------------------------------------
+@pytest.mark.parametrize("B,L,V,E,H,T,forced", [
+    (8, 6, 1000, 32, 512, 1.0, False),        # c1-like
+    (8, 16, 1000, 32, 512, 100.0, True),      # saturated softmax, teacher forcing
+    (256, 20, 10000, 512, 512, 1.0, False),   # c2: 128 LSTM tiles, 126 projection tiles
+    (200, 5, 10000, 64, 256, 5.0, False),     # ragged last row block
+    (130, 4, 4004, 64, 128, 1.0, True),       # V not a multiple of the tile width
+    (128, 3, 30000, 512, 1024, 1.0, False),   # c4 per-GPU shape: one row block, 118 projection tiles, 128 LSTM tiles
+])
+def test_persistent_decode_matches_per_step_kernels(B, L, V, E, H, T, forced):
+    """Decoder.sample in TF32 mode as one persistent launch (GIC_DECODE_PERSISTENT=1, opt-in) and as 2 L per-step kernels
+    (=0, the default): same operands, same arithmetic per step, so the sampled ids must be IDENTICAL, the probabilities equal to
+    round-off, and the saved states (through the next step's input) follow."""
+    import gic_b200
+    import gic_b200.generator as G
+    from gic_b200.args import default_args
+    a = default_args(vocab_size=V, gen_embed_dim=E, gen_hidden_dim=H, gen_num_layers=1, conditional_gan=0, device="cuda")
+    torch.manual_seed(7)
+    gen = G.Generator(a).to("cuda:0"); gen.train(); gen.decoder.temperature = T
+    g = torch.Generator(device="cuda:0").manual_seed(8)
+    u = torch.rand(L, B, V, generator=g, device="cuda:0")
+    feats = torch.randn(B, E, generator=g, device="cuda:0") * 0.05
+    fz = torch.randint(0, V, (B, L), generator=g, device="cuda:0") if forced else None
+    old = gic_b200.get_gemm_mode()
+    gic_b200.set_gemm_mode(gic_b200.GEMM_TF32)
+    res = []
+    try:
+        for flag in ("1", "0"):
+            os.environ["GIC_DECODE_PERSISTENT"] = flag
+            with torch.no_grad():
+                p, ids = gen.decoder.sample(feats, max_caption_len=L, u=u, forced_ids=fz)
+            torch.cuda.synchronize()
+            res.append((p.clone(), ids.clone()))
+    finally:
+        os.environ.pop("GIC_DECODE_PERSISTENT", None)
+        gic_b200.set_gemm_mode(old)
+    (p1, i1), (p0, i0) = res
+    mism = int((i1 != i0).sum())
+    err = float((p1 - p0).abs().max())
+    REPORT[f"decode_persistent/B{B}V{V}T{T}"] = dict(err=err, scale=float(p0.max()), rel=err / float(p0.max()), id_mismatches=mism)
+    assert mism == 0, f"{mism} of {i0.numel()} sampled ids differ between the persistent and the per-step decode"
+    assert err <= 1e-5 * float(p0.max()) + 1e-12
+    assert float((p1.sum(-1) - 1).abs().max()) < 1e-4
+
+
 # ---- fused dz kernel (dz_fused_tcgen05.cu): D-embedding input gradient + tempered-softmax backward + db_out ------------
 def _adv_grads(fused_dz, B, L, V, E, H, T=1.0):
     import gic_b200
