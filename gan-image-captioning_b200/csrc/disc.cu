@@ -624,6 +624,13 @@ head_collapse_kernel(const float* __restrict__ W_f, const float* __restrict__ b_
   }
 }
 
+// tensor-core modes: exp and reciprocal on the MUFU unit (2 ulp each); the exact-fp32 mode keeps expf and the IEEE division
+template <bool FAST>
+__device__ __forceinline__ float sigmoid_sel(float x) {
+  if (FAST) return __fdividef(1.0f, 1.0f + __expf(-x));
+  return sigmoidf_acc(x);
+}
+
 constexpr int MAX_HEADS = 4;
 struct HeadPtrs {
   const uint8_t* keep[MAX_HEADS];
@@ -661,7 +668,7 @@ head_fwd_kernel(const float* __restrict__ hpre, const float* __restrict__ pooled
 
 // float4 variant of head_fwd_kernel for F % 4 == 0: one warp per row, every lane issues all of its loads of the row
 // (up to NQ float4 of hpre and pooled plus the uchar4 mask words) before the first use.
-template <int NQ>
+template <int NQ, bool FAST>
 __global__ void __launch_bounds__(256)
 head_fwd_vec_kernel(const float* __restrict__ hpre, const float* __restrict__ pooled, int rows, int F,
                     const float* __restrict__ weff, float drop_scale, HeadPtrs hp) {
@@ -697,7 +704,7 @@ head_fwd_vec_kernel(const float* __restrict__ hpre, const float* __restrict__ po
       float yw[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float sg = sigmoidf_acc(hh[e]);
+        const float sg = sigmoid_sel<FAST>(hh[e]);
         yw[e] = (sg * fmaxf(hh[e], 0.f) + (1.f - sg) * xx[e]) * wv[e];
       }
 #pragma unroll
@@ -766,7 +773,7 @@ head_bwd_vec_kernel(const float* __restrict__ dlogit, const uint8_t* __restrict_
       float dhv[4], dxv[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float sg = sigmoidf_acc(hh[e]);
+        const float sg = sigmoid_sel<DH_BF16>(hh[e]);      // DH_BF16 <=> GIC_GEMM_BF16 mode
         const float rl = fmaxf(hh[e], 0.f);
         const float y = sg * rl + (1.f - sg) * xx[e];
         const float dy = dl[j] * kp[e] * wj[e];
@@ -778,8 +785,8 @@ head_bwd_vec_kernel(const float* __restrict__ dlogit, const uint8_t* __restrict_
       const size_t i = (size_t)r * F4 + q;
       if (DH_BF16) {
         uint2 pk;
-        pk.x = (unsigned int)f2bf(dhv[0]) | ((unsigned int)f2bf(dhv[1]) << 16);
-        pk.y = (unsigned int)f2bf(dhv[2]) | ((unsigned int)f2bf(dhv[3]) << 16);
+        pk.x = (unsigned int)cvt_bf16(dhv[0]) | ((unsigned int)cvt_bf16(dhv[1]) << 16);
+        pk.y = (unsigned int)cvt_bf16(dhv[2]) | ((unsigned int)cvt_bf16(dhv[3]) << 16);
         *reinterpret_cast<uint2*>(reinterpret_cast<unsigned short*>(dh) + (size_t)r * Fp + 4 * q) = pk;
       } else {
         reinterpret_cast<float4*>(dh)[i] = make_float4(dhv[0], dhv[1], dhv[2], dhv[3]);
@@ -1044,9 +1051,11 @@ int disc_forward(int mode, const float* inp_soft, const int64_t* ids, const Disc
     const int nq = cdiv(d.F / 4, 32);
     const int grid = cdiv((long long)rows, 8);
     const float dsc = 1.f / (1.f - drop_p);
-    if (nq <= 2) head_fwd_vec_kernel<2><<<grid, 256, 0, s>>>(hpre, pooled, (int)rows, d.F, weff, dsc, hp);
-    else if (nq <= 4) head_fwd_vec_kernel<4><<<grid, 256, 0, s>>>(hpre, pooled, (int)rows, d.F, weff, dsc, hp);
-    else head_fwd_vec_kernel<8><<<grid, 256, 0, s>>>(hpre, pooled, (int)rows, d.F, weff, dsc, hp);
+    const bool fast = (mode == GEMM_TF32 || mode == GEMM_BF16);
+#define GIC_HF(NQ_) do { if (fast) head_fwd_vec_kernel<NQ_, true><<<grid, 256, 0, s>>>(hpre, pooled, (int)rows, d.F, weff, dsc, hp); \
+                         else head_fwd_vec_kernel<NQ_, false><<<grid, 256, 0, s>>>(hpre, pooled, (int)rows, d.F, weff, dsc, hp); } while (0)
+    if (nq <= 2) GIC_HF(2); else if (nq <= 4) GIC_HF(4); else GIC_HF(8);
+#undef GIC_HF
   } else {
     head_fwd_kernel<<<cdiv((long long)rows, 8), 256, 0, s>>>(hpre, pooled, (int)rows, d.F, weff, 1.f / (1.f - drop_p), hp);
   }
