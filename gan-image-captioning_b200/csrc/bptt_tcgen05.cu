@@ -322,7 +322,6 @@ bptt_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           const unsigned int want = (unsigned int)st * gridDim.x;
           const long long t0 = clock64();
           while (ld_acquire_u32(a.counter) < want) {
-            __nanosleep(32);
             if (clock64() - t0 > 4000000000ll) __trap();   // a protocol bug traps instead of hanging the GPU
           }
           asm volatile("fence.proxy.async;" ::: "memory");
@@ -364,6 +363,8 @@ bptt_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       ld8(a.cs + (size_t)(t - 1) * BH + (size_t)b * H + j, cp);
       ld8(a.cs + (size_t)t * BH + (size_t)b * H + j, cc);
       ld8(a.dh_top + ((size_t)b * a.L + (t - 1)) * H + j, dt);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) cc[e] = tanhf(cc[e]);  // off the critical path: the contraction has not finished yet
     }
     if (epi) {
       mbar_wait(tmem_full, (uint32_t)(st & 1));
@@ -400,7 +401,7 @@ bptt_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const float d = dh[e] + dt[e];
-          const float tcv = tanhf(cc[e]);
+          const float tcv = cc[e];
           const float dc = d * go[e] * (1.f - tcv * tcv) + dcr[e];
           di[e] = dc * gg[e] * gi[e] * (1.f - gi[e]);
           df[e] = dc * cp[e] * gf[e] * (1.f - gf[e]);
@@ -412,14 +413,14 @@ bptt_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         st8(gr, di); st8(gr + H, df); st8(gr + 2 * H, dgg); st8(gr + 3 * H, dout);
       }
       __threadfence();                                   // this thread's part of dG[t-1] is visible device-wide
-    }
-    __syncwarp();
-    bp_cluster_sync();                                   // peers have read this CTA's partial; all epilogue stores fenced
-    if (threadIdx.x == 64) {                             // one arrival per CTA on the grid counter
-      __threadfence();
-      atomicAdd(a.counter, 1u);
+      asm volatile("bar.sync 1, 128;" ::: "memory");     // the four epilogue warps
+      // One arrival per CTA.  No second cluster barrier: this CTA's `part` is overwritten only after its producer has
+      // passed the next grid-wide wait, which needs the arrival of every peer -- issued after the peer's DSMEM reads.
+      if (threadIdx.x == 64) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(a.counter) : "memory");
     }
   }
+  __syncwarp();
+  bp_cluster_sync();                                     // no CTA leaves while a peer may still read its shared memory
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
