@@ -163,12 +163,9 @@ static int decode_fwd(int mode, const float* features, const float* W_emb, const
     // tensor-core modes, one layer, Gumbel-softmax sampling: all L steps in ONE persistent launch (LSTM step and fused
     // projection / sample as two phases of a resident grid, vocab_sample_tcgen05.cu)
     bool persistent = false;
-    {
-      ProfScope prof(PROF_VOCAB_SAMPLE, 8.0 * B * V * L, s);
-      GIC_TRY(decode_persistent_tc(W_ih[0], W_hh[0], b_ih[0], b_hh[0], W_out, b_out, u, T, temperature_device(), B, L, V, E, H,
-                                   out, ids, forced, W_emb, saved + sv.xs, saved + sv.hs(0), saved + sv.cs(0), saved + sv.acts(0),
-                                   saved + sv.htop, vs_scratch, s, &persistent));
-    }
+    GIC_TRY(decode_persistent_tc(W_ih[0], W_hh[0], b_ih[0], b_hh[0], W_out, b_out, u, T, temperature_device(), B, L, V, E, H,
+                                 out, ids, forced, W_emb, saved + sv.xs, saved + sv.hs(0), saved + sv.cs(0), saved + sv.acts(0),
+                                 saved + sv.htop, vs_scratch, s, &persistent));
     if (persistent) return GIC_OK;
   }
   for (int t = 0; t < L; ++t) {

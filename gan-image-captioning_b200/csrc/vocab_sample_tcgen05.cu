@@ -1123,6 +1123,7 @@ int decode_persistent_tc(const float* W_ih, const float* W_hh, const float* b_ih
   cudaError_t e = cudaMemsetAsync(scratch, 0, (2 * pf + 4) * sizeof(float), stream);   // statistics "not ready", counter 0
   if (e != cudaSuccess) { set_error("decode_persistent memset: %s", cudaGetErrorString(e)); return GIC_ERR_CUDA; }
   bool fits = false;
+  ProfScope prof(PROF_VOCAB_SAMPLE, 8.0 * B * V * L, stream);        // the whole decode is one launch of this class
   switch (BN) {
     case 128: e = launch_dp<128>(tx, th, twi, twh, tb, tu, tp, d, grid, stream, &fits); break;
     case 160: e = launch_dp<160>(tx, th, twi, twh, tb, tu, tp, d, grid, stream, &fits); break;
