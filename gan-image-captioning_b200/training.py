@@ -87,6 +87,8 @@ class GANInstructor:
         # opt-in (args.sync_bn / GIC_SYNC_BN=1): the reference is single-GPU, per-shard statistics are the documented default
         self.sync_bn = bool(getattr(args, "sync_bn", 0)) or os.environ.get("GIC_SYNC_BN", "0") == "1"
         self.overlap = os.environ.get("GIC_NO_OVERLAP", "0") != "1"
+        self.d_priority = os.environ.get("GIC_D_PRIORITY", "0") == "1"
+        self._hp = None
         self.world = 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size()
@@ -487,22 +489,35 @@ class GANInstructor:
                     gen_chain(bws2, side.cuda_stream)
                     gen_done.record(side)
                 g_bucketed = self._gen_backward_early_bucket(_bwd)
-            if real_bwd_done is None:
-                disc_bwd(seeds[0], k0, None, captions, saved_r, 1, 0, None, bws, stream)
-                self._mark("D chain: backward(real) done")
-            else:
-                main.wait_event(real_bwd_done)         # fake accumulates onto real's parameter gradients
-            disc_bwd(seeds[1], k1, probs, None, saved_f, 1, 1, None, bws, stream)
-            self._mark("D chain: backward(fake) done")
-            if self.world > 1:
-                parallel.allreduce_sum_(fd.grad)
+            # GIC_D_PRIORITY=1 (experiment): the D chain on a high-priority stream, so that it finishes ahead of the
+            # generator chain and its gradient all-reduce runs under the generator chain's tail
+            dst = main
+            if self.d_priority:
+                if self._hp is None:
+                    self._hp = torch.cuda.Stream(device=self.device, priority=-1)
+                dst = self._hp
+                dst.wait_stream(main)
+            with torch.cuda.stream(dst):
+                ds = dst.cuda_stream
+                if real_bwd_done is None:
+                    disc_bwd(seeds[0], k0, None, captions, saved_r, 1, 0, None, bws, ds)
+                    self._mark("D chain: backward(real) done")
+                else:
+                    dst.wait_event(real_bwd_done)         # fake accumulates onto real's parameter gradients
+                disc_bwd(seeds[1], k1, probs, None, saved_f, 1, 1, None, bws, ds)
+                self._mark("D chain: backward(fake) done")
+                if self.world > 1:
+                    parallel.allreduce_sum_(fd.grad)
             with torch.cuda.stream(side):
                 self._gen_allreduce_rest(g_bucketed)
                 out["g_sqnorm"] = self._clip_adam(fg, a.gen_lr, update, 3)
                 self._mark("G chain: clip + Adam done")
-            main.wait_event(gen_done)
-            out["d_sqnorm"] = self._clip_adam(fd, a.disc_lr, update, 1)
-            self._mark("D chain: clip + Adam done")
+            with torch.cuda.stream(dst):
+                dst.wait_event(gen_done)
+                out["d_sqnorm"] = self._clip_adam(fd, a.disc_lr, update, 1)
+                self._mark("D chain: clip + Adam done")
+            if dst is not main:
+                main.wait_stream(dst)
             main.wait_stream(side)
             self._mark("end")
         else:
