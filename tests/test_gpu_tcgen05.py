@@ -111,7 +111,7 @@ def test_gemm_bf16_vs_fp64(tA, tB, M, N, K):
 
 
 @pytest.mark.parametrize("tB,M,N,K", [(1, 16384 + 130, 900, 900), (0, 4096 + 256 + 8, 900, 900), (1, 8192, 256, 512),
-                                      (0, 19200, 1024, 192)])
+                                      (0, 19200, 1024, 192), (1, 18944, 200, 72), (0, 18944, 328, 1000)])
 def test_gemm_bf16_cta_pair_kernel_bias_ragged_rows(tB, M, N, K):
     """Shapes that take the cta_group::2 kernel (gemm_pair_tcgen05.cu): rows that are not a multiple of the 256-row pair
     tile, bias, alpha, padded pitches; and the same call with GIC_GEMM_2CTA=0 (one CTA per tile)."""
@@ -273,7 +273,8 @@ def test_fused_dz_matches_separate_kernels(B, L, V, E, H, T):
 
 
 # ---- fused BPTT step (bptt_tcgen05.cu): recurrent contraction over an 8-CTA cluster + cell backward in one kernel ------
-@pytest.mark.parametrize("B,L,V,E,H", [(256, 6, 1000, 512, 512), (200, 5, 1000, 64, 64), (130, 5, 1000, 128, 1024), (256, 20, 1000, 512, 512)])
+@pytest.mark.parametrize("B,L,V,E,H", [(256, 6, 1000, 512, 512), (200, 5, 1000, 64, 64), (130, 5, 1000, 128, 1024), (256, 20, 1000, 512, 512),
+                                       (8, 5, 1000, 32, 512), (40, 5, 1000, 64, 128)])
 def test_fused_bptt_step_matches_gemm_plus_cell_kernel(B, L, V, E, H):
     """TF32 mode with GIC_BPTT_FUSED=1 (split-K over a cluster, DSMEM reduction in rank order, cell backward in the
     epilogue) and =0 (stream-K GEMM + lstm_cell_bwd_kernel): same TF32 products, different association of the K sum, so
@@ -383,6 +384,7 @@ def _conv_pool_pair(N, L, V, fsz, nfl, seed=0, R=64):
     (5, 32, 500, [2, 3, 4, 5], [100, 52, 300, 20]), # c5 length; groups that are not multiples of 16 channels
     (3, 6, 200, [3, 5], [24, 40]),                  # short captions: T = 2 for the widest filter
     (2, 8, 300, [5, 1], [16, 36]),                  # f = 5 (all taps of a part) and f = 1
+    (3, 34, 300, [3, 4, 5], [20, 16, 12]),          # T = 32 for the narrowest filter: the largest step the 5-bit tag holds
 ])
 def test_conv_pool_mma_matches_cuda_core_kernel(N, L, V, fsz, nfl):
     (p1, a1, l1), (p0, a0, l0) = _conv_pool_pair(N, L, V, fsz, nfl)
