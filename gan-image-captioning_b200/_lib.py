@@ -68,6 +68,9 @@ def _declare(L):
     L.gic_last_error.restype = C.c_char_p
     L.gic_check_device.restype = I
     L.gic_launch_count.restype = C.c_ulonglong
+    L.gic_kernel_launches.restype = C.c_ulonglong
+    L.gic_kernel_launches.argtypes = [C.c_char_p]
+    L.gic_kernel_names.argtypes = [C.c_char_p, I]
     L.gic_prof_begin.restype = None
     L.gic_prof_end.restype = None
     L.gic_prof_end.argtypes = [P, P, P]
@@ -75,6 +78,8 @@ def _declare(L):
     L.gic_gemm_bf16.argtypes = [I, I, I, I, I, F, P, I, P, I, F, P, I, P, P]
     L.gic_encoder_fwd.argtypes = [I, P, I, I, I, P, P, P, P, F, P, P, P, P, P]
     L.gic_encoder_bwd.argtypes = [I, P, P, P, P, P, P, P, I, I, I, P, P, P, P, P, I, P]
+    L.gic_encoder_bn_running_update.argtypes = [P, P, I, F, F, F, P, P, P, P]
+    L.gic_encoder_fwd_eval.argtypes = [I, P, I, I, I, P, P, P, P, F, P, P, P, P, P]
     L.gic_sample_step.argtypes = [I, P, P, F, I, I, I, I, P, P, P, P, I, P, P]
     for f in (L.gic_decode_saved_floats, L.gic_decode_fwd_workspace_floats, L.gic_decode_bwd_workspace_floats,
               L.gic_disc_saved_floats, L.gic_disc_fwd_workspace_floats, L.gic_disc_bwd_workspace_floats,
@@ -134,6 +139,40 @@ def _declare(L):
     L.gic_disc_set_prepared.argtypes = [P]
     for name in header_symbols():      # every declared entry point must be exported
         getattr(L, name)
+
+
+def kernel_launches(name=None) -> int:
+    """Launches so far of the kernel `name` (e.g. "vocab_sample_kernel"); None = every kernel of the library."""
+    return int(lib().gic_kernel_launches(None if name is None else name.encode()))
+
+
+def kernel_counts() -> dict:
+    """{kernel name: launches so far} for every kernel this process has launched."""
+    buf = C.create_string_buffer(8192)
+    lib().gic_kernel_names(buf, 8192)
+    return {n: kernel_launches(n) for n in buf.value.decode().split("\n") if n}
+
+
+class expect_kernels:
+    """Context manager for tests: every kernel named must be launched at least once inside the block -- a fused path
+    that silently declines (handled = false) fails the test instead of comparing the fallback with itself."""
+
+    def __init__(self, *names, absent=()):
+        self.names, self.absent = names, tuple(absent)
+
+    def __enter__(self):
+        self.before = {n: kernel_launches(n) for n in self.names + self.absent}
+        return self
+
+    def __exit__(self, et, ev, tb):
+        if et is not None:
+            return False
+        self.delta = {n: kernel_launches(n) - self.before[n] for n in self.names + self.absent}
+        missing = [n for n in self.names if self.delta[n] <= 0]
+        extra = [n for n in self.absent if self.delta[n] > 0]
+        if missing or extra:
+            raise AssertionError("kernels expected but not launched: %s; launched but expected absent: %s" % (missing, extra))
+        return False
 
 
 def check(rc: int, what: str = ""):

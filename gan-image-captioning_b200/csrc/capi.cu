@@ -62,6 +62,8 @@ void set_rng(unsigned long long, unsigned long long, const unsigned long long*);
 int philox_uniform(uint32_t, unsigned long long, size_t, float*, cudaStream_t);
 int philox_keep_mask(uint32_t, size_t, float, uint8_t*, cudaStream_t);
 int bn_stats(const float*, int, int, float*, cudaStream_t);
+int bn_running_update(const float*, const float*, int, float, float, float, float*, float*, long long*, cudaStream_t);
+int bn_eval(const float*, int, int, const float*, const float*, float, const float*, const float*, float*, cudaStream_t);
 int bn_apply(const float*, int, int, const float*, const float*, float, const float*, float, float*, float*, float*, cudaStream_t);
 int bn_bwd_stats(const float*, const float*, int, int, const float*, const float*, float*, cudaStream_t);
 int bn_bwd_apply(const float*, const float*, int, int, const float*, const float*, const float*, const float*, float, float,
@@ -73,6 +75,8 @@ int disc_prepare(int, const float*, const float*, const float*, int, const float
 size_t disc_fwd_workspace_floats(int);
 const char* last_error();
 unsigned long long launch_count();
+unsigned long long kernel_launches(const char*);
+int kernel_names(char*, int);
 void prof_begin();
 void prof_end(double*, double*, unsigned long long*);
 // disc_api.cu-style wrappers implemented in disc.cu
@@ -553,6 +557,8 @@ int gic_version(void) { return 100; }
 const char* gic_last_error(void) { return last_error(); }
 int gic_check_device(void) { return require_device(); }
 unsigned long long gic_launch_count(void) { return launch_count(); }
+unsigned long long gic_kernel_launches(const char* name) { return kernel_launches(name); }
+int gic_kernel_names(char* buf, int cap) { return kernel_names(buf, cap); }
 void gic_prof_begin(void) { prof_begin(); }
 void gic_prof_end(double* ms, double* work, unsigned long long* calls) { prof_end(ms, work, calls); }
 
@@ -592,6 +598,27 @@ int gic_encoder_bwd(int mode, const float* dfeatures, const float* pooled, const
   GIC_TRY(bn_bwd(lin_out, dfeatures, B, E, gamma, save_mean, save_rstd, dlin_ws, dgamma, dbeta, S(stream)));
   GIC_TRY(gemm(mode, true, false, E, Fin, B, 1.f, dlin_ws, E, pooled, Fin, 0.f, dW, Fin, nullptr, S(stream)));
   return colsum_f32(dlin_ws, B, E, E, 1.f, false, db, S(stream));
+}
+
+int gic_encoder_bn_running_update(const float* save_mean, const float* save_rstd, int E, float eps, float count,
+                                  float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                                  gic_stream_t stream) {
+  GIC_TRY(require_device());
+  GIC_REQUIRE(E >= 1 && count >= 1.f && momentum >= 0.f && momentum <= 1.f, GIC_ERR_SHAPE, "encoder_bn_running_update: bad argument");
+  GIC_REQUIRE(save_mean && save_rstd && running_mean && running_var, GIC_ERR_NULL, "encoder_bn_running_update: NULL pointer");
+  return bn_running_update(save_mean, save_rstd, E, eps, count, momentum, running_mean, running_var,
+                           reinterpret_cast<long long*>(num_batches_tracked), S(stream));
+}
+
+int gic_encoder_fwd_eval(int mode, const float* pooled, int B, int Fin, int E, const float* W, const float* b,
+                         const float* gamma, const float* beta, float eps, const float* running_mean,
+                         const float* running_var, float* lin_out, float* features, gic_stream_t stream) {
+  GIC_TRY(require_device());
+  GIC_REQUIRE(B >= 1 && Fin >= 1 && E >= 1, GIC_ERR_SHAPE, "encoder_fwd_eval: bad shape");
+  GIC_REQUIRE(pooled && W && b && gamma && beta && running_mean && running_var && lin_out && features, GIC_ERR_NULL,
+              "encoder_fwd_eval: NULL pointer");
+  GIC_TRY(gemm(mode, false, true, B, E, Fin, 1.f, pooled, Fin, W, Fin, 0.f, lin_out, E, b, S(stream)));
+  return bn_eval(lin_out, B, E, gamma, beta, eps, running_mean, running_var, features, S(stream));
 }
 
 // ---- synchronised-BatchNorm variant of the encoder projection (data parallel; see decode.cu) ----

@@ -844,6 +844,40 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ y, const float* __
   }
   if (lane == 0) { dgamma[j] = sdx * grad_share; dbeta[j] = sd * grad_share; }
 }
+// BatchNorm1d bookkeeping of a training-mode forward (src/generator.py:16: momentum 0.01): running_mean / running_var
+// move towards the batch mean / UNBIASED batch variance, num_batches_tracked += 1.  count = rows the statistics ran over.
+__global__ void bn_running_update_kernel(const float* __restrict__ save_mean, const float* __restrict__ save_rstd, int E,
+                                         float eps, float count, float momentum, float* __restrict__ running_mean,
+                                         float* __restrict__ running_var, long long* __restrict__ nbt) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j == 0 && nbt) nbt[0] += 1;
+  if (j >= E) return;
+  const float r = save_rstd[j];
+  const float var_b = fmaxf(1.0f / (r * r) - eps, 0.f);                       // biased batch variance
+  const float var_u = count > 1.f ? var_b * (count / (count - 1.f)) : var_b;  // what BatchNorm stores
+  running_mean[j] = (1.f - momentum) * running_mean[j] + momentum * save_mean[j];
+  running_var[j] = (1.f - momentum) * running_var[j] + momentum * var_u;
+}
+int bn_running_update(const float* save_mean, const float* save_rstd, int E, float eps, float count, float momentum,
+                      float* running_mean, float* running_var, long long* nbt, cudaStream_t s) {
+  bn_running_update_kernel<<<cdiv(E, 128), 128, 0, s>>>(save_mean, save_rstd, E, eps, count, momentum, running_mean,
+                                                        running_var, nbt);
+  return check_launch("bn_running_update_kernel");
+}
+// eval-mode BatchNorm1d (gen.eval() in the reference's validation loops, src/training.py:213): running statistics
+__global__ void bn_eval_kernel(const float* __restrict__ y, int B, int E, const float* __restrict__ gamma,
+                               const float* __restrict__ beta, float eps, const float* __restrict__ running_mean,
+                               const float* __restrict__ running_var, float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * E) return;
+  const int j = (int)(i % E);
+  out[i] = (y[i] - running_mean[j]) * (1.0f / sqrtf(running_var[j] + eps)) * gamma[j] + beta[j];
+}
+int bn_eval(const float* y, int B, int E, const float* gamma, const float* beta, float eps, const float* running_mean,
+            const float* running_var, float* out, cudaStream_t s) {
+  bn_eval_kernel<<<cdiv((long long)B * E, 256), 256, 0, s>>>(y, B, E, gamma, beta, eps, running_mean, running_var, out);
+  return check_launch("bn_eval_kernel");
+}
 int bn_stats(const float* y, int B, int E, float* stats, cudaStream_t s) {
   bn_stats_kernel<<<cdiv(E, 4), 128, 0, s>>>(y, B, E, stats);
   return check_launch("bn_stats_kernel");

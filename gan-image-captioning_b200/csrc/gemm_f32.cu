@@ -26,8 +26,37 @@ const char* last_error() { return g_err; }
 static unsigned long long g_launches = 0;
 unsigned long long launch_count() { return g_launches; }
 
+// per-kernel launch counters (gic_kernel_launches): the tests assert that a fused kernel actually ran instead of its
+// fallback.  `what` is always a string literal, so the table is keyed by name and stays tiny.
+struct KernelCount { const char* name; unsigned long long n; };
+static KernelCount g_kcounts[96];
+static int g_nk = 0;
+static void count_kernel(const char* what) {
+  for (int i = 0; i < g_nk; ++i)
+    if (g_kcounts[i].name == what || strcmp(g_kcounts[i].name, what) == 0) { ++g_kcounts[i].n; return; }
+  if (g_nk < 96) { g_kcounts[g_nk].name = what; g_kcounts[g_nk].n = 1; ++g_nk; }
+}
+unsigned long long kernel_launches(const char* name) {
+  unsigned long long n = 0;
+  if (!name) return launch_count();
+  for (int i = 0; i < g_nk; ++i)
+    if (strcmp(g_kcounts[i].name, name) == 0) n += g_kcounts[i].n;
+  return n;
+}
+int kernel_names(char* buf, int cap) {
+  int used = 0;
+  for (int i = 0; i < g_nk; ++i) {
+    const int len = (int)strlen(g_kcounts[i].name);
+    if (used + len + 2 > cap) break;
+    memcpy(buf + used, g_kcounts[i].name, len); used += len; buf[used++] = '\n';
+  }
+  if (cap > 0) buf[used < cap ? used : cap - 1] = 0;
+  return g_nk;
+}
+
 int check_launch(const char* what) {
   ++g_launches;
+  count_kernel(what);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("%s: %s", what, cudaGetErrorString(e));

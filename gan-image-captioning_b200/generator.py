@@ -22,7 +22,7 @@ class _EncoderProject(torch.autograd.Function):
     """Encoder.linear + Encoder.bn, train mode (src/generator.py:23-24)."""
 
     @staticmethod
-    def forward(ctx, pooled, W, b, gamma, beta, eps, mode):
+    def forward(ctx, pooled, W, b, gamma, beta, eps, mode, running=None):
         _lib.require_cuda()
         pooled, W, b, gamma, beta = map(_f32c, (pooled, W, b, gamma, beta))
         B, Fin = pooled.shape
@@ -34,6 +34,8 @@ class _EncoderProject(torch.autograd.Function):
         _lib.check(_lib.lib().gic_encoder_fwd(mode, _lib.ptr(pooled), B, Fin, E, _lib.ptr(W), _lib.ptr(b),
                                               _lib.ptr(gamma), _lib.ptr(beta), eps, _lib.ptr(lin), _lib.ptr(mean),
                                               _lib.ptr(rstd), _lib.ptr(feats), _lib.stream()), "gic_encoder_fwd")
+        if running is not None:
+            bn_running_update(running, mean, rstd, eps, B)
         ctx.save_for_backward(pooled, W, gamma, lin, mean, rstd)
         ctx.mode = mode
         return feats
@@ -51,7 +53,37 @@ class _EncoderProject(torch.autograd.Function):
                                               _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(W), _lib.ptr(gamma), B, Fin, E,
                                               _lib.ptr(ws), _lib.ptr(dW), _lib.ptr(db), _lib.ptr(dgamma),
                                               _lib.ptr(dbeta), 0, _lib.stream()), "gic_encoder_bwd")
-        return None, dW, db, dgamma, dbeta, None, None
+        return None, dW, db, dgamma, dbeta, None, None, None
+
+
+def bn_running_update(bn, mean, rstd, eps, count):
+    """nn.BatchNorm1d's training-mode bookkeeping (momentum 0.01, src/generator.py:16) from the batch statistics the
+    projection kernel saved: running_mean / running_var (unbiased) / num_batches_tracked, so that checkpoints and the
+    eval-mode forward see what the reference's would."""
+    if bn.running_mean is None or not bn.track_running_stats:
+        return
+    mom = 0.1 if bn.momentum is None else float(bn.momentum)
+    _lib.check(_lib.lib().gic_encoder_bn_running_update(_lib.ptr(mean), _lib.ptr(rstd), mean.numel(), float(eps), float(count),
+                                                        mom, _lib.ptr(bn.running_mean), _lib.ptr(bn.running_var),
+                                                        _lib.ptr(bn.num_batches_tracked), _lib.stream()),
+               "gic_encoder_bn_running_update")
+
+
+def encoder_eval(enc, pooled, mode):
+    """Encoder.linear + Encoder.bn with the running statistics (gen.eval(), src/training.py:213-214); forward only."""
+    _lib.require_cuda()
+    pooled = _f32c(pooled)
+    B, Fin = pooled.shape
+    E = enc.linear.weight.shape[0]
+    lin = torch.empty(B, E, device=pooled.device)
+    feats = torch.empty(B, E, device=pooled.device)
+    bn = enc.bn
+    _lib.check(_lib.lib().gic_encoder_fwd_eval(mode, _lib.ptr(pooled), B, Fin, E, _lib.ptr(_f32c(enc.linear.weight)),
+                                               _lib.ptr(_f32c(enc.linear.bias)), _lib.ptr(_f32c(bn.weight)),
+                                               _lib.ptr(_f32c(bn.bias)), bn.eps, _lib.ptr(bn.running_mean),
+                                               _lib.ptr(bn.running_var), _lib.ptr(lin), _lib.ptr(feats), _lib.stream()),
+               "gic_encoder_fwd_eval")
+    return feats
 
 
 class Encoder(nn.Module):
@@ -72,9 +104,11 @@ class Encoder(nn.Module):
         if pooled.dim() != 2 or pooled.shape[1] != self.feature_dim:
             raise ValueError("Encoder expects pooled CNN features [B, %d]" % self.feature_dim)
         if not self.training:
-            raise NotImplementedError("Encoder.bn eval mode (running statistics) is not on the hot path")
+            # eval mode (the reference validates with gen.eval(), src/training.py:213): running statistics, no autograd
+            with torch.no_grad():
+                return encoder_eval(self, pooled, gic_b200.get_gemm_mode())
         return _EncoderProject.apply(pooled, self.linear.weight, self.linear.bias, self.bn.weight, self.bn.bias,
-                                     self.bn.eps, gic_b200.get_gemm_mode())
+                                     self.bn.eps, gic_b200.get_gemm_mode(), self.bn)
 
 
 class _DecodeSample(torch.autograd.Function):

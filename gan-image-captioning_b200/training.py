@@ -20,7 +20,7 @@ import torch.nn as nn
 import gic_b200
 from . import _lib, parallel
 from .discriminator import Discriminator, disc_fwd_raw
-from .generator import Generator
+from .generator import Generator, bn_running_update
 from .utils import get_fixed_temperature, get_losses
 
 
@@ -89,9 +89,24 @@ class GANInstructor:
         self.overlap = os.environ.get("GIC_NO_OVERLAP", "0") != "1"
         self.d_priority = os.environ.get("GIC_D_PRIORITY", "0") == "1"
         self._hp = None
-        self.world = 1
+        self.world, self.rank = 1, 0
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size()
+            self.rank = torch.distributed.get_rank()
+        self._passthrough = {}       # encoder.resnet.* tensors of a reference-written checkpoint (re-emitted on save)
+
+    # ---- library-side random draws: one Philox stream per (seed, rank, step) -------------------------------------
+    RANK_SHIFT = 40
+
+    def _next_rng_offset(self):
+        """Philox offset of the next step's library-side draws.  The rank sits in the high bits (it reaches the counter
+        word that also carries the stream tag, philox.cuh): data-parallel ranks seeded identically -- main.py seeds 1008
+        everywhere so that the weights agree -- still draw DIFFERENT Gumbel noise and dropout masks for their rows."""
+        if self._rng_seed is None:
+            self._rng_seed = int(torch.initial_seed()) & ((1 << 63) - 1)
+        self._rng_offset += 1
+        assert self._rng_offset < (1 << self.RANK_SHIFT)
+        return (int(self.rank) << self.RANK_SHIFT) | self._rng_offset
 
     # ---- reference-compatible pieces -------------------------------------------------------------
     def update_temperature(self, i, N):
@@ -166,10 +181,17 @@ class GANInstructor:
 
     def _encoder_fwd(self, mode, pooled, B, Fin, E, lin, mean, rstd, feats, stream):
         lib, P, enc = _lib.lib(), _lib.ptr, self.gen.encoder
+        if not enc.training:
+            # gen.eval() (the reference's validation loops, src/training.py:213-215): running statistics, row-local
+            _lib.check(lib.gic_encoder_fwd_eval(mode, P(pooled), B, Fin, E, P(enc.linear.weight), P(enc.linear.bias),
+                                                P(enc.bn.weight), P(enc.bn.bias), enc.bn.eps, P(enc.bn.running_mean),
+                                                P(enc.bn.running_var), P(lin), P(feats), stream), "gic_encoder_fwd_eval")
+            return
         if not self._sync_bn_on():
             _lib.check(lib.gic_encoder_fwd(mode, P(pooled), B, Fin, E, P(enc.linear.weight), P(enc.linear.bias),
                                            P(enc.bn.weight), P(enc.bn.bias), enc.bn.eps, P(lin), P(mean), P(rstd),
                                            P(feats), stream), "gic_encoder_fwd")
+            bn_running_update(enc.bn, mean, rstd, enc.bn.eps, B)
             return
         # SyncBN: local sums -> all-reduce of [2, E] -> normalise with the global-batch statistics
         stats = self._buf("enc_stats", 2 * E)
@@ -178,9 +200,13 @@ class GANInstructor:
         parallel.allreduce_sum_(stats)
         _lib.check(lib.gic_encoder_fwd_apply(P(lin), B, E, P(enc.bn.weight), P(enc.bn.bias), enc.bn.eps, P(stats),
                                              float(B * self.world), P(mean), P(rstd), P(feats), stream), "gic_encoder_fwd_apply")
+        bn_running_update(enc.bn, mean, rstd, enc.bn.eps, B * self.world)
 
     def _encoder_bwd(self, mode, dfeat, pooled, lin, mean, rstd, B, E, stream):
         lib, P, enc = _lib.lib(), _lib.ptr, self.gen.encoder
+        if not enc.training:
+            raise NotImplementedError("training step with the encoder in eval mode: call gen.train() (the reference trains "
+                                      "with gen.train(), src/training.py:215)")
         gg = self._flat_g.g
         dlin = self._buf("enc_dlin", B * E)
         if not self._sync_bn_on():
@@ -219,12 +245,39 @@ class GANInstructor:
                d.out2logits.bias]
         return ps
 
+    def _rehome(self, old, params):
+        """(Re)builds the flat buffers.  When a parameter was moved out of them (gen.to(), .float(),
+        load_state_dict(assign=True)) the Adam moments and step counts of every parameter that kept its shape carry
+        over, and the captured graphs -- which address the OLD buffers -- are dropped."""
+        new = FlatParams(params, self.device)
+        if old is not None:
+            new.step = old.step
+            if hasattr(old, "m_pre"):
+                new.m_pre, new.v_pre, new.step_pre = torch.zeros_like(new.m), torch.zeros_like(new.v), old.step_pre
+            old_at = {id(p): (o, n) for p, o, n in zip(old.params, old.offsets, old.sizes)}
+            for p, o, n in zip(new.params, new.offsets, new.sizes):
+                if old_at.get(id(p), (0, -1))[1] == n:
+                    oo = old_at[id(p)][0]
+                    new.m[o:o + n].copy_(old.m[oo:oo + n]); new.v[o:o + n].copy_(old.v[oo:oo + n])
+                    if hasattr(old, "m_pre"):
+                        new.m_pre[o:o + n].copy_(old.m_pre[oo:oo + n]); new.v_pre[o:o + n].copy_(old.v_pre[oo:oo + n])
+            self._graphs.clear()
+        return new
+
     def _ensure_flat(self):
         if self._flat_g is None or not self._flat_g.homed():
-            self._flat_g = FlatParams(self._gen_params(), self.device)
+            self._flat_g = self._rehome(self._flat_g, self._gen_params())
             self._flat_g.n_early = self._flat_g.offsets[2]          # [linear.weight | linear.bias]
         if self._flat_d is None or not self._flat_d.homed():
-            self._flat_d = FlatParams(self._disc_params(), self.device)
+            self._flat_d = self._rehome(self._flat_d, self._disc_params())
+
+    def _zero_unwritten_attn_grads(self):
+        """A step that does not run the attention cell (no grid; the policy-gradient step) writes no attn_* gradients:
+        clear those slots so that Adam does not re-apply the gradients of an earlier attention step."""
+        dec = self.gen.decoder
+        if dec.attention:
+            for p_ in dec.attn_params():
+                self._flat_g.g(p_).zero_()
 
     def _buf(self, key, numel, dtype=torch.float32):
         t = self._cache.get(key)
@@ -247,7 +300,9 @@ class GANInstructor:
 
         graph=True replays the whole step as one CUDA graph (captured on first use per batch shape): inputs are
         copied into static buffers, the temperature and Adam's bias corrections are read from device memory
-        (gic_set_temperature_device / gic_clip_adam_dyn), so one replay call enqueues all ~150 kernels."""
+        (gic_set_temperature_device / gic_clip_adam_dyn), so one replay call enqueues all ~150 kernels.  The tensors
+        in the dict a replay returns (losses, probs, ids, D logits) are the graph's STATIC buffers: the next replay
+        overwrites them -- clone what must outlive the step."""
         if graph:
             if grid is not None:
                 raise NotImplementedError("graph replay with the attention grid: pass graph=False")
@@ -305,13 +360,11 @@ class GANInstructor:
         if u is None or (train and keep is None):
             # draws not supplied: Philox inside the library (the Gumbel uniforms are generated in the fused decode kernel
             # itself; the reference draws with uniform_ / nn.Dropout, src/generator.py:86-90, src/discriminator.py:30)
-            if self._rng_seed is None:
-                self._rng_seed = int(torch.initial_seed()) & ((1 << 63) - 1)
             if self._in_graph:
                 lib.gic_set_rng(0, 0, P(self._rng_dyn))
             else:
-                self._rng_offset += 1
-                lib.gic_set_rng(self._rng_seed, self._rng_offset, None)
+                off = self._next_rng_offset()
+                lib.gic_set_rng(self._rng_seed, off, None)
         if train:
             if keep is None:
                 keep = self._buf("keep_u8", 3 * B * R * Fd, dtype=torch.uint8).view(3, B * R, Fd)
@@ -462,6 +515,7 @@ class GANInstructor:
                     _lib.ptr_array([gg(w) for w in b_hh]), P(gg(dec.linear.weight)), P(gg(dec.linear.bias)), P(dfeat),
                     st), "gic_decode_sample_bwd_attn")
             else:
+                self._zero_unwritten_attn_grads()
                 _lib.check(lib.gic_decode_sample_bwd_factored(
                     mode, P(demb), P(emb), P(disc.embeddings.weight), De, P(probs), P(fed), P(dec.embed.weight),
                     _lib.ptr_array(W_ih), _lib.ptr_array(W_hh), P(dec.linear.weight), T, B, L, V, E, H, layers,
@@ -560,7 +614,8 @@ class GANInstructor:
         a, dev = self.args, self.device
         loss_type = loss_type or a.adv_loss_type
         B, L = captions.shape
-        key = (B, L, loss_type, pooled is not None, u is not None, keep is not None)
+        key = (B, L, loss_type, pooled is not None, u is not None, keep is not None, bool(self.gen.encoder.training),
+               gic_b200.get_gemm_mode())
         if static:
             key = key + tuple(None if t is None else t.data_ptr() for t in (captions, pooled, u, keep))
         st = self._graphs.get(key)
@@ -606,12 +661,10 @@ class GANInstructor:
                 h[slot] = lr / (1.0 - 0.9 ** t)
                 h[slot + 1] = 1.0 / (1.0 - 0.999 ** t) ** 0.5
             self._dyn.copy_(h, non_blocking=True)
-            if self._rng_seed is None:
-                self._rng_seed = int(torch.initial_seed()) & ((1 << 63) - 1)
-            self._rng_offset += 1
+            off = self._next_rng_offset()
             hr = self._rng_host[i]
             hr[0] = self._rng_seed
-            hr[1] = self._rng_offset
+            hr[1] = off
             self._rng_dyn.copy_(hr, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()
@@ -668,9 +721,7 @@ class GANInstructor:
             Fin = pooled.shape[1]
             lin, mean, rstd = self._buf("enc_lin", B * E).view(B, E), self._buf("enc_mean", E), self._buf("enc_rstd", E)
             feats = self._buf("feats", B * E).view(B, E)
-            _lib.check(lib.gic_encoder_fwd(mode, P(pooled), B, Fin, E, P(enc.linear.weight), P(enc.linear.bias),
-                                           P(enc.bn.weight), P(enc.bn.bias), enc.bn.eps, P(lin), P(mean), P(rstd),
-                                           P(feats), stream), "gic_encoder_fwd")
+            self._encoder_fwd(mode, pooled, B, Fin, E, lin, mean, rstd, feats, stream)
         else:
             feats = dec.embed.weight[1].expand(B, E).contiguous()
         logits = self._buf("pg_logits", B * L * V).view(B, L, V)
@@ -842,6 +893,7 @@ class GANInstructor:
         _lib.check(lib.gic_pg_loss_fwd_bwd(P(logits), P(ids), P(Q), int(baseline_mode), B, L, V, P(loss), P(dlogits), None,
                                            stream), "gic_pg_loss_fwd_bwd")
         gg = fg.g
+        self._zero_unwritten_attn_grads()
         gws = self._buf("dec_bws", lib.gic_decode_bwd_workspace_floats(B, L, V, E, H, layers))
         dfeat = self._buf("dfeat", B * E).view(B, E)
         _lib.check(lib.gic_decode_sample_bwd(
@@ -892,31 +944,48 @@ class GANInstructor:
 
     def save_pretrained(self, path):
         """pretrained_model.ckpt: the generator's state_dict, exactly as src/training.py:118."""
-        torch.save(self.gen.state_dict(), path)
+        torch.save(self._gen_state(), path)
 
     def save_checkpoint(self, path, resume_state=True):
         """adv_model.ckpt: {"generator": ..., "discriminator": ...} as src/training.py:225-226 (+ "gic_resume")."""
-        blob = {"generator": self.gen.state_dict(), "discriminator": self.disc.state_dict()}
+        blob = {"generator": self._gen_state(), "discriminator": self.disc.state_dict()}
         if resume_state:
             blob["gic_resume"] = {"optim": self._optim_state(), "temperature": float(self.gen.decoder.temperature),
                                   "adv_epoch": int(self.adv_epoch), "pretrain_steps": int(self.pretrain_steps),
                                   "gen_steps": int(self.gen_steps), "disc_steps": int(self.disc_steps), "format": 1}
         torch.save(blob, path)
 
-    def load_checkpoint(self, path, strict=True):
+    RESNET_PREFIX = "encoder.resnet."
+
+    def _load_gen_state(self, sd, strict):
+        """The reference's Generator.state_dict() always carries the frozen ResNet trunk (encoder.resnet.*,
+        src/generator.py:12-14), which is outside this path: those tensors are set aside --
+        and written back by save_checkpoint / save_pretrained, so a file that came from the reference can go back to it --
+        and everything else is loaded with the requested strictness."""
+        self._passthrough = {k: v for k, v in sd.items() if k.startswith(self.RESNET_PREFIX)}
+        self.gen.load_state_dict({k: v for k, v in sd.items() if not k.startswith(self.RESNET_PREFIX)}, strict=strict)
+
+    def _gen_state(self):
+        sd = self.gen.state_dict()
+        sd.update(self._passthrough)
+        return sd
+
+    def load_checkpoint(self, path, strict=True, unsafe_pickle=False):
         """Loads either file format (a bare generator state_dict, or the generator/discriminator dict) and, when the
         file carries it, the resume state.  Parameters stay views of the flat buffers (load_state_dict copies in place),
-        captured CUDA graphs stay valid.  Returns True when optimizer / schedule state was restored."""
-        blob = torch.load(path, map_location="cpu", weights_only=False)
+        captured CUDA graphs stay valid.  Returns True when optimizer / schedule state was restored.
+        Files are read with torch.load(weights_only=True) -- both formats hold only tensors and plain containers;
+        unsafe_pickle=True opts into full unpickling for files from a trusted source that hold anything else."""
+        blob = torch.load(path, map_location="cpu", weights_only=not unsafe_pickle)
         if not isinstance(blob, dict):
             raise ValueError("%s: not a checkpoint written by this code or the reference" % path)
         if "generator" in blob or "discriminator" in blob:
             if "generator" in blob:
-                self.gen.load_state_dict(blob["generator"], strict=strict)
+                self._load_gen_state(blob["generator"], strict)
             if "discriminator" in blob:
                 self.disc.load_state_dict(blob["discriminator"], strict=strict)
         else:
-            self.gen.load_state_dict(blob, strict=strict)              # pretrained_model.ckpt
+            self._load_gen_state(blob, strict)              # pretrained_model.ckpt
         rs = blob.get("gic_resume") if isinstance(blob.get("gic_resume", None), dict) else None
         if rs is None:
             return False
@@ -947,8 +1016,10 @@ class GANInstructor:
         nb = total_batches or (len(batches) if hasattr(batches, "__len__") else 1)
         for i, (pooled, captions) in enumerate(batches, start=1):
             r = self.adv_step(captions, pooled=pooled, train=(what == "train"), graph=(graph and what == "train"))
-            gen_loss.append(r["g_loss"])
-            disc_loss.append(r["d_loss"])
+            # graph replay returns views of the graph's static loss buffer (overwritten by the next replay): keep copies,
+            # so that the mean is over the per-batch values as the reference's np.mean(gen_loss) is (src/training.py:185)
+            gen_loss.append(r["g_loss"].clone())
+            disc_loss.append(r["d_loss"].clone())
             self.gen_steps += 1
             self.disc_steps += 1
             self.update_temperature(self.adv_epoch + i / nb, self.args.adv_epochs)      # :183

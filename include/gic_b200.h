@@ -61,6 +61,12 @@ const char* gic_last_error(void);
 int gic_check_device(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches). */
 unsigned long long gic_launch_count(void);
+/* launches of ONE kernel so far, by its __global__ name without template arguments ("vocab_sample_kernel",
+ * "gemm_pair_kernel", "bptt_persistent_kernel", ...; NULL = all).  The tests use it to assert that a fused kernel ran
+ * rather than the fallback it replaces.  gic_kernel_names writes the names seen so far, newline separated, into buf
+ * (cap bytes) and returns their number. */
+unsigned long long gic_kernel_launches(const char* name);
+int gic_kernel_names(char* buf, int cap);
 /* Optional per-kernel-class device timing for bench.py's roofline: between gic_prof_begin() and gic_prof_end()
  * every launch of a profiled class is bracketed by CUDA events on its own stream.  gic_prof_end (call after the
  * stream is synchronised) fills ms[k], work[k] (algorithmic flops for k=0 GEMM, bytes otherwise) and calls[k] for
@@ -91,6 +97,20 @@ int gic_encoder_bwd(int mode, const float* dfeatures /*[B,E]*/, const float* poo
                     const float* save_mean, const float* save_rstd, const float* W, const float* gamma, int B,
                     int Fin, int E, float* dlin_ws /*[B,E] workspace*/, float* dW, float* db, float* dgamma,
                     float* dbeta, int accumulate, gic_stream_t stream);
+
+/* BatchNorm1d bookkeeping of a training-mode forward (nn.BatchNorm1d(E, momentum=0.01), src/generator.py:16): from the
+ * save_mean / save_rstd gic_encoder_fwd (or gic_encoder_fwd_apply) left behind, running_mean and running_var move by
+ * `momentum` towards the batch mean and the UNBIASED batch variance over `count` rows; *num_batches_tracked (int64, may
+ * be NULL) is incremented.  Checkpoints then carry the statistics the reference's would. */
+int gic_encoder_bn_running_update(const float* save_mean, const float* save_rstd, int E, float eps, float count,
+                                  float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                                  gic_stream_t stream);
+/* Encoder.linear + Encoder.bn in eval mode (gen.eval() in the validation loops, src/training.py:213): normalises with
+ * the running statistics.  Forward only. */
+int gic_encoder_fwd_eval(int mode, const float* pooled, int B, int Fin, int E, const float* W, const float* b,
+                         const float* gamma, const float* beta, float eps, const float* running_mean,
+                         const float* running_var, float* lin_out /*[B,E] workspace*/, float* features /*[B,E]*/,
+                         gic_stream_t stream);
 
 /* ---- one fused sampling step (K4): Gumbel + temperature + vocab softmax + first-max + embedding gather.
  * Decoder.add_gumbel + F.softmax + pred.max(1) + self.embed (src/generator.py:68-76, 84-96).

@@ -158,3 +158,84 @@ def test_checkpoint_formats_and_resume_state_roundtrip(tmp_path):
     third = GANInstructor(a, device="cpu")
     assert third.load_checkpoint(pre) is False                       # weights only: no optimizer state in that format
     assert torch.equal(third.gen.state_dict()["decoder.linear.weight"], inst.gen.state_dict()["decoder.linear.weight"])
+
+
+def test_reference_written_checkpoint_round_trip(tmp_path):
+    """A file written by the REFERENCE (Generator.state_dict() always carries the frozen ResNet trunk as
+    encoder.resnet.*, src/generator.py:12-14, and BatchNorm's running statistics) loads with strict=True: the trunk's
+    tensors are set aside, everything else lands in our modules; saving writes them back, so the file can return to the
+    reference.  weights_only loading is the default."""
+    from gic_b200.args import default_args
+    from gic_b200.training import GANInstructor
+    a = default_args(vocab_size=30, gen_embed_dim=8, gen_hidden_dim=16, disc_num_filters=[4, 4, 4], conditional_gan=1,
+                     feature_dim=12, device="cpu")
+    torch.manual_seed(3)
+    src = GANInstructor(a, device="cpu")
+    ref_sd = {k: v.clone() for k, v in src.gen.state_dict().items()}
+    ref_sd["encoder.bn.running_mean"] = torch.full_like(ref_sd["encoder.bn.running_mean"], 0.25)
+    ref_sd["encoder.bn.num_batches_tracked"] = torch.tensor(11)
+    trunk = {"encoder.resnet.0.weight": torch.randn(4, 3, 3, 3), "encoder.resnet.1.running_var": torch.rand(4)}
+    ref_sd.update(trunk)
+    path = str(tmp_path / "ref_adv_model.ckpt")
+    torch.save({"generator": ref_sd, "discriminator": src.disc.state_dict()}, path)       # src/training.py:225-226
+    inst = GANInstructor(a, device="cpu")
+    assert inst.load_checkpoint(path, strict=True) is False
+    assert float(inst.gen.encoder.bn.running_mean[0]) == 0.25 and int(inst.gen.encoder.bn.num_batches_tracked) == 11
+    out = str(tmp_path / "ours.ckpt")
+    inst.save_checkpoint(out)
+    back = torch.load(out, map_location="cpu", weights_only=True)["generator"]
+    assert set(back) == set(ref_sd)
+    for k, v in trunk.items():
+        assert torch.equal(back[k], v)
+    inst.save_pretrained(str(tmp_path / "pre.ckpt"))
+    assert set(torch.load(str(tmp_path / "pre.ckpt"), map_location="cpu", weights_only=True)) == set(ref_sd)
+
+
+def test_rehoming_parameters_keeps_adam_state_and_drops_graphs():
+    """gen.to() / .float() / load_state_dict(assign=True) move parameters out of the flat buffers: the rebuilt flat
+    buffers must carry the Adam moments and step counts over, and captured graphs (which address the old buffers) go."""
+    from gic_b200.args import default_args
+    from gic_b200.training import GANInstructor
+    a = default_args(vocab_size=30, gen_embed_dim=8, gen_hidden_dim=16, disc_num_filters=[4, 4, 4], device="cpu")
+    inst = GANInstructor(a, device="cpu")
+    inst._ensure_flat()
+    fg = inst._flat_g
+    fg.m.uniform_(-1, 1); fg.v.uniform_(0, 1); fg.step = 5
+    fg.m_pre, fg.v_pre, fg.step_pre = torch.rand_like(fg.m), torch.rand_like(fg.v), 2
+    w = inst.gen.decoder.linear.weight
+    o, n = fg.offsets[fg._index[id(w)]], w.numel()
+    m_w, mp_w = fg.m[o:o + n].clone(), fg.m_pre[o:o + n].clone()
+    inst._graphs["stale"] = object()
+    w.data = w.data.clone()                      # re-homed: no longer a view of the flat buffer
+    assert not fg.homed()
+    inst._ensure_flat()
+    f2 = inst._flat_g
+    assert f2 is not fg and f2.homed() and f2.step == 5 and f2.step_pre == 2 and not inst._graphs
+    o2 = f2.offsets[f2._index[id(w)]]
+    assert torch.equal(f2.m[o2:o2 + n], m_w) and torch.equal(f2.m_pre[o2:o2 + n], mp_w)
+    assert f2.n_early == f2.offsets[2]
+
+
+def test_library_side_rng_offsets_differ_per_rank():
+    """Data-parallel ranks are seeded identically (main.py seeds 1008 everywhere so the weights agree); the Philox offset
+    of the library-side draws carries the rank, so two ranks never share a (seed, offset) pair."""
+    from gic_b200.args import default_args
+    from gic_b200.training import GANInstructor
+    a = default_args(vocab_size=30, gen_embed_dim=8, gen_hidden_dim=16, disc_num_filters=[4, 4, 4], device="cpu")
+    torch.manual_seed(1008)
+    r0, r1 = GANInstructor(a, device="cpu"), GANInstructor(a, device="cpu")
+    r1.rank = 1
+    offs0 = [r0._next_rng_offset() for _ in range(4)]
+    offs1 = [r1._next_rng_offset() for _ in range(4)]
+    assert r0._rng_seed == r1._rng_seed
+    assert not set(offs0) & set(offs1)
+    assert [o & ((1 << 40) - 1) for o in offs1] == [1, 2, 3, 4] and all(o >> 40 == 1 for o in offs1)
+
+
+def test_kernel_launch_counters_are_exported(built):
+    from gic_b200 import _lib
+    assert _lib.kernel_launches("vocab_sample_kernel") == 0      # nothing can launch without a GPU
+    assert _lib.kernel_counts() == {} or all(v >= 0 for v in _lib.kernel_counts().values())
+    with pytest.raises(AssertionError):
+        with _lib.expect_kernels("vocab_sample_kernel"):
+            pass
