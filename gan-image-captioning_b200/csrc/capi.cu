@@ -39,10 +39,14 @@ int bptt_step_tc(const float* dG_t, const float* W_hh, const float* acts_prev, c
                  bool* handled);
 int bptt_persistent_tc(float* dG, const float* W_hh, const float* acts, const float* cs, const float* dh_top, const float* dc_in,
                        unsigned int* counter, int B, int H, int L, cudaStream_t stream, bool* handled);
-int decode_persistent_tc(const float* W_ih, const float* W_hh, const float* b_ih, const float* b_hh, const float* W_out,
-                         const float* b_out, const float* u, float T, const float* T_dev, int B, int L, int V, int E, int H,
-                         float* out, int64_t* ids, const int64_t* forced, const float* embed, float* xs, float* hs, float* cs,
-                         float* acts, float* htop, float* scratch, cudaStream_t stream, bool* handled);
+// vocab_sample_tcgen05.cu: fused decode step (projection + sample of step t, recurrent contraction and cell of step t + 1)
+bool decode_step_plan(int B, int V, int H);
+size_t decode_step_scratch_floats(int B, int V, int H);
+int decode_step_tc(const float* hs_t1, const float* W_out, const float* b_out, const float* W_hh, const float* b_ih,
+                   const float* b_hh, const float* EW, float* R, unsigned int* rec_done, const float* u_t, float T,
+                   const float* T_dev, int B, int V, int H, int L, int t, int last, float* out, int64_t* ids,
+                   const int64_t* forced, const float* embed, int E, float* x_next, const float* c_prev, float* c_out,
+                   float* h_out, float* acts, float* htop, float* scratch, cudaStream_t stream, bool* handled);
 int lstm_step_tc(const float*, int, const float*, const float*, const float*, const float*, const float*, const float*,
                  int, int, float*, float*, float*, float*, int, int, cudaStream_t, bool*);
 // disc.cu
@@ -163,14 +167,37 @@ static int decode_fwd(int mode, const float* features, const float* W_emb, const
     GIC_TRY(gemm(mode, false, true, B * at->P, E, at->Cf, 1.f, at->grid, at->Cf, at->W_v, at->Cf, 0.f, at->saved + al.Av, E,
                  nullptr, s));
   }
-  if (pretrain == 0 && !at && layers == 1 && (mode == GEMM_TF32 || mode == GEMM_BF16)) {
-    // tensor-core modes, one layer, Gumbel-softmax sampling: all L steps in ONE persistent launch (LSTM step and fused
-    // projection / sample as two phases of a resident grid, vocab_sample_tcgen05.cu)
-    bool persistent = false;
-    GIC_TRY(decode_persistent_tc(W_ih[0], W_hh[0], b_ih[0], b_hh[0], W_out, b_out, u, T, temperature_device(), B, L, V, E, H,
-                                 out, ids, forced, W_emb, saved + sv.xs, saved + sv.hs(0), saved + sv.cs(0), saved + sv.acts(0),
-                                 saved + sv.htop, vs_scratch, s, &persistent));
-    if (persistent) return GIC_OK;
+  if (pretrain == 0 && !at && layers == 1 && (mode == GEMM_TF32 || mode == GEMM_BF16) && (E % 4) == 0 && decode_step_plan(B, V, H)) {
+    // Tensor-core modes, one layer, Gumbel-softmax sampling: ONE kernel per decode step (vocab_sample_tcgen05.cu).  The
+    // LSTM pre-activation of step t + 1 is embed[tok_t] W_ih^T + h_t W_hh^T + biases: the recurrent half needs only h_t, so
+    // it runs as extra tiles of step t's projection / sample launch, and the token-dependent half is a row of
+    // EW = embed W_ih^T [V, 4H], rebuilt once per decode (the weights change every optimizer step), added in the cell
+    // tail of the CTA that sampled the token.  Step 0 (input = features, h = 0) is the stand-alone LSTM kernel.
+    float* ds = u_slice + a4((size_t)B * V);
+    float* EW = ds;
+    float* R = EW + (size_t)V * 4 * H;
+    unsigned int* rec_done = reinterpret_cast<unsigned int*>(R + (size_t)B * 4 * H);
+    bool ok0 = false;
+    GIC_TRY(lstm_step_tc(saved + sv.xs, E, saved + sv.hs(0), W_ih[0], W_hh[0], b_ih[0], b_hh[0], saved + sv.cs(0), B, H,
+                         saved + sv.acts(0), saved + sv.cs(0) + BH, saved + sv.hs(0) + BH, saved + sv.htop, L, 0, s, &ok0));
+    if (ok0) {
+      if (L > 1)
+        GIC_TRY(gemm(mode, false, true, V, 4 * H, E, 1.f, W_emb, E, W_ih[0], E, 0.f, EW, 4 * H, nullptr, s, PROF_GEMM_DECODE));
+      cudaMemsetAsync(rec_done, 0, 64 * sizeof(unsigned int), s);
+      for (int t = 0; t < L; ++t) {
+        const int last = (t + 1 == L);
+        bool done = false;
+        ProfScope prof(PROF_VOCAB_SAMPLE, 8.0 * B * V, s);
+        GIC_TRY(decode_step_tc(saved + sv.hs(0) + (size_t)(t + 1) * BH, W_out, b_out, W_hh[0], b_ih[0], b_hh[0], EW, R, rec_done,
+                               u ? u + (size_t)t * B * V : nullptr, T, temperature_device(), B, V, H, L, t, last, out, ids, forced,
+                               W_emb, E, last ? nullptr : saved + sv.xs + (size_t)(t + 1) * BE,
+                               saved + sv.cs(0) + (size_t)(t + 1) * BH, saved + sv.cs(0) + (size_t)(t + 2) * BH,
+                               saved + sv.hs(0) + (size_t)(t + 2) * BH, saved + sv.acts(0) + (size_t)(t + 1) * BH * 4,
+                               saved + sv.htop, vs_scratch, s, &done));
+        GIC_REQUIRE(done, GIC_ERR_UNSUPPORTED, "decode_sample_fwd: fused decode step declined after its plan accepted the shape");
+      }
+      return GIC_OK;
+    }
   }
   for (int t = 0; t < L; ++t) {
     if (at) {
@@ -713,7 +740,8 @@ int gic_sample_cdf_step(const float* logits, const float* u, int B, int V, int L
 
 size_t gic_decode_saved_floats(int B, int L, int E, int H, int layers) { return DecodeSaved(B, L, E, H, layers).total; }
 size_t gic_decode_fwd_workspace_floats(int B, int V, int H) {
-  return a4((size_t)4 * B * H) + 2 * a4((size_t)B * V) + a4(vocab_sample_scratch_floats(B, V));
+  return a4((size_t)4 * B * H) + 2 * a4((size_t)B * V) + a4(vocab_sample_scratch_floats(B, V)) +
+         a4(decode_step_scratch_floats(B, V, H));
 }
 size_t gic_decode_bwd_workspace_floats(int B, int L, int V, int E, int H, int layers) {
   return DecodeBwdWs(B, L, V, E, H, layers).total;

@@ -1019,10 +1019,11 @@ int disc_forward(int mode, const float* inp_soft, const int64_t* ids, const Disc
         use_mma = false;
       }
     }
-    if (use_mma) {}
-    else if (es1) conv_pool_fwd_kernel<true><<<dim3(d.N, slices), 256, smem, s>>>(emb, d.L, d.De, d.R, d.es, g, cs, pooled, arg, pbf, Fp);
-    else conv_pool_fwd_kernel<false><<<dim3(d.N, slices), 256, smem, s>>>(emb, d.L, d.De, d.R, d.es, g, cs, pooled, arg, pbf, Fp);
-    GIC_TRY(check_launch("conv_pool_fwd_kernel"));
+    if (!use_mma) {
+      if (es1) conv_pool_fwd_kernel<true><<<dim3(d.N, slices), 256, smem, s>>>(emb, d.L, d.De, d.R, d.es, g, cs, pooled, arg, pbf, Fp);
+      else conv_pool_fwd_kernel<false><<<dim3(d.N, slices), 256, smem, s>>>(emb, d.L, d.De, d.R, d.es, g, cs, pooled, arg, pbf, Fp);
+      GIC_TRY(check_launch("conv_pool_fwd_kernel"));
+    }
   }
   // 3. highway pre-activation
   if (bf) {

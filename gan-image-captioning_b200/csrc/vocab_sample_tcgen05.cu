@@ -18,6 +18,18 @@
 // Warp roles (576 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..17 = epilogue: four
 // warps per TMEM lane quarter split the tile's columns in 16-column units; they turn u into the Gumbel term while the
 // main loop runs (pass 0), so only the exp / normalise passes remain after the last MMA.
+//
+// FUSED DECODE STEP (single-layer decoder; decode_step_tc below).  The LSTM pre-activation of the NEXT step is
+//     gates_{t+1} = embed[tok_t] W_ih^T + h_t W_hh^T + b_ih + b_hh              (src/generator.py:61,75-76)
+// and only its first term depends on the token this kernel is about to sample.  So the same launch also carries
+//   * "rec" tiles (the CTAs with the LOWEST block indices, on the SMs the projection tiles leave idle): plain 128 x RBN
+//     tiles of R = h_t W_hh^T, same A operand and pipeline as the projection tiles, accumulator stored to global memory,
+//     one arrival per tile on a per-row-block counter;
+//   * a cell tail in the projection tiles: the CTA that ends up holding a row's maximum (= knows tok_t) waits for the
+//     row block's rec tiles, adds the token's row of EW = embed W_ih^T (a [V, 4H] table rebuilt once per decode,
+//     decode_step_tc) and the biases, applies the LSTM cell and writes h_{t+1}, c_{t+1}, the saved activations and
+//     htop -- one warp per row, rows dealt over all 16 epilogue warps.
+// One launch per decode step instead of two, and the recurrent contraction runs UNDER the projection instead of after it.
 #include "tcgen05_common.cuh"
 #include "philox.cuh"
 
@@ -37,7 +49,7 @@ struct VSCfg {
   static constexpr int AVAIL = 227 * 1024 - 1024 - U_BYTES - BAR_BYTES;
   static constexpr int STAGES = (AVAIL / STAGE) > 6 ? 6 : (AVAIL / STAGE);
   static constexpr int TOTAL = STAGES * STAGE + U_BYTES + BAR_BYTES + 1024;
-  static constexpr uint32_t TMEM_COLS = (BN <= 128) ? 128 : 256;
+  static constexpr uint32_t TMEM_COLS = 256;           // a rec tile of the fused decode step is up to 256 columns wide
   static_assert(STAGES >= 2, "vocab_sample: shared memory ring too small");
   static_assert(BN % 32 == 0 && BN <= 256, "vocab_sample: BN must be a multiple of 32, <= 256");
 };
@@ -58,7 +70,32 @@ struct VSArgs {
   long long* stamps;          // debug (GIC_VS_STAMPS=1): 16 clock64 stamps per CTA, else null
   int use_rng;                // no uniforms supplied: draw u[t, m, n] in the kernel (Philox, same numbers as gic_philox_uniform)
   RngState rng;
+  // ---- fused decode step (all zero / null for the plain projection + sample kernel) ----
+  int n_rec;                  // CTAs [0, n_rec) are rec tiles; projection tile index = blockIdx.x - n_rec
+  int rec_tiles_n, RBN;       // rec column tiles per row block, their width (multiple of 16, <= 256)
+  int G4;                     // 4 H
+  float* R;                   // [M, 4H] h_t W_hh^T
+  unsigned int* rec_done;     // [tiles_m] arrivals of rec tiles (monotonic over the steps of one decode)
+  unsigned int rec_expect;    // value rec_done[mtile] has reached when this launch's rec tiles of the row block are done
+  int do_cell;                // apply the LSTM cell of step t + 1 for the rows whose token this CTA feeds back
+  const float* EW;            // [V, 4H] embed W_ih^T
+  const float* b_ih;          // [4H]
+  const float* b_hh;          // [4H]
+  const float* c_prev;        // [M, H] c_t
+  float* c_out;               // [M, H] c_{t+1}
+  float* h_out;               // [M, H] h_{t+1}
+  float* acts;                // [M, 4H] sig(i), sig(f), tanh(g), sig(o) of step t + 1 (saved for the backward)
+  float* htop;                // [M, L, H]: row (m, t + 1) written
 };
+
+template <int BN>
+struct RecCfg {               // operand ring of a rec tile: it has no u / p tile, so the whole carve-out is ring
+  static constexpr int STAGE = BM * BK * 4 + 256 * BK * 4;     // A 16 KB + up to 256 rows of W_hh
+  static constexpr int STAGES = ((VSCfg<BN>::STAGES * VSCfg<BN>::STAGE + VSCfg<BN>::U_BYTES) / STAGE) > 4
+                                    ? 4 : ((VSCfg<BN>::STAGES * VSCfg<BN>::STAGE + VSCfg<BN>::U_BYTES) / STAGE);
+  static_assert(STAGES >= 2, "decode step: rec ring too small");
+};
+constexpr int VS_NBAR = 8;    // mbarrier slots per direction (>= the stages of either ring)
 
 #define VS_STAMP(i) do { if (a.stamps) a.stamps[blockIdx.x * 16 + (i)] = (long long)globaltimer_ns(); } while (0)
 
@@ -86,7 +123,8 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"
 template <int BN>
 __global__ void __launch_bounds__(VS_THREADS, 1)
 vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmP, VSArgs a) {
+                    const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmP,
+                    const __grid_constant__ CUtensorMap tmW, VSArgs a) {
   using S = VSCfg<BN>;
   constexpr int NUNIT = BN / 16;                     // 16-column units, dealt round-robin to the VS_G warps of a quarter
   constexpr int MAXU = (NUNIT + VS_G - 1) / VS_G;
@@ -94,29 +132,41 @@ vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* ubox = smem + S::STAGES * S::STAGE;                    // NBOX boxes of [128 rows][128 B], 128B-swizzled
   uint64_t* full = reinterpret_cast<uint64_t*>(ubox + S::U_BYTES);
-  uint64_t* empty = full + S::STAGES;
-  uint64_t* tmem_full = empty + S::STAGES;
+  uint64_t* empty = full + VS_NBAR;
+  uint64_t* tmem_full = empty + VS_NBAR;
   uint64_t* u_full = tmem_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(u_full + 1);
   // small exchange buffers of the epilogue live in stage 0 of the operand ring, which is dead once tmem_full fires
   float2 (*s_part)[BM] = reinterpret_cast<float2 (*)[BM]>(smem);              // [VS_G][BM] row statistics of pass 1
   float4* s_row = reinterpret_cast<float4*>(smem + VS_G * BM * 8);            // [VS_G][BM] (M, S, first tile, -) per group
   int* s_hit = reinterpret_cast<int*>(smem + VS_G * BM * 8 + VS_G * BM * 16); // first column holding the row maximum
-  static_assert(VS_G * BM * 8 + VS_G * BM * 16 + BM * 4 <= S::STAGE, "vocab_sample: exchange buffers exceed one stage");
+  int* s_fed = s_hit + BM;                                                    // token this CTA feeds back for the row, or -1
+  int* s_list = s_fed + BM;                                                   // rows this CTA feeds back, compacted
+  int* s_cnt = s_list + BM;                                                   // their number
+  static_assert(VS_G * BM * 8 + VS_G * BM * 16 + 3 * BM * 4 + 16 <= S::STAGE, "vocab_sample: exchange buffers exceed one stage");
+  // "this row block's rec tiles have arrived": set by the producer thread (idle once its loads are issued), read by the
+  // cell tail; lives next to the mbarriers because the operand ring is still in use when it may be set
+  uint32_t* s_recflag = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(full) + 192);
+  static_assert(S::STAGES <= VS_NBAR && RecCfg<BN>::STAGES <= VS_NBAR, "vocab_sample: mbarrier slots");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (a.K + BK - 1) / BK;
-  const int mtile = blockIdx.x / a.tiles_n, ntile = blockIdx.x % a.tiles_n;
-  const int m0 = mtile * BM, n0 = ntile * BN;
+  const bool is_rec = (int)blockIdx.x < a.n_rec;
+  const int vb = (int)blockIdx.x - a.n_rec;                       // projection tile index
+  const int mtile = is_rec ? (int)blockIdx.x / a.rec_tiles_n : vb / a.tiles_n;
+  const int ntile = is_rec ? (int)blockIdx.x % a.rec_tiles_n : vb % a.tiles_n;
+  const int m0 = mtile * BM, n0 = ntile * (is_rec ? a.RBN : BN);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmU) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmP) : "memory");
-    for (int s = 0; s < S::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    if (a.n_rec) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    for (int s = 0; s < VS_NBAR; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(tmem_full, 1);
     mbar_init(u_full, 1);
+    *s_recflag = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -130,6 +180,68 @@ vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   pdl_wait();                      // the LSTM step that produced h_t has completed; the set-up above overlapped its tail
   pdl_trigger();
 
+  if (is_rec) {
+    // ===== rec tile: R[m0 : m0+128, n0 : n0+RBN] = h_t W_hh^T (K = H), accumulator straight to global memory =====
+    using RC = RecCfg<BN>;
+    const uint32_t b_bytes = (uint32_t)a.RBN * BK * 4;
+    if (warp == 0) {
+      if (lane == 0) {
+        VS_STAMP(0);
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int s = kb % RC::STAGES;
+          const uint32_t ph = (kb / RC::STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* sa = smem + s * RC::STAGE;
+          mbar_expect_tx(&full[s], S::A_BYTES + b_bytes);
+          tma_load_2d(sa, &tmA, &full[s], kb * BK, m0);
+          tma_load_2d(sa + S::A_BYTES, &tmW, &full[s], kb * BK, n0);      // RBN rows of W_hh
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        const uint32_t idesc = make_idesc(0, 0, a.RBN);
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int s = kb % RC::STAGES;
+          const uint32_t ph = (kb / RC::STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + s * RC::STAGE);
+          const uint32_t sb = sa + S::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = make_desc(sa + k * 32, 16, 1024, 2);
+            const uint64_t db = make_desc(sb + k * 32, 16, 1024, 2);
+            umma_tf32(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(tmem_full);
+        VS_STAMP(3);
+      }
+    } else {
+      const int q = warp & 3, g = (warp - 2) >> 2;
+      const int m = m0 + q * 32 + lane;
+      mbar_wait(tmem_full, 0);
+      tcgen05_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+      const int nunit = a.RBN >> 4;
+      for (int j = g; j < nunit; j += VS_G) {                     // warp-uniform
+        uint32_t r[16];
+        tmem_ld16(t_addr + 16 * j, r);
+        const int n = n0 + 16 * j;
+        if (m < a.M && n < a.G4) {                                // 4H % 16 == 0: a unit is entirely inside or outside
+          float4* dst = reinterpret_cast<float4*>(a.R + (size_t)m * a.G4 + n);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            dst[k] = make_float4(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1]), __uint_as_float(r[4 * k + 2]),
+                                 __uint_as_float(r[4 * k + 3]));
+        }
+      }
+      __threadfence();                                            // this thread's slice of R before the arrival below
+      epi_bar();
+      if (threadIdx.x == 64) { atomicAdd(a.rec_done + mtile, 1u); VS_STAMP(12); }   // one arrival per rec tile (release: fence + barrier above)
+    }
+  } else
   if (warp == 0) {
     // ===== TMA producer: operand ring; the u tile is queued once the ring is primed (the epilogue warps turn it into
     //       Gumbel noise underneath the rest of the main loop) =====
@@ -150,6 +262,20 @@ vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
       VS_STAMP(1);
+      if (a.do_cell) {
+        // the row block's rec tiles (lower block indices: scheduled before this CTA) have stored R and arrived; polled
+        // here, off the epilogue's critical path, and handed over through shared memory
+        const unsigned long long t0 = globaltimer_ns();
+        for (;;) {
+          unsigned int v;
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.rec_done + mtile) : "memory");
+          if (v >= a.rec_expect) break;
+          __nanosleep(100);
+          if (globaltimer_ns() - t0 > 4000000000ull) __trap();   // a protocol bug traps instead of hanging the GPU
+        }
+        asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(s_recflag)), "r"(1u) : "memory");
+        VS_STAMP(13);
+      }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
@@ -279,6 +405,7 @@ vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     s_part[g][row] = make_float2(m_run, s_run);
     if (g == 0) s_hit[row] = 0x7fffffff;
+    if (etid == 0) *s_cnt = 0;
     if (etid == 0) VS_STAMP(7);
     epi_bar();
 
@@ -412,26 +539,93 @@ vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           fed = (fz >= 0 && fz < a.N) ? (int)fz : 0;
         }
       }
-      if (a.x_next != nullptr) {
-        unsigned mask = __ballot_sync(0xffffffffu, fed >= 0);
-        const bool vec = ((a.E & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.embed) & 15u) == 0) &&
-                         ((reinterpret_cast<uintptr_t>(a.x_next) & 15u) == 0);
-        while (mask) {
-          const int src = __ffs(mask) - 1;
-          mask &= mask - 1;
-          const int tok = __shfl_sync(0xffffffffu, fed, src);
+      s_fed[row] = fed;
+      if (fed >= 0) s_list[atomicAdd(s_cnt, 1)] = row;
+    }
+    epi_bar();
+    // ---- next-step input x_{t+1} = embed[fed] and, in the fused decode step, the LSTM cell of step t + 1 for the rows
+    //      this CTA feeds back (a row block's 128 rows are spread over its column tiles by where the maxima fell; under
+    //      teacher forcing tile 0 takes them all).  A team of four warps per row, four rows at a time: every lane issues
+    //      all loads of its four hidden units at once (R, the token's row of EW, biases, c), so a row costs ONE round trip
+    //      to L2 / HBM instead of a chain of them.
+    if (a.x_next != nullptr || a.do_cell) {
+      const int ew = warp - 2;                         // 0 .. 15
+      const int team = ew >> 2, tl = (ew & 3) * 32 + lane;      // lane 0 .. 127 inside the team
+      const int nrows = *s_cnt;
+      const bool vec = ((a.E & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.embed) & 15u) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(a.x_next) & 15u) == 0);
+      bool rec_ready = !a.do_cell;
+      const int H = a.G4 >> 2;
+      for (int i = team; i < nrows; i += VS_G) {
+        const int r = s_list[i];
+        const int tok = s_fed[r];
+        const int mr = m0 + r;
+        if (a.x_next != nullptr) {
           const float* er = a.embed + (size_t)tok * a.E;
-          float* xr = a.x_next + (size_t)(m0 + q * 32 + src) * a.E;
+          float* xr = a.x_next + (size_t)mr * a.E;
           if (vec) {
-            for (int i = lane; i < (a.E >> 2); i += 32) reinterpret_cast<float4*>(xr)[i] = __ldg(reinterpret_cast<const float4*>(er) + i);
+            for (int c = tl; c < (a.E >> 2); c += 128) reinterpret_cast<float4*>(xr)[c] = __ldg(reinterpret_cast<const float4*>(er) + c);
           } else {
-            for (int i = lane; i < a.E; i += 32) xr[i] = __ldg(er + i);
+            for (int c = tl; c < a.E; c += 128) xr[c] = __ldg(er + c);
           }
         }
+        if (!a.do_cell) continue;
+        const float* Rr = a.R + (size_t)mr * a.G4;
+        const float* Er = a.EW + (size_t)tok * a.G4;
+        for (int j = 4 * tl; j < H; j += 512) {
+          // token-dependent and constant operands first: they do not wait for the rec tiles
+          float4 ev[4], bi[4], bh[4], rv[4];
+#pragma unroll
+          for (int gt = 0; gt < 4; ++gt) {
+            ev[gt] = __ldg(reinterpret_cast<const float4*>(Er + gt * H + j));
+            bi[gt] = __ldg(reinterpret_cast<const float4*>(a.b_ih + gt * H + j));
+            bh[gt] = __ldg(reinterpret_cast<const float4*>(a.b_hh + gt * H + j));
+          }
+          const float4 cp4 = *reinterpret_cast<const float4*>(a.c_prev + (size_t)mr * H + j);
+          if (!rec_ready) {
+            const unsigned am = __activemask();        // H % 128 != 0: the last warp of a team is partly idle
+            if (lane == 0) {
+              uint32_t f = 0;
+              const unsigned long long t0 = globaltimer_ns();
+              while (f == 0) {
+                asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(f) : "r"(smem_u32(s_recflag)) : "memory");
+                if (globaltimer_ns() - t0 > 4000000000ull) __trap();
+              }
+            }
+            __syncwarp(am);
+            rec_ready = true;
+          }
+#pragma unroll
+          for (int gt = 0; gt < 4; ++gt) rv[gt] = __ldcg(reinterpret_cast<const float4*>(Rr + gt * H + j));   // written by another SM in this launch
+          float pre[4][4];
+#pragma unroll
+          for (int gt = 0; gt < 4; ++gt) {
+            pre[gt][0] = (ev[gt].x + rv[gt].x) + (bi[gt].x + bh[gt].x); pre[gt][1] = (ev[gt].y + rv[gt].y) + (bi[gt].y + bh[gt].y);
+            pre[gt][2] = (ev[gt].z + rv[gt].z) + (bi[gt].z + bh[gt].z); pre[gt][3] = (ev[gt].w + rv[gt].w) + (bi[gt].w + bh[gt].w);
+          }
+          const float cp[4] = {cp4.x, cp4.y, cp4.z, cp4.w};
+          float ai[4], af[4], ag[4], ao[4], cn[4], hn[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            ai[e] = sigmoidf_acc(pre[0][e]); af[e] = sigmoidf_acc(pre[1][e]); ag[e] = tanhf(pre[2][e]); ao[e] = sigmoidf_acc(pre[3][e]);
+            cn[e] = af[e] * cp[e] + ai[e] * ag[e];
+            hn[e] = ao[e] * tanhf(cn[e]);
+          }
+          float* arow = a.acts + (size_t)mr * a.G4 + j;
+          *reinterpret_cast<float4*>(arow) = make_float4(ai[0], ai[1], ai[2], ai[3]);
+          *reinterpret_cast<float4*>(arow + H) = make_float4(af[0], af[1], af[2], af[3]);
+          *reinterpret_cast<float4*>(arow + 2 * H) = make_float4(ag[0], ag[1], ag[2], ag[3]);
+          *reinterpret_cast<float4*>(arow + 3 * H) = make_float4(ao[0], ao[1], ao[2], ao[3]);
+          *reinterpret_cast<float4*>(a.c_out + (size_t)mr * H + j) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+          const float4 h4 = make_float4(hn[0], hn[1], hn[2], hn[3]);
+          *reinterpret_cast<float4*>(a.h_out + (size_t)mr * H + j) = h4;
+          *reinterpret_cast<float4*>(a.htop + ((size_t)mr * a.L + (a.t + 1)) * H + j) = h4;
+        }
       }
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem may be released; the writes land by grid end
-      if (etid == 0) VS_STAMP(12);
     }
+    if (etid == 0) VS_STAMP(14);
+    if (g == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem may be released; the writes land by grid end
+    if (etid == 0) VS_STAMP(12);
 #undef VS_CHUNK
   }
   tcgen05_fence_before();
@@ -443,508 +637,20 @@ vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 template <int BN>
-static int launch_vs(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tu, const CUtensorMap& tp, const VSArgs& a,
-                     int grid, cudaStream_t s) {
+static int launch_vs(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tu, const CUtensorMap& tp,
+                     const CUtensorMap& tw, const VSArgs& a, int grid, cudaStream_t s) {
   using S = VSCfg<BN>;
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(vocab_sample_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
     attr = true;
   }
-  cudaError_t e = launch_pdl(vocab_sample_kernel<BN>, dim3(grid), dim3(VS_THREADS), S::TOTAL, s, ta, tb, tu, tp, a);
+  cudaError_t e = launch_pdl(vocab_sample_kernel<BN>, dim3(grid), dim3(VS_THREADS), S::TOTAL, s, ta, tb, tu, tp, tw, a);
   if (e != cudaSuccess) { set_error("vocab_sample_kernel launch: %s", cudaGetErrorString(e)); return GIC_ERR_CUDA; }
-  return check_launch("vocab_sample_kernel");
+  // the same kernel, counted under the role it was launched in (tests assert on the names)
+  return check_launch((a.n_rec > 0 || a.do_cell) ? "decode_step_kernel" : "vocab_sample_kernel");
 }
 
-
-// =========================================================================================================
-// Persistent decode: ALL L steps of Decoder.sample (src/generator.py:55-81) in one launch.  The per-step kernels above
-// spend about as long on being kernels (launch, barrier / TMEM set-up, first-load latency, tear-down: ~8 us each, 40 of
-// them in a row at c2) as in their main loops.  Here the grid stays resident and every CTA owns one LSTM tile (128 rows x
-// U hidden units, as lstm_step_tf32_kernel) AND one projection tile (128 rows x BN vocabulary columns, as
-// vocab_sample_kernel); a step is
-//     phase L   gates = x_t W_ih^T + h_{t-1} W_hh^T (TMA ring -> tcgen05 -> TMEM columns 256..), cell update, h_t / c_t
-//     arrive + wait on the grid counter                      (every CTA's slice of h_t is visible)
-//     phase V   logits tile, Gumbel-softmax, row statistics exchanged between the column tiles, p TMA-stored in place,
-//               token id and the next step's input x_{t+1} = embed[tok] by the tile that holds the row maximum
-//     arrive + wait on the grid counter                      (x_{t+1} is visible)
-// Two monotonic counters, one per phase kind (a CTA without an LSTM tile arrives for phase L of step t+1 right after its
-// phase-V arrival of step t: on a shared counter that early arrival could stand in for a missing phase-V arrival of a
-// slower CTA); consumers are the TMA producer threads, which cross into the async proxy after the acquire.  The LSTM ring aliases the projection ring (the phases never overlap inside a CTA).
-// Requires the whole grid co-resident (grid <= SMs, one CTA per SM: the launch checks occupancy).
-// =========================================================================================================
-struct DPArgs {
-  VSArgs v;                      // projection phase (t, part, part_next, x_next are set per step in the kernel)
-  int B, H, In, U, l_tiles_n, tiles_l, tiles_v, L;
-  const float* b_ih;
-  const float* b_hh;
-  float* cs;                     // [(L+1)][B][H]  cs[t] = cell state entering step t
-  float* hs;                     // [(L+1)][B][H]
-  float* acts;                   // [L][B][4H] or null
-  float* htop;                   // [B][L][H]
-  float* xs;                     // [L][B][E]
-  float2* part0;                 // two statistics buffers, alternating by step parity
-  float2* part1;
-  unsigned int* counter;         // [2] zero on entry: LSTM-phase arrivals, projection-phase arrivals
-};
-
-__device__ __forceinline__ unsigned int dp_ld_acquire(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void dp_grid_wait(const unsigned int* ctr, unsigned int want) {
-  const long long t0 = clock64();
-  while (dp_ld_acquire(ctr) < want) {
-    __nanosleep(32);
-    if (clock64() - t0 > 4000000000ll) __trap();       // a protocol bug traps instead of hanging the GPU
-  }
-  asm volatile("fence.proxy.async;" ::: "memory");     // the data is read through TMA next
-}
-__device__ __forceinline__ void lstm_bar() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
-
-constexpr uint32_t DP_LCOL = 256;                       // first TMEM column of the LSTM accumulator
-constexpr int DP_LSTAGES = 6;
-
-template <int BN>
-__global__ void __launch_bounds__(VS_THREADS, 1)
-decode_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmH,
-                         const __grid_constant__ CUtensorMap tmWih, const __grid_constant__ CUtensorMap tmWhh,
-                         const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmU,
-                         const __grid_constant__ CUtensorMap tmP, DPArgs d) {
-  using S = VSCfg<BN>;
-  constexpr int NUNIT = BN / 16;
-  constexpr int MAXU = (NUNIT + VS_G - 1) / VS_G;
-  const VSArgs& a = d.v;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* ubox = smem + S::STAGES * S::STAGE;
-  uint64_t* full = reinterpret_cast<uint64_t*>(ubox + S::U_BYTES);
-  uint64_t* empty = full + S::STAGES;
-  uint64_t* tmem_full = empty + S::STAGES;
-  uint64_t* u_full = tmem_full + 1;
-  uint64_t* lfull = u_full + 1;                        // [DP_LSTAGES]
-  uint64_t* lempty = lfull + DP_LSTAGES;               // [DP_LSTAGES]
-  uint64_t* ltmem_full = lempty + DP_LSTAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ltmem_full + 1);
-  static_assert((2 * 6 + 2 + 2 * DP_LSTAGES + 1) * 8 + 4 <= 256, "persistent decode: barrier block overflows");
-  float2 (*s_part)[BM] = reinterpret_cast<float2 (*)[BM]>(smem);
-  float4* s_row = reinterpret_cast<float4*>(smem + VS_G * BM * 8);
-  int* s_hit = reinterpret_cast<int*>(smem + VS_G * BM * 8 + VS_G * BM * 16);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int G = gridDim.x;
-  const bool has_l = (int)blockIdx.x < d.tiles_l, has_v = (int)blockIdx.x < d.tiles_v;
-  // projection tile
-  const int nkb = (a.K + BK - 1) / BK;
-  const int mtile = blockIdx.x / a.tiles_n, ntile = blockIdx.x % a.tiles_n;
-  const int m0 = mtile * BM, n0 = ntile * BN;
-  // LSTM tile
-  const int U = d.U, H = d.H;
-  const int lm0 = (blockIdx.x / d.l_tiles_n) * BM, j0 = (blockIdx.x % d.l_tiles_n) * U;
-  const int nkb1 = (d.In + BK - 1) / BK, nkb2 = (H + BK - 1) / BK, lnkb = nkb1 + nkb2;
-  const int LSTAGE = BM * BK * 4 + 4 * U * BK * 4;     // 16 KB + 4 gate slabs of U rows x 128 B
-  int lstages = (S::STAGES * S::STAGE) / LSTAGE;
-  if (lstages > DP_LSTAGES) lstages = DP_LSTAGES;
-
-  if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmH) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWih) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWhh) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmU) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmP) : "memory");
-    for (int s = 0; s < S::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < DP_LSTAGES; ++s) { mbar_init(&lfull[s], 1); mbar_init(&lempty[s], 1); }
-    mbar_init(tmem_full, 1);
-    mbar_init(u_full, 1);
-    mbar_init(ltmem_full, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  uint32_t itV = 0, itL = 0;                           // ring positions (producer and MMA threads count alike)
-  const int q = warp & 3;
-  const int g = (warp - 2) >> 2;
-  const int row = q * 32 + lane;
-  const int etid = threadIdx.x - 64;
-  const float eps = 1e-10f;
-  uint8_t* urow = ubox + row * 128;
-  const int sw = row & 7;
-#define VS_CHUNK(j, k) (urow + ((j) >> 1) * S::BOX_BYTES + (((4 * ((j) & 1) + (k)) ^ sw) << 4))
-  float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 256);
-  if (warp >= 2 && has_v && etid < BN / 4) {           // the bias tile does not change between steps
-    const int n = n0 + 4 * etid;
-    reinterpret_cast<float4*>(s_bias)[etid] = (n < a.N) ? __ldg(reinterpret_cast<const float4*>(a.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-
-  for (int t = 0; t < d.L; ++t) {
-    const size_t BH = (size_t)d.B * H;
-    // ======================================= phase L: LSTM step =======================================
-    if (warp == 0) {
-      if (lane == 0) {
-        if (t > 0) dp_grid_wait(d.counter + 1, (unsigned int)t * G);        // every projection phase of step t-1 has arrived: x_t complete
-        if (has_l) {
-          for (int kb = 0; kb < lnkb; ++kb, ++itL) {
-            const int s = itL % lstages;
-            const uint32_t ph = (itL / lstages) & 1;
-            mbar_wait(&lempty[s], ph ^ 1);
-            uint8_t* sa = smem + s * LSTAGE;
-            uint8_t* sb = sa + BM * BK * 4;
-            mbar_expect_tx(&lfull[s], LSTAGE);
-            const bool first = kb < nkb1;
-            const int k0 = (first ? kb : kb - nkb1) * BK;
-            tma_load_2d(sa, first ? &tmX : &tmH, &lfull[s], k0, t * d.B + lm0);
-            for (int gi = 0; gi < 4; ++gi) tma_load_2d(sb + gi * (U * 128), first ? &tmWih : &tmWhh, &lfull[s], k0, gi * H + j0);
-          }
-        }
-      }
-    } else if (warp == 1) {
-      if (lane == 0 && has_l) {
-        const uint32_t idesc = make_idesc(0, 0, 4 * U);
-        for (int kb = 0; kb < lnkb; ++kb, ++itL) {
-          const int s = itL % lstages;
-          const uint32_t ph = (itL / lstages) & 1;
-          mbar_wait(&lfull[s], ph);
-          tcgen05_fence_after();
-          const uint32_t sa = smem_u32(smem + s * LSTAGE);
-          const uint32_t sb = sa + BM * BK * 4;
-#pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_tf32(tmem_base + DP_LCOL, make_desc(sa + k * 32, 16, 1024, 2), make_desc(sb + k * 32, 16, 1024, 2), idesc,
-                      (kb > 0 || k > 0) ? 1u : 0u);
-          umma_commit(&lempty[s]);
-        }
-        umma_commit(ltmem_full);
-      }
-    } else if (g == 0) {
-      // cell update on the accumulator tile: thread = batch row, 8 units at a time (as lstm_step_tf32_kernel)
-      if (has_l) {
-        const int b = lm0 + row;
-        const float* c_prev = d.cs + (size_t)t * BH;
-        float* c_out = d.cs + (size_t)(t + 1) * BH;
-        float* h_out = d.hs + (size_t)(t + 1) * BH;
-        mbar_wait(ltmem_full, (uint32_t)(t & 1));
-        tcgen05_fence_after();
-        const uint32_t lane_addr = tmem_base + DP_LCOL + ((uint32_t)(q * 32) << 16);
-        for (int u0 = 0; u0 < U; u0 += 8) {
-          uint32_t ri[8], rf[8], rg[8], ro[8];
-          tmem_ld8(lane_addr + 0 * U + u0, ri);
-          tmem_ld8(lane_addr + 1 * U + u0, rf);
-          tmem_ld8(lane_addr + 2 * U + u0, rg);
-          tmem_ld8(lane_addr + 3 * U + u0, ro);
-          if (b < d.B) {
-            const int j = j0 + u0;
-            float cp[8], ai[8], af[8], ag[8], ao[8], cn[8], hn[8];
-            *reinterpret_cast<float4*>(cp) = *reinterpret_cast<const float4*>(c_prev + (size_t)b * H + j);
-            *reinterpret_cast<float4*>(cp + 4) = *reinterpret_cast<const float4*>(c_prev + (size_t)b * H + j + 4);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float pi = __uint_as_float(ri[e]) + d.b_ih[0 * H + j + e] + d.b_hh[0 * H + j + e];
-              const float pf = __uint_as_float(rf[e]) + d.b_ih[1 * H + j + e] + d.b_hh[1 * H + j + e];
-              const float pg = __uint_as_float(rg[e]) + d.b_ih[2 * H + j + e] + d.b_hh[2 * H + j + e];
-              const float po = __uint_as_float(ro[e]) + d.b_ih[3 * H + j + e] + d.b_hh[3 * H + j + e];
-              ai[e] = sigmoidf_acc(pi); af[e] = sigmoidf_acc(pf); ag[e] = tanhf(pg); ao[e] = sigmoidf_acc(po);
-              cn[e] = af[e] * cp[e] + ai[e] * ag[e];
-              hn[e] = ao[e] * tanhf(cn[e]);
-            }
-            auto st8 = [](float* dst, const float* v) {
-              *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-              *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
-            };
-            if (d.acts) {
-              float* arow = d.acts + (size_t)t * BH * 4 + (size_t)b * 4 * H + j;
-              st8(arow, ai); st8(arow + H, af); st8(arow + 2 * H, ag); st8(arow + 3 * H, ao);
-            }
-            st8(c_out + (size_t)b * H + j, cn);
-            st8(h_out + (size_t)b * H + j, hn);
-            st8(d.htop + ((size_t)b * d.L + t) * H + j, hn);
-          }
-        }
-        tcgen05_fence_before();
-        __threadfence();                               // this thread's slice of h_t is visible device-wide
-      }
-      lstm_bar();                                      // the four cell warps
-      if (etid == 0) { __threadfence(); atomicAdd(d.counter, 1u); }   // LSTM-phase arrival of step t
-    }
-
-    // ======================================= phase V: projection + sample ==============================
-    float2* part = (t & 1) ? d.part1 : d.part0;
-    float2* part_next = (t & 1) ? d.part0 : d.part1;
-    float* x_next = (t + 1 < d.L) ? d.xs + (size_t)(t + 1) * d.B * a.E : nullptr;
-    if (warp == 0) {
-      if (lane == 0) {
-        dp_grid_wait(d.counter, (unsigned int)(t + 1) * G);                 // every LSTM phase of step t has arrived: h_t complete
-        if (has_v) {
-          for (int kb = 0; kb < nkb; ++kb, ++itV) {
-            const int s = itV % S::STAGES;
-            const uint32_t ph = (itV / S::STAGES) & 1;
-            mbar_wait(&empty[s], ph ^ 1);
-            uint8_t* sa = smem + s * S::STAGE;
-            mbar_expect_tx(&full[s], S::STAGE);
-            tma_load_2d(sa, &tmH, &full[s], kb * BK, (t + 1) * d.B + m0);
-            tma_load_2d(sa + S::A_BYTES, &tmB, &full[s], kb * BK, n0);
-            if (!a.use_rng && kb == min(nkb, S::STAGES) - 1) {
-              mbar_expect_tx(u_full, S::U_BYTES);
-#pragma unroll
-              for (int c = 0; c < S::NBOX; ++c) tma_load_2d(ubox + c * S::BOX_BYTES, &tmU, u_full, n0 + 32 * c, t * d.B + m0);
-            }
-          }
-        }
-      }
-    } else if (warp == 1) {
-      if (lane == 0 && has_v) {
-        constexpr uint32_t idesc = make_idesc(0, 0, BN);
-        for (int kb = 0; kb < nkb; ++kb, ++itV) {
-          const int s = itV % S::STAGES;
-          const uint32_t ph = (itV / S::STAGES) & 1;
-          mbar_wait(&full[s], ph);
-          tcgen05_fence_after();
-          const uint32_t sa = smem_u32(smem + s * S::STAGE);
-          const uint32_t sb = sa + S::A_BYTES;
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_tf32(tmem_base, make_desc(sa + k * 32, 16, 1024, 2), make_desc(sb + k * 32, 16, 1024, 2), idesc,
-                      (kb > 0 || k > 0) ? 1u : 0u);
-          umma_commit(&empty[s]);
-        }
-        umma_commit(tmem_full);
-      }
-    } else if (has_v) {
-      const int m = m0 + row;
-      const float T = a.T_dev ? __ldg(a.T_dev) : a.T;
-      if (g == VS_G - 1) st_relaxed_f2(part_next + (size_t)ntile * a.Mpad + m, make_float2(0.f, 0.f));
-      // ---- pass 0: u -> log2(-log(u + eps) + eps)
-      unsigned long long rseed = 0ull, roff = 0ull;
-      if (a.use_rng) rng_load(a.rng, rseed, roff); else mbar_wait(u_full, (uint32_t)(t & 1));
-#pragma unroll
-      for (int i = 0; i < MAXU; ++i) {
-        const int j = g + i * VS_G;
-        if (j < NUNIT && n0 + 16 * j < a.N) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            float4* sp = reinterpret_cast<float4*>(VS_CHUNK(j, k));
-            float4 u4;
-            if (a.use_rng) {
-              const int n = n0 + 16 * j + 4 * k;
-              const unsigned long long e = ((unsigned long long)t * a.M + (unsigned long long)min(m, a.M - 1)) * a.N + min(n, a.N - 4);
-              u4 = philox_uniform4(rseed, roff, RNG_TAG_GUMBEL, e >> 2);
-            } else {
-              u4 = *sp;
-            }
-            u4.x = __log2f(-logf(u4.x + eps) + eps); u4.y = __log2f(-logf(u4.y + eps) + eps);
-            u4.z = __log2f(-logf(u4.z + eps) + eps); u4.w = __log2f(-logf(u4.w + eps) + eps);
-            *sp = u4;
-          }
-        }
-      }
-      // ---- pass 1
-      epi_bar();
-      mbar_wait(tmem_full, (uint32_t)(t & 1));
-      tcgen05_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-      float m_run = -INFINITY, s_run = 0.f;
-      float mrun_u[MAXU];
-#pragma unroll
-      for (int i = 0; i < MAXU; ++i) {
-        const int j = g + i * VS_G;
-        mrun_u[i] = -INFINITY;
-        if (j < NUNIT) {
-          uint32_t r[16];
-          tmem_ld16(t_addr + 16 * j, r);
-          float z[16];
-          float cm = -INFINITY;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int n = n0 + 16 * j + 4 * k;
-            if (n < a.N) {
-              const float4 ng = *reinterpret_cast<const float4*>(VS_CHUNK(j, k));
-              const float4 b4 = *reinterpret_cast<const float4*>(s_bias + 16 * j + 4 * k);
-              constexpr float LN2 = 0.693147182f;
-              z[4 * k + 0] = (__uint_as_float(r[4 * k + 0]) + b4.x - ng.x * LN2) * T;
-              z[4 * k + 1] = (__uint_as_float(r[4 * k + 1]) + b4.y - ng.y * LN2) * T;
-              z[4 * k + 2] = (__uint_as_float(r[4 * k + 2]) + b4.z - ng.z * LN2) * T;
-              z[4 * k + 3] = (__uint_as_float(r[4 * k + 3]) + b4.w - ng.w * LN2) * T;
-            } else {
-              z[4 * k + 0] = z[4 * k + 1] = z[4 * k + 2] = z[4 * k + 3] = -INFINITY;
-            }
-            cm = fmaxf(cm, fmaxf(fmaxf(z[4 * k + 0], z[4 * k + 1]), fmaxf(z[4 * k + 2], z[4 * k + 3])));
-          }
-          if (cm > -INFINITY) {
-            const float m_new = fmaxf(m_run, cm);
-            s_run *= (m_run > -INFINITY) ? __expf(m_run - m_new) : 0.f;
-            m_run = m_new;
-            float cs = 0.f;
-#pragma unroll
-            for (int e = 0; e < 16; ++e) { z[e] = __expf(z[e] - m_new); cs += z[e]; }
-            s_run += cs;
-          } else {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) z[e] = 0.f;
-          }
-          mrun_u[i] = m_run;
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            *reinterpret_cast<float4*>(VS_CHUNK(j, k)) = make_float4(z[4 * k + 0], z[4 * k + 1], z[4 * k + 2], z[4 * k + 3]);
-        }
-      }
-      tcgen05_fence_before();
-      s_part[g][row] = make_float2(m_run, s_run);
-      if (g == 0) s_hit[row] = 0x7fffffff;
-      epi_bar();
-      if (g == 0) {
-        float Mt = -INFINITY, St = 0.f;
-#pragma unroll
-        for (int i = 0; i < VS_G; ++i) {
-          const float2 v = s_part[i][row];
-          if (v.x > Mt) { St = St * ((Mt > -INFINITY) ? __expf(Mt - v.x) : 0.f) + v.y; Mt = v.x; }
-          else if (v.x > -INFINITY) St += v.y * __expf(v.x - Mt);
-        }
-        if (St == 0.f) St = 1e-37f;
-        st_relaxed_f2(part + (size_t)ntile * a.Mpad + m, make_float2(Mt, St));
-      }
-      {
-        float Mg = -INFINITY, Sg = 0.f;
-        int jb = 0x7fffffff;
-        const float2* pp = part + m;
-        const unsigned long long t0 = globaltimer_ns();
-        for (int jj0 = g; jj0 < a.tiles_n; jj0 += 8 * VS_G) {
-          float2 v[8];
-          for (;;) {
-            bool ready = true;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int j = jj0 + i * VS_G;
-              v[i] = (j < a.tiles_n) ? ld_relaxed_f2(pp + (size_t)j * a.Mpad) : make_float2(-INFINITY, 1.f);
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) ready = ready && (__float_as_uint(v[i].y) != 0u);
-            if (ready) break;
-            __nanosleep(20);
-            if (globaltimer_ns() - t0 > 4000000000ull) __trap();
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (jj0 + i * VS_G >= a.tiles_n) continue;
-            if (v[i].x > Mg) {
-              Sg = Sg * ((Mg > -INFINITY) ? __expf(Mg - v[i].x) : 0.f) + v[i].y;
-              Mg = v[i].x; jb = jj0 + i * VS_G;
-            } else if (v[i].x > -INFINITY) {
-              Sg += v[i].y * __expf(v[i].x - Mg);
-            }
-          }
-        }
-        s_row[g * BM + row] = make_float4(Mg, Sg, __int_as_float(jb), 0.f);
-      }
-      epi_bar();
-      float Mx = -INFINITY, Ssum = 0.f;
-      int jbest = 0x7fffffff;
-#pragma unroll
-      for (int i = 0; i < VS_G; ++i) {
-        const float4 v = s_row[i * BM + row];
-        const int jv = __float_as_int(v.z);
-        if (v.x > Mx) {
-          Ssum = Ssum * ((Mx > -INFINITY) ? __expf(Mx - v.x) : 0.f) + v.y;
-          Mx = v.x; jbest = jv;
-        } else if (v.x > -INFINITY) {
-          Ssum += v.y * __expf(v.x - Mx);
-          if (v.x == Mx && jv < jbest) jbest = jv;
-        }
-      }
-      if (jbest == 0x7fffffff) jbest = 0;
-      const float inv = 1.0f / Ssum;
-      const bool winner = (jbest == ntile);
-      int hit = 0x7fffffff;
-#pragma unroll
-      for (int i = 0; i < MAXU; ++i) {
-        const int j = g + i * VS_G;
-        if (j < NUNIT && n0 + 16 * j < a.N) {
-          const float f = __expf(mrun_u[i] - Mx) * inv;
-          const bool may_hit = winner && (mrun_u[i] == Mx) && (hit == 0x7fffffff);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            float4* sp = reinterpret_cast<float4*>(VS_CHUNK(j, k));
-            float4 e = *sp;
-            if (may_hit && hit == 0x7fffffff) {
-              if (e.x == 1.0f) hit = 16 * j + 4 * k;
-              else if (e.y == 1.0f) hit = 16 * j + 4 * k + 1;
-              else if (e.z == 1.0f) hit = 16 * j + 4 * k + 2;
-              else if (e.w == 1.0f) hit = 16 * j + 4 * k + 3;
-            }
-            e.x *= f; e.y *= f; e.z *= f; e.w *= f;
-            *sp = e;
-          }
-        }
-      }
-      if (hit != 0x7fffffff) atomicMin(&s_hit[row], hit);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      epi_bar();
-      if (g == 0) {
-        if (lane == 0) {
-#pragma unroll
-          for (int c = 0; c < S::NBOX; ++c) {
-            if (n0 + 32 * c < a.N)
-              asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-                           ::"l"(&tmP), "r"(smem_u32(ubox + c * S::BOX_BYTES + q * 4096)), "r"(n0 + 32 * c), "r"(t), "r"(m0 + q * 32)
-                           : "memory");
-          }
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
-        int fed = -1;
-        const bool m_ok = m < a.M;
-        if (winner && m_ok) {
-          const int h = s_hit[row];
-          int tok = n0 + (h == 0x7fffffff ? 0 : h);
-          if (tok >= a.N) tok = a.N - 1;
-          a.ids[(size_t)m * a.L + t] = tok;
-          fed = tok;
-        }
-        if (a.forced != nullptr) {
-          fed = -1;
-          if (ntile == 0 && m_ok) {
-            const int64_t fz = a.forced[(size_t)m * a.L + t];
-            fed = (fz >= 0 && fz < a.N) ? (int)fz : 0;
-          }
-        }
-        if (x_next != nullptr) {
-          unsigned mask = __ballot_sync(0xffffffffu, fed >= 0);
-          while (mask) {
-            const int src = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const int tok = __shfl_sync(0xffffffffu, fed, src);
-            const float* er = a.embed + (size_t)tok * a.E;
-            float* xr = x_next + (size_t)(m0 + q * 32 + src) * a.E;
-            for (int i = lane; i < (a.E >> 2); i += 32) reinterpret_cast<float4*>(xr)[i] = __ldg(reinterpret_cast<const float4*>(er) + i);
-          }
-        }
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the p tile may be overwritten next step
-      }
-      __threadfence();                                 // ids / x_{t+1} / cleared statistics visible device-wide
-      epi_bar();
-      if (etid == 0) { __threadfence(); atomicAdd(d.counter + 1, 1u); }  // projection-phase arrival of step t
-    } else {
-      // CTA without a projection tile: its arrival only
-      if (etid == 0) atomicAdd(d.counter + 1, 1u);
-    }
-    __syncwarp();
-  }
-#undef VS_CHUNK
-  if (warp >= 2 && g == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-  tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
-  }
-}
 
 }  // namespace tc
 
@@ -972,11 +678,12 @@ extern "C" void gic_vs_stamps_table(int ncta) {
   cudaMemcpy(h, g_stamps, sizeof(h), cudaMemcpyDeviceToHost);
   long long t0 = h[0];
   for (int c = 0; c < ncta; ++c) if (h[c * 16] && h[c * 16] < t0) t0 = h[c * 16];
-  printf("cta start first_ops u_landed pass0 tmem_full pass1 publish polled combine pass2 end (ns since the earliest CTA start)\n");
+  printf("cta start first_ops last_mma u_landed pass0 tmem_full pass1 publish polled combine pass2 rec_seen tail_done end (ns since the earliest CTA start; -1 = not stamped)\n");
   for (int c = 0; c < ncta; ++c) {
     const long long* r = h + c * 16;
-    printf("%3d %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld\n", c, r[0] - t0, r[2] - t0, r[4] - t0, r[5] - t0,
-           r[6] - t0, r[7] - t0, r[8] - t0, r[9] - t0, r[10] - t0, r[11] - t0, r[12] - t0);
+    auto d = [&](int i) { return r[i] ? r[i] - t0 : -1ll; };
+    printf("%3d %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld\n", c, d(0), d(2), d(3), d(4), d(5),
+           d(6), d(7), d(8), d(9), d(10), d(11), d(13), d(14), d(12));
   }
 }
 
@@ -986,7 +693,7 @@ static size_t vs_part_floats(int B, int V) {
   const size_t Mpad = (size_t)cdiv(B, tc::BM) * tc::BM;
   return 2 * Mpad * (size_t)cdiv(V, 128);
 }
-size_t vocab_sample_scratch_floats(int B, int V) { return 2 * vs_part_floats(B, V) + 4; }   // + the persistent decode's grid counter
+size_t vocab_sample_scratch_floats(int B, int V) { return 2 * vs_part_floats(B, V) + 4; }
 
 // One fused decode step on the tensor cores.  handled = false (nothing launched) when the shape does not fit the
 // co-resident grid or TMA's alignment rules; the caller then runs the separate projection + sampler kernels.
@@ -1026,6 +733,9 @@ int vocab_sample_tc(const float* htop, int lda, const float* W_out, const float*
   a.stamps = vs_stamps_buffer();
   a.use_rng = (u_t == nullptr) ? 1 : 0;
   a.rng = rng_state();
+  a.n_rec = 0; a.rec_tiles_n = 1; a.RBN = 16; a.G4 = 0; a.R = nullptr; a.rec_done = nullptr; a.rec_expect = 0u; a.do_cell = 0;
+  a.EW = nullptr; a.b_ih = nullptr; a.b_hh = nullptr; a.c_prev = nullptr; a.c_out = nullptr; a.h_out = nullptr; a.acts = nullptr;
+  a.htop = nullptr;
   if (t == 0) {
     cudaError_t e = cudaMemsetAsync(scratch, 0, 2 * pf * sizeof(float), stream);   // both statistics buffers "not ready"
     if (e != cudaSuccess) { set_error("vocab_sample memset: %s", cudaGetErrorString(e)); return GIC_ERR_CUDA; }
@@ -1033,107 +743,114 @@ int vocab_sample_tc(const float* htop, int lda, const float* W_out, const float*
   int rc;
   const int grid = tiles_m * tiles_n;
   switch (BN) {
-    case 128: rc = launch_vs<128>(ta, tb, tu, tp, a, grid, stream); break;
-    case 160: rc = launch_vs<160>(ta, tb, tu, tp, a, grid, stream); break;
-    case 192: rc = launch_vs<192>(ta, tb, tu, tp, a, grid, stream); break;
-    case 224: rc = launch_vs<224>(ta, tb, tu, tp, a, grid, stream); break;
-    default: rc = launch_vs<256>(ta, tb, tu, tp, a, grid, stream); break;
+    case 128: rc = launch_vs<128>(ta, tb, tu, tp, ta, a, grid, stream); break;
+    case 160: rc = launch_vs<160>(ta, tb, tu, tp, ta, a, grid, stream); break;
+    case 192: rc = launch_vs<192>(ta, tb, tu, tp, ta, a, grid, stream); break;
+    case 224: rc = launch_vs<224>(ta, tb, tu, tp, ta, a, grid, stream); break;
+    default: rc = launch_vs<256>(ta, tb, tu, tp, ta, a, grid, stream); break;
   }
   if (rc == GIC_OK) *handled = true;
   return rc;
 }
 
-template <int BN>
-static cudaError_t launch_dp(const CUtensorMap& tx, const CUtensorMap& th, const CUtensorMap& twi, const CUtensorMap& twh,
-                             const CUtensorMap& tb, const CUtensorMap& tu, const CUtensorMap& tp, const tc::DPArgs& d, int grid,
-                             cudaStream_t s, bool* fits) {
+// ---------------------------------------------------------------------------------------------------------
+// Fused decode step (single layer, Gumbel-softmax mode): projection + sample of step t, the recurrent contraction
+// R = h_t W_hh^T of step t + 1 on the SMs the projection leaves idle, and the LSTM cell of step t + 1 in the tail of the
+// CTA that sampled the row's token (kernel comment at the top of this file).
+//   hs_t1  [B, H]  h after LSTM step t (the projection's and the rec tiles' A operand)
+//   EW     [V, 4H] embed W_ih^T (decode_step_prepare), R [B, 4H] scratch, rec_done: tiles_m counters zeroed by the caller
+//          before step 0, `scratch` as vocab_sample_tc (zeroed by this function at t == 0)
+//   last != 0: no next step -- the kernel degenerates to the plain projection + sample.
+// decode_step_plan says whether the shape fits (co-resident grid: projection tiles + at least ceil(4H / 256) rec tiles per
+// row block <= SMs); the caller falls back to lstm_step_tc + vocab_sample_tc otherwise.
+// ---------------------------------------------------------------------------------------------------------
+struct DecodeStepPlan { int BN, tiles_m, tiles_n, rec_tiles_n, RBN; };
+
+static bool decode_step_plan_impl(int B, int V, int H, DecodeStepPlan* p) {
   using namespace tc;
-  using S = VSCfg<BN>;
-  static int max_blocks = -1;
-  if (max_blocks < 0) {
-    cudaFuncSetAttribute(decode_persistent_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_persistent_kernel<BN>, VS_THREADS, S::TOTAL) != cudaSuccess) {
-      cudaGetLastError();
-      per_sm = 0;
-    }
-    max_blocks = per_sm * num_sms();
+  if (B <= 0 || V <= 0 || H <= 0 || (V % 4) || (H % 32)) return false;
+  const int tiles_m = cdiv(B, BM);
+  if (tiles_m > 64) return false;
+  const int G = num_sms(), G4 = 4 * H;
+  static const int kBN[6] = {128, 160, 192, 224, 256, 0};
+  for (int i = 0; kBN[i]; ++i) {
+    const int tiles_v = tiles_m * cdiv(V, kBN[i]);
+    const int spare = G - tiles_v;
+    if (spare < tiles_m * cdiv(G4, 256)) continue;
+    int per = spare / tiles_m;                                   // rec tiles per row block
+    if (per > G4 / 32) per = G4 / 32;                            // no narrower than 32 columns
+    int RBN = ((cdiv(G4, per) + 15) / 16) * 16;
+    if (RBN > 256) RBN = 256;
+    p->BN = kBN[i]; p->tiles_m = tiles_m; p->tiles_n = cdiv(V, kBN[i]); p->RBN = RBN; p->rec_tiles_n = cdiv(G4, RBN);
+    return true;
   }
-  *fits = grid <= max_blocks;                 // the grid-wide barriers need every CTA resident
-  if (!*fits) return cudaSuccess;
-  decode_persistent_kernel<BN><<<grid, VS_THREADS, S::TOTAL, s>>>(tx, th, twi, twh, tb, tu, tp, d);
-  return cudaGetLastError();
+  return false;
+}
+bool decode_step_plan(int B, int V, int H) {
+  { const char* e = getenv("GIC_FUSED_SAMPLE"); if (e && e[0] == '0') return false; }     // read per call: tests toggle them
+  { const char* e = getenv("GIC_DECODE_STEP"); if (e && e[0] == '0') return false; }
+  DecodeStepPlan p;
+  return decode_step_plan_impl(B, V, H, &p);
+}
+size_t decode_step_scratch_floats(int B, int V, int H) {          // EW | R | rec_done counters
+  return ((size_t)V * 4 * H + (size_t)B * 4 * H + 64 + 3) & ~(size_t)3;
 }
 
-// All L steps of Decoder.sample in one persistent launch (single layer, no attention, Gumbel-softmax mode).  xs / hs / cs /
-// acts / htop are the decode's saved-for-backward buffers (xs[0] = features, hs[0] = cs[0] = 0 on entry).  handled = false
-// (nothing launched) when the shape does not fit; the caller then runs the per-step kernels.
-int decode_persistent_tc(const float* W_ih, const float* W_hh, const float* b_ih, const float* b_hh, const float* W_out,
-                         const float* b_out, const float* u, float T, const float* T_dev, int B, int L, int V, int E, int H,
-                         float* out, int64_t* ids, const int64_t* forced, const float* embed, float* xs, float* hs, float* cs,
-                         float* acts, float* htop, float* scratch, cudaStream_t stream, bool* handled) {
+int decode_step_tc(const float* hs_t1, const float* W_out, const float* b_out, const float* W_hh, const float* b_ih,
+                   const float* b_hh, const float* EW, float* R, unsigned int* rec_done, const float* u_t, float T,
+                   const float* T_dev, int B, int V, int H, int L, int t, int last, float* out, int64_t* ids,
+                   const int64_t* forced, const float* embed, int E, float* x_next, const float* c_prev, float* c_out,
+                   float* h_out, float* acts, float* htop, float* scratch, cudaStream_t stream, bool* handled) {
   extern RngState rng_state();
   using namespace tc;
   *handled = false;
-  // Measured at c2 (bench43_dp*.log): decode 0.891 ms against 0.759 ms for the 2 L per-step kernels, step 2.518 vs 2.425 ms.
-  // Replayed from a CUDA graph, a kernel boundary of the decode chain costs less than a grid-wide arrival / acquire round
-  // through L2 (two per step here, on top of the statistics exchange inside the projection phase), and the phases of a
-  // resident CTA cannot overlap the way consecutive kernels' tails and heads do.  Opt-in (GIC_DECODE_PERSISTENT=1); read
-  // per call so that the tests can toggle it.
-  { const char* e = getenv("GIC_DECODE_PERSISTENT"); if (!(e && e[0] == '1')) return GIC_OK; }
-  { const char* e = getenv("GIC_FUSED_SAMPLE"); if (e && e[0] == '0') return GIC_OK; }
-  { const char* e = getenv("GIC_LSTM_SPLITK"); if (e && e[0] == '1') return GIC_OK; }
-  if (B <= 0 || L < 1 || (V % 4) || (H % 32) || (E % 32) || (((size_t)L * V) % 4) || vs_stamps_buffer()) return GIC_OK;
-  const void* ptrs[] = {W_ih, W_hh, b_ih, b_hh, W_out, b_out, out, embed, xs, hs, cs, htop, acts ? acts : hs, u ? u : hs};
+  DecodeStepPlan pl;
+  if (!decode_step_plan_impl(B, V, H, &pl)) return GIC_OK;
+  const void* ptrs[] = {hs_t1, W_out, b_out, W_hh, b_ih, b_hh, EW, R, out, c_prev, c_out, h_out, acts, htop, u_t ? u_t : out};
   for (const void* p : ptrs)
     if (!aligned16(p)) return GIC_OK;
-  const int G = num_sms();
-  const int tiles_m = cdiv(B, BM);
-  static const int kBN[6] = {128, 160, 192, 224, 256, 0};
-  int BN = 0;
-  for (int i = 0; kBN[i]; ++i)
-    if ((long long)tiles_m * cdiv(V, kBN[i]) <= G) { BN = kBN[i]; break; }
-  if (!BN) return GIC_OK;
-  int U = 8;
-  while (U <= 32 && ((H % U) || (long long)tiles_m * (H / U) > G)) U *= 2;
-  if (U > 32) return GIC_OK;
-  const int tiles_n = cdiv(V, BN), tiles_v = tiles_m * tiles_n, l_tiles_n = H / U, tiles_l = tiles_m * l_tiles_n;
-  const int grid = tiles_v > tiles_l ? tiles_v : tiles_l;
+  if (((size_t)L * V) % 4) return GIC_OK;
   const bool rn = tf32_round_in_tma();
-  CUtensorMap tx, th, twi, twh, tb, tu, tp;
-  bool ok = make_map(&tx, xs, L * B, E, E, BK, BM, rn, false) && make_map(&th, hs, (L + 1) * B, H, H, BK, BM, rn, false) &&
-            make_map(&twi, W_ih, 4 * H, E, E, BK, U, rn, false) && make_map(&twh, W_hh, 4 * H, H, H, BK, U, rn, false) &&
-            make_map(&tb, W_out, V, H, H, BK, BN, rn, false) &&
-            make_map(&tu, u ? u : out, u ? L * B : B, V, V, 32, BM, false, false) &&
-            make_map_3d(&tp, out, V, L, B, V, (long long)L * V, 32, 1, 32);
+  CUtensorMap ta, tb, tu, tp, tw;
+  bool ok = make_map(&ta, hs_t1, B, H, H, BK, BM, rn, false) && make_map(&tb, W_out, V, H, H, BK, pl.BN, rn, false) &&
+            make_map(&tu, u_t ? u_t : out, B, V, V, 32, BM, false, false) &&
+            make_map(&tp, out + (size_t)t * V, B, V, L * V, 32, 32, false, false) &&
+            make_map(&tw, W_hh, 4 * H, H, H, BK, pl.RBN, rn, false);
   if (!ok) return GIC_OK;
-  DPArgs d;
-  VSArgs& a = d.v;
-  a.M = B; a.N = V; a.K = H; a.tiles_n = tiles_n; a.Mpad = tiles_m * BM;
-  a.bias = b_out; a.T = T; a.T_dev = T_dev; a.part = nullptr; a.part_next = nullptr;
-  a.ids = ids; a.forced = forced; a.L = L; a.t = 0; a.embed = embed; a.E = E; a.x_next = nullptr; a.stamps = nullptr;
-  a.use_rng = (u == nullptr) ? 1 : 0;
-  a.rng = rng_state();
-  d.B = B; d.H = H; d.In = E; d.U = U; d.l_tiles_n = l_tiles_n; d.tiles_l = tiles_l; d.tiles_v = tiles_v; d.L = L;
-  d.b_ih = b_ih; d.b_hh = b_hh; d.cs = cs; d.hs = hs; d.acts = acts; d.htop = htop; d.xs = xs;
+  VSArgs a;
+  a.M = B; a.N = V; a.K = H; a.tiles_n = pl.tiles_n; a.Mpad = pl.tiles_m * BM;
+  a.bias = b_out; a.T = T; a.T_dev = T_dev;
   const size_t pf = vs_part_floats(B, V);
-  d.part0 = reinterpret_cast<float2*>(scratch);
-  d.part1 = reinterpret_cast<float2*>(scratch + pf);
-  d.counter = reinterpret_cast<unsigned int*>(scratch + 2 * pf);
-  cudaError_t e = cudaMemsetAsync(scratch, 0, (2 * pf + 4) * sizeof(float), stream);   // statistics "not ready", counter 0
-  if (e != cudaSuccess) { set_error("decode_persistent memset: %s", cudaGetErrorString(e)); return GIC_ERR_CUDA; }
-  bool fits = false;
-  ProfScope prof(PROF_VOCAB_SAMPLE, 8.0 * B * V * L, stream);        // the whole decode is one launch of this class
-  switch (BN) {
-    case 128: e = launch_dp<128>(tx, th, twi, twh, tb, tu, tp, d, grid, stream, &fits); break;
-    case 160: e = launch_dp<160>(tx, th, twi, twh, tb, tu, tp, d, grid, stream, &fits); break;
-    case 192: e = launch_dp<192>(tx, th, twi, twh, tb, tu, tp, d, grid, stream, &fits); break;
-    case 224: e = launch_dp<224>(tx, th, twi, twh, tb, tu, tp, d, grid, stream, &fits); break;
-    default: e = launch_dp<256>(tx, th, twi, twh, tb, tu, tp, d, grid, stream, &fits); break;
+  a.part = reinterpret_cast<float2*>(scratch + (size_t)(t & 1) * pf);
+  a.part_next = reinterpret_cast<float2*>(scratch + (size_t)((t + 1) & 1) * pf);
+  a.ids = ids; a.forced = forced; a.L = L; a.t = t; a.embed = embed; a.E = E; a.x_next = x_next;
+  a.stamps = nullptr;
+  if (long long* sb = vs_stamps_buffer()) {       // debug timeline of ONE step (GIC_VS_STAMPS=1, GIC_VS_STAMPS_T=t; default L - 2)
+    const char* e = getenv("GIC_VS_STAMPS_T");
+    if (t == (e ? atoi(e) : L - 2)) a.stamps = sb;
   }
-  if (e != cudaSuccess) { set_error("decode_persistent_kernel launch: %s", cudaGetErrorString(e)); return GIC_ERR_CUDA; }
-  if (fits) *handled = true;
-  return GIC_OK;
+  a.use_rng = (u_t == nullptr) ? 1 : 0;
+  a.rng = rng_state();
+  a.n_rec = last ? 0 : pl.tiles_m * pl.rec_tiles_n;
+  a.rec_tiles_n = pl.rec_tiles_n; a.RBN = pl.RBN; a.G4 = 4 * H; a.R = R; a.rec_done = rec_done;
+  a.rec_expect = (unsigned int)(t + 1) * (unsigned int)pl.rec_tiles_n;
+  a.do_cell = last ? 0 : 1;
+  a.EW = EW; a.b_ih = b_ih; a.b_hh = b_hh; a.c_prev = c_prev; a.c_out = c_out; a.h_out = h_out; a.acts = acts; a.htop = htop;
+  if (t == 0) {
+    cudaError_t e = cudaMemsetAsync(scratch, 0, 2 * pf * sizeof(float), stream);   // both statistics buffers "not ready"
+    if (e != cudaSuccess) { set_error("decode_step memset: %s", cudaGetErrorString(e)); return GIC_ERR_CUDA; }
+  }
+  int rc;
+  const int grid = a.n_rec + pl.tiles_m * pl.tiles_n;
+  switch (pl.BN) {
+    case 128: rc = launch_vs<128>(ta, tb, tu, tp, tw, a, grid, stream); break;
+    case 160: rc = launch_vs<160>(ta, tb, tu, tp, tw, a, grid, stream); break;
+    case 192: rc = launch_vs<192>(ta, tb, tu, tp, tw, a, grid, stream); break;
+    case 224: rc = launch_vs<224>(ta, tb, tu, tp, tw, a, grid, stream); break;
+    default: rc = launch_vs<256>(ta, tb, tu, tp, tw, a, grid, stream); break;
+  }
+  if (rc == GIC_OK) *handled = true;
+  return rc;
 }
 
 }  // namespace gic

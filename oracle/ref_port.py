@@ -166,7 +166,7 @@ def gumbel_noise(u: Tensor, eps: float = 1e-10) -> Tensor:
 
 def decoder_sample(p: Params, features: Tensor, u: Optional[Tensor], temperature: float,
                    L: int, layers: int = 1, pretrain: bool = False,
-                   forced_ids: Optional[Tensor] = None):
+                   forced_ids: Optional[Tensor] = None, return_hidden: bool = False):
     """Decoder.sample (src/generator.py:55-81).  Returns (outputs[B,L,V], ids[B,L], logits[B,L,V]).
 
     ``forced_ids`` (teacher forcing for parity runs, SURVEY.md §7 "hard parts"): the token fed
@@ -177,7 +177,7 @@ def decoder_sample(p: Params, features: Tensor, u: Optional[Tensor], temperature
     h = [features.new_zeros(B, H) for _ in range(layers)]
     c = [features.new_zeros(B, H) for _ in range(layers)]
     x = features
-    outs, ids, logit_list = [], [], []
+    outs, ids, logit_list, hid = [], [], [], []
     for t in range(L):
         inp = x
         for l in range(layers):
@@ -187,6 +187,7 @@ def decoder_sample(p: Params, features: Tensor, u: Optional[Tensor], temperature
             inp = h[l]
         logits = F.linear(inp, p["decoder.linear.weight"], p["decoder.linear.bias"])   # :64,68
         logit_list.append(logits)
+        hid.append(inp)
         if pretrain:
             outs.append(logits)                                                       # :65
             pred = F.softmax(logits, dim=-1)                                          # :66
@@ -197,6 +198,8 @@ def decoder_sample(p: Params, features: Tensor, u: Optional[Tensor], temperature
         ids.append(tok)
         fed = tok if forced_ids is None else forced_ids[:, t]
         x = p["decoder.embed.weight"][fed.detach()]                                   # :75
+    if return_hidden:      # top-layer hidden states [B,L,H]: the tests derive per-row rounding bounds on the logits from them
+        return torch.stack(outs, 1), torch.stack(ids, 1), torch.stack(logit_list, 1), torch.stack(hid, 1)
     return torch.stack(outs, 1), torch.stack(ids, 1), torch.stack(logit_list, 1)
 
 
@@ -235,7 +238,7 @@ def disc_forward(p: Params, inp: Tensor, keep: Optional[Tensor], filter_sizes: S
     z = F.linear(yd, p["feature2out.weight"], p["feature2out.bias"])  # :58
     logits = F.linear(z, p["out2logits.weight"], p["out2logits.bias"]).squeeze(1)  # :60
     if return_parts:
-        return logits, dict(emb=emb, pooled=x, highway=y)
+        return logits, dict(emb=emb, pooled=x, highway=y, hw=hw)
     return logits
 
 
@@ -330,8 +333,8 @@ def adversarial_step(inp: dict, temperature: float, loss_type: str = "standard",
     B, L = caps.shape
     fs = a.disc_filter_sizes
     feats = encoder_project(gp, inp["pooled"]) if a.conditional_gan else start_features(gp, B)   # :144-147
-    probs, ids, logits = decoder_sample(gp, feats, inp["u"], temperature, L, a.gen_num_layers,
-                                        forced_ids=forced_ids)                                 # :150
+    probs, ids, logits, htop = decoder_sample(gp, feats, inp["u"], temperature, L, a.gen_num_layers,
+                                              forced_ids=forced_ids, return_hidden=True)       # :150
     fake = probs.detach()                                                                       # :151
     real = F.one_hot(caps, a.vocab_size).float()                                                # :158
     keep = inp["keep"] if train else [None, None, None]
@@ -339,7 +342,7 @@ def adversarial_step(inp: dict, temperature: float, loss_type: str = "standard",
     d_fake = disc_forward(dp, fake, keep[1], fs)                                                # :163
     g_out = disc_forward(dp, probs, keep[2], fs)                                                # :164
     g_loss, d_loss = get_losses(d_real, d_fake, g_out, loss_type)                               # :165
-    out = dict(features=feats.detach(), probs=probs.detach(), ids=ids, logits=logits.detach(),
+    out = dict(features=feats.detach(), probs=probs.detach(), ids=ids, logits=logits.detach(), htop=htop.detach(),
                d_real=d_real.detach(), d_fake=d_fake.detach(), g_out=g_out.detach(),
                g_loss=g_loss.detach(), d_loss=d_loss.detach())
     if not train:
