@@ -8,6 +8,7 @@
 namespace gic {
 // decode.cu
 int gather_rows(const float*, const int64_t*, int, int, int, float*, cudaStream_t);
+int vec_add(const float*, const float*, int, float*, cudaStream_t);
 int sample_step(bool, const float*, const float*, float, int, int, int, int, float*, int64_t*, const int64_t*,
                 const float*, int, float*, cudaStream_t, bool fast_math = false);
 int softmax_bwd(const float*, const float*, float, int, int, float*, cudaStream_t);
@@ -42,8 +43,7 @@ int bptt_persistent_tc(float* dG, const float* W_hh, const float* acts, const fl
 // vocab_sample_tcgen05.cu: fused decode step (projection + sample of step t, recurrent contraction and cell of step t + 1)
 bool decode_step_plan(int B, int V, int H);
 size_t decode_step_scratch_floats(int B, int V, int H);
-int decode_step_tc(const float* hs_t1, const float* W_out, const float* b_out, const float* W_hh, const float* b_ih,
-                   const float* b_hh, const float* EW, float* R, unsigned int* rec_done, const float* u_t, float T,
+int decode_step_tc(const float* hs_t1, const float* W_out, const float* b_out, const float* W_hh, const float* EW, float* R, unsigned int* rec_done, const float* u_t, float T,
                    const float* T_dev, int B, int V, int H, int L, int t, int last, float* out, int64_t* ids,
                    const int64_t* forced, const float* embed, int E, float* x_next, const float* c_prev, float* c_out,
                    float* h_out, float* acts, float* htop, float* scratch, cudaStream_t stream, bool* handled);
@@ -177,18 +177,21 @@ static int decode_fwd(int mode, const float* features, const float* W_emb, const
     float* EW = ds;
     float* R = EW + (size_t)V * 4 * H;
     unsigned int* rec_done = reinterpret_cast<unsigned int*>(R + (size_t)B * 4 * H);
+    float* bsum = R + (size_t)B * 4 * H + 64;
     bool ok0 = false;
     GIC_TRY(lstm_step_tc(saved + sv.xs, E, saved + sv.hs(0), W_ih[0], W_hh[0], b_ih[0], b_hh[0], saved + sv.cs(0), B, H,
                          saved + sv.acts(0), saved + sv.cs(0) + BH, saved + sv.hs(0) + BH, saved + sv.htop, L, 0, s, &ok0));
     if (ok0) {
-      if (L > 1)
-        GIC_TRY(gemm(mode, false, true, V, 4 * H, E, 1.f, W_emb, E, W_ih[0], E, 0.f, EW, 4 * H, nullptr, s, PROF_GEMM_DECODE));
+      if (L > 1) {
+        GIC_TRY(vec_add(b_ih[0], b_hh[0], 4 * H, bsum, s));
+        GIC_TRY(gemm(mode, false, true, V, 4 * H, E, 1.f, W_emb, E, W_ih[0], E, 0.f, EW, 4 * H, bsum, s, PROF_GEMM_DECODE));
+      }
       cudaMemsetAsync(rec_done, 0, 64 * sizeof(unsigned int), s);
       for (int t = 0; t < L; ++t) {
         const int last = (t + 1 == L);
         bool done = false;
         ProfScope prof(PROF_VOCAB_SAMPLE, 8.0 * B * V, s);
-        GIC_TRY(decode_step_tc(saved + sv.hs(0) + (size_t)(t + 1) * BH, W_out, b_out, W_hh[0], b_ih[0], b_hh[0], EW, R, rec_done,
+        GIC_TRY(decode_step_tc(saved + sv.hs(0) + (size_t)(t + 1) * BH, W_out, b_out, W_hh[0], EW, R, rec_done,
                                u ? u + (size_t)t * B * V : nullptr, T, temperature_device(), B, V, H, L, t, last, out, ids, forced,
                                W_emb, E, last ? nullptr : saved + sv.xs + (size_t)(t + 1) * BE,
                                saved + sv.cs(0) + (size_t)(t + 1) * BH, saved + sv.cs(0) + (size_t)(t + 2) * BH,

@@ -844,6 +844,14 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ y, const float* __
   }
   if (lane == 0) { dgamma[j] = sdx * grad_share; dbeta[j] = sd * grad_share; }
 }
+__global__ void vec_add_kernel(const float* __restrict__ a, const float* __restrict__ b, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + b[i];
+}
+int vec_add(const float* a, const float* b, int n, float* out, cudaStream_t s) {
+  vec_add_kernel<<<cdiv(n, 256), 256, 0, s>>>(a, b, n, out);
+  return check_launch("vec_add_kernel");
+}
 // BatchNorm1d bookkeeping of a training-mode forward (src/generator.py:16: momentum 0.01): running_mean / running_var
 // move towards the batch mean / UNBIASED batch variance, num_batches_tracked += 1.  count = rows the statistics ran over.
 __global__ void bn_running_update_kernel(const float* __restrict__ save_mean, const float* __restrict__ save_rstd, int E,

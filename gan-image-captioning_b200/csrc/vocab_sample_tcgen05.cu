@@ -26,8 +26,8 @@
 //     tiles of R = h_t W_hh^T, same A operand and pipeline as the projection tiles, accumulator stored to global memory,
 //     one arrival per tile on a per-row-block counter;
 //   * a cell tail in the projection tiles: the CTA that ends up holding a row's maximum (= knows tok_t) waits for the
-//     row block's rec tiles, adds the token's row of EW = embed W_ih^T (a [V, 4H] table rebuilt once per decode,
-//     decode_step_tc) and the biases, applies the LSTM cell and writes h_{t+1}, c_{t+1}, the saved activations and
+//     row block's rec tiles, adds the token's row of EW = embed W_ih^T + b_ih + b_hh (a [V, 4H] table rebuilt once per
+//     decode by the caller), applies the LSTM cell and writes h_{t+1}, c_{t+1}, the saved activations and
 //     htop -- one warp per row, rows dealt over all 16 epilogue warps.
 // One launch per decode step instead of two, and the recurrent contraction runs UNDER the projection instead of after it.
 #include "tcgen05_common.cuh"
@@ -78,9 +78,7 @@ struct VSArgs {
   unsigned int* rec_done;     // [tiles_m] arrivals of rec tiles (monotonic over the steps of one decode)
   unsigned int rec_expect;    // value rec_done[mtile] has reached when this launch's rec tiles of the row block are done
   int do_cell;                // apply the LSTM cell of step t + 1 for the rows whose token this CTA feeds back
-  const float* EW;            // [V, 4H] embed W_ih^T
-  const float* b_ih;          // [4H]
-  const float* b_hh;          // [4H]
+  const float* EW;            // [V, 4H] embed W_ih^T + b_ih + b_hh
   const float* c_prev;        // [M, H] c_t
   float* c_out;               // [M, H] c_{t+1}
   float* h_out;               // [M, H] h_{t+1}
@@ -97,7 +95,7 @@ struct RecCfg {               // operand ring of a rec tile: it has no u / p til
 };
 constexpr int VS_NBAR = 8;    // mbarrier slots per direction (>= the stages of either ring)
 
-#define VS_STAMP(i) do { if (a.stamps) a.stamps[blockIdx.x * 16 + (i)] = (long long)globaltimer_ns(); } while (0)
+#define VS_STAMP(i) do { if (a.stamps) a.stamps[blockIdx.x * 32 + (i)] = (long long)globaltimer_ns(); } while (0)
 
 __device__ __forceinline__ float2 ld_relaxed_f2(const float2* p) {
   float2 v;
@@ -119,6 +117,89 @@ constexpr int VS_EPI_THREADS = 128 * VS_G;
 constexpr int VS_THREADS = 64 + VS_EPI_THREADS;      // warp 0 = TMA producer, warp 1 = MMA issuer, 16 epilogue warps
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(VS_EPI_THREADS) : "memory"); }
+
+// LSTM cell of step t + 1 for the rows a projection tile feeds back (fused decode step), and the next-step input
+// x_{t+1} = embed[fed].  A team of four warps per row, four rows at a time; every lane issues all loads of its four hidden
+// units at once as 16-byte loads -- the token's row of EW (biases folded in), c_t, R -- so a row costs ONE round trip to L2 /
+// HBM.  (Thread-per-unit with 4-byte loads, four rows per thread, was measured slower: four times the load instructions.)
+// Activations use the MUFU forms (ex2 + rcp; |error| ~3e-7, far below the TF32 rounding of the pre-activations).
+// The FIRST pass (rows 0..3 of the tile's list, one per team, units 0..511) is inlined into the kernel's epilogue, where its
+// loads are issued BEFORE the normalisation pass and the p tile's TMA stores and consumed after them.  The out-of-line
+// function is the remainder: further rows (a tile rarely wins more than four), hidden units beyond 512, x_{t+1} when it did
+// not ride along, and the whole job for the plain projection + sample kernel (x_{t+1} only).
+struct CellTailArgs {       // by value: a reference to the kernel's parameter block would force a local-memory copy of it
+  const float* embed; float* x_next; const float* R; const float* EW; const float* c_prev;
+  float* c_out; float* h_out; float* acts; float* htop;
+  int E, G4, L, t, do_cell;
+};
+__device__ __forceinline__ float sigmoid_mufu(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_mufu(float x) { return 2.f * __fdividef(1.f, 1.f + __expf(-2.f * x)) - 1.f; }
+
+// four hidden units (j .. j+3) of one row: pre-activations = EW row + R row, cell, stores
+__device__ __forceinline__ void lstm_cell_store4(const CellTailArgs& a, int H, int mr, int j, const float4 (&ev)[4], const float4 (&rv)[4],
+                                                 float4 cp) {
+  float ai[4], af[4], ag[4], ao[4], cn[4], hn[4];
+  const float pi[4] = {ev[0].x + rv[0].x, ev[0].y + rv[0].y, ev[0].z + rv[0].z, ev[0].w + rv[0].w};
+  const float pf[4] = {ev[1].x + rv[1].x, ev[1].y + rv[1].y, ev[1].z + rv[1].z, ev[1].w + rv[1].w};
+  const float pg[4] = {ev[2].x + rv[2].x, ev[2].y + rv[2].y, ev[2].z + rv[2].z, ev[2].w + rv[2].w};
+  const float po[4] = {ev[3].x + rv[3].x, ev[3].y + rv[3].y, ev[3].z + rv[3].z, ev[3].w + rv[3].w};
+  const float cpv[4] = {cp.x, cp.y, cp.z, cp.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    ai[e] = sigmoid_mufu(pi[e]); af[e] = sigmoid_mufu(pf[e]); ag[e] = tanh_mufu(pg[e]); ao[e] = sigmoid_mufu(po[e]);
+    cn[e] = af[e] * cpv[e] + ai[e] * ag[e];
+    hn[e] = ao[e] * tanh_mufu(cn[e]);
+  }
+  float* arow = a.acts + (size_t)mr * a.G4 + j;
+  *reinterpret_cast<float4*>(arow) = make_float4(ai[0], ai[1], ai[2], ai[3]);
+  *reinterpret_cast<float4*>(arow + H) = make_float4(af[0], af[1], af[2], af[3]);
+  *reinterpret_cast<float4*>(arow + 2 * H) = make_float4(ag[0], ag[1], ag[2], ag[3]);
+  *reinterpret_cast<float4*>(arow + 3 * H) = make_float4(ao[0], ao[1], ao[2], ao[3]);
+  *reinterpret_cast<float4*>(a.c_out + (size_t)mr * H + j) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+  const float4 h4 = make_float4(hn[0], hn[1], hn[2], hn[3]);
+  *reinterpret_cast<float4*>(a.h_out + (size_t)mr * H + j) = h4;
+  *reinterpret_cast<float4*>(a.htop + ((size_t)mr * a.L + (a.t + 1)) * H + j) = h4;
+}
+
+// Remainder of the cell (see the comment above CellTailArgs).  A team of four warps per row; lane tl of the team owns the
+// hidden units 4 tl .. 4 tl + 3 (+ 512 per further pass over H).  first_done: the epilogue already handled the units
+// [0, 512) of the rows s_list[0..3] (one row per team) and, if x_first_done, their x.
+__device__ __noinline__ void decode_cell_tail(const CellTailArgs a, int etid, int m0, const int* s_list, const int* s_fed,
+                                              int nrows, bool first_done, bool x_first_done) {
+  const int team = etid >> 7, tl = etid & 127;
+  if (a.do_cell) {
+    const int H = a.G4 >> 2;
+    for (int i = team; i < nrows; i += VS_G) {
+      const int r = s_list[i];
+      const int mr = m0 + r, tok = s_fed[r];
+      const float* Er = a.EW + (size_t)tok * a.G4;
+      const float* Rr = a.R + (size_t)mr * a.G4;
+      for (int j = 4 * tl + ((first_done && i < VS_G) ? 4 * 128 : 0); j < H; j += 4 * 128) {
+        float4 ev[4], rv[4];
+#pragma unroll
+        for (int gt = 0; gt < 4; ++gt) {
+          ev[gt] = __ldcg(reinterpret_cast<const float4*>(Er + gt * H + j));
+          rv[gt] = __ldcg(reinterpret_cast<const float4*>(Rr + gt * H + j));
+        }
+        const float4 cp = __ldcg(reinterpret_cast<const float4*>(a.c_prev + (size_t)mr * H + j));
+        lstm_cell_store4(a, H, mr, j, ev, rv, cp);
+      }
+    }
+  }
+  // x_{t+1} = embed[fed]
+  if (a.x_next != nullptr) {
+    const bool vec = ((a.E & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.embed) & 15u) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(a.x_next) & 15u) == 0);
+    for (int i = team; i < nrows; i += VS_G) {
+      if (x_first_done && i < VS_G) continue;
+      const int r = s_list[i];
+      const float* er = a.embed + (size_t)s_fed[r] * a.E;
+      float* xr = a.x_next + (size_t)(m0 + r) * a.E;
+      if (vec) { for (int c = tl; c < (a.E >> 2); c += 128) reinterpret_cast<float4*>(xr)[c] = __ldcg(reinterpret_cast<const float4*>(er) + c); }
+      else { for (int c = tl; c < a.E; c += 128) xr[c] = __ldg(er + c); }
+    }
+  }
+}
 
 template <int BN>
 __global__ void __launch_bounds__(VS_THREADS, 1)
@@ -143,7 +224,8 @@ vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   int* s_fed = s_hit + BM;                                                    // token this CTA feeds back for the row, or -1
   int* s_list = s_fed + BM;                                                   // rows this CTA feeds back, compacted
   int* s_cnt = s_list + BM;                                                   // their number
-  static_assert(VS_G * BM * 8 + VS_G * BM * 16 + 3 * BM * 4 + 16 <= S::STAGE, "vocab_sample: exchange buffers exceed one stage");
+  static_assert(VS_G * BM * 8 + VS_G * BM * 16 + 3 * BM * 4 + 16 <= 16384, "vocab_sample: exchange buffers exceed 16 KB");
+  static_assert(16384 + ((BN / 16 + VS_G - 1) / VS_G) * VS_EPI_THREADS * 4 <= S::STAGE, "vocab_sample: per-unit running maxima exceed stage 0");
   // "this row block's rec tiles have arrived": set by the producer thread (idle once its loads are issued), read by the
   // cell tail; lives next to the mbarriers because the operand ring is still in use when it may be set
   uint32_t* s_recflag = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(full) + 192);
@@ -326,11 +408,14 @@ vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     unsigned long long rseed = 0ull, roff = 0ull;
     if (a.use_rng) rng_load(a.rng, rseed, roff); else mbar_wait(u_full, 0);
     if (etid == 0) VS_STAMP(4);
-#pragma unroll
+    // (the unit loops of the three passes are deliberately NOT unrolled: fully unrolled this kernel was 107 KB of SASS, every
+    //  pass straight-line code that a warp executes once per launch, and ncu showed an instruction-cache hit rate of 66 %
+    //  with "no instruction" the second largest stall reason -- the epilogue was fetch-bound, not math-bound)
+#pragma unroll 1
     for (int i = 0; i < MAXU; ++i) {
       const int j = g + i * VS_G;
       if (j < NUNIT && n0 + 16 * j < a.N) {
-#pragma unroll
+#pragma unroll 1
         for (int k = 0; k < 4; ++k) {
           float4* sp = reinterpret_cast<float4*>(VS_CHUNK(j, k));
           float4 u4;
@@ -359,11 +444,10 @@ vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tcgen05_fence_after();
     const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     float m_run = -INFINITY, s_run = 0.f;
-    float mrun_u[MAXU];
-#pragma unroll
+    float* s_mrun = reinterpret_cast<float*>(smem + 16384) + etid;    // [MAXU][VS_EPI_THREADS]: running max after each of this thread's units
+#pragma unroll 1
     for (int i = 0; i < MAXU; ++i) {
       const int j = g + i * VS_G;
-      mrun_u[i] = -INFINITY;
       if (j < NUNIT) {                                 // warp-uniform
         uint32_t r[16];
         tmem_ld16(t_addr + 16 * j, r);
@@ -397,7 +481,7 @@ vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int e = 0; e < 16; ++e) z[e] = 0.f;
         }
-        mrun_u[i] = m_run;
+        s_mrun[i * VS_EPI_THREADS] = m_run;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           *reinterpret_cast<float4*>(VS_CHUNK(j, k)) = make_float4(z[4 * k + 0], z[4 * k + 1], z[4 * k + 2], z[4 * k + 3]);
@@ -483,46 +567,31 @@ vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const bool winner = (jbest == ntile);
     if (etid == 0) VS_STAMP(10);
 
-    // ---- pass 2: p = e * exp(m_running - M) / S in shared memory; first-max column in the winner tile
-    int hit = 0x7fffffff;
-#pragma unroll
-    for (int i = 0; i < MAXU; ++i) {
-      const int j = g + i * VS_G;
-      if (j < NUNIT && n0 + 16 * j < a.N) {
-        const float f = __expf(mrun_u[i] - M) * inv;
-        const bool may_hit = winner && (mrun_u[i] == M) && (hit == 0x7fffffff);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float4* sp = reinterpret_cast<float4*>(VS_CHUNK(j, k));
-          float4 e = *sp;
-          if (may_hit && hit == 0x7fffffff) {
+    // ---- first-max column of the rows this tile won, BEFORE the normalisation pass: the token -- and with it the gather
+    //      loads of the cell below -- is known one pass earlier.  e == 1 marks a column that equals the running maximum of
+    //      its unit; the first such column of the first unit whose running maximum is the row maximum M is the first maximum.
+    if (winner) {
+      int hit = 0x7fffffff;
+#pragma unroll 1
+      for (int i = 0; i < MAXU && hit == 0x7fffffff; ++i) {
+        const int j = g + i * VS_G;
+        if (j < NUNIT && n0 + 16 * j < a.N && s_mrun[i * VS_EPI_THREADS] == M) {
+#pragma unroll 1
+          for (int k = 0; k < 4 && hit == 0x7fffffff; ++k) {
+            const float4 e = *reinterpret_cast<const float4*>(VS_CHUNK(j, k));
             if (e.x == 1.0f) hit = 16 * j + 4 * k;
             else if (e.y == 1.0f) hit = 16 * j + 4 * k + 1;
             else if (e.z == 1.0f) hit = 16 * j + 4 * k + 2;
             else if (e.w == 1.0f) hit = 16 * j + 4 * k + 3;
           }
-          e.x *= f; e.y *= f; e.z *= f; e.w *= f;
-          *sp = e;
         }
       }
+      if (hit != 0x7fffffff) atomicMin(&s_hit[row], hit);
     }
-    if (hit != 0x7fffffff) atomicMin(&s_hit[row], hit);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    if (etid == 0) VS_STAMP(11);
     epi_bar();
 
-    // ---- TMA stores of the finished tile (one 32 x 32 box per quarter and column box), token id, next-step input
+    // ---- token id and the rows this CTA feeds back to the next step
     if (g == 0) {
-      if (lane == 0) {
-#pragma unroll
-        for (int c = 0; c < S::NBOX; ++c) {
-          if (n0 + 32 * c < a.N)
-            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                         ::"l"(&tmP), "r"(smem_u32(ubox + c * S::BOX_BYTES + q * 4096)), "r"(n0 + 32 * c), "r"(m0 + q * 32)
-                         : "memory");
-        }
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      }
       int fed = -1;
       const bool m_ok = m < a.M;
       if (winner && m_ok) {
@@ -543,86 +612,90 @@ vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (fed >= 0) s_list[atomicAdd(s_cnt, 1)] = row;
     }
     epi_bar();
-    // ---- next-step input x_{t+1} = embed[fed] and, in the fused decode step, the LSTM cell of step t + 1 for the rows
-    //      this CTA feeds back (a row block's 128 rows are spread over its column tiles by where the maxima fell; under
-    //      teacher forcing tile 0 takes them all).  A team of four warps per row, four rows at a time: every lane issues
-    //      all loads of its four hidden units at once (R, the token's row of EW, biases, c), so a row costs ONE round trip
-    //      to L2 / HBM instead of a chain of them.
-    if (a.x_next != nullptr || a.do_cell) {
-      const int ew = warp - 2;                         // 0 .. 15
-      const int team = ew >> 2, tl = (ew & 3) * 32 + lane;      // lane 0 .. 127 inside the team
-      const int nrows = *s_cnt;
-      const bool vec = ((a.E & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.embed) & 15u) == 0) &&
-                       ((reinterpret_cast<uintptr_t>(a.x_next) & 15u) == 0);
-      bool rec_ready = !a.do_cell;
-      const int H = a.G4 >> 2;
-      for (int i = team; i < nrows; i += VS_G) {
-        const int r = s_list[i];
-        const int tok = s_fed[r];
-        const int mr = m0 + r;
-        if (a.x_next != nullptr) {
-          const float* er = a.embed + (size_t)tok * a.E;
-          float* xr = a.x_next + (size_t)mr * a.E;
-          if (vec) {
-            for (int c = tl; c < (a.E >> 2); c += 128) reinterpret_cast<float4*>(xr)[c] = __ldg(reinterpret_cast<const float4*>(er) + c);
-          } else {
-            for (int c = tl; c < a.E; c += 128) xr[c] = __ldg(er + c);
+    if (etid == 0) VS_STAMP(11);
+
+    // ---- fused decode step, first pass of the cell (decode_cell_tail's comment): issue every load of up to four fed-back
+    //      rows now -- thread = hidden unit; x_{t+1} rides along, one float4 per thread and row
+    CellTailArgs ct;
+    ct.embed = a.embed; ct.x_next = a.x_next; ct.R = a.R; ct.EW = a.EW; ct.c_prev = a.c_prev; ct.c_out = a.c_out;
+    ct.h_out = a.h_out; ct.acts = a.acts; ct.htop = a.htop; ct.E = a.E; ct.G4 = a.G4; ct.L = a.L; ct.t = a.t; ct.do_cell = a.do_cell;
+    const int nrows = *s_cnt;
+    const int Hh = a.G4 >> 2;
+    const int team = etid >> 7, tl = etid & 127;          // team of four warps per fed-back row; lane tl owns units 4 tl .. 4 tl + 3
+    const bool cell_first = a.do_cell && team < nrows;
+    const bool has_u = cell_first && 4 * tl < Hh;
+    const bool x_first = a.do_cell && a.x_next != nullptr && ((a.E & 3) == 0) && (a.E >> 2) <= 128 &&
+                         ((reinterpret_cast<uintptr_t>(a.embed) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(a.x_next) & 15u) == 0);
+    const bool has_x = x_first && team < nrows && tl < (a.E >> 2);
+    int mr1 = 0;
+    float4 ev[4], rv[4], cp4 = make_float4(0.f, 0.f, 0.f, 0.f), xv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cell_first) {
+      const int r = s_list[team];
+      const int tok1 = s_fed[r];
+      mr1 = m0 + r;
+      // ld.global.cg (L2 only): the shared-memory carve-out leaves L1 ~29 KB, a row is 20 KB of gathers (EW 8, R 8, c 2, x 2)
+      if (has_u) {
+        const float* Er = a.EW + (size_t)tok1 * a.G4 + 4 * tl;
+#pragma unroll
+        for (int gt = 0; gt < 4; ++gt) ev[gt] = __ldcg(reinterpret_cast<const float4*>(Er + gt * Hh));
+        cp4 = __ldcg(reinterpret_cast<const float4*>(a.c_prev + (size_t)mr1 * Hh + 4 * tl));
+      }
+      if (has_x) xv = __ldcg(reinterpret_cast<const float4*>(a.embed + (size_t)tok1 * a.E) + tl);
+      if (has_u) {
+        // the row block's rec tiles have stored R and arrived (polled by the producer thread, handed over in shared memory)
+        const unsigned am = __activemask();
+        if (lane == 0) {
+          uint32_t f = 0;
+          const unsigned long long t0 = globaltimer_ns();
+          while (f == 0) {
+            asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(f) : "r"(smem_u32(s_recflag)) : "memory");
+            if (globaltimer_ns() - t0 > 4000000000ull) __trap();
           }
         }
-        if (!a.do_cell) continue;
-        const float* Rr = a.R + (size_t)mr * a.G4;
-        const float* Er = a.EW + (size_t)tok * a.G4;
-        for (int j = 4 * tl; j < H; j += 512) {
-          // token-dependent and constant operands first: they do not wait for the rec tiles
-          float4 ev[4], bi[4], bh[4], rv[4];
+        __syncwarp(am);
+        const float* Rr = a.R + (size_t)mr1 * a.G4 + 4 * tl;       // written by another SM in this launch: L2, not L1
 #pragma unroll
-          for (int gt = 0; gt < 4; ++gt) {
-            ev[gt] = __ldg(reinterpret_cast<const float4*>(Er + gt * H + j));
-            bi[gt] = __ldg(reinterpret_cast<const float4*>(a.b_ih + gt * H + j));
-            bh[gt] = __ldg(reinterpret_cast<const float4*>(a.b_hh + gt * H + j));
-          }
-          const float4 cp4 = *reinterpret_cast<const float4*>(a.c_prev + (size_t)mr * H + j);
-          if (!rec_ready) {
-            const unsigned am = __activemask();        // H % 128 != 0: the last warp of a team is partly idle
-            if (lane == 0) {
-              uint32_t f = 0;
-              const unsigned long long t0 = globaltimer_ns();
-              while (f == 0) {
-                asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(f) : "r"(smem_u32(s_recflag)) : "memory");
-                if (globaltimer_ns() - t0 > 4000000000ull) __trap();
-              }
-            }
-            __syncwarp(am);
-            rec_ready = true;
-          }
+        for (int gt = 0; gt < 4; ++gt) rv[gt] = __ldcg(reinterpret_cast<const float4*>(Rr + gt * Hh));
+      }
+    }
+    if (etid == 0) VS_STAMP(15);
+
+    // ---- pass 2: p = e * exp(m_running - M) / S in shared memory
+#pragma unroll 1
+    for (int i = 0; i < MAXU; ++i) {
+      const int j = g + i * VS_G;
+      if (j < NUNIT && n0 + 16 * j < a.N) {
+        const float f = __expf(s_mrun[i * VS_EPI_THREADS] - M) * inv;
 #pragma unroll
-          for (int gt = 0; gt < 4; ++gt) rv[gt] = __ldcg(reinterpret_cast<const float4*>(Rr + gt * H + j));   // written by another SM in this launch
-          float pre[4][4];
-#pragma unroll
-          for (int gt = 0; gt < 4; ++gt) {
-            pre[gt][0] = (ev[gt].x + rv[gt].x) + (bi[gt].x + bh[gt].x); pre[gt][1] = (ev[gt].y + rv[gt].y) + (bi[gt].y + bh[gt].y);
-            pre[gt][2] = (ev[gt].z + rv[gt].z) + (bi[gt].z + bh[gt].z); pre[gt][3] = (ev[gt].w + rv[gt].w) + (bi[gt].w + bh[gt].w);
-          }
-          const float cp[4] = {cp4.x, cp4.y, cp4.z, cp4.w};
-          float ai[4], af[4], ag[4], ao[4], cn[4], hn[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            ai[e] = sigmoidf_acc(pre[0][e]); af[e] = sigmoidf_acc(pre[1][e]); ag[e] = tanhf(pre[2][e]); ao[e] = sigmoidf_acc(pre[3][e]);
-            cn[e] = af[e] * cp[e] + ai[e] * ag[e];
-            hn[e] = ao[e] * tanhf(cn[e]);
-          }
-          float* arow = a.acts + (size_t)mr * a.G4 + j;
-          *reinterpret_cast<float4*>(arow) = make_float4(ai[0], ai[1], ai[2], ai[3]);
-          *reinterpret_cast<float4*>(arow + H) = make_float4(af[0], af[1], af[2], af[3]);
-          *reinterpret_cast<float4*>(arow + 2 * H) = make_float4(ag[0], ag[1], ag[2], ag[3]);
-          *reinterpret_cast<float4*>(arow + 3 * H) = make_float4(ao[0], ao[1], ao[2], ao[3]);
-          *reinterpret_cast<float4*>(a.c_out + (size_t)mr * H + j) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-          const float4 h4 = make_float4(hn[0], hn[1], hn[2], hn[3]);
-          *reinterpret_cast<float4*>(a.h_out + (size_t)mr * H + j) = h4;
-          *reinterpret_cast<float4*>(a.htop + ((size_t)mr * a.L + (a.t + 1)) * H + j) = h4;
+        for (int k = 0; k < 4; ++k) {
+          float4* sp = reinterpret_cast<float4*>(VS_CHUNK(j, k));
+          float4 e = *sp;
+          e.x *= f; e.y *= f; e.z *= f; e.w *= f;
+          *sp = e;
         }
       }
     }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    epi_bar();
+
+    // ---- TMA stores of the finished tile (one 32 x 32 box per row quarter and column box)
+    if (g == 0 && lane == 0) {
+#pragma unroll
+      for (int c = 0; c < S::NBOX; ++c) {
+        if (n0 + 32 * c < a.N)
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                       ::"l"(&tmP), "r"(smem_u32(ubox + c * S::BOX_BYTES + q * 4096)), "r"(n0 + 32 * c), "r"(m0 + q * 32)
+                       : "memory");
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    if (etid == 0) VS_STAMP(16);
+    // ---- the cell of the first four rows (one per team), then whatever is left (further rows, units beyond 512, x_{t+1} otherwise)
+    if (has_x) reinterpret_cast<float4*>(a.x_next + (size_t)mr1 * a.E)[tl] = xv;
+    if (has_u) lstm_cell_store4(ct, Hh, mr1, 4 * tl, ev, rv, cp4);
+    if (etid == 0) VS_STAMP(17);
+    if ((a.x_next != nullptr && !(x_first && nrows <= VS_G)) || (a.do_cell && (nrows > VS_G || Hh > 4 * 128)))
+      decode_cell_tail(ct, etid, m0, s_list, s_fed, nrows, a.do_cell != 0, x_first);
     if (etid == 0) VS_STAMP(14);
     if (g == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem may be released; the writes land by grid end
     if (etid == 0) VS_STAMP(12);
@@ -659,31 +732,31 @@ static long long* g_stamps = nullptr;
 long long* vs_stamps_buffer() {
   const char* e = getenv("GIC_VS_STAMPS");
   if (!(e && e[0] == '1')) return nullptr;
-  if (!g_stamps) { cudaMalloc(&g_stamps, 256 * 16 * sizeof(long long)); cudaMemset(g_stamps, 0, 256 * 16 * sizeof(long long)); }
+  if (!g_stamps) { cudaMalloc(&g_stamps, 256 * 32 * sizeof(long long)); cudaMemset(g_stamps, 0, 256 * 32 * sizeof(long long)); }
   return g_stamps;
 }
 extern "C" void gic_vs_stamps_dump(int cta) {
   if (!g_stamps) return;
   long long h[16];
   cudaDeviceSynchronize();
-  cudaMemcpy(h, g_stamps + cta * 16, sizeof(h), cudaMemcpyDeviceToHost);
+  cudaMemcpy(h, g_stamps + cta * 32, sizeof(h), cudaMemcpyDeviceToHost);
   static const char* nm[13] = {"producer start", "last load issued", "first operands landed", "last mma issued", "u tile landed",
                                "pass0 done", "tmem_full", "pass1 done", "barrier in", "barrier out", "combine done", "pass2 done", "end"};
   for (int i = 0; i < 13; ++i) printf("  cta %3d  %-22s %8lld ns\n", cta, nm[i], h[i] ? h[i] - h[0] : -1);
 }
 extern "C" void gic_vs_stamps_table(int ncta) {
   if (!g_stamps) return;
-  static long long h[256 * 16];
+  static long long h[256 * 32];
   cudaDeviceSynchronize();
   cudaMemcpy(h, g_stamps, sizeof(h), cudaMemcpyDeviceToHost);
   long long t0 = h[0];
-  for (int c = 0; c < ncta; ++c) if (h[c * 16] && h[c * 16] < t0) t0 = h[c * 16];
-  printf("cta start first_ops last_mma u_landed pass0 tmem_full pass1 publish polled combine pass2 rec_seen tail_done end (ns since the earliest CTA start; -1 = not stamped)\n");
+  for (int c = 0; c < ncta; ++c) if (h[c * 32] && h[c * 32] < t0) t0 = h[c * 32];
+  printf("cta start first_ops last_mma u_landed pass0 tmem_full pass1 publish polled combine tokens_known rec_seen tail_done end cell_loads_in stores_issued cell_done - (ns since the earliest CTA start; -1 = not stamped)\n");
   for (int c = 0; c < ncta; ++c) {
-    const long long* r = h + c * 16;
+    const long long* r = h + c * 32;
     auto d = [&](int i) { return r[i] ? r[i] - t0 : -1ll; };
-    printf("%3d %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld\n", c, d(0), d(2), d(3), d(4), d(5),
-           d(6), d(7), d(8), d(9), d(10), d(11), d(13), d(14), d(12));
+    printf("%3d %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld %6lld\n", c, d(0), d(2), d(3), d(4), d(5),
+           d(6), d(7), d(8), d(9), d(10), d(11), d(13), d(14), d(12), d(15), d(16), d(17), d(18), d(19), d(20), d(21));
   }
 }
 
@@ -734,7 +807,7 @@ int vocab_sample_tc(const float* htop, int lda, const float* W_out, const float*
   a.use_rng = (u_t == nullptr) ? 1 : 0;
   a.rng = rng_state();
   a.n_rec = 0; a.rec_tiles_n = 1; a.RBN = 16; a.G4 = 0; a.R = nullptr; a.rec_done = nullptr; a.rec_expect = 0u; a.do_cell = 0;
-  a.EW = nullptr; a.b_ih = nullptr; a.b_hh = nullptr; a.c_prev = nullptr; a.c_out = nullptr; a.h_out = nullptr; a.acts = nullptr;
+  a.EW = nullptr; a.c_prev = nullptr; a.c_out = nullptr; a.h_out = nullptr; a.acts = nullptr;
   a.htop = nullptr;
   if (t == 0) {
     cudaError_t e = cudaMemsetAsync(scratch, 0, 2 * pf * sizeof(float), stream);   // both statistics buffers "not ready"
@@ -758,7 +831,7 @@ int vocab_sample_tc(const float* htop, int lda, const float* W_out, const float*
 // R = h_t W_hh^T of step t + 1 on the SMs the projection leaves idle, and the LSTM cell of step t + 1 in the tail of the
 // CTA that sampled the row's token (kernel comment at the top of this file).
 //   hs_t1  [B, H]  h after LSTM step t (the projection's and the rec tiles' A operand)
-//   EW     [V, 4H] embed W_ih^T (decode_step_prepare), R [B, 4H] scratch, rec_done: tiles_m counters zeroed by the caller
+//   EW     [V, 4H] embed W_ih^T + b_ih + b_hh (built by the caller), R [B, 4H] scratch, rec_done: tiles_m counters zeroed by the caller
 //          before step 0, `scratch` as vocab_sample_tc (zeroed by this function at t == 0)
 //   last != 0: no next step -- the kernel degenerates to the plain projection + sample.
 // decode_step_plan says whether the shape fits (co-resident grid: projection tiles + at least ceil(4H / 256) rec tiles per
@@ -792,12 +865,11 @@ bool decode_step_plan(int B, int V, int H) {
   DecodeStepPlan p;
   return decode_step_plan_impl(B, V, H, &p);
 }
-size_t decode_step_scratch_floats(int B, int V, int H) {          // EW | R | rec_done counters
-  return ((size_t)V * 4 * H + (size_t)B * 4 * H + 64 + 3) & ~(size_t)3;
+size_t decode_step_scratch_floats(int B, int V, int H) {          // EW | R | rec_done counters | b_ih + b_hh
+  return ((size_t)V * 4 * H + (size_t)B * 4 * H + 64 + (size_t)4 * H + 3) & ~(size_t)3;
 }
 
-int decode_step_tc(const float* hs_t1, const float* W_out, const float* b_out, const float* W_hh, const float* b_ih,
-                   const float* b_hh, const float* EW, float* R, unsigned int* rec_done, const float* u_t, float T,
+int decode_step_tc(const float* hs_t1, const float* W_out, const float* b_out, const float* W_hh, const float* EW, float* R, unsigned int* rec_done, const float* u_t, float T,
                    const float* T_dev, int B, int V, int H, int L, int t, int last, float* out, int64_t* ids,
                    const int64_t* forced, const float* embed, int E, float* x_next, const float* c_prev, float* c_out,
                    float* h_out, float* acts, float* htop, float* scratch, cudaStream_t stream, bool* handled) {
@@ -806,7 +878,7 @@ int decode_step_tc(const float* hs_t1, const float* W_out, const float* b_out, c
   *handled = false;
   DecodeStepPlan pl;
   if (!decode_step_plan_impl(B, V, H, &pl)) return GIC_OK;
-  const void* ptrs[] = {hs_t1, W_out, b_out, W_hh, b_ih, b_hh, EW, R, out, c_prev, c_out, h_out, acts, htop, u_t ? u_t : out};
+  const void* ptrs[] = {hs_t1, W_out, b_out, W_hh, EW, R, out, c_prev, c_out, h_out, acts, htop, u_t ? u_t : out};
   for (const void* p : ptrs)
     if (!aligned16(p)) return GIC_OK;
   if (((size_t)L * V) % 4) return GIC_OK;
@@ -835,7 +907,7 @@ int decode_step_tc(const float* hs_t1, const float* W_out, const float* b_out, c
   a.rec_tiles_n = pl.rec_tiles_n; a.RBN = pl.RBN; a.G4 = 4 * H; a.R = R; a.rec_done = rec_done;
   a.rec_expect = (unsigned int)(t + 1) * (unsigned int)pl.rec_tiles_n;
   a.do_cell = last ? 0 : 1;
-  a.EW = EW; a.b_ih = b_ih; a.b_hh = b_hh; a.c_prev = c_prev; a.c_out = c_out; a.h_out = h_out; a.acts = acts; a.htop = htop;
+  a.EW = EW; a.c_prev = c_prev; a.c_out = c_out; a.h_out = h_out; a.acts = acts; a.htop = htop;
   if (t == 0) {
     cudaError_t e = cudaMemsetAsync(scratch, 0, 2 * pf * sizeof(float), stream);   // both statistics buffers "not ready"
     if (e != cudaSuccess) { set_error("decode_step memset: %s", cudaGetErrorString(e)); return GIC_ERR_CUDA; }
