@@ -137,6 +137,21 @@ def _declare(L):
     L.gic_set_vocab_grads_event.argtypes = [P]
     L.gic_disc_set_prepared.restype = None
     L.gic_disc_set_prepared.argtypes = [P]
+    L.gic_comm_create.restype = P
+    L.gic_comm_create.argtypes = [I, I, Z]
+    L.gic_comm_handle_bytes.restype = Z
+    L.gic_comm_ipc_handle.argtypes = [P, P]
+    L.gic_comm_open.argtypes = [P, P]
+    L.gic_comm_buffer.restype = P
+    L.gic_comm_buffer.argtypes = [P]
+    L.gic_comm_buffer_bytes.restype = Z
+    L.gic_comm_buffer_bytes.argtypes = [P]
+    L.gic_comm_error.argtypes = [P]
+    L.gic_comm_destroy.restype = None
+    L.gic_comm_destroy.argtypes = [P]
+    L.gic_allreduce.argtypes = [P, Z, P, I, P, P]
+    L.gic_comm_local_group.argtypes = [P, I]
+    L.gic_allreduce_local_group.argtypes = [P, P, P, Z, I, I, P]
     for name in header_symbols():      # every declared entry point must be exported
         getattr(L, name)
 

@@ -28,7 +28,7 @@ class FlatParams:
     """Re-homes a list of parameters into one contiguous fp32 buffer (params become views), with matching
     flat grad / Adam-moment buffers.  state_dict keys and nn.Parameter identities are unchanged."""
 
-    def __init__(self, params, device):
+    def __init__(self, params, device, grad_alloc=None):
         self.params = [p for p in params]
         self.sizes = [p.numel() for p in self.params]
         self.offsets = []
@@ -38,7 +38,9 @@ class FlatParams:
             off += (n + 3) & ~3          # keep every tensor 16-byte aligned inside the flat buffer
         self.n = off
         self.flat = torch.zeros(self.n, device=device)
-        self.grad = torch.zeros(self.n, device=device)
+        # data parallel: the gradient buffer lives in the peer communicator's symmetric allocation (gic_allreduce reduces it
+        # in place over NVLink peer memory); otherwise a plain tensor
+        self.grad = grad_alloc(self.n) if grad_alloc is not None else torch.zeros(self.n, device=device)
         self.m = torch.zeros(self.n, device=device)
         self.v = torch.zeros(self.n, device=device)
         self.step = 0
@@ -93,6 +95,9 @@ class GANInstructor:
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size()
             self.rank = torch.distributed.get_rank()
+        self._peer = None            # parallel.PeerComm: symmetric gradient buffers + one-kernel all-reduce over peer memory
+        self._peer_failed = False
+        self.skip_allreduce = False  # measurement only (bench.py comm_ms_exposed): run the step without the gradient exchange
         self._passthrough = {}       # encoder.resnet.* tensors of a reference-written checkpoint (re-emitted on save)
 
     # ---- library-side random draws: one Philox stream per (seed, rank, step) -------------------------------------
@@ -161,7 +166,7 @@ class GANInstructor:
         comm = self._comm_stream()
         comm.wait_event(ev)
         with torch.cuda.stream(comm):
-            parallel.allreduce_sum_(fg.grad[:fg.n_early])
+            self._allreduce(fg.grad[:fg.n_early], 1, self._sq_g)
         return True
 
     def _gen_allreduce_rest(self, bucketed):
@@ -170,10 +175,37 @@ class GANInstructor:
         if self.world <= 1:
             return
         if bucketed:
-            parallel.allreduce_sum_(fg.grad[fg.n_early:])
+            self._allreduce(fg.grad[fg.n_early:], 2, self._sq_g)
             torch.cuda.current_stream().wait_stream(self._comm_stream())
         else:
-            parallel.allreduce_sum_(fg.grad)
+            self._allreduce(fg.grad, 2, self._sq_g)
+
+    # ---- gradient exchange -------------------------------------------------------------------------------------------
+    def _allreduce(self, t, channel, sq=None):
+        """Sum of a flat gradient slice over the ranks, in place, on the current stream.  Peer transport: ONE kernel that
+        also adds the square norm of the reduced slice to `sq` (a device scalar; returns True then).  NCCL fallback:
+        torch.distributed, the norm is left to gic_grad_sqnorm (returns False)."""
+        if self.world <= 1 or self.skip_allreduce:
+            return False
+        if self._peer is not None and self._peer.owns(t):
+            self._peer.allreduce_(t, channel, sq)
+            return sq is not None
+        parallel.allreduce_sum_(t)
+        return False
+
+    def _peer_alloc(self, n_total_floats):
+        """Creates the peer communicator on first use (data parallel only); None -> plain gradient tensors + NCCL."""
+        if self.world <= 1 or self._peer_failed or not parallel.peer_transport_enabled() or self.device.type != "cuda":
+            return None
+        if self._peer is None:
+            try:
+                self._peer = parallel.PeerComm(int(n_total_floats) * 4 + 4096, self.device)
+            except Exception as exc:             # peers cannot be mapped (no IPC / no P2P): documented fallback
+                self._peer_failed = True
+                import warnings
+                warnings.warn("gic_b200: peer-memory all-reduce unavailable (%s); using torch.distributed" % (exc,))
+                return None
+        return self._peer.alloc
 
     # ---- Encoder.linear + Encoder.bn (src/generator.py:15-16,23-24), per-shard or synchronised statistics ------------
     def _sync_bn_on(self):
@@ -245,11 +277,14 @@ class GANInstructor:
                d.out2logits.bias]
         return ps
 
-    def _rehome(self, old, params):
+    def _rehome(self, old, params, grad_alloc=None):
         """(Re)builds the flat buffers.  When a parameter was moved out of them (gen.to(), .float(),
         load_state_dict(assign=True)) the Adam moments and step counts of every parameter that kept its shape carry
         over, and the captured graphs -- which address the OLD buffers -- are dropped."""
-        new = FlatParams(params, self.device)
+        try:
+            new = FlatParams(params, self.device, grad_alloc)
+        except MemoryError:                      # the symmetric buffer was sized for the first layout: plain tensor + NCCL
+            new = FlatParams(params, self.device)
         if old is not None:
             new.step = old.step
             if hasattr(old, "m_pre"):
@@ -265,11 +300,18 @@ class GANInstructor:
         return new
 
     def _ensure_flat(self):
-        if self._flat_g is None or not self._flat_g.homed():
-            self._flat_g = self._rehome(self._flat_g, self._gen_params())
+        need_g = self._flat_g is None or not self._flat_g.homed()
+        need_d = self._flat_d is None or not self._flat_d.homed()
+        if not (need_g or need_d):
+            return
+        gp, dp = self._gen_params(), self._disc_params()
+        total = sum((p.numel() + 3) & ~3 for p in gp) + sum((p.numel() + 3) & ~3 for p in dp) + 256
+        alloc = self._peer_alloc(total)
+        if need_g:
+            self._flat_g = self._rehome(self._flat_g, gp, alloc)
             self._flat_g.n_early = self._flat_g.offsets[2]          # [linear.weight | linear.bias]
-        if self._flat_d is None or not self._flat_d.homed():
-            self._flat_d = self._rehome(self._flat_d, self._disc_params())
+        if need_d:
+            self._flat_d = self._rehome(self._flat_d, dp, alloc)
 
     def _zero_unwritten_attn_grads(self):
         """A step that does not run the attention cell (no grid; the policy-gradient step) writes no attn_* gradients:
@@ -533,6 +575,8 @@ class GANInstructor:
         # chain (D input gradient -> decoder BPTT).  The generator chain is latency-bound (L serial BPTT steps), so it
         # runs on a side stream under the D chain.  Q1: both read the PRE-update weights, so D's Adam waits for the
         # generator chain's last read of D weights.
+        self._sq_g = torch.zeros(1, device=dev)      # square norms of the reduced gradients (peer all-reduce accumulates them)
+        self._sq_d = torch.zeros(1, device=dev)
         if side is not None and g_has_grad:
             bws2 = self._buf("disc_bws2", lib.gic_disc_bwd_workspace_floats(B, L, De, R, Fd))
             side.wait_stream(main)
@@ -560,15 +604,15 @@ class GANInstructor:
                     dst.wait_event(real_bwd_done)         # fake accumulates onto real's parameter gradients
                 disc_bwd(seeds[1], k1, probs, None, saved_f, 1, 1, None, bws, ds)
                 self._mark("D chain: backward(fake) done")
-                if self.world > 1:
-                    parallel.allreduce_sum_(fd.grad)
+                d_sq = self._allreduce(fd.grad, 0, self._sq_d)
             with torch.cuda.stream(side):
                 self._gen_allreduce_rest(g_bucketed)
-                out["g_sqnorm"] = self._clip_adam(fg, a.gen_lr, update, 3)
+                g_sq = self._peer is not None and self.world > 1 and not self.skip_allreduce and self._peer.owns(fg.grad)
+                out["g_sqnorm"] = self._clip_adam(fg, a.gen_lr, update, 3, self._sq_g if g_sq else None)
                 self._mark("G chain: clip + Adam done")
             with torch.cuda.stream(dst):
                 dst.wait_event(gen_done)
-                out["d_sqnorm"] = self._clip_adam(fd, a.disc_lr, update, 1)
+                out["d_sqnorm"] = self._clip_adam(fd, a.disc_lr, update, 1, self._sq_d if d_sq else None)
                 self._mark("D chain: clip + Adam done")
             if dst is not main:
                 main.wait_stream(dst)
@@ -580,21 +624,21 @@ class GANInstructor:
             if g_has_grad:
                 gen_chain(bws, stream)
             # -- data-parallel exchange: summed gradients, averaged inside the optimizer kernel
-            if self.world > 1:
-                parallel.allreduce_sum_(fd.grad)
-                if g_has_grad:
-                    parallel.allreduce_sum_(fg.grad)
-            out["d_sqnorm"] = self._clip_adam(fd, a.disc_lr, update, 1)
+            d_sq = self._allreduce(fd.grad, 0, self._sq_d)
+            g_sq = self._allreduce(fg.grad, 2, self._sq_g) if g_has_grad else False
+            out["d_sqnorm"] = self._clip_adam(fd, a.disc_lr, update, 1, self._sq_d if d_sq else None)
             if g_has_grad:
-                out["g_sqnorm"] = self._clip_adam(fg, a.gen_lr, update, 3)
+                out["g_sqnorm"] = self._clip_adam(fg, a.gen_lr, update, 3, self._sq_g if g_sq else None)
         out["g_has_grad"] = g_has_grad
         return out
 
-    def _clip_adam(self, fp: FlatParams, lr: float, update: bool, dyn_slot: int = 1):
+    def _clip_adam(self, fp: FlatParams, lr: float, update: bool, dyn_slot: int = 1, sq=None):
+        """sq: square norm of fp.grad already on the device (the peer all-reduce computes it in the same pass)."""
         lib = _lib.lib()
-        sq = torch.zeros(1, device=self.device)
         stream = _lib.stream()
-        _lib.check(lib.gic_grad_sqnorm(_lib.ptr(fp.grad), fp.n, _lib.ptr(sq), stream), "gic_grad_sqnorm")
+        if sq is None:
+            sq = torch.zeros(1, device=self.device)
+            _lib.check(lib.gic_grad_sqnorm(_lib.ptr(fp.grad), fp.n, _lib.ptr(sq), stream), "gic_grad_sqnorm")
         if update and self._in_graph:
             _lib.check(lib.gic_clip_adam_dyn(_lib.ptr(fp.flat), _lib.ptr(fp.grad), _lib.ptr(fp.m), _lib.ptr(fp.v), fp.n,
                                              _lib.ptr(sq), float(self.args.clip_norm), 1.0 / self.world,
@@ -755,7 +799,7 @@ class GANInstructor:
                                            P(gg(enc.bn.bias)), 0, stream), "gic_encoder_bwd")
         else:
             gg(dec.embed.weight)[1] += dfeat.sum(0)
-        parallel.allreduce_sum_(fg.grad)
+        self._allreduce(fg.grad, 2)
         # pretrain_opt is its own Adam instance in the reference (:24-26): separate moments and step count
         if not hasattr(fg, "m_pre"):
             fg.m_pre, fg.v_pre, fg.step_pre = torch.zeros_like(fg.m), torch.zeros_like(fg.v), 0
@@ -815,7 +859,7 @@ class GANInstructor:
                                         P(g(disc.highway.bias)), P(g(disc.feature2out.weight)),
                                         P(g(disc.feature2out.bias)), P(g(disc.out2logits.weight)),
                                         P(g(disc.out2logits.bias)), None, 1, acc, stream), "gic_disc_bwd")
-        parallel.allreduce_sum_(fd.grad)
+        self._allreduce(fd.grad, 0)
         return dict(d_loss=losses[1], d_real=d_real, d_fake=d_fake, d_sqnorm=self._clip_adam(fd, a.disc_lr, update, 1))
 
     # ---- EXTENSION: SeqGAN-style policy-gradient step (north-star stages 2-4; not in the reference) -------------
@@ -910,8 +954,7 @@ class GANInstructor:
             gg(dec.embed.weight)[1] += dfeat.sum(0)
         out = dict(ids=ids, roll_ids=roll_ids, Q=Q, pg_loss=loss[0], logp=logp, logits=logits, roll_logits=roll_logits,
                    main_logits=main_logits)
-        if self.world > 1:
-            parallel.allreduce_sum_(fg.grad)
+        self._allreduce(fg.grad, 2)
         out["g_sqnorm"] = self._clip_adam(fg, a.gen_lr, update, 3)
         if d_update:
             d = self.disc_step(captions, ids, keep=keep, update=update)

@@ -365,6 +365,39 @@ int gic_pack_captions(const int32_t* tokens, const int32_t* offsets, int B, int 
  * the backward (the reference is single-GPU). */
 void gic_set_vocab_grads_event(void* cuda_event);
 
+/* ---- data-parallel gradient exchange over NVLink / NVSwitch peer memory ("gic_allreduce") ----
+ * The reference is single-GPU (--device-ids is parsed and ignored, src/args.py:213-216,276); data parallelism over the
+ * image batch needs ONE exchange per step: the sum over ranks of the flat G and D gradients, before clip_grad_norm_
+ * (src/training.py:198).  gic_allreduce does it in one kernel over peer memory -- reduce-scatter + all-gather with direct
+ * NVLink loads / stores, sums in rank order (bit-identical on every rank), the square norm of the reduced gradient
+ * accumulated in the same pass (what gic_grad_sqnorm would compute next) -- see csrc/allreduce.cu.
+ *
+ * A communicator owns the one allocation this library makes: a symmetric buffer of data_bytes that every rank of the
+ * node maps through CUDA IPC.  Gradient buffers to be reduced must live inside it (gic_comm_buffer); one process per GPU.
+ *   gic_comm_create       allocate this rank's buffer (device = current device); NULL on error
+ *   gic_comm_ipc_handle   write gic_comm_handle_bytes() bytes describing it; the caller all-gathers them by rank
+ *   gic_comm_open         map every peer's buffer from the gathered handles (world * gic_comm_handle_bytes() bytes)
+ *   gic_allreduce         buf[0..n) (inside the buffer, 16-byte aligned, n % 4 == 0) := sum over ranks, in place, on `stream`;
+ *                         every rank must call it with the same offset, n and channel.  channel (0..3): independent flag
+ *                         sets -- calls that may overlap in time (different streams) need different channels.  sqnorm
+ *                         (device float, may be NULL): += sum of squares of the reduced buf, the same value on every rank.
+ *   gic_comm_error        non-zero after a wait on a peer expired (2 s): the ranks lost step
+ * In-process group (tests on one GPU): W communicators of one process become each other's peers (gic_comm_local_group)
+ * and gic_allreduce_local_group runs all W ranks as ONE launch (the ranks' CTAs are co-resident by construction). */
+typedef struct gic_comm gic_comm_t;
+gic_comm_t* gic_comm_create(int rank, int world, size_t data_bytes);
+size_t gic_comm_handle_bytes(void);
+int gic_comm_ipc_handle(gic_comm_t* comm, void* out_handle);
+int gic_comm_open(gic_comm_t* comm, const void* handles_by_rank);
+void* gic_comm_buffer(gic_comm_t* comm);
+size_t gic_comm_buffer_bytes(gic_comm_t* comm);
+int gic_comm_error(gic_comm_t* comm);
+void gic_comm_destroy(gic_comm_t* comm);
+int gic_allreduce(float* buf, size_t n, gic_comm_t* comm, int channel, float* sqnorm, gic_stream_t stream);
+int gic_comm_local_group(gic_comm_t* const* comms, int world);
+int gic_allreduce_local_group(gic_comm_t* const* comms, float* const* bufs, float* const* sqnorms, size_t n, int world,
+                              int channel, gic_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,5 +1,11 @@
-"""Data-parallel consistency check (run under torchrun on >= 2 GPUs): the bucketed, overlapped all-reduce of the
-generator gradient must give the same parameters as the single all-reduce, eager and graph-replayed.
+"""Data-parallel consistency check (run under torchrun on >= 2 GPUs):
+  * gic_allreduce (one kernel over NVLink peer memory) is bit-identical on every rank, bit-equal to the rank-order sum and
+    within fp32 rounding of NCCL; its fused square norm is the norm of the result;
+  * peer / NCCL transport x bucketed / single all-reduce x eager / graph replay give the same parameters, and the ranks
+    stay bit-identical replicas;
+  * identically seeded ranks draw different library-side noise;
+  * synchronised Encoder.bn reproduces the full-batch step.
+Prints DP_CHECK OK or DP_CHECK FAILED.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 profiles/dp_check.py
 """
@@ -86,27 +92,120 @@ def sync_bn_check():
     return bool(t.item() > 0.5)
 
 
+def allreduce_exactness():
+    """gic_allreduce (one kernel over NVLink peer memory) on rank-dependent data: bit-identical on every rank, bit-equal to
+    the sum formed in rank order, within fp32 rounding of NCCL's result, and the fused square norm is that of the result."""
+    from gic_b200 import parallel
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+    ok = True
+    sizes = [4, 1000, 4096 * 13 + 8, 14_500_000]
+    comm = parallel.PeerComm(sum((n * 4 + 255) & ~255 for n in sizes) + 4096, dev)
+    for ch, n in enumerate(sizes):
+        g = torch.Generator(device=dev).manual_seed(1000 * ch + rank)
+        x = torch.randn(n, generator=g, device=dev) * (1.0 + rank)
+        t = comm.alloc(n); t.copy_(x)
+        parts = [torch.empty_like(x) for _ in range(world)]
+        dist.all_gather(parts, x)
+        want = parts[0].clone()
+        for p_ in parts[1:]:
+            want += p_                                              # rank order, fp32: what the kernel computes
+        nccl = x.clone(); dist.all_reduce(nccl)
+        sq = torch.zeros(1, device=dev)
+        for rep in range(3):                                         # the same channel three times: epochs
+            t.copy_(x); sq.zero_()
+            torch.cuda.synchronize(); dist.barrier()
+            comm.allreduce_(t, ch % 4, sq)
+            torch.cuda.synchronize()
+            exact = bool(torch.equal(t, want))
+            q = t.clone(); dist.broadcast(q, 0)
+            same = bool(torch.equal(q, t))
+            sqs = sq.clone(); dist.broadcast(sqs, 0)
+            sq_same = bool(torch.equal(sqs, sq))
+            sq_rel = abs(float(sq) - float((want.double() ** 2).sum())) / max(float((want.double() ** 2).sum()), 1e-30)
+            nccl_rel = float((t - nccl).abs().max()) / float(want.abs().max())
+            good = exact and same and sq_same and sq_rel < 1e-5 and nccl_rel < 1e-5
+            ok = ok and good
+            if rank == 0 and (rep == 0 or not good):
+                print(f"allreduce n={n}: == rank-order sum {exact}, ranks identical {same}, sqnorm identical {sq_same} (rel err {sq_rel:.1e}), "
+                      f"vs NCCL rel {nccl_rel:.1e}", flush=True)
+    ok = ok and not comm.error()
+    t_ = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.all_reduce(t_, op=dist.ReduceOp.MIN)
+    return bool(t_.item() > 0.5)
+
+
+def noise_check():
+    """Identically seeded ranks draw DIFFERENT library-side Gumbel noise / dropout masks (the rank is folded into the Philox
+    offset), yet stay bit-identical replicas after training steps."""
+    from gic_b200.args import default_args
+    from gic_b200.training import GANInstructor
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+    B, L, V = 32, 10, 2000
+    a = default_args(vocab_size=V, gen_embed_dim=64, gen_hidden_dim=128, gen_num_layers=1, conditional_gan=0, device="cuda")
+    torch.manual_seed(1008)
+    inst = GANInstructor(a, device=dev)
+    inst.gen.train(); inst.disc.train(); inst.gen.decoder.temperature = 1.0
+    caps = torch.randint(4, V, (B, L), generator=torch.Generator(device=dev).manual_seed(5), device=dev)   # same captions on every rank
+    ids = None
+    for _ in range(3):
+        r = inst.adv_step(caps)                                    # u = None, keep = None: drawn by the library
+        ids = r["ids"].clone()
+    torch.cuda.synchronize()
+    all_ids = [torch.empty_like(ids) for _ in range(world)]
+    dist.all_gather(all_ids, ids)
+    differ = all(not torch.equal(all_ids[0], all_ids[k]) for k in range(1, world))
+    p = torch.cat([inst._flat_g.flat, inst._flat_d.flat]).clone()
+    q = p.clone(); dist.broadcast(q, 0)
+    same = bool(torch.equal(p, q))
+    if rank == 0:
+        print(f"library-side draws: sampled ids differ across ranks {differ}; replicas identical after 3 steps {same}", flush=True)
+    t_ = torch.tensor([1.0 if (differ and same) else 0.0], device=dev)
+    dist.all_reduce(t_, op=dist.ReduceOp.MIN)
+    return bool(t_.item() > 0.5)
+
+
 def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import gic_b200
     gic_b200.set_gemm_mode(gic_b200.GEMM_BF16)
+    rank = dist.get_rank()
+    ok = allreduce_exactness()
+    if rank == 0:
+        print("allreduce exactness:", "ok" if ok else "FAILED", flush=True)
+    # reference run: NCCL transport, one all-reduce per network, eager
+    os.environ["GIC_ALLREDUCE"] = "nccl"
     ref, l0 = run(False, False)
-    ok = True
-    for bucketed, graph in ((True, False), (False, True), (True, True)):
-        p, l = run(bucketed, graph)
-        err = float((p - ref).abs().max()); scale = float(ref.abs().max())
-        # ranks must agree exactly (same all-reduced gradients); against the reference path only fp32 atomics order differs
-        q = p.clone(); dist.broadcast(q, 0)
-        same = bool(torch.equal(q, p))
-        if dist.get_rank() == 0:
-            print(f"bucketed={bucketed} graph={graph}: max |dparam| {err:.3e} (scale {scale:.3e}) ranks identical={same} losses {l[-1]:.6f} vs {l0[-1]:.6f}", flush=True)
-        # the step is not bit-reproducible run to run (fp32 atomics of the stream-K GEMMs; a max-over-time tie can re-route a
-        # gradient, DESIGN.md "Ties"), and Adam normalises: bound = a fraction of lr * steps
-        ok = ok and same and err <= 0.5 * 1e-4 * 4 and abs(l[-1] - l0[-1]) <= 1e-4 * abs(l0[-1])
-    ok = sync_bn_check() and ok
-    if dist.get_rank() == 0:
+    os.environ.pop("GIC_ALLREDUCE")
+    lr_steps = 1e-4 * 4
+    for transport in ("peer", "nccl"):
+        for bucketed, graph in ((False, False), (True, False), (False, True), (True, True)):
+            if transport == "nccl" and not bucketed and not graph:
+                continue
+            os.environ["GIC_ALLREDUCE"] = transport
+            p, l = run(bucketed, graph)
+            os.environ.pop("GIC_ALLREDUCE")
+            d = (p - ref).abs()
+            err, scale = float(d.max()), float(ref.abs().max())
+            frac = float((d > 0.05 * lr_steps).float().mean())
+            q = p.clone(); dist.broadcast(q, 0)
+            same = bool(torch.equal(q, p))        # ranks must agree EXACTLY: same reduced gradients, same norm, same update
+            # two runs of the same step differ in the order of fp32 atomics (stream-K GEMMs, scatter-adds) and a max-over-time
+            # tie can re-route a gradient (DESIGN.md "Ties"); Adam normalises, so a gradient whose sign flips moves its parameter
+            # by up to 2 lr per step: the hard bound is 2 lr steps, and all but a sliver of the parameters agree to 5 % of lr steps
+            good = same and err <= 2.0 * lr_steps * 1.01 and frac < 2e-3 and abs(l[-1] - l0[-1]) <= 2e-3 * abs(l0[-1])
+            ok = ok and good
+            if rank == 0:
+                print(f"{transport:4s} bucketed={bucketed!s:5s} graph={graph!s:5s}: max |dparam| {err:.2e} (bound {2 * lr_steps:.1e}, scale {scale:.2e}), "
+                      f"{frac:.1e} of parameters off by > 5 % of lr*steps, ranks identical={same}, loss {l[-1]:.6f} vs {l0[-1]:.6f}  "
+                      f"{'ok' if good else 'FAILED'}", flush=True)
+    n_ok = noise_check()
+    s_ok = sync_bn_check()
+    ok = ok and n_ok and s_ok
+    if rank == 0:
         print("DP_CHECK", "OK" if ok else "FAILED", flush=True)
     torch.cuda.synchronize(); dist.barrier()
     import threading
