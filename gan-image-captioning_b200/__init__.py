@@ -6,18 +6,18 @@ behaviour); all compute goes through the C ABI of libgic_b200.so (include/gic_b2
 CPU fallback: constructing the modules works anywhere, running them needs a B200.
 """
 from . import _lib  # noqa: F401
-from ._lib import GEMM_BF16, GEMM_FP32, GEMM_TF32, GEMM_TF32X3, GicError  # noqa: F401
+from ._lib import GEMM_BF16, GEMM_FP32, GEMM_TF32, GicError  # noqa: F401
 
-__all__ = ["GEMM_FP32", "GEMM_TF32", "GEMM_TF32X3", "GEMM_BF16", "GicError"]
+__all__ = ["GEMM_FP32", "GEMM_TF32", "GEMM_BF16", "GicError"]
 
 _default_mode = GEMM_FP32
 
 
 def set_gemm_mode(mode: int) -> None:
-    """Precision of the dense contractions: GEMM_FP32 (exact, CUDA cores), GEMM_TF32 (tcgen05 single
-    pass) or GEMM_TF32X3 (tcgen05 3-pass split, fp32-equivalent)."""
+    """Precision of the dense contractions: GEMM_FP32 (exact, CUDA cores), GEMM_TF32 (tcgen05 kind::tf32, fp32
+    accumulate) or GEMM_BF16 (as TF32, with bf16 operands on the discriminator's and the vocab-backward contractions)."""
     global _default_mode
-    if mode not in (GEMM_FP32, GEMM_TF32, GEMM_TF32X3, GEMM_BF16):
+    if mode not in (GEMM_FP32, GEMM_TF32, GEMM_BF16):
         raise ValueError("unknown GEMM mode %r" % (mode,))
     _default_mode = mode
 

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libgic_b200.so")
 HEADER = os.path.join(os.path.dirname(HERE), "include", "gic_b200.h")
 
-GEMM_FP32, GEMM_TF32, GEMM_TF32X3, GEMM_BF16 = 0, 1, 2, 3
+GEMM_FP32, GEMM_TF32, GEMM_BF16 = 0, 1, 3
 LOSS_TYPES = {"standard": 0, "JS": 1, "KL": 2, "hinge": 3, "tv": 4, "rsgan": 5}
 
 _lib = None

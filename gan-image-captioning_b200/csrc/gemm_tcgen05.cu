@@ -216,7 +216,7 @@ int gemm_tc(int mode, bool transA, bool transB, int M, int N, int K, float alpha
             bool* handled) {
   using namespace tc;
   *handled = false;
-  if (mode != GEMM_TF32) return GIC_OK;                 // GEMM_TF32X3 is served by the exact-fp32 kernel for now
+  if (mode != GEMM_TF32) return GIC_OK;
   if (M <= 0 || N <= 0 || K <= 0) return GIC_OK;
   if (!aligned16(A) || !aligned16(B) || (lda % 4) || (ldb % 4)) return GIC_OK;
   if ((long long)M * N < 64 * 64 || K < 32) return GIC_OK;   // tiny problems: launch-latency bound either way

@@ -56,7 +56,6 @@ int gemm_f32(bool transA, bool transB, int M, int N, int K, float alpha, const f
 enum GemmMode : int {
   GEMM_FP32 = 0,     // CUDA-core FFMA, exact fp32 (parity mode)
   GEMM_TF32 = 1,     // tcgen05 kind::tf32, single pass (throughput mode)
-  GEMM_TF32X3 = 2,   // tcgen05 kind::tf32, 3-pass split (fp32-equivalent on tensor cores)
   GEMM_BF16 = 3      // as GEMM_TF32, with the discriminator's [N*R,F] x [F,F] contractions on bf16 operands (kind::f16)
 };
 

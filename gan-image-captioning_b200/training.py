@@ -346,9 +346,9 @@ class GANInstructor:
         in the dict a replay returns (losses, probs, ids, D logits) are the graph's STATIC buffers: the next replay
         overwrites them -- clone what must outlive the step."""
         if graph:
-            if grid is not None:
-                raise NotImplementedError("graph replay with the attention grid: pass graph=False")
-            return self._adv_step_graph(captions, pooled, u, keep, loss_type, static=(graph == "static"))
+            if grid is not None and graph != "static":
+                raise NotImplementedError("graph replay with the attention grid: pass graph='static' (resident inputs) or graph=False")
+            return self._adv_step_graph(captions, pooled, u, keep, loss_type, static=(graph == "static"), grid=grid)
         _lib.require_cuda()
         lib = _lib.lib()
         a, dev = self.args, self.device
@@ -652,7 +652,7 @@ class GANInstructor:
         return sq
 
     # ---- CUDA-graph replay of the fused step -------------------------------------------------------
-    def _adv_step_graph(self, captions, pooled, u, keep, loss_type, static=False):
+    def _adv_step_graph(self, captions, pooled, u, keep, loss_type, static=False, grid=None):
         """static=True: the given device tensors themselves are the graph's inputs (no copies; one graph per distinct
         set of buffers) -- for callers that keep their batches resident."""
         a, dev = self.args, self.device
@@ -661,7 +661,7 @@ class GANInstructor:
         key = (B, L, loss_type, pooled is not None, u is not None, keep is not None, bool(self.gen.encoder.training),
                gic_b200.get_gemm_mode())
         if static:
-            key = key + tuple(None if t is None else t.data_ptr() for t in (captions, pooled, u, keep))
+            key = key + tuple(None if t is None else t.data_ptr() for t in (captions, pooled, u, keep, grid))
         st = self._graphs.get(key)
         if self._dyn is None:
             self._dyn = torch.zeros(8, device=dev)
@@ -673,7 +673,7 @@ class GANInstructor:
             self._rng_dyn = torch.zeros(2, dtype=torch.int64, device=dev)
             self._rng_host = [torch.zeros(2, dtype=torch.int64).pin_memory() for _ in range(16)]
         if st is None and static:
-            st = dict(captions=captions, pooled=pooled, u=u, keep=keep)
+            st = dict(captions=captions, pooled=pooled, u=u, keep=keep, grid=grid)
             self._graphs[key] = st
         if st is None:
             st = dict(captions=torch.empty(B, L, dtype=torch.int64, device=dev),
@@ -718,7 +718,8 @@ class GANInstructor:
         if "graph" not in st:
             # one eager step allocates every cached buffer and compiles nothing new during capture; it is a real
             # training step (same semantics), so the captured replay starts at step 2
-            out = self.adv_step(st["captions"], pooled=st["pooled"], u=st["u"], keep=st["keep"], loss_type=loss_type)
+            out = self.adv_step(st["captions"], pooled=st["pooled"], u=st["u"], keep=st["keep"], loss_type=loss_type,
+                                grid=st.get("grid"))
             torch.cuda.synchronize(dev)
             load_scalars()
             g = torch.cuda.CUDAGraph()
@@ -727,7 +728,7 @@ class GANInstructor:
             try:
                 with torch.cuda.graph(g):
                     st["out"] = self.adv_step(st["captions"], pooled=st["pooled"], u=st["u"], keep=st["keep"],
-                                              loss_type=loss_type)
+                                              loss_type=loss_type, grid=st.get("grid"))
             finally:
                 self._in_graph = False
                 _lib.lib().gic_set_temperature_device(None)

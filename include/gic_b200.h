@@ -43,7 +43,7 @@ typedef void* gic_stream_t; /* cudaStream_t */
 /* precision of the dense contractions (see DESIGN.md "GEMM modes") */
 #define GIC_GEMM_FP32 0   /* CUDA-core FFMA, exact fp32                                   */
 #define GIC_GEMM_TF32 1   /* tcgen05 kind::tf32, one pass, fp32 accumulate in TMEM         */
-#define GIC_GEMM_TF32X3 2 /* tcgen05 kind::tf32, 3-pass hi/lo split: fp32-equivalent       */
+/* (2 is unassigned: a 3-pass TF32 split was planned and never built; the exact mode is GIC_GEMM_FP32) */
 #define GIC_GEMM_BF16 3   /* as TF32, with the discriminator's [N*R,F]x[F,F] contractions (highway forward, dx, dW_h) on
                              bf16 operands (tcgen05 kind::f16, fp32 accumulate): "bf16 GEMM inputs, stated separately" */
 

@@ -39,6 +39,19 @@ class PortDecoder(nn.Module):
         return torch.stack(outs, 1), torch.stack(ids, 1)
 
 
+class PortEncoder(nn.Module):
+    """Encoder.linear + Encoder.bn on pooled CNN features (src/generator.py:15-16,23-24; the frozen ResNet trunk is out of
+    the path: the configs feed pooled features)."""
+
+    def __init__(self, a):
+        super().__init__()
+        self.linear = nn.Linear(a.feature_dim, a.gen_embed_dim)
+        self.bn = nn.BatchNorm1d(a.gen_embed_dim, momentum=0.01)
+
+    def forward(self, pooled):
+        return self.bn(self.linear(pooled))
+
+
 class PortDiscriminator(nn.Module):
     """src/discriminator.py:9-62."""
 
@@ -65,17 +78,24 @@ class PortDiscriminator(nn.Module):
         return self.out2logits(self.feature2out(y)).squeeze(1)
 
 
-def load_port(a, gen_params, disc_params):
+def load_port(a, gen_params, disc_params, with_encoder=False):
     dec, disc = PortDecoder(a), PortDiscriminator(a)
     dec.load_state_dict({k[len("decoder."):]: v.clone() for k, v in gen_params.items() if k.startswith("decoder.")})
     disc.load_state_dict({k: v.clone() for k, v in disc_params.items()})
+    if with_encoder:
+        enc = PortEncoder(a)
+        enc.load_state_dict({k[len("encoder."):]: v.clone() for k, v in gen_params.items() if k.startswith("encoder.")}, strict=False)
+        return enc.train(), dec.train(), disc.train()
     return dec.train(), disc.train()
 
 
-def port_adv_step(a, dec, disc, g_opt, d_opt, captions, feats, u=None, keep=None):
-    """src/training.py:144-169 + optimize (:194-199) with the Q1 ordering fix."""
+def port_adv_step(a, dec, disc, g_opt, d_opt, captions, feats, u=None, keep=None, enc=None, pooled=None):
+    """src/training.py:144-169 + optimize (:194-199) with the Q1 ordering fix.  enc + pooled: conditional mode, the features
+    come from Encoder.linear + bn (:144-145) and the encoder's parameters are trained with the generator's."""
     bce = nn.BCEWithLogitsLoss()
     B, L = captions.shape
+    if enc is not None:
+        feats = enc(pooled)
     gen_caps, _ = dec.sample(feats, L, u)
     fake = gen_caps.detach()
     real = F.one_hot(captions, a.vocab_size).float()
@@ -83,7 +103,7 @@ def port_adv_step(a, dec, disc, g_opt, d_opt, captions, feats, u=None, keep=None
     d_real, d_fake, g_out = disc(real, k[0]), disc(fake, k[1]), disc(gen_caps, k[2])
     d_loss = bce(d_real, torch.ones_like(d_real)) + bce(d_fake, torch.zeros_like(d_fake))
     g_loss = bce(g_out, torch.ones_like(g_out))
-    dps, gps = list(disc.parameters()), list(dec.parameters())
+    dps, gps = list(disc.parameters()), list(dec.parameters()) + (list(enc.parameters()) if enc is not None else [])
     dg = torch.autograd.grad(d_loss, dps, retain_graph=True)
     gg = torch.autograd.grad(g_loss, gps, allow_unused=True)
     for p, g in zip(dps, dg):
