@@ -319,9 +319,33 @@ def run_ours(args):
     sustained = None
     if not args.no_sustained:
         n_long = int(min(2000, max(200, 1.0 / (ms_step * 1e-3))))
-        lms, _, lclocks = timed(step_resident, n_long, 3, sample_clocks=True)
+        # chunks of 50 steps with an event between them and the host's enqueue time beside them: tells a GPU that slows down
+        # from a host that cannot enqueue a replay per step time
+        sampler = ClockSampler(local) if rank == 0 else None
+        for i in range(3):
+            step_resident(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        if sampler:
+            sampler.start()
+        evs = [torch.cuda.Event(enable_timing=True)]
+        evs[0].record()
+        h0 = time.perf_counter()
+        for i in range(n_long):
+            step_resident(3 + i)
+            if (i + 1) % 50 == 0 or i + 1 == n_long:
+                e = torch.cuda.Event(enable_timing=True); e.record(); evs.append(e)
+        host_ms = (time.perf_counter() - h0) * 1e3
+        torch.cuda.synchronize()
+        lclocks = sampler.stop() if sampler else None
+        lms = evs[0].elapsed_time(evs[-1])
+        if world > 1:
+            t = torch.tensor([lms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); lms = float(t.item())
+        chunks = [evs[j].elapsed_time(evs[j + 1]) / min(50, n_long - 50 * j) for j in range(len(evs) - 1)]
         sustained = {"steps": n_long, "ms_per_step": lms / n_long, "value": world / (lms / n_long * 1e-3), "unit": "steps/s",
-                     "clocks": lclocks}
+                     "ms_per_step_first_50": chunks[0], "ms_per_step_last_50": chunks[-1],
+                     "host_enqueue_ms_per_step": host_ms / n_long, "clocks": lclocks}
 
     # ---- exposed cost of the gradient exchange (N > 1): the same step with the all-reduce left out
     comm = None
@@ -442,14 +466,18 @@ def run_ours(args):
         # read u, write p) and tensor (2 B V H + 2 B 4H H flop per launch).
         c = classes.get("vocab_sample_fused")
         if c:
-            us = c["ms_per_step"] * 1e3 / c["calls_per_step"]
+            us_eager = c["ms_per_step"] * 1e3 / c["calls_per_step"]
+            # per decode step inside the replayed graph (decode_ms covers L steps + the one-off EW GEMM and step-0 LSTM kernel):
+            # the eager, event-bracketed figure also contains the host's tensor-map encoding between the two event records
+            us = dms / args.steps * 1e3 / L
             by = 8.0 * B * V
             fl = 2.0 * B * V * cfg["H"] + 2.0 * B * 4 * cfg["H"] * cfg["H"]
             roofline["time_dominant"] = {
                 "kernel": "vocab_sample_kernel in its fused-decode-step role (decode_step_kernel): projection + Gumbel-softmax + sample of "
                           "step t, recurrent contraction and LSTM cell of step t + 1; tcgen05 kind::tf32",
                 "bound": "latency (serial chain); HBM and tensor figures for reference",
-                "launches_per_step": c["calls_per_step"], "us_per_launch": us, "share_of_step": c["ms_per_step"] / ms_serial,
+                "launches_per_step": c["calls_per_step"], "us_per_launch": us, "us_per_launch_eager_events": us_eager,
+                "share_of_step": (dms / args.steps) / ms_step,
                 "hbm": {"achieved": by / (us * 1e-6) / 1e9, "peak": peaks["hbm"], "unit": "GB/s", "frac": by / (us * 1e-6) / 1e9 / peaks["hbm"],
                         "algorithmic_bytes_per_launch": by},
                 "tensor": {"achieved": fl / (us * 1e-6) / 1e12, "peak": peaks["tf_burst"] / 2, "unit": "TFLOP/s (TF32 = half the bf16 peak)",

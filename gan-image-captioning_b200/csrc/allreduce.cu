@@ -69,9 +69,11 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ float4 ld_peer_f4(const float4* p) {        // peer memory: never from a stale cache line
+// peer memory: never from a stale cache line.  No "memory" clobber: these loads only have to stay behind the start barrier
+// (a __syncthreads) and ahead of the stores that consume them, and they must be free to overlap one another.
+__device__ __forceinline__ float4 ld_peer_f4(const float4* p) {
   float4 v;
-  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
 __device__ __forceinline__ unsigned long long ar_now() {
@@ -87,6 +89,37 @@ __device__ __forceinline__ bool ar_wait(const unsigned int* flag, unsigned int e
     if (ar_now() - t0 > 2000000000ull) { atomicExch(err, 1u); return false; }
   }
   return true;
+}
+
+// U elements per thread and trip: U x W loads in flight, sums in rank order, U x W stores
+template <int U>
+__device__ __forceinline__ float ar_body(const ArRank& me, int W, size_t i0, size_t s1, size_t stride) {
+  float sq = 0.f;
+  for (size_t i = i0; i < s1; i += U * stride) {
+    float4 v[U][AR_MAX_WORLD];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t iu = i + u * stride;
+#pragma unroll
+      for (int p = 0; p < AR_MAX_WORLD; ++p)
+        if (p < W && iu < s1) v[u][p] = ld_peer_f4(reinterpret_cast<const float4*>(me.data[p]) + iu);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t iu = i + u * stride;
+      if (iu < s1) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int p = 0; p < AR_MAX_WORLD; ++p)                   // rank order: the same sum on every rank
+          if (p < W) { acc.x += v[u][p].x; acc.y += v[u][p].y; acc.z += v[u][p].z; acc.w += v[u][p].w; }
+        sq = fmaf(acc.x, acc.x, fmaf(acc.y, acc.y, fmaf(acc.z, acc.z, fmaf(acc.w, acc.w, sq))));
+#pragma unroll
+        for (int p = 0; p < AR_MAX_WORLD; ++p)
+          if (p < W) reinterpret_cast<float4*>(me.data[p])[iu] = acc;
+      }
+    }
+  }
+  return sq;
 }
 
 __global__ void __launch_bounds__(AR_THREADS, 1) allreduce_p2p_kernel(const __grid_constant__ ArArgs a) {
@@ -111,17 +144,13 @@ __global__ void __launch_bounds__(AR_THREADS, 1) allreduce_p2p_kernel(const __gr
   const size_t s0 = (size_t)rank * per;
   const size_t s1 = (s0 + per < a.n4) ? s0 + per : a.n4;
   float sq = 0.f;
-  for (size_t i = s0 + (size_t)c * AR_THREADS + tid; i < s1; i += (size_t)AR_CTAS * AR_THREADS) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-    for (int p = 0; p < W; ++p) {                              // rank order: the same sum on every rank
-      const float4 v = ld_peer_f4(reinterpret_cast<const float4*>(me.data[p]) + i);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-    }
-    sq = fmaf(acc.x, acc.x, fmaf(acc.y, acc.y, fmaf(acc.z, acc.z, fmaf(acc.w, acc.w, sq))));
-#pragma unroll 4
-    for (int p = 0; p < W; ++p) reinterpret_cast<float4*>(me.data[p])[i] = acc;
-  }
+  const size_t stride = (size_t)AR_CTAS * AR_THREADS;
+  const size_t i0 = s0 + (size_t)c * AR_THREADS + tid;
+  // NVLink's latency-bandwidth product (~2 us x 750 GB/s) needs ~1.5 MB of loads in flight per rank: every thread keeps 8
+  // 16-byte peer loads outstanding -- U elements x W ranks, all issued before the first one is consumed
+  if (W == 2) sq = ar_body<4>(me, W, i0, s1, stride);
+  else if (W <= 4) sq = ar_body<2>(me, W, i0, s1, stride);
+  else sq = ar_body<1>(me, W, i0, s1, stride);
   // partial square norm of this chunk: block reduction in a fixed order, pushed to every rank
   sq = warp_sum(sq);
   if ((tid & 31) == 0) s_red[tid >> 5] = sq;

@@ -25,6 +25,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 // Bounded wait: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
+  unsigned long long t_start = 0ull;
   for (uint32_t spin = 0;; ++spin) {
     uint32_t done;
     asm volatile(
@@ -33,7 +34,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(addr), "r"(parity) : "memory");
     if (done) return;
-    if (spin > (1u << 26)) __trap();
+    if ((spin & 0xfffffu) == 0xfffffu) {            // every ~1 M polls: a stall of more than 4 s is a protocol bug
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t_start == 0ull) t_start = now;
+      else if (now - t_start > 4000000000ull) __trap();
+    }
   }
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {

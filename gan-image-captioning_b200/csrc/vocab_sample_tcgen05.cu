@@ -70,6 +70,7 @@ struct VSArgs {
   long long* stamps;          // debug (GIC_VS_STAMPS=1): 16 clock64 stamps per CTA, else null
   int use_rng;                // no uniforms supplied: draw u[t, m, n] in the kernel (Philox, same numbers as gic_philox_uniform)
   RngState rng;
+  int2* tokpub;               // [Mpad] (token fed back, step tag t + 1) per row: one 8-byte store, polled by the row's assigned tile
   // ---- fused decode step (all zero / null for the plain projection + sample kernel) ----
   int n_rec;                  // CTAs [0, n_rec) are rec tiles; projection tile index = blockIdx.x - n_rec
   int rec_tiles_n, RBN;       // rec column tiles per row block, their width (multiple of 16, <= 256)
@@ -118,20 +119,44 @@ constexpr int VS_THREADS = 64 + VS_EPI_THREADS;      // warp 0 = TMA producer, w
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(VS_EPI_THREADS) : "memory"); }
 
-// LSTM cell of step t + 1 for the rows a projection tile feeds back (fused decode step), and the next-step input
-// x_{t+1} = embed[fed].  A team of four warps per row, four rows at a time; every lane issues all loads of its four hidden
-// units at once as 16-byte loads -- the token's row of EW (biases folded in), c_t, R -- so a row costs ONE round trip to L2 /
-// HBM.  (Thread-per-unit with 4-byte loads, four rows per thread, was measured slower: four times the load instructions.)
-// Activations use the MUFU forms (ex2 + rcp; |error| ~3e-7, far below the TF32 rounding of the pre-activations).
-// The FIRST pass (rows 0..3 of the tile's list, one per team, units 0..511) is inlined into the kernel's epilogue, where its
-// loads are issued BEFORE the normalisation pass and the p tile's TMA stores and consumed after them.  The out-of-line
-// function is the remainder: further rows (a tile rarely wins more than four), hidden units beyond 512, x_{t+1} when it did
-// not ride along, and the whole job for the plain projection + sample kernel (x_{t+1} only).
+// LSTM cell of step t + 1 (fused decode step) and the next-step input x_{t+1} = embed[fed], for the rows a projection
+// tile is ASSIGNED: row r of a row block belongs to column tile r mod tiles_n, whatever tile sampled its token.  (Letting
+// the tile that holds a row's maximum do the row's cell was the first design; the sampled tokens of a trained -- or
+// collapsing -- generator concentrate on a few vocabulary entries, one tile then wins most of the 128 rows and its tail
+// serialises: the step slowed from 2.4 to 3.1 ms over 400 training steps.)  The sampling tile publishes (token, step tag) as
+// one 8-byte store to tokpub[row]; the assigned tile polls that entry -- the same self-flagging idiom as the row statistics.
+// A team of four warps per row, four rows at a time; every lane issues all loads of its four hidden units at once as 16-byte
+// loads -- the token's row of EW (biases folded in), c_t, R -- so a row costs ONE round trip to L2 / HBM.  (Thread-per-unit
+// with 4-byte loads was measured slower: four times the load instructions.)  Activations use the MUFU forms (ex2 + rcp;
+// |error| ~3e-7, far below the TF32 rounding of the pre-activations).
+// The FIRST round (one row per team, units 0..511) is inlined into the kernel's epilogue, where its loads are issued BEFORE
+// the normalisation pass and the p tile's TMA stores and consumed after them.  The out-of-line function is the remainder:
+// further rounds (tiles_n < 32), hidden units beyond 512, x_{t+1} when it did not ride along, and the whole job for the plain
+// projection + sample kernel (x_{t+1} only).
 struct CellTailArgs {       // by value: a reference to the kernel's parameter block would force a local-memory copy of it
   const float* embed; float* x_next; const float* R; const float* EW; const float* c_prev;
   float* c_out; float* h_out; float* acts; float* htop;
   int E, G4, L, t, do_cell;
+  const int2* tokpub; int ntile, tiles_n, M;
 };
+__device__ __forceinline__ void st_relaxed_i2(int2* p, int2 v) {
+  asm volatile("st.relaxed.gpu.global.v2.s32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+// the token fed back for global row m at step tag - 1, once its sampling tile has published it (bounded wait)
+__device__ __forceinline__ int wait_token(const int2* tokpub, int m, int tag, int lane) {
+  int tok = 0;
+  if (lane == 0) {
+    const unsigned long long t0 = globaltimer_ns();
+    for (;;) {
+      int2 v;
+      asm volatile("ld.relaxed.gpu.global.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(tokpub + m) : "memory");
+      if (v.y == tag) { tok = v.x; break; }
+      __nanosleep(20);
+      if (globaltimer_ns() - t0 > 4000000000ull) __trap();   // a protocol bug traps instead of hanging the GPU
+    }
+  }
+  return __shfl_sync(0xffffffffu, tok, 0);
+}
 __device__ __forceinline__ float sigmoid_mufu(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float tanh_mufu(float x) { return 2.f * __fdividef(1.f, 1.f + __expf(-2.f * x)) - 1.f; }
 
@@ -161,20 +186,24 @@ __device__ __forceinline__ void lstm_cell_store4(const CellTailArgs& a, int H, i
   *reinterpret_cast<float4*>(a.htop + ((size_t)mr * a.L + (a.t + 1)) * H + j) = h4;
 }
 
-// Remainder of the cell (see the comment above CellTailArgs).  A team of four warps per row; lane tl of the team owns the
-// hidden units 4 tl .. 4 tl + 3 (+ 512 per further pass over H).  first_done: the epilogue already handled the units
-// [0, 512) of the rows s_list[0..3] (one row per team) and, if x_first_done, their x.
-__device__ __noinline__ void decode_cell_tail(const CellTailArgs a, int etid, int m0, const int* s_list, const int* s_fed,
-                                              int nrows, bool first_done, bool x_first_done) {
-  const int team = etid >> 7, tl = etid & 127;
-  if (a.do_cell) {
-    const int H = a.G4 >> 2;
-    for (int i = team; i < nrows; i += VS_G) {
-      const int r = s_list[i];
-      const int mr = m0 + r, tok = s_fed[r];
+// Remainder of the cell (see the comment above CellTailArgs).  Team k of four warps takes the assigned rows
+// ntile + (k + 4 j) tiles_n, j = 0, 1, ...; lane tl of the team owns the hidden units 4 tl .. 4 tl + 3 (+ 512 per further pass
+// over H).  first_done: the epilogue already handled round j = 0 for the units [0, 512) and, if x_first_done, its x.
+__device__ __noinline__ void decode_cell_tail(const CellTailArgs a, int etid, int m0, bool first_done, bool x_first_done) {
+  const int team = etid >> 7, tl = etid & 127, lane = etid & 31;
+  const int H = a.G4 >> 2;
+  const bool vec = ((a.E & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.embed) & 15u) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(a.x_next) & 15u) == 0);
+  for (int round = 0, r = a.ntile + team * a.tiles_n; r < BM && m0 + r < a.M; ++round, r += VS_G * a.tiles_n) {
+    const bool cell_round = a.do_cell && !(first_done && round == 0 && H <= 4 * 128);     // uniform over the CTA
+    const bool x_todo = a.x_next != nullptr && !(x_first_done && round == 0);
+    if (!cell_round && !x_todo) continue;
+    const int mr = m0 + r;
+    const int tok = wait_token(a.tokpub, mr, a.t + 1, lane);
+    if (cell_round) {
       const float* Er = a.EW + (size_t)tok * a.G4;
       const float* Rr = a.R + (size_t)mr * a.G4;
-      for (int j = 4 * tl + ((first_done && i < VS_G) ? 4 * 128 : 0); j < H; j += 4 * 128) {
+      for (int j = 4 * tl + ((first_done && round == 0) ? 4 * 128 : 0); j < H; j += 4 * 128) {
         float4 ev[4], rv[4];
 #pragma unroll
         for (int gt = 0; gt < 4; ++gt) {
@@ -185,16 +214,9 @@ __device__ __noinline__ void decode_cell_tail(const CellTailArgs a, int etid, in
         lstm_cell_store4(a, H, mr, j, ev, rv, cp);
       }
     }
-  }
-  // x_{t+1} = embed[fed]
-  if (a.x_next != nullptr) {
-    const bool vec = ((a.E & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.embed) & 15u) == 0) &&
-                     ((reinterpret_cast<uintptr_t>(a.x_next) & 15u) == 0);
-    for (int i = team; i < nrows; i += VS_G) {
-      if (x_first_done && i < VS_G) continue;
-      const int r = s_list[i];
-      const float* er = a.embed + (size_t)s_fed[r] * a.E;
-      float* xr = a.x_next + (size_t)(m0 + r) * a.E;
+    if (x_todo) {
+      const float* er = a.embed + (size_t)tok * a.E;
+      float* xr = a.x_next + (size_t)mr * a.E;
       if (vec) { for (int c = tl; c < (a.E >> 2); c += 128) reinterpret_cast<float4*>(xr)[c] = __ldcg(reinterpret_cast<const float4*>(er) + c); }
       else { for (int c = tl; c < a.E; c += 128) xr[c] = __ldg(er + c); }
     }
@@ -221,9 +243,6 @@ vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   float2 (*s_part)[BM] = reinterpret_cast<float2 (*)[BM]>(smem);              // [VS_G][BM] row statistics of pass 1
   float4* s_row = reinterpret_cast<float4*>(smem + VS_G * BM * 8);            // [VS_G][BM] (M, S, first tile, -) per group
   int* s_hit = reinterpret_cast<int*>(smem + VS_G * BM * 8 + VS_G * BM * 16); // first column holding the row maximum
-  int* s_fed = s_hit + BM;                                                    // token this CTA feeds back for the row, or -1
-  int* s_list = s_fed + BM;                                                   // rows this CTA feeds back, compacted
-  int* s_cnt = s_list + BM;                                                   // their number
   static_assert(VS_G * BM * 8 + VS_G * BM * 16 + 3 * BM * 4 + 16 <= 16384, "vocab_sample: exchange buffers exceed 16 KB");
   static_assert(16384 + ((BN / 16 + VS_G - 1) / VS_G) * VS_EPI_THREADS * 4 <= S::STAGE, "vocab_sample: per-unit running maxima exceed stage 0");
   // "this row block's rec tiles have arrived": set by the producer thread (idle once its loads are issued), read by the
@@ -489,7 +508,6 @@ vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     s_part[g][row] = make_float2(m_run, s_run);
     if (g == 0) s_hit[row] = 0x7fffffff;
-    if (etid == 0) *s_cnt = 0;
     if (etid == 0) VS_STAMP(7);
     epi_bar();
 
@@ -590,7 +608,7 @@ vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     epi_bar();
 
-    // ---- token id and the rows this CTA feeds back to the next step
+    // ---- token id; (token, step tag) published for the tile the row is assigned to (decode_cell_tail's comment)
     if (g == 0) {
       int fed = -1;
       const bool m_ok = m < a.M;
@@ -608,10 +626,8 @@ vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           fed = (fz >= 0 && fz < a.N) ? (int)fz : 0;
         }
       }
-      s_fed[row] = fed;
-      if (fed >= 0) s_list[atomicAdd(s_cnt, 1)] = row;
+      if (fed >= 0 && a.tokpub != nullptr) st_relaxed_i2(a.tokpub + m, make_int2(fed, a.t + 1));
     }
-    epi_bar();
     if (etid == 0) VS_STAMP(11);
 
     // ---- fused decode step, first pass of the cell (decode_cell_tail's comment): issue every load of up to four fed-back
@@ -619,20 +635,21 @@ vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     CellTailArgs ct;
     ct.embed = a.embed; ct.x_next = a.x_next; ct.R = a.R; ct.EW = a.EW; ct.c_prev = a.c_prev; ct.c_out = a.c_out;
     ct.h_out = a.h_out; ct.acts = a.acts; ct.htop = a.htop; ct.E = a.E; ct.G4 = a.G4; ct.L = a.L; ct.t = a.t; ct.do_cell = a.do_cell;
-    const int nrows = *s_cnt;
+    ct.tokpub = a.tokpub; ct.ntile = ntile; ct.tiles_n = a.tiles_n; ct.M = a.M;
     const int Hh = a.G4 >> 2;
-    const int team = etid >> 7, tl = etid & 127;          // team of four warps per fed-back row; lane tl owns units 4 tl .. 4 tl + 3
-    const bool cell_first = a.do_cell && team < nrows;
+    const int team = etid >> 7, tl = etid & 127;          // team of four warps per assigned row; lane tl owns units 4 tl .. 4 tl + 3
+    const int r1 = ntile + team * a.tiles_n;              // this team's row of round 0
+    const bool row_first = r1 < BM && m0 + r1 < a.M;
+    const bool cell_first = a.do_cell && row_first;
     const bool has_u = cell_first && 4 * tl < Hh;
     const bool x_first = a.do_cell && a.x_next != nullptr && ((a.E & 3) == 0) && (a.E >> 2) <= 128 &&
                          ((reinterpret_cast<uintptr_t>(a.embed) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(a.x_next) & 15u) == 0);
-    const bool has_x = x_first && team < nrows && tl < (a.E >> 2);
+    const bool has_x = x_first && row_first && tl < (a.E >> 2);
     int mr1 = 0;
     float4 ev[4], rv[4], cp4 = make_float4(0.f, 0.f, 0.f, 0.f), xv = make_float4(0.f, 0.f, 0.f, 0.f);
     if (cell_first) {
-      const int r = s_list[team];
-      const int tok1 = s_fed[r];
-      mr1 = m0 + r;
+      mr1 = m0 + r1;
+      const int tok1 = wait_token(a.tokpub, mr1, a.t + 1, lane);
       // ld.global.cg (L2 only): the shared-memory carve-out leaves L1 ~29 KB, a row is 20 KB of gathers (EW 8, R 8, c 2, x 2)
       if (has_u) {
         const float* Er = a.EW + (size_t)tok1 * a.G4 + 4 * tl;
@@ -694,8 +711,9 @@ vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (has_x) reinterpret_cast<float4*>(a.x_next + (size_t)mr1 * a.E)[tl] = xv;
     if (has_u) lstm_cell_store4(ct, Hh, mr1, 4 * tl, ev, rv, cp4);
     if (etid == 0) VS_STAMP(17);
-    if ((a.x_next != nullptr && !(x_first && nrows <= VS_G)) || (a.do_cell && (nrows > VS_G || Hh > 4 * 128)))
-      decode_cell_tail(ct, etid, m0, s_list, s_fed, nrows, a.do_cell != 0, x_first);
+    const bool more_rounds = ntile + VS_G * a.tiles_n < BM;
+    if ((a.x_next != nullptr && (!x_first || more_rounds)) || (a.do_cell && (more_rounds || Hh > 4 * 128)))
+      decode_cell_tail(ct, etid, m0, a.do_cell != 0, x_first);
     if (etid == 0) VS_STAMP(14);
     if (g == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem may be released; the writes land by grid end
     if (etid == 0) VS_STAMP(12);
@@ -766,7 +784,8 @@ static size_t vs_part_floats(int B, int V) {
   const size_t Mpad = (size_t)cdiv(B, tc::BM) * tc::BM;
   return 2 * Mpad * (size_t)cdiv(V, 128);
 }
-size_t vocab_sample_scratch_floats(int B, int V) { return 2 * vs_part_floats(B, V) + 4; }
+static size_t vs_tok_floats(int B) { return 2 * (size_t)cdiv(B, tc::BM) * tc::BM; }
+size_t vocab_sample_scratch_floats(int B, int V) { return 2 * vs_part_floats(B, V) + vs_tok_floats(B) + 4; }
 
 // One fused decode step on the tensor cores.  handled = false (nothing launched) when the shape does not fit the
 // co-resident grid or TMA's alignment rules; the caller then runs the separate projection + sampler kernels.
@@ -809,8 +828,9 @@ int vocab_sample_tc(const float* htop, int lda, const float* W_out, const float*
   a.n_rec = 0; a.rec_tiles_n = 1; a.RBN = 16; a.G4 = 0; a.R = nullptr; a.rec_done = nullptr; a.rec_expect = 0u; a.do_cell = 0;
   a.EW = nullptr; a.c_prev = nullptr; a.c_out = nullptr; a.h_out = nullptr; a.acts = nullptr;
   a.htop = nullptr;
+  a.tokpub = reinterpret_cast<int2*>(scratch + 2 * pf);
   if (t == 0) {
-    cudaError_t e = cudaMemsetAsync(scratch, 0, 2 * pf * sizeof(float), stream);   // both statistics buffers "not ready"
+    cudaError_t e = cudaMemsetAsync(scratch, 0, (2 * pf + vs_tok_floats(B)) * sizeof(float), stream);   // statistics "not ready", token tags 0
     if (e != cudaSuccess) { set_error("vocab_sample memset: %s", cudaGetErrorString(e)); return GIC_ERR_CUDA; }
   }
   int rc;
@@ -908,8 +928,9 @@ int decode_step_tc(const float* hs_t1, const float* W_out, const float* b_out, c
   a.rec_expect = (unsigned int)(t + 1) * (unsigned int)pl.rec_tiles_n;
   a.do_cell = last ? 0 : 1;
   a.EW = EW; a.c_prev = c_prev; a.c_out = c_out; a.h_out = h_out; a.acts = acts; a.htop = htop;
+  a.tokpub = reinterpret_cast<int2*>(scratch + 2 * pf);
   if (t == 0) {
-    cudaError_t e = cudaMemsetAsync(scratch, 0, 2 * pf * sizeof(float), stream);   // both statistics buffers "not ready"
+    cudaError_t e = cudaMemsetAsync(scratch, 0, (2 * pf + vs_tok_floats(B)) * sizeof(float), stream);   // statistics "not ready", token tags 0
     if (e != cudaSuccess) { set_error("decode_step memset: %s", cudaGetErrorString(e)); return GIC_ERR_CUDA; }
   }
   int rc;
