@@ -350,20 +350,24 @@ def run_ours(args):
     # ---- exposed cost of the gradient exchange (N > 1): the same step with the all-reduce left out
     comm = None
     if world > 1:
+        # after identical updates from identical reduced gradients the replicas must be bit-identical (checked BEFORE the
+        # no-exchange run below, which lets every rank follow its own shard's gradient)
+        flat = torch.cat([inst._flat_g.flat, inst._flat_d.flat])
+        ref0 = flat.clone(); dist.broadcast(ref0, 0)
+        same = torch.tensor([1.0 if torch.equal(ref0, flat) else 0.0], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
         inst.skip_allreduce = True
         inst._graphs.clear()
         nms, _, _ = timed(step_resident, args.steps, args.warmup)
         inst.skip_allreduce = False
         inst._graphs.clear()
+        for fp in (inst._flat_g, inst._flat_d):          # back to identical replicas: rank 0's parameters and Adam moments
+            for t in (fp.flat, fp.m, fp.v):
+                dist.broadcast(t, 0)
         for i in range(3):
             step_resident(i)                 # re-capture the real step (the later measurements replay it)
         torch.cuda.synchronize()
         nbytes = 4 * (inst._flat_g.n + inst._flat_d.n)
-        # after identical updates from identical reduced gradients the replicas must be bit-identical
-        flat = torch.cat([inst._flat_g.flat, inst._flat_d.flat])
-        ref0 = flat.clone(); dist.broadcast(ref0, 0)
-        same = torch.tensor([1.0 if torch.equal(ref0, flat) else 0.0], device=dev)
-        dist.all_reduce(same, op=dist.ReduceOp.MIN)
         peer = inst._peer is not None
         comm = {"comm_ms_exposed": ms_step - nms / args.steps, "ms_per_step_without_exchange": nms / args.steps,
                 "allreduce_bytes_per_step": nbytes,

@@ -146,11 +146,12 @@ __global__ void __launch_bounds__(AR_THREADS, 1) allreduce_p2p_kernel(const __gr
   float sq = 0.f;
   const size_t stride = (size_t)AR_CTAS * AR_THREADS;
   const size_t i0 = s0 + (size_t)c * AR_THREADS + tid;
-  // NVLink's latency-bandwidth product (~2 us x 750 GB/s) needs ~1.5 MB of loads in flight per rank: every thread keeps 8
-  // 16-byte peer loads outstanding -- U elements x W ranks, all issued before the first one is consumed
-  if (W == 2) sq = ar_body<4>(me, W, i0, s1, stride);
-  else if (W <= 4) sq = ar_body<2>(me, W, i0, s1, stride);
-  else sq = ar_body<1>(me, W, i0, s1, stride);
+  // NVLink's latency-bandwidth product (~2 us x 750 GB/s) needs ~1.5 MB of loads in flight per rank, and a trip also has to
+  // hide its own W stores: every thread keeps 16 16-byte peer loads outstanding -- U elements x W ranks, all issued before
+  // the first one is consumed
+  if (W <= 2) sq = ar_body<8>(me, W, i0, s1, stride);
+  else if (W <= 4) sq = ar_body<4>(me, W, i0, s1, stride);
+  else sq = ar_body<2>(me, W, i0, s1, stride);
   // partial square norm of this chunk: block reduction in a fixed order, pushed to every rank
   sq = warp_sum(sq);
   if ((tid & 31) == 0) s_red[tid >> 5] = sq;

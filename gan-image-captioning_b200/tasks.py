@@ -42,8 +42,15 @@ def collate_fn(batch):
     images = torch.zeros(len(batch), 3, image_size, image_size)
     for i, (img, _) in enumerate(batch):
         images[i] = img
-    flat, offsets, max_caption_len = ragged_to_csr(_token_lists(batch))
-    B = len(batch)
+    captions, lengths, max_caption_len = collate_captions(_token_lists(batch))
+    return images, captions, lengths, max_caption_len
+
+
+def collate_captions(token_lists):
+    """The caption half of collate_fn (src/tasks.py:143-156) on the host: captions[B, longest + 2] int64 = <S>, tokens, <E>,
+    <PAD>...; lengths[B] int32 = len + 2; max_caption_len."""
+    flat, offsets, max_caption_len = ragged_to_csr(token_lists)
+    B = len(token_lists)
     captions = torch.zeros(B, max_caption_len, dtype=torch.long)
     lengths = (offsets[1:] - offsets[:-1] + 2).to(torch.int32)
     pos = torch.arange(max_caption_len).unsqueeze(0)                     # [1, Lm]
@@ -55,7 +62,7 @@ def collate_fn(batch):
         inside = (pos >= 1) & (pos <= ln)
         captions = torch.where(inside, tok, captions)
     captions = torch.where(pos == ln + 1, torch.full_like(captions, END), captions)
-    return images, captions, lengths, max_caption_len
+    return captions, lengths, max_caption_len
 
 
 def pack_captions_device(token_lists: Sequence[Sequence[int]], device, max_caption_len: int = None):
