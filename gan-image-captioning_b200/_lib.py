@@ -152,6 +152,11 @@ def _declare(L):
     L.gic_allreduce.argtypes = [P, Z, P, I, P, P]
     L.gic_comm_local_group.argtypes = [P, I]
     L.gic_allreduce_local_group.argtypes = [P, P, P, Z, I, I, P]
+    L.gic_ctx_create.restype = P
+    L.gic_ctx_set_current.restype = P
+    L.gic_ctx_set_current.argtypes = [P]
+    L.gic_ctx_destroy.restype = None
+    L.gic_ctx_destroy.argtypes = [P]
     for name in header_symbols():      # every declared entry point must be exported
         getattr(L, name)
 
@@ -188,6 +193,34 @@ class expect_kernels:
         if missing or extra:
             raise AssertionError("kernels expected but not launched: %s; launched but expected absent: %s" % (missing, extra))
         return False
+
+
+class Context:
+    """A library context (include/gic_b200.h "contexts"): the temperature pointer, prepared discriminator weights, Philox
+    state and vocab-gradient event that the setters install are per context, not per process.  ``with ctx:`` makes it the
+    calling thread's current context for the block (re-entrant)."""
+
+    def __init__(self):
+        self.handle = lib().gic_ctx_create()
+        if not self.handle:
+            raise MemoryError("gic_ctx_create")
+        self._prev = []
+
+    def __enter__(self):
+        self._prev.append(lib().gic_ctx_set_current(self.handle))
+        return self
+
+    def __exit__(self, *exc):
+        lib().gic_ctx_set_current(self._prev.pop())
+        return False
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None) and _lib is not None:
+                _lib.gic_ctx_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
 
 
 def check(rc: int, what: str = ""):

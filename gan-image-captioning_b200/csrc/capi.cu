@@ -2,6 +2,7 @@
 // composition of the decode forward/backward passes.
 #include "../../include/gic_b200.h"
 #include <stdlib.h>
+#include <new>
 
 #include "gic_internal.cuh"
 
@@ -61,6 +62,7 @@ int rollout_q(const float*, const float*, int, int, int, int, float*, cudaStream
 int pg_loss(const float*, const int64_t*, const float*, int, int, int, int, float*, float*, float*, cudaStream_t);
 int clip_adam(float*, const float*, float*, float*, size_t, const float*, float, float, int, float, float, float,
               float, const float*, cudaStream_t);
+Ctx* ctx_set_current(Ctx*);
 void set_temperature_device(const float*);
 void set_rng(unsigned long long, unsigned long long, const unsigned long long*);
 int philox_uniform(uint32_t, unsigned long long, size_t, float*, cudaStream_t);
@@ -296,10 +298,10 @@ struct DecodeBwdWs {
 // Data-parallel hook: dW_out / db_out (40 % of the generator's gradient bytes at c2) are final long before the serial
 // BPTT tail.  When the caller registered an event (gic_set_vocab_grads_event) it is recorded on the stream right after
 // those two buffers are complete, so their all-reduce can run on another stream underneath the rest of the backward.
-static cudaEvent_t g_vocab_grads_event = nullptr;
 static int record_vocab_grads_event(cudaStream_t s) {
-  if (!g_vocab_grads_event) return GIC_OK;
-  cudaError_t e = cudaEventRecord(g_vocab_grads_event, s);
+  cudaEvent_t ev = ctx().vocab_grads_event;
+  if (!ev) return GIC_OK;
+  cudaError_t e = cudaEventRecord(ev, s);
   if (e != cudaSuccess) { set_error("cudaEventRecord(vocab grads): %s", cudaGetErrorString(e)); return GIC_ERR_CUDA; }
   return GIC_OK;
 }
@@ -915,6 +917,14 @@ int gic_philox_keep_mask(unsigned int tag, size_t n, float p, uint8_t* out, gic_
   GIC_TRY(require_device());
   return philox_keep_mask(tag, n, p, out, S(stream));
 }
-void gic_set_vocab_grads_event(void* cuda_event) { g_vocab_grads_event = reinterpret_cast<cudaEvent_t>(cuda_event); }
+void gic_set_vocab_grads_event(void* cuda_event) { ctx().vocab_grads_event = reinterpret_cast<cudaEvent_t>(cuda_event); }
+
+gic_ctx_t* gic_ctx_create(void) { return reinterpret_cast<gic_ctx_t*>(new (std::nothrow) Ctx()); }
+void gic_ctx_destroy(gic_ctx_t* c) {
+  Ctx* p = reinterpret_cast<Ctx*>(c);
+  if (p && &ctx() == p) ctx_set_current(nullptr);
+  delete p;
+}
+gic_ctx_t* gic_ctx_set_current(gic_ctx_t* c) { return reinterpret_cast<gic_ctx_t*>(ctx_set_current(reinterpret_cast<Ctx*>(c))); }
 
 }  // extern "C"

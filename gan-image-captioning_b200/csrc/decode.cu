@@ -9,19 +9,20 @@ namespace gic {
 
 // Temperature source: the by-value argument, or (CUDA-graph replay: by-value arguments are frozen at capture) a device
 // scalar registered with gic_set_temperature_device().
-static const float* g_t_dev = nullptr;
-void set_temperature_device(const float* p) { g_t_dev = p; }
-const float* temperature_device() { return g_t_dev; }
+void set_temperature_device(const float* p) { ctx().t_dev = p; }
+const float* temperature_device() { return ctx().t_dev; }
+#define g_t_dev (ctx().t_dev)
 __device__ __forceinline__ float pick_t(float by_value, const float* t_dev) { return t_dev ? __ldg(t_dev) : by_value; }
 
 // ---------------------------------------------------------------------------------------
 // shim-side random draws (caller passed no uniforms / no dropout masks): Philox4x32-10, see philox.cuh
 // ---------------------------------------------------------------------------------------
-static RngState g_rng = {0ull, 0ull, nullptr};
 void set_rng(unsigned long long seed, unsigned long long offset, const unsigned long long* state_dev) {
-  g_rng.seed = seed; g_rng.offset = offset; g_rng.dev = state_dev;
+  Ctx& c = ctx();
+  c.rng.seed = seed; c.rng.offset = offset; c.rng.dev = state_dev;
 }
-RngState rng_state() { return g_rng; }
+RngState rng_state() { const Ctx& c = ctx(); RngState r; r.seed = c.rng.seed; r.offset = c.rng.offset; r.dev = c.rng.dev; return r; }
+#define g_rng (rng_state())
 
 __global__ void philox_uniform_kernel(RngState st, uint32_t tag, unsigned long long base, size_t n, float* __restrict__ out) {
   unsigned long long seed, offset;

@@ -933,8 +933,8 @@ int disc_fill_groups(ConvGroups& g, int ngroups, const int* fs, const int* nf, c
 // layout = the forward workspace, weff[F+1] | W_h_bf(bf16)[F*Fp].  While a prepared blob is registered the forward /
 // backward read it instead of recomputing (one adversarial step makes 2 forward and 3 backward calls on the same
 // pre-update weights).
-static const float* g_prepared = nullptr;
-void disc_set_prepared(const float* prep) { g_prepared = prep; }
+void disc_set_prepared(const float* prep) { ctx().prepared = prep; }
+#define g_prepared (ctx().prepared)
 
 int disc_prepare(int mode, const float* W_h, const float* W_f, const float* b_f, int Hd, const float* W_o,
                  const float* b_o, int F, float* prep, cudaStream_t s) {

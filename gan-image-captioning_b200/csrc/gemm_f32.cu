@@ -65,6 +65,11 @@ int check_launch(const char* what) {
   return GIC_OK;
 }
 
+static thread_local Ctx tl_default_ctx;
+static thread_local Ctx* tl_ctx = nullptr;
+Ctx& ctx() { return tl_ctx ? *tl_ctx : tl_default_ctx; }
+Ctx* ctx_set_current(Ctx* c) { Ctx* prev = tl_ctx; tl_ctx = c; return prev; }
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {

@@ -32,6 +32,18 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 
 int num_sms();
 
+// ---- per-caller state (include/gic_b200.h "contexts") ------------------------------------------------------------
+// What used to be process-global setters lives in a context; every host thread has a current one (a thread-local default
+// until gic_ctx_set_current installs another), so two instructors -- or two threads -- in one process cannot corrupt each other.
+struct RngStateHost { unsigned long long seed, offset; const unsigned long long* dev; };
+struct Ctx {
+  const float* t_dev = nullptr;           // gic_set_temperature_device
+  const float* prepared = nullptr;        // gic_disc_set_prepared
+  RngStateHost rng = {0ull, 0ull, nullptr};   // gic_set_rng
+  cudaEvent_t vocab_grads_event = nullptr;    // gic_set_vocab_grads_event
+};
+Ctx& ctx();                               // the calling thread's current context
+
 // ---- optional per-kernel-class device timing (bench.py roofline): CUDA events on the launching stream ----
 enum ProfKind : int { PROF_GEMM = 0, PROF_SAMPLE = 1, PROF_CONVPOOL = 2, PROF_SOFTMAX_BWD = 3, PROF_ADAM = 4,
                       PROF_HEAD = 5, PROF_GEMM_D = 6, PROF_GEMM_DECODE = 7, PROF_VOCAB_SAMPLE = 8, PROF_KINDS = 9 };

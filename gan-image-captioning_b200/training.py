@@ -24,6 +24,18 @@ from .generator import Generator, bn_running_update
 from .utils import get_fixed_temperature, get_losses
 
 
+def _in_ctx(fn):
+    """Runs a GANInstructor method with the instructor's library context current (include/gic_b200.h "contexts"): the
+    temperature pointer, prepared discriminator weights, Philox state and event hooks it installs are its own."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *args, **kwargs):
+        with self._ctx:
+            return fn(self, *args, **kwargs)
+    return wrapped
+
+
 class FlatParams:
     """Re-homes a list of parameters into one contiguous fp32 buffer (params become views), with matching
     flat grad / Adam-moment buffers.  state_dict keys and nn.Parameter identities are unchanged."""
@@ -61,6 +73,7 @@ class FlatParams:
 class GANInstructor:
     def __init__(self, args, train_dataset=None, dev_dataset=None, device=None):
         _lib.lib()        # fail loudly at construction if the CUDA library is missing
+        self._ctx = _lib.Context()
         self.args = args
         self.device = torch.device(device if device is not None else args.device)
         self.gen = Generator(args).to(self.device)
@@ -331,6 +344,7 @@ class GANInstructor:
         return t[:int(numel)]            # a smaller batch after a larger one reuses the front of the cached buffer
 
     # ---- the fused adversarial step ---------------------------------------------------------------
+    @_in_ctx
     @torch.no_grad()
     def adv_step(self, captions, pooled=None, u=None, keep=None, train=True, forced_ids=None, loss_type=None,
                  update=True, graph=False, grid=None):
@@ -744,6 +758,7 @@ class GANInstructor:
         return st["out"]
 
     # ---- generator pre-training step (src/training.py:53-95) -------------------------------
+    @_in_ctx
     @torch.no_grad()
     def pretrain_step(self, captions, pooled=None, update=True):
         """Free-running greedy decode (sample(pretrain=True), :71) -> CrossEntropyLoss over all positions incl. PAD
@@ -816,6 +831,7 @@ class GANInstructor:
 
     # ---- discriminator step on hard captions (real vs generated ids): D pre-training sweep (BASELINE configs[4]) and
     #      the D half of the policy-gradient step.  F.one_hot is never materialised (column gather, src/training.py:158).
+    @_in_ctx
     @torch.no_grad()
     def disc_step(self, real_ids, fake_ids, keep=None, update=True):
         _lib.require_cuda()
@@ -864,6 +880,7 @@ class GANInstructor:
         return dict(d_loss=losses[1], d_real=d_real, d_fake=d_fake, d_sqnorm=self._clip_adam(fd, a.disc_lr, update, 1))
 
     # ---- EXTENSION: SeqGAN-style policy-gradient step (north-star stages 2-4; not in the reference) -------------
+    @_in_ctx
     @torch.no_grad()
     def pg_step(self, captions, pooled=None, u=None, u_roll=None, keep=None, n_roll=16, baseline_mode=1, update=True,
                 d_update=True, score_chunk=2048):

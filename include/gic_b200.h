@@ -287,11 +287,26 @@ int gic_decode_sample_bwd_attn(const gic_attn_t* attn, int mode, const float* do
                                float* const* dW_hh, float* const* db_ih, float* const* db_hh, float* dW_out,
                                float* db_out, float* dfeatures, gic_stream_t stream);
 
+/* ---- contexts: the state behind the four setters below ----
+ * gic_set_temperature_device, gic_disc_set_prepared, gic_set_rng and gic_set_vocab_grads_event configure the calls that
+ * FOLLOW them.  That state is not process-global: it lives in a context, and every host thread has a current context --
+ * a private thread-local default until gic_ctx_set_current installs one the caller created.  Two training loops in one
+ * process (or two threads) therefore cannot overwrite each other's temperature pointer, prepared weights, generator state or
+ * event: give each its own context and make it current around its calls (the Python mirror's GANInstructor does).
+ *   gic_ctx_create        a fresh context (all settings cleared); NULL when out of memory
+ *   gic_ctx_set_current   install ctx as the calling thread's current context (NULL = back to the thread's default);
+ *                         returns the previous one (NULL if that was the default)
+ *   gic_ctx_destroy       free it (it stops being current first) */
+typedef struct gic_ctx gic_ctx_t;
+gic_ctx_t* gic_ctx_create(void);
+gic_ctx_t* gic_ctx_set_current(gic_ctx_t* ctx);
+void gic_ctx_destroy(gic_ctx_t* ctx);
+
 /* ---- CUDA-graph replay support ----
  * By-value scalars are frozen when a launch is captured into a CUDA graph, but the reference changes two of them every
  * batch: the temperature (update_temperature, src/training.py:183,190-191) and Adam's bias corrections (step count).
  * gic_set_temperature_device(t_dev): while t_dev is non-NULL every entry point that takes `temperature` reads it from
- *   *t_dev when its kernels run and ignores the by-value argument (process-wide; pass NULL to switch back).
+ *   *t_dev when its kernels run and ignores the by-value argument (current context; pass NULL to switch back).
  * gic_clip_adam_dyn: gic_clip_adam with the step-dependent factors read from device memory:
  *   bias_corr_dev[0] = lr / (1 - beta1^t), bias_corr_dev[1] = 1 / sqrt(1 - beta2^t). */
 void gic_set_temperature_device(const float* t_dev);
@@ -305,7 +320,7 @@ int gic_clip_adam_dyn(float* p, const float* g, float* m, float* v, size_t n, co
  * alone -- the collapsed score head w_eff = out2logits.weight * feature2out.weight (src/discriminator.py:58-60) and, in
  * GIC_GEMM_BF16 mode, the bf16 copy of highway.weight -- can therefore be computed once:
  * gic_disc_prepare fills prepared[gic_disc_prepared_floats(F)] from the current weights; while
- * gic_disc_set_prepared(prepared) is non-NULL (process-wide, NULL switches back) gic_disc_fwd / gic_disc_bwd read it
+ * gic_disc_set_prepared(prepared) is non-NULL (current context, NULL switches back) gic_disc_fwd / gic_disc_bwd read it
  * instead of recomputing.  The caller must clear it (or prepare again) before the weights change. */
 size_t gic_disc_prepared_floats(int F);
 int gic_disc_prepare(int mode, const float* W_h /*[F,F]*/, const float* W_f /*[Hd,F]*/, const float* b_f, int Hd,
@@ -317,7 +332,7 @@ void gic_disc_set_prepared(const float* prepared);
  * (nn.Dropout, src/discriminator.py:30,58).  Parity runs pass them in (u[L,B,V], keep masks); a production step passes
  * u = NULL to gic_decode_sample_fwd and the uniforms are then generated INSIDE the fused decode kernel (Philox4x32-10,
  * counter = element index of the logical u[L,B,V], no 4*L*B*V-byte tensor is written or read).
- * gic_set_rng(seed, offset, state_dev): generator state for the calls that follow (process-wide).  state_dev != NULL:
+ * gic_set_rng(seed, offset, state_dev): generator state for the calls that follow (current context).  state_dev != NULL:
  *   {seed, offset} are read from device memory when the kernels run (CUDA-graph replay with a fresh offset per step).
  * gic_philox_uniform(tag, n, out): the first n elements of the logical stream `tag` (GIC_RNG_TAG_GUMBEL: exactly the
  *   uniforms the decode uses for u = NULL, so out[L*B*V] passed back in as `u` reproduces that decode bit for bit).
@@ -359,7 +374,7 @@ int gic_pack_captions(const int32_t* tokens, const int32_t* offsets, int B, int 
                       int32_t* lengths, gic_stream_t stream);
 
 /* ---- data-parallel overlap hook ----
- * gic_set_vocab_grads_event(ev): while ev (a cudaEvent_t, NULL to clear; process-wide) is registered,
+ * gic_set_vocab_grads_event(ev): while ev (a cudaEvent_t, NULL to clear; current context) is registered,
  * gic_decode_sample_bwd / _bwd_factored / _bwd_attn record it on their stream as soon as dW_out and db_out are final
  * -- before the serial BPTT tail -- so the caller can all-reduce that bucket on another stream underneath the rest of
  * the backward (the reference is single-GPU). */

@@ -239,3 +239,33 @@ def test_kernel_launch_counters_are_exported(built):
     with pytest.raises(AssertionError):
         with _lib.expect_kernels("vocab_sample_kernel"):
             pass
+
+
+def test_contexts_isolate_the_setters(built):
+    """The temperature pointer / prepared weights / Philox state / event hook live in a context; a thread's current context
+    is its own.  (Host-side bookkeeping only: nothing is launched.)"""
+    import threading
+    from gic_b200 import _lib
+    L = _lib.lib()
+    a, b = _lib.Context(), _lib.Context()
+    assert a.handle and b.handle and a.handle != b.handle
+    with a:
+        L.gic_set_rng(11, 22, None)
+        with b:                                       # nested: b is current, a's state untouched
+            L.gic_set_rng(33, 44, None)
+        prev = L.gic_ctx_set_current(a.handle)        # already current: returns a
+        assert prev == a.handle
+    assert L.gic_ctx_set_current(None) in (None, 0)   # outside every `with`: the thread's default was current
+    seen = {}
+
+    def other():
+        seen["prev"] = L.gic_ctx_set_current(b.handle)    # a fresh thread starts on ITS default, whatever the main thread did
+        L.gic_ctx_set_current(None)
+    with a:
+        t = threading.Thread(target=other); t.start(); t.join()
+    assert seen["prev"] in (None, 0)
+    from gic_b200.args import default_args
+    from gic_b200.training import GANInstructor
+    args = default_args(vocab_size=30, gen_embed_dim=8, gen_hidden_dim=16, disc_num_filters=[4, 4, 4], device="cpu")
+    i1, i2 = GANInstructor(args, device="cpu"), GANInstructor(args, device="cpu")
+    assert i1._ctx.handle != i2._ctx.handle

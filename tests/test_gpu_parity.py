@@ -677,3 +677,38 @@ def test_full_size_c2_properties_and_row_locality():
         close("c2/row_locality/d", acc_d / 2, ref_d, rtol=5e-3, atol=1e-12, outlier_frac=1e-3)
     finally:
         gic_b200.set_gemm_mode(old)
+
+
+def test_two_instructors_in_one_process_do_not_share_state():
+    """The temperature pointer, prepared discriminator weights and Philox state are per library context (one per
+    GANInstructor): two instructors stepping alternately -- different temperatures, graph replay, library-side draws -- give
+    exactly what each gives alone."""
+    from gic_b200.training import GANInstructor
+    inp = rp.make_inputs(rp.CONFIGS["c1"])
+    a = inp["args"]; a.device = "cuda"
+    caps, pooled = inp["captions"].cuda(), inp["pooled"].cuda()
+
+    def fresh(seed):
+        torch.manual_seed(seed)
+        inst = GANInstructor(a, device="cuda:0")
+        sd = inst.gen.state_dict(); sd.update({k: v.clone() for k, v in inp["gen"].items()}); inst.gen.load_state_dict(sd)
+        inst.disc.load_state_dict({k: v.clone() for k, v in inp["disc"].items()})
+        inst.gen.train(); inst.disc.train()
+        return inst
+
+    def run(insts, temps, steps=4):
+        outs = [[] for _ in insts]
+        for s in range(steps):
+            for k, (inst, T) in enumerate(zip(insts, temps)):
+                inst.gen.decoder.temperature = T * (1 + s)
+                r = inst.adv_step(caps, pooled=pooled, graph=True)          # u / keep drawn by the library (per-context Philox state)
+                outs[k].append((r["ids"].clone(), float(r["g_loss"]), float(r["d_loss"])))
+        torch.cuda.synchronize()
+        return outs
+    solo_a = run([fresh(11)], [1.0])[0]
+    solo_b = run([fresh(22)], [3.0])[0]
+    both = run([fresh(11), fresh(22)], [1.0, 3.0])
+    for solo, mixed in ((solo_a, both[0]), (solo_b, both[1])):
+        for (i0, g0, d0), (i1, g1, d1) in zip(solo, mixed):
+            assert torch.equal(i0, i1)
+            assert abs(g0 - g1) <= 1e-5 * max(1.0, abs(g0)) and abs(d0 - d1) <= 1e-5 * max(1.0, abs(d0))
