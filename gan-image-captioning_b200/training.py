@@ -93,7 +93,8 @@ class GANInstructor:
         self._side = None
         self._comm = None
         self.timeline = None         # list of (name, timing event) when a profiling script asks for markers
-        self._rng_seed = None        # Philox state of the library-side draws (u / dropout masks not supplied by the caller)
+        # Philox key of the library-side draws (u / dropout masks not supplied by the caller): torch's seed at construction
+        self._rng_seed = int(torch.initial_seed()) & ((1 << 63) - 1)
         self._rng_offset = 0
         self._rng_dyn = None
         self._vocab_ev = None
