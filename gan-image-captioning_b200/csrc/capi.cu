@@ -33,8 +33,10 @@ int gemm_dz(int, int, int, int, const float*, int, const float*, int, const floa
             cudaStream_t, bool*);
 // attn.cu
 int attn_fwd(const float*, const float*, const float*, const float*, int, int, int, int, float*, float*, cudaStream_t);
-int attn_bwd(const float*, const float*, const float*, const float*, const float*, const float*, int, int, int, int,
-             float*, float*, float*, float*, cudaStream_t);
+int attn_bwd_step(const float*, const float*, const float*, const float*, const float*, const float*, int, int, int, int,
+                  float*, float*, cudaStream_t);
+int attn_bwd_accum(const float*, const float*, const float*, const float*, const float*, const float*, int, int, int, int, int,
+                   float*, float*, float*, cudaStream_t);
 // lstm_tcgen05.cu
 int bptt_step_tc(const float* dG_t, const float* W_hh, const float* acts_prev, const float* c_prev, const float* c_cur,
                  const float* dh_top, float* dc_rec, float* dG_out, int B, int H, int L, int t, cudaStream_t stream,
@@ -102,14 +104,15 @@ int disc_bwd_entry(int mode, const float* dlogits, const uint8_t* keep, float dr
 static size_t a4(size_t x) { return (x + 3) & ~(size_t)3; }
 
 // attention saved layout (floats): Ak[B,P,Da] | Av[B,P,E] | q[L,B,Da] | alpha[L,B,P]
-// attention backward workspace:    dAk[B,P,Da] | dAv[B,P,E] | dq[L,B,Da]
+// attention backward workspace:    dAk[B,P,Da] | dAv[B,P,E] | dq[L,B,Da] | ds[L,B,P]
 struct AttnLayout {
   size_t Ak, Av, q, alpha, total;      // saved
-  size_t dAk, dAv, dq, ws_total;       // workspace
+  size_t dAk, dAv, dq, ds, ws_total;   // workspace
   AttnLayout(int B, int L, int P, int Da, int E) {
     Ak = 0; Av = a4((size_t)B * P * Da); q = Av + a4((size_t)B * P * E); alpha = q + a4((size_t)L * B * Da);
     total = alpha + a4((size_t)L * B * P);
-    dAk = 0; dAv = a4((size_t)B * P * Da); dq = dAv + a4((size_t)B * P * E); ws_total = dq + a4((size_t)L * B * Da);
+    dAk = 0; dAv = a4((size_t)B * P * Da); dq = dAv + a4((size_t)B * P * E); ds = dq + a4((size_t)L * B * Da);
+    ws_total = ds + a4((size_t)L * B * P);
   }
 };
 
@@ -319,8 +322,7 @@ static int decode_bwd(int mode, const float* dout, const float* demb, const floa
     GIC_REQUIRE(at->grid && at->W_k && at->W_v && at->W_q && at->w_e && at->saved && at->ws && at->dW_k && at->dW_v &&
                     at->dW_q && at->dw_e, GIC_ERR_NULL, "decode_sample_bwd_attn: incomplete attention block");
     GIC_REQUIRE(!accumulate, GIC_ERR_UNSUPPORTED, "decode_sample_bwd_attn: accumulate is not supported");
-    cudaMemsetAsync(at->ws + al.dAk, 0, (al.dq - al.dAk) * sizeof(float), s);      // dAk, dAv accumulate over t
-    cudaMemsetAsync(at->dw_e, 0, (size_t)at->Da * sizeof(float), s);
+    cudaMemsetAsync(at->dw_e, 0, (size_t)at->Da * sizeof(float), s);               // accumulated with atomics
   }
   if (B == 0) return GIC_OK;
   GIC_REQUIRE((dout || (demb && emb && W_e && De >= 1)) && fed && W_emb && W_ih && W_hh && W_out && saved && ws && dW_emb && dW_ih && dW_hh && db_ih &&
@@ -455,9 +457,9 @@ static int decode_bwd(int mode, const float* dout, const float* demb, const floa
         float* dXt = ws + w.dX + (size_t)t * BE;
         float* dq_t = at->ws + al.dq + (size_t)t * B * at->Da;
         GIC_TRY(gemm(mode, false, false, B, E, 4 * H, 1.f, dG_lt, 4 * H, W_ih[0], E, 0.f, dXt, E, nullptr, s));
-        GIC_TRY(attn_bwd(dXt, at->saved + al.alpha + (size_t)t * B * at->P, at->saved + al.q + (size_t)t * B * at->Da,
-                         at->saved + al.Ak, at->saved + al.Av, at->w_e, B, at->P, at->Da, E, dq_t, at->ws + al.dAk,
-                         at->ws + al.dAv, at->dw_e, s));
+        GIC_TRY(attn_bwd_step(dXt, at->saved + al.alpha + (size_t)t * B * at->P, at->saved + al.q + (size_t)t * B * at->Da,
+                              at->saved + al.Ak, at->saved + al.Av, at->w_e, B, at->P, at->Da, E, dq_t,
+                              at->ws + al.ds + (size_t)t * B * at->P, s));
         if (t > 0)   // q_t = h_{t-1} W_q^T: dh_{t-1} += dq_t W_q
           GIC_TRY(gemm(mode, false, false, B, H, at->Da, 1.f, dq_t, at->Da, at->W_q, H, 1.f, dhrec, H, nullptr, s));
       }
@@ -488,6 +490,9 @@ static int decode_bwd(int mode, const float* dout, const float* demb, const floa
     if (rec_bf) GIC_TRY(gemm_bf16(false, false, L * B, E, 4 * H, 1.f, dG_bf, 4 * H, ws + w.wih_bf, E, 0.f, ws + w.dX, E, nullptr, s));
     else GIC_TRY(gemm(mode, false, false, L * B, E, 4 * H, 1.f, ws + w.dG, 4 * H, W_ih[0], E, 0.f, ws + w.dX, E, nullptr, s));
   } else {
+    // dAk, dAv, dw_e: sums over the L steps, formed once (attn.cu)
+    GIC_TRY(attn_bwd_accum(at->saved + al.alpha, at->ws + al.ds, at->saved + al.q, ws + w.dX, at->saved + al.Ak, at->w_e, B, L,
+                           at->P, at->Da, E, at->ws + al.dAk, at->ws + al.dAv, at->dw_e, s));
     // attention parameter gradients: dW_q = sum_t dq_t^T h_{t-1} (step 0 sees h = 0), dW_k = dAk^T grid, dW_v = dAv^T grid
     GIC_TRY(gemm(mode, true, false, at->Da, H, L * B, 1.f, at->ws + al.dq, at->Da, saved + sv.hs(0), H, 0.f, at->dW_q, H,
                  nullptr, s));
