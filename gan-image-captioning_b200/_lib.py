@@ -157,6 +157,10 @@ def _declare(L):
     L.gic_ctx_set_current.argtypes = [P]
     L.gic_ctx_destroy.restype = None
     L.gic_ctx_destroy.argtypes = [P]
+    L.gic_ctx_set_option.argtypes = [C.c_char_p, I]
+    L.gic_ctx_clear_option.restype = None
+    L.gic_ctx_clear_option.argtypes = [C.c_char_p]
+    L.gic_ctx_get_option.argtypes = [C.c_char_p, I]
     for name in header_symbols():      # every declared entry point must be exported
         getattr(L, name)
 
@@ -214,6 +218,18 @@ class Context:
         lib().gic_ctx_set_current(self._prev.pop())
         return False
 
+    def set_option(self, name: str, value: int):
+        with self:
+            set_option(name, value)
+
+    def clear_option(self, name: str):
+        with self:
+            clear_option(name)
+
+    def get_option(self, name: str, default: int = 0) -> int:
+        with self:
+            return get_option(name, default)
+
     def __del__(self):
         try:
             if getattr(self, "handle", None) and _lib is not None:
@@ -221,6 +237,37 @@ class Context:
                 self.handle = None
         except Exception:
             pass
+
+
+def set_option(name: str, value: int):
+    """Set a kernel-variant / tuning switch of the calling thread's CURRENT context (gic_ctx_set_option)."""
+    check(lib().gic_ctx_set_option(name.encode(), int(value)), "gic_ctx_set_option")
+
+
+def clear_option(name: str):
+    lib().gic_ctx_clear_option(name.encode())
+
+
+def get_option(name: str, default: int = 0) -> int:
+    return int(lib().gic_ctx_get_option(name.encode(), int(default)))
+
+
+class options:
+    """``with _lib.options(GIC_DECODE_STEP=0, ...):`` -- switches of the current context for the block, cleared afterwards
+    (back to environment / built-in default)."""
+
+    def __init__(self, **kw):
+        self.kw = kw
+
+    def __enter__(self):
+        for k, v in self.kw.items():
+            set_option(k, v)
+        return self
+
+    def __exit__(self, *exc):
+        for k in self.kw:
+            clear_option(k)
+        return False
 
 
 def check(rc: int, what: str = ""):

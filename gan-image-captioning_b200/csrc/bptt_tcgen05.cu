@@ -438,12 +438,12 @@ int bptt_step_tc(const float* dG_t, const float* W_hh, const float* acts_prev, c
                  bool* handled) {
   using namespace tc;
   *handled = false;
-  { const char* e = getenv("GIC_BPTT_FUSED"); if (e && e[0] == '0') return GIC_OK; }     // read per call (tests, A/B runs)
+  if (option("GIC_BPTT_FUSED", 1) == 0) return GIC_OK;
   // Cluster size: 8 CTAs x 64 columns would need 16 co-resident clusters of 8 at c2, and a B200 fits 15
   // (cudaOccupancyMaxActiveClusters; two waves: 2.585 ms per step against 2.503 with clusters of 4), so 4 x 32 columns
   // is the default.
   int CL = 4;
-  { const char* e = getenv("GIC_BPTT_CL"); if (e && atoi(e) == 8) CL = 8; }
+  if (option("GIC_BPTT_CL", 0) == 8) CL = 8;
   const int BP_BN = 8 * CL;
   if (B <= 0 || t < 1 || (H % BP_BN) || ((4 * H) % (BK * CL))) return GIC_OK;
   const void* ptrs[] = {dG_t, W_hh, acts_prev, c_prev, c_cur, dh_top, dc_rec, dG_out};
@@ -472,7 +472,7 @@ int bptt_step_tc(const float* dG_t, const float* W_hh, const float* acts_prev, c
   at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   static int shown = 0;
-  if (!shown && getenv("GIC_BPTT_DEBUG")) {
+  if (!shown && option("GIC_BPTT_DEBUG", 0)) {
     shown = 1;
     int nc = -1;
     if (CL == 8) cudaOccupancyMaxActiveClusters(&nc, bptt_step_kernel<8>, &cfg); else cudaOccupancyMaxActiveClusters(&nc, bptt_step_kernel<4>, &cfg);
@@ -492,7 +492,7 @@ int bptt_persistent_tc(float* dG, const float* W_hh, const float* acts, const fl
                        unsigned int* counter, int B, int H, int L, cudaStream_t stream, bool* handled) {
   using namespace tc;
   *handled = false;
-  { const char* e = getenv("GIC_BPTT_PERSISTENT"); if (e && e[0] == '0') return GIC_OK; }   // read per call (tests, A/B runs)
+  if (option("GIC_BPTT_PERSISTENT", 1) == 0) return GIC_OK;
   if (B <= 0 || L < 2 || (H % BPP_BN) || ((4 * H) % (BK * BPP_CL)) || (4 * H) / BK / BPP_CL > BPP_MAX_KB) return GIC_OK;
   const void* ptrs[] = {dG, W_hh, acts, cs, dh_top, dc_in};
   for (const void* p : ptrs)

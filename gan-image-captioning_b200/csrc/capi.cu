@@ -398,8 +398,7 @@ static int decode_bwd(int mode, const float* dout, const float* demb, const floa
   // to half the time.  dG is written in both precisions by the cell kernel (fp32 for the bias gradients).
   // Measured at c2: the GEMM class gets ~50 us shorter, the four conversions cost ~25 us and the step time does not move
   // (the BPTT GEMMs are launch / stream-K-epilogue bound, not ingest bound) -> opt-in only (GIC_REC_BF16=1).
-  static int rec_env = -1;
-  if (rec_env < 0) { const char* e = getenv("GIC_REC_BF16"); rec_env = (e && e[0] == '1') ? 1 : 0; }
+  const int rec_env = option("GIC_REC_BF16", 0);
   const bool rec_bf = rec_env && (mode == GEMM_BF16) && layers == 1 && !at && (H % 8 == 0) && (E % 8 == 0);
   void* dG_bf = rec_bf ? (void*)(ws + w.dG_bf) : nullptr;
   if (rec_bf) {
@@ -931,5 +930,13 @@ void gic_ctx_destroy(gic_ctx_t* c) {
   delete p;
 }
 gic_ctx_t* gic_ctx_set_current(gic_ctx_t* c) { return reinterpret_cast<gic_ctx_t*>(ctx_set_current(reinterpret_cast<Ctx*>(c))); }
+int gic_ctx_set_option(const char* name, int value) {
+  GIC_REQUIRE(name && *name && strlen(name) < sizeof(Ctx::Opt().name), GIC_ERR_SHAPE, "gic_ctx_set_option: bad option name");
+  option_set(name, value);
+  GIC_REQUIRE(option_is_set(name), GIC_ERR_UNSUPPORTED, "gic_ctx_set_option: option table full");
+  return GIC_OK;
+}
+void gic_ctx_clear_option(const char* name) { if (name) option_clear(name); }
+int gic_ctx_get_option(const char* name, int dflt) { return name ? option(name, dflt) : dflt; }
 
 }  // extern "C"

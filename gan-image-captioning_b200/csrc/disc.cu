@@ -998,14 +998,14 @@ int disc_forward(int mode, const float* inp_soft, const int64_t* ids, const Disc
     for (int i = 0; i < g.ngroups; ++i) fmin = min(fmin, g.f[i]);
     bool use_mma = (mode == GEMM_TF32 || mode == GEMM_BF16) && d.es == 1 && d.De == d.R && (d.R % 8 == 0) && g.kmax <= CM_FMAX &&
                    d.L >= g.kmax && d.L - fmin + 1 <= 32;
-    { const char* e = getenv("GIC_CONV_MMA"); if (e && e[0] == '0') use_mma = false; }
+    if (option("GIC_CONV_MMA", 1) == 0) use_mma = false;
     if (use_mma) {
       const int nblocks = conv_mma_blocks(g);
       const int Tmax = d.L - fmin + 1;
       // slices: enough CTAs to balance the SMs, and at least two so that a CTA's weight fragments leave room for a second
       // resident CTA next to the B-fragment table (measured: c5 shape 3.09 ms with one slice, 2.63 ms with two)
       int sl = max(1, min(max(2, cdiv(4 * num_sms(), d.N)), nblocks));
-      { const char* e = getenv("GIC_CONV_MMA_SLICES"); if (e && atoi(e) > 0) sl = min(atoi(e), nblocks); }   // tuning
+      { const int o = option("GIC_CONV_MMA_SLICES", 0); if (o > 0) sl = min(o, nblocks); }   // tuning
       const int bps = cdiv(nblocks, sl);
       sl = cdiv(nblocks, bps);
       const size_t msmem = (size_t)Tmax * 4 * CM_XS * 8 + (size_t)bps * 16 * CM_WS * 4 + (size_t)bps * 16 * 4 + (size_t)bps * 16 +
@@ -1098,7 +1098,7 @@ int disc_backward(int mode, const float* dlogit, const uint8_t* keep, float drop
   if ((d.F % 4 == 0) && (!keep || (reinterpret_cast<uintptr_t>(keep) & 3u) == 0)) {
     const int colb = cdiv(d.F / 4, 256);
     int per_sm = 3;           // measured (ncu, c2): 3 -> 51 us, 4 -> 55, 6 -> 61, 8 -> 69, 2 -> 52, 1 -> 69
-    { const char* e = getenv("GIC_HB_CTAS_PER_SM"); if (e && atoi(e) > 0) per_sm = atoi(e); }   // tuning
+    { const int o = option("GIC_HB_CTAS_PER_SM", 0); if (o > 0) per_sm = o; }   // tuning
     int chunks = max(1, (per_sm * num_sms()) / colb);
     int rpc = cdiv((long long)rows, chunks);
     rpc = (rpc + 3) & ~3;
@@ -1176,7 +1176,7 @@ int disc_backward(int mode, const float* dlogit, const uint8_t* keep, float drop
     if (want_param) {
       const int colb = cdiv(d.F, 256);
       int per_sm = 4;
-      { const char* e = getenv("GIC_DW_CTAS_PER_SM"); if (e && atoi(e) > 0) per_sm = atoi(e); }   // tuning
+      { const int o = option("GIC_DW_CTAS_PER_SM", 0); if (o > 0) per_sm = o; }   // tuning
       int chunks = max(1, (per_sm * num_sms()) / colb);
       int rpc = cdiv((long long)rows, chunks);
       rpc = ((rpc + DW_RC - 1) / DW_RC) * DW_RC;

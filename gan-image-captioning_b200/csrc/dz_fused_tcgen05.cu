@@ -254,7 +254,7 @@ int dz_fused_tc(const float* demb, int K, const float* W_e, const float* p, cons
                 int M, int V, void* dz_bf, int Vp, float* db_out, int accumulate, cudaStream_t stream, bool* handled) {
   using namespace tc;
   *handled = false;
-  { const char* e = getenv("GIC_FUSED_DZ_BF16"); if (e && e[0] == '0') return GIC_OK; }
+  if (option("GIC_FUSED_DZ_BF16", 1) == 0) return GIC_OK;
   if (M <= 0 || V <= 0 || K <= 0 || K > 64 || (K % 4) || (V % 4) || (Vp % 8)) return GIC_OK;
   if (!aligned16(demb) || !aligned16(W_e) || !aligned16(p) || !aligned16(dz_bf)) return GIC_OK;
   const bool rn = tf32_round_in_tma();

@@ -49,9 +49,7 @@ int gemm_dz(int mode, int M, int N, int K, const float* demb, int lda, const flo
   if (mode != GEMM_TF32) return GIC_OK;
   // The register/LSU epilogue cannot keep enough bytes of p in flight (measured 1.16 ms at c2, profiles/README.md);
   // until the aux tile is TMA-prefetched the unfused pair (GEMM with TMA store + streaming softmax backward) is used.
-  static int fused = -1;
-  if (fused < 0) { const char* e = getenv("GIC_FUSED_DZ"); fused = (e && e[0] == '1') ? 1 : 0; }
-  if (!fused) return GIC_OK;
+  if (option("GIC_FUSED_DZ", 0) != 1) return GIC_OK;
   ProfScope prof(PROF_GEMM, 2.0 * M * N * K, stream);
   return gemm_tc_persistent(false, false, M, N, K, 1.f, demb, lda, W, ldb, 0.f, dz, ldc, nullptr, 1, p, dot, T, stream,
                             handled);

@@ -70,6 +70,45 @@ static thread_local Ctx* tl_ctx = nullptr;
 Ctx& ctx() { return tl_ctx ? *tl_ctx : tl_default_ctx; }
 Ctx* ctx_set_current(Ctx* c) { Ctx* prev = tl_ctx; tl_ctx = c; return prev; }
 
+static Ctx::Opt* option_find(Ctx& c, const char* name) {
+  for (int i = 0; i < c.n_opts; ++i)
+    if (strcmp(c.opts[i].name, name) == 0) return &c.opts[i];
+  return nullptr;
+}
+static Ctx::Opt* option_slot(Ctx& c, const char* name) {
+  if (Ctx::Opt* o = option_find(c, name)) return o;
+  if (c.n_opts >= Ctx::MAX_OPTS || strlen(name) >= sizeof(c.opts[0].name)) return nullptr;
+  Ctx::Opt* o = &c.opts[c.n_opts++];
+  strcpy(o->name, name);
+  o->has = false; o->value = 0;
+  return o;
+}
+static Ctx::Opt* option_lookup(const char* name) {
+  Ctx& c = ctx();
+  if (Ctx::Opt* o = option_find(c, name)) return o;
+  Ctx::Opt* o = option_slot(c, name);
+  if (o) {                                         // first lookup in this context: the environment, once
+    const char* e = getenv(name);
+    if (e && *e) { o->has = true; o->value = atoi(e); }
+  }
+  return o;
+}
+int option(const char* name, int dflt) {
+  const Ctx::Opt* o = option_lookup(name);
+  return (o && o->has) ? o->value : dflt;
+}
+bool option_is_set(const char* name) {
+  const Ctx::Opt* o = option_lookup(name);
+  return o && o->has;
+}
+void option_set(const char* name, int value) {
+  if (Ctx::Opt* o = option_slot(ctx(), name)) { o->has = true; o->value = value; }
+}
+void option_clear(const char* name) {
+  Ctx& c = ctx();
+  if (Ctx::Opt* o = option_find(c, name)) { *o = c.opts[c.n_opts - 1]; --c.n_opts; }
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -82,8 +121,7 @@ int num_sms() {
 }
 
 bool pdl_enabled() {
-  const char* e = getenv("GIC_PDL");
-  return !(e && e[0] == '0');
+  return option("GIC_PDL", 1) != 0;
 }
 
 // ---------------------------------------------------------------------------------------

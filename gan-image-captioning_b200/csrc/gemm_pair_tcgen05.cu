@@ -234,7 +234,7 @@ int gemm_tc_bf16_pair(bool b_mn, int M, int N, int K, float alpha, const void* A
                       int ldc, const float* bias, cudaStream_t stream, bool* handled) {
   using namespace tc;
   *handled = false;
-  { const char* e = getenv("GIC_GEMM_2CTA"); if (e && e[0] == '0') return GIC_OK; }     // read per call (tests, A/B runs)
+  if (option("GIC_GEMM_2CTA", 1) == 0) return GIC_OK;
   if (M < 512 || N < 192 || K < 64) return GIC_OK;
   if (!aligned16(A) || !aligned16(B) || !aligned16(C) || (lda % 8) || (ldb % 8) || (ldc % 4) || (bias && !aligned16(bias))) return GIC_OK;
   const int tiles_n = cdiv(N, PBN), tiles = tiles_n * cdiv(M, 256);

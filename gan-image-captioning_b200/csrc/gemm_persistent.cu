@@ -403,9 +403,7 @@ static int choose_bn(int M, int N, int K, bool b_mn, bool allow_sk) {
 }  // namespace tc
 
 static bool use_v1() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("GIC_GEMM_V1"); v = (e && e[0] == '1') ? 1 : 0; }
-  return v == 1;
+  return option("GIC_GEMM_V1", 0) == 1;
 }
 
 // Persistent GEMM entry.  handled = false (nothing launched) when the operands do not meet TMA's constraints.
@@ -436,11 +434,7 @@ int gemm_tc_persistent(bool transA, bool transB, int M, int N, int K, float alph
   const int G = num_sms();
   const int tiles_n = cdiv(N, BN), tiles_m = cdiv(M, BM), tiles = tiles_n * tiles_m, nkb = cdiv(K, BK);
   int dp_tiles = tiles;
-  static int sk_env = -1, dbg_env = 0;
-  if (sk_env < 0) {
-    const char* e = getenv("GIC_SK"); sk_env = (e && e[0] == '0') ? 0 : 1;
-    const char* d = getenv("GIC_GEMM_DBG"); dbg_env = d ? atoi(d) : 0;
-  }
+  const int sk_env = option("GIC_SK", 1), dbg_env = option("GIC_GEMM_DBG", 0);
   if (allow_sk && sk_env) {
     // stream-K only when whole tiles cannot occupy half the machine (long-K / small-MN shapes of the backward pass):
     // every CTA gets an equal share of the (tile, k-block) iteration space.  fp32 reductions into L2 cost ~5 ps per

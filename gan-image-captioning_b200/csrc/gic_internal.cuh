@@ -41,8 +41,18 @@ struct Ctx {
   const float* prepared = nullptr;        // gic_disc_set_prepared
   RngStateHost rng = {0ull, 0ull, nullptr};   // gic_set_rng
   cudaEvent_t vocab_grads_event = nullptr;    // gic_set_vocab_grads_event
+  // A/B and tuning switches (gic_ctx_set_option).  A name that was never set is looked up in the environment ONCE per
+  // context (the first time a launch path asks) and remembered: no getenv on the launch paths after that.
+  struct Opt { char name[28]; int value; bool has; };
+  static constexpr int MAX_OPTS = 48;
+  Opt opts[MAX_OPTS];
+  int n_opts = 0;
 };
 Ctx& ctx();                               // the calling thread's current context
+int option(const char* name, int dflt);   // the current context's value of a switch (set_option > environment > dflt)
+bool option_is_set(const char* name);
+void option_set(const char* name, int value);
+void option_clear(const char* name);      // forget it: the next lookup consults the environment again
 
 // ---- optional per-kernel-class device timing (bench.py roofline): CUDA events on the launching stream ----
 enum ProfKind : int { PROF_GEMM = 0, PROF_SAMPLE = 1, PROF_CONVPOOL = 2, PROF_SOFTMAX_BWD = 3, PROF_ADAM = 4,

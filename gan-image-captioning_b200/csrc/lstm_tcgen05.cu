@@ -378,7 +378,7 @@ int lstm_step_tc(const float* x, int In, const float* h_prev, const float* W_ih,
   int U = 32;
   if ((H % 32) || (H / 32) * mt * 4 < 3 * num_sms()) U = 16;
   if (U == 16 && ((H % 16) || (H / 16) * mt * 4 < 3 * num_sms())) U = 8;
-  { const char* e = getenv("GIC_LSTM_U"); if (e) { const int u = atoi(e); if ((u == 8 || u == 16 || u == 32) && H % u == 0) U = u; } }   // tuning experiments
+  { const int u = option("GIC_LSTM_U", 0); if ((u == 8 || u == 16 || u == 32) && H % u == 0) U = u; }   // tuning experiments
   const bool rn = tf32_round_in_tma();
   CUtensorMap tx, th, twi, twh;
   bool ok = make_map(&tx, x, B, In, In, BK, BM, rn, false) && make_map(&th, h_prev, B, H, H, BK, BM, rn, false) &&
@@ -396,12 +396,11 @@ int lstm_step_tc(const float* x, int In, const float* h_prev, const float* W_ih,
   {
     // Measured at c2 (bench32*.log): 23.3 us per launch against 22.0 us for the one-CTA-per-tile kernel, decode 0.822 vs
     // 0.799 ms -- the two cluster barriers, the TMEM -> shared staging and the DSMEM reads cost more than the shorter
-    // main loop saves.  Opt-in (GIC_LSTM_SPLITK=1); read per call so that the tests can toggle it.
-    const char* ske = getenv("GIC_LSTM_SPLITK");
-    const int sk_env = (ske && ske[0] == '1') ? 1 : 0;
+    // main loop saves.  Opt-in (option GIC_LSTM_SPLITK = 1).
+    const int sk_env = option("GIC_LSTM_SPLITK", 0) == 1;
     const int nkb = cdiv(In, BK) + cdiv(H, BK);
     if (sk_env && (H % SK_U) == 0 && (In % BK) == 0 && (H % BK) == 0 && (nkb % SK_CL) == 0 && nkb / SK_CL >= 2 &&
-        (H / SK_U) * SK_CL * mt * 2 >= num_sms() && !getenv("GIC_LSTM_U")) {
+        (H / SK_U) * SK_CL * mt * 2 >= num_sms() && !option_is_set("GIC_LSTM_U")) {
       CUtensorMap swi, swh;
       if (make_map(&swi, W_ih, 4 * H, In, In, BK, SK_U, rn, false) && make_map(&swh, W_hh, 4 * H, H, H, BK, SK_U, rn, false)) {
         static bool sk_attr = false;

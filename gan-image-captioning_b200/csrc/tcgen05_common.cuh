@@ -163,12 +163,7 @@ inline bool make_map_3d(CUtensorMap* m, const float* base, int d0, int d1, int d
 }
 
 inline bool tf32_round_in_tma() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("GIC_TMA_TF32_RN");
-    v = (e && e[0] == '0') ? 0 : 1;
-  }
-  return v == 1;
+  return option("GIC_TMA_TF32_RN", 1) != 0;
 }
 
 

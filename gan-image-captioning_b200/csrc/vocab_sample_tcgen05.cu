@@ -748,8 +748,7 @@ static int launch_vs(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
 // debug timeline (GIC_VS_STAMPS=1): a static device buffer of 16 clock64 stamps per CTA, printed by gic_vs_stamps_dump()
 static long long* g_stamps = nullptr;
 long long* vs_stamps_buffer() {
-  const char* e = getenv("GIC_VS_STAMPS");
-  if (!(e && e[0] == '1')) return nullptr;
+  if (option("GIC_VS_STAMPS", 0) != 1) return nullptr;
   if (!g_stamps) { cudaMalloc(&g_stamps, 256 * 32 * sizeof(long long)); cudaMemset(g_stamps, 0, 256 * 32 * sizeof(long long)); }
   return g_stamps;
 }
@@ -795,7 +794,7 @@ int vocab_sample_tc(const float* htop, int lda, const float* W_out, const float*
   extern RngState rng_state();
   using namespace tc;
   *handled = false;
-  { const char* e = getenv("GIC_FUSED_SAMPLE"); if (e && e[0] == '0') return GIC_OK; }   // read per call: tests toggle it
+  if (option("GIC_FUSED_SAMPLE", 1) == 0) return GIC_OK;
   if (B <= 0 || V <= 0 || H <= 0) return GIC_OK;
   if ((V % 4) || (H % 4) || (lda % 4) || !aligned16(htop) || !aligned16(W_out) || !aligned16(b_out) || (u_t && !aligned16(u_t)) ||
       !aligned16(out) || (((size_t)L * V) % 4))
@@ -880,8 +879,7 @@ static bool decode_step_plan_impl(int B, int V, int H, DecodeStepPlan* p) {
   return false;
 }
 bool decode_step_plan(int B, int V, int H) {
-  { const char* e = getenv("GIC_FUSED_SAMPLE"); if (e && e[0] == '0') return false; }     // read per call: tests toggle them
-  { const char* e = getenv("GIC_DECODE_STEP"); if (e && e[0] == '0') return false; }
+  if (option("GIC_FUSED_SAMPLE", 1) == 0 || option("GIC_DECODE_STEP", 1) == 0) return false;
   DecodeStepPlan p;
   return decode_step_plan_impl(B, V, H, &p);
 }
@@ -918,8 +916,7 @@ int decode_step_tc(const float* hs_t1, const float* W_out, const float* b_out, c
   a.ids = ids; a.forced = forced; a.L = L; a.t = t; a.embed = embed; a.E = E; a.x_next = x_next;
   a.stamps = nullptr;
   if (long long* sb = vs_stamps_buffer()) {       // debug timeline of ONE step (GIC_VS_STAMPS=1, GIC_VS_STAMPS_T=t; default L - 2)
-    const char* e = getenv("GIC_VS_STAMPS_T");
-    if (t == (e ? atoi(e) : L - 2)) a.stamps = sb;
+    if (t == option("GIC_VS_STAMPS_T", L - 2)) a.stamps = sb;
   }
   a.use_rng = (u_t == nullptr) ? 1 : 0;
   a.rng = rng_state();

@@ -301,6 +301,17 @@ typedef struct gic_ctx gic_ctx_t;
 gic_ctx_t* gic_ctx_create(void);
 gic_ctx_t* gic_ctx_set_current(gic_ctx_t* ctx);
 void gic_ctx_destroy(gic_ctx_t* ctx);
+/* A/B and tuning switches of the CURRENT context (which kernel variant a launch path takes: GIC_DECODE_STEP, GIC_FUSED_SAMPLE,
+ * GIC_GEMM_2CTA, GIC_CONV_MMA, GIC_BPTT_PERSISTENT, GIC_BPTT_FUSED, GIC_FUSED_DZ_BF16, GIC_LSTM_SPLITK, GIC_PDL, ...; the
+ * full table is in DESIGN.md).  They are integers held by the context; a switch nobody set is looked up in the process
+ * environment under the same name ONCE per context -- the first time a launch path asks -- and remembered, so no launch
+ * path calls getenv twice and a running job cannot be re-routed by a later setenv.
+ *   gic_ctx_set_option    set name = value (GIC_ERR_SHAPE: empty or too long a name; GIC_ERR_UNSUPPORTED: table full)
+ *   gic_ctx_clear_option  forget it: the next lookup consults the environment again, then the built-in default
+ *   gic_ctx_get_option    the value a launch path would see (dflt when neither set nor in the environment) */
+int gic_ctx_set_option(const char* name, int value);
+void gic_ctx_clear_option(const char* name);
+int gic_ctx_get_option(const char* name, int dflt);
 
 /* ---- CUDA-graph replay support ----
  * By-value scalars are frozen when a launch is captured into a CUDA graph, but the reference changes two of them every

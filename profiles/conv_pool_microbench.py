@@ -13,9 +13,10 @@ def run(N,L,V=10000,fsz=[3,4,5],nfl=[300,300,300],R=64):
     ids=torch.randint(0,V,(N,L),generator=g,device=d)
     gic_b200.prof_enable(True) if hasattr(gic_b200,'prof_enable') else None
     for flag,sl in (("0",""),("1",""),("1","2"),("1","3"),("1","6"),("1","8")):
-        os.environ["GIC_CONV_MMA"]=flag
-        if sl: os.environ["GIC_CONV_MMA_SLICES"]=sl
-        else: os.environ.pop("GIC_CONV_MMA_SLICES",None)
+        from gic_b200 import _lib
+        _lib.set_option("GIC_CONV_MMA", int(flag))
+        if sl: _lib.set_option("GIC_CONV_MMA_SLICES", int(sl))
+        else: _lib.clear_option("GIC_CONV_MMA_SLICES")
         for _ in range(3): disc_fwd_raw(lib,gic_b200.GEMM_BF16,None,ids,N,L,V,De,R,fsz,nfl,W_e,cw,cb,W_h,b_h,W_f,b_f,W_o,b_o,[None],0.0,d)
         torch.cuda.synchronize()
         e0=torch.cuda.Event(enable_timing=True); e1=torch.cuda.Event(enable_timing=True)

@@ -19,7 +19,8 @@ gic_b200.set_gemm_mode(gic_b200.GEMM_TF32)
 
 
 def timed(tag, env):
-    os.environ.update(env)
+    for k, v in env.items():                 # switches of the current library context (gic_ctx_set_option)
+        _lib.set_option(k, int(v))
     try:
         graphs = []
         with torch.no_grad():
@@ -43,7 +44,7 @@ def timed(tag, env):
               f"{ {k: v for k, v in _lib.kernel_counts().items() if 'step' in k or 'vocab' in k} }", flush=True)
     finally:
         for k in env:
-            os.environ.pop(k, None)
+            _lib.clear_option(k)
 
 
 if os.environ.get("GIC_VS_STAMPS") == "1":

@@ -15,7 +15,7 @@ def bench(tB, M, N, K, iters=100, ld=None):
     C = torch.zeros(M, N, device=dev); s = L.stream()
     out = []
     for flag in ("0", "1"):
-        os.environ["GIC_GEMM_2CTA"] = flag
+        L.set_option("GIC_GEMM_2CTA", int(flag))
         def run():
             L.check(lib.gic_gemm_bf16(0, tB, M, N, K, 1.0, L.ptr(A), lda, L.ptr(B), ldb, 0.0, L.ptr(C), N, None, s), "g")
         for _ in range(5): run()
@@ -26,7 +26,7 @@ def bench(tB, M, N, K, iters=100, ld=None):
         e1.record(); torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / iters
         out.append(us)
-    os.environ.pop("GIC_GEMM_2CTA", None)
+    L.clear_option("GIC_GEMM_2CTA")
     f = 2.0 * M * N * K / 1e6
     print(f"tB{tB} {M}x{N}x{K} ld{lda}: one CTA per tile {out[0]:7.1f} us {f/out[0]:6.0f} TF/s | CTA pair {out[1]:7.1f} us {f/out[1]:6.0f} TF/s", flush=True)
 

@@ -269,3 +269,26 @@ def test_contexts_isolate_the_setters(built):
     args = default_args(vocab_size=30, gen_embed_dim=8, gen_hidden_dim=16, disc_num_filters=[4, 4, 4], device="cpu")
     i1, i2 = GANInstructor(args, device="cpu"), GANInstructor(args, device="cpu")
     assert i1._ctx.handle != i2._ctx.handle
+
+
+def test_context_options_are_per_context_and_read_environment_once(monkeypatch):
+    """Kernel-variant switches live in the library context (include/gic_b200.h gic_ctx_set_option): set > environment (read
+    once per context) > built-in default; another context does not see them."""
+    from gic_b200 import _lib
+    monkeypatch.setenv("GIC_TEST_OPT_A", "7")
+    a, b = _lib.Context(), _lib.Context()
+    assert a.get_option("GIC_TEST_OPT_A", 1) == 7              # from the environment, first lookup
+    monkeypatch.setenv("GIC_TEST_OPT_A", "9")
+    assert a.get_option("GIC_TEST_OPT_A", 1) == 7              # remembered: a later setenv does not re-route context a
+    assert b.get_option("GIC_TEST_OPT_A", 1) == 9              # context b looks for the first time now
+    a.set_option("GIC_TEST_OPT_A", 3)
+    assert a.get_option("GIC_TEST_OPT_A", 1) == 3 and b.get_option("GIC_TEST_OPT_A", 1) == 9
+    a.clear_option("GIC_TEST_OPT_A")
+    assert a.get_option("GIC_TEST_OPT_A", 1) == 9              # cleared: the environment again
+    monkeypatch.delenv("GIC_TEST_OPT_A")
+    assert _lib.Context().get_option("GIC_TEST_OPT_A", 5) == 5   # neither set nor in the environment: the default
+    with a, _lib.options(GIC_TEST_OPT_B=0):
+        assert _lib.get_option("GIC_TEST_OPT_B", 1) == 0
+    assert a.get_option("GIC_TEST_OPT_B", 1) == 1
+    with pytest.raises(_lib.GicError):
+        _lib.set_option("X" * 40, 1)

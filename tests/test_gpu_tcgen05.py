@@ -123,12 +123,8 @@ def test_gemm_bf16_cta_pair_kernel_bias_ragged_rows(tB, M, N, K):
         err, scale = run_gemm_bf16(0, tB, M, N, K, alpha=0.5, use_bias=True, seed=9, pad=8)
     REPORT[f"bf16_pair/{M}x{N}x{K}/tB{tB}"] = dict(err=err, scale=scale, rel=err / scale)
     assert err <= 2e-5 * scale, f"rel err {err / scale:.3e}"
-    os.environ["GIC_GEMM_2CTA"] = "0"
-    try:
-        with _lib.expect_kernels("gemm_p_kernel", absent=("gemm_pair_kernel",)):
-            err0, _ = run_gemm_bf16(0, tB, M, N, K, alpha=0.5, use_bias=True, seed=9, pad=8)
-    finally:
-        os.environ.pop("GIC_GEMM_2CTA", None)
+    with _lib.options(GIC_GEMM_2CTA=0), _lib.expect_kernels("gemm_p_kernel", absent=("gemm_pair_kernel",)):
+        err0, _ = run_gemm_bf16(0, tB, M, N, K, alpha=0.5, use_bias=True, seed=9, pad=8)
     assert err0 <= 2e-5 * scale
 
 
@@ -168,19 +164,14 @@ def _decode_variants(B, L, V, E, H, T, forced=False, seed=0, variants=("step", "
     res = {}
     try:
         for v in variants:
-            os.environ.update(_DECODE_ENV[v])
-            try:
-                want, absent = _DECODE_KERNELS[v]
-                with _lib.expect_kernels(*want, absent=absent) as ek:
-                    with torch.no_grad():
-                        p, ids = gen.decoder.sample(feats, max_caption_len=L, u=u, forced_ids=fz)
-                    torch.cuda.synchronize()
-                if v == "step":      # step 0's LSTM kernel, L - 1 fused steps, and the last step (nothing follows it) as the plain kernel
-                    assert ek.delta["decode_step_kernel"] == L - 1 and ek.delta["lstm_step_tf32_kernel"] == 1, ek.delta
-                res[v] = (p.clone(), ids.clone())
-            finally:
-                for k in _DECODE_ENV[v]:
-                    os.environ.pop(k, None)
+            want, absent = _DECODE_KERNELS[v]
+            with _lib.options(**_DECODE_ENV[v]), _lib.expect_kernels(*want, absent=absent) as ek:
+                with torch.no_grad():
+                    p, ids = gen.decoder.sample(feats, max_caption_len=L, u=u, forced_ids=fz)
+                torch.cuda.synchronize()
+            if v == "step":      # step 0's LSTM kernel, L - 1 fused steps, and the last step (nothing follows it) as the plain kernel
+                assert ek.delta["decode_step_kernel"] == L - 1 and ek.delta["lstm_step_tf32_kernel"] == 1, ek.delta
+            res[v] = (p.clone(), ids.clone())
     finally:
         gic_b200.set_gemm_mode(old)
     return res
@@ -237,7 +228,7 @@ def test_fused_decode_step_matches_two_kernel_path(B, L, V, E, H, T):
 
 
 # ---- fused dz kernel (dz_fused_tcgen05.cu): D-embedding input gradient + tempered-softmax backward + db_out ------------
-def _adv_grads(fused_dz, B, L, V, E, H, T=1.0, expect=(), absent=()):
+def _adv_grads(fused_dz, B, L, V, E, H, T=1.0, expect=(), absent=(), options=None):
     import gic_b200
     from gic_b200 import _lib
     from gic_b200.args import default_args
@@ -250,13 +241,12 @@ def _adv_grads(fused_dz, B, L, V, E, H, T=1.0, expect=(), absent=()):
     caps = torch.randint(4, V, (B, L), generator=g, device="cuda:0")
     u = torch.rand(L, B, V, generator=g, device="cuda:0")
     keep = (torch.rand(3, B * 64, 900, generator=g, device="cuda:0") >= 0.2).to(torch.uint8)
-    os.environ["GIC_FUSED_DZ_BF16"] = "1" if fused_dz else "0"
-    try:
-        with _lib.expect_kernels(*expect, absent=absent):
-            inst.adv_step(caps, u=u, keep=keep, update=False)
-            torch.cuda.synchronize()
-    finally:
-        os.environ.pop("GIC_FUSED_DZ_BF16", None)
+    inst._ctx.set_option("GIC_FUSED_DZ_BF16", 1 if fused_dz else 0)       # switches are per context: the instructor's own
+    for k, v in (options or {}).items():
+        inst._ctx.set_option(k, v)
+    with _lib.expect_kernels(*expect, absent=absent):
+        inst.adv_step(caps, u=u, keep=keep, update=False)
+        torch.cuda.synchronize()
     return {k: inst._flat_g.g(p).clone() for k, p in inst.gen.named_parameters() if id(p) in inst._flat_g._index}
 
 
@@ -299,12 +289,9 @@ def test_fused_bptt_step_matches_gemm_plus_cell_kernel(B, L, V, E, H):
                 ("1", "1", ("bptt_persistent_kernel",) if pers_ok else ("bptt_step_kernel",), ()),
                 ("0", "1", ("bptt_step_kernel",), ("bptt_persistent_kernel",)),
                 ("0", "0", ("lstm_cell_bwd_kernel",), ("bptt_persistent_kernel", "bptt_step_kernel"))):
-            os.environ["GIC_BPTT_PERSISTENT"] = pers
-            os.environ["GIC_BPTT_FUSED"] = fused
-            res.append(_adv_grads(True, B, L, V, E, H, 1.0, expect=want, absent=gone))
+            res.append(_adv_grads(True, B, L, V, E, H, 1.0, expect=want, absent=gone,
+                                  options=dict(GIC_BPTT_PERSISTENT=int(pers), GIC_BPTT_FUSED=int(fused))))
     finally:
-        os.environ.pop("GIC_BPTT_FUSED", None)
-        os.environ.pop("GIC_BPTT_PERSISTENT", None)
         gic_b200.set_gemm_mode(old)
     gp, g1, g0 = res
     for nm, gx in (("persistent", gp), ("step", g1)):
@@ -335,19 +322,16 @@ def test_lstm_splitk_cluster_matches_single_cta_kernel(B, L, V, E, H):
     res = []
     try:
         from gic_b200 import _lib
-        os.environ["GIC_DECODE_STEP"] = "0"          # the per-step LSTM kernel is what this test is about
         for flag in ("1", "0"):
-            os.environ["GIC_LSTM_SPLITK"] = flag
             want = "lstm_step_splitk_kernel" if flag == "1" else "lstm_step_tf32_kernel"
             gone = "lstm_step_tf32_kernel" if flag == "1" else "lstm_step_splitk_kernel"
-            with _lib.expect_kernels(want, absent=(gone,)):
+            # GIC_DECODE_STEP = 0: the per-step LSTM kernel is what this test is about
+            with _lib.options(GIC_DECODE_STEP=0, GIC_LSTM_SPLITK=int(flag)), _lib.expect_kernels(want, absent=(gone,)):
                 with torch.no_grad():
                     p, ids = gen.decoder.sample(feats, max_caption_len=L, u=u, forced_ids=fz)
                 torch.cuda.synchronize()
             res.append((p.clone(), ids.clone()))
     finally:
-        os.environ.pop("GIC_LSTM_SPLITK", None)
-        os.environ.pop("GIC_DECODE_STEP", None)
         gic_b200.set_gemm_mode(old)
     (p1, i1), (p0, i0) = res
     err = float((p1 - p0).abs().max()); scale = float(p0.max())
@@ -380,22 +364,18 @@ def _conv_pool_pair(N, L, V, fsz, nfl, seed=0, R=64):
     W_h, b_h, W_f, b_f, W_o, b_o = u(Fd, Fd), u(Fd), u(Hd, Fd), u(Hd), u(1, Hd), u(1)
     ids = torch.randint(0, V, (N, L), generator=g, device=d)
     res = []
-    try:
-        for flag in ("1", "0"):
-            os.environ["GIC_CONV_MMA"] = flag
-            want, gone = ("conv_pool_fwd_mma_kernel", "conv_pool_fwd_kernel") if flag == "1" else ("conv_pool_fwd_kernel", "conv_pool_fwd_mma_kernel")
-            with _lib.expect_kernels(want, absent=(gone,)):
-                logits, saved = disc_fwd_raw(lib, gic_b200.GEMM_TF32, None, ids, N, L, V, De, R, fsz, nfl, W_e, cw, cb, W_h, b_h,
-                                             W_f, b_f, W_o, b_o, [None], 0.0, d)
-                torch.cuda.synchronize()
-            rows = N * R
-            o = _a4(N * L * De)
-            pooled = saved[o:o + rows * Fd].view(rows, Fd).clone()
-            o2 = o + 2 * _a4(rows * Fd)
-            arg = saved[o2:o2 + _a4((rows * Fd + 3) // 4)].view(torch.uint8)[:rows * Fd].view(rows, Fd).clone()
-            res.append((pooled, arg, logits[0].clone()))
-    finally:
-        os.environ.pop("GIC_CONV_MMA", None)
+    for flag in ("1", "0"):
+        want, gone = ("conv_pool_fwd_mma_kernel", "conv_pool_fwd_kernel") if flag == "1" else ("conv_pool_fwd_kernel", "conv_pool_fwd_mma_kernel")
+        with _lib.options(GIC_CONV_MMA=int(flag)), _lib.expect_kernels(want, absent=(gone,)):
+            logits, saved = disc_fwd_raw(lib, gic_b200.GEMM_TF32, None, ids, N, L, V, De, R, fsz, nfl, W_e, cw, cb, W_h, b_h,
+                                         W_f, b_f, W_o, b_o, [None], 0.0, d)
+            torch.cuda.synchronize()
+        rows = N * R
+        o = _a4(N * L * De)
+        pooled = saved[o:o + rows * Fd].view(rows, Fd).clone()
+        o2 = o + 2 * _a4(rows * Fd)
+        arg = saved[o2:o2 + _a4((rows * Fd + 3) // 4)].view(torch.uint8)[:rows * Fd].view(rows, Fd).clone()
+        res.append((pooled, arg, logits[0].clone()))
     return res
 
 
