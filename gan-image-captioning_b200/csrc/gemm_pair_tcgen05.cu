@@ -26,7 +26,8 @@ constexpr int P_B_BYTES = (PBN / 2) * 128;                // this CTA's half of 
 constexpr int P_STAGE = P_A_BYTES + P_B_BYTES;            // 32 KB
 constexpr int P_STAGES = 5;
 constexpr int P_STG_WARP = 4096;                          // per-warp 32 x 32 fp32 TMA-store tile (128B-swizzled)
-constexpr int P_SMEM = P_STAGES * P_STAGE + 4 * P_STG_WARP + 512 + 1024;
+constexpr int P_BIAS = PBN * 4;                           // the tile's slice of the bias, staged once per tile
+constexpr int P_SMEM = P_STAGES * P_STAGE + 4 * P_STG_WARP + 512 + P_BIAS + 1024;
 
 __device__ __forceinline__ uint32_t cluster_rank() {
   uint32_t r;
@@ -84,6 +85,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tmem_full = empty + P_STAGES;      // [2]
   uint64_t* tmem_empty = tmem_full + 2;        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* bias_s = reinterpret_cast<float*>(stg_all + 4 * P_STG_WARP + 512);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_rank();
@@ -172,6 +174,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t acc = seg & 1, accph = (seg >> 1) & 1;
       const int m_base = (tile / a.tiles_n) * 256 + (int)rank * BM + q * 32;
       const int n0 = (tile % a.tiles_n) * PBN;
+      if (a.bias != nullptr) {
+        // bias slice -> shared memory while the tile's MMAs still run (not a dependent global load per 32-column block)
+        asm volatile("bar.sync 1, 128;" ::: "memory");        // the previous tile's readers are done
+        for (int j = (int)threadIdx.x - 64; j < PBN; j += 128) bias_s[j] = (n0 + j < a.N) ? a.bias[n0 + j] : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
       mbar_wait(&tmem_full[acc], accph);
       tcgen05_fence_after();
       const uint32_t t_addr = tmem_base + acc * PBN + ((uint32_t)(q * 32) << 16);
@@ -194,15 +202,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           v.x = a.alpha * __uint_as_float(r[4 * c + 0]); v.y = a.alpha * __uint_as_float(r[4 * c + 1]);
           v.z = a.alpha * __uint_as_float(r[4 * c + 2]); v.w = a.alpha * __uint_as_float(r[4 * c + 3]);
           if (a.bias != nullptr) {
-            const int nb = n0 + c0 + 4 * c;
-            if (nb + 3 < a.N) {
-              const float4 bb = *reinterpret_cast<const float4*>(a.bias + nb);
-              v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
-            } else {
-              if (nb + 0 < a.N) v.x += a.bias[nb + 0];
-              if (nb + 1 < a.N) v.y += a.bias[nb + 1];
-              if (nb + 2 < a.N) v.z += a.bias[nb + 2];
-            }
+            const float4 bb = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * c);
+            v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
           }
           *reinterpret_cast<float4*>(srow + ((c ^ (lane & 7)) << 4)) = v;
         }
