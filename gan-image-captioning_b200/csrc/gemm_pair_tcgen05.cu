@@ -154,8 +154,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + s * P_STAGE);
           const uint32_t sb = sa + P_A_BYTES;
+          // the last k-block issues only the MMAs (16 elements of K each) that hold data: K = 900 leaves 4 of 64
+          // elements in block 15, TMA zero-fills the rest and three of its four MMAs would multiply zeros
+          const int kmax = min(4, (a.K - kb * 64 + 15) >> 4);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
+            if (k >= kmax) break;
             const uint64_t da = make_desc(sa + k * 32, 16, 1024, 2);
             const uint64_t db = B_MN ? make_desc(sb + k * 2048, 8192, 1024, 2) : make_desc(sb + k * 32, 16, 1024, 2);
             umma_bf16_pair(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);

@@ -177,8 +177,10 @@ gemm_p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + s * S::STAGE);
           const uint32_t sb = sa + S::A_BYTES;
+          const int kmax = min(4, (K - kb * BKE + (BKE / 4) - 1) / (BKE / 4));   // K tail: only the MMAs that hold data (TMA zero-fills the rest)
 #pragma unroll
           for (int k = 0; k < 4; ++k) {          // 4 MMAs of 32 bytes of K per k-block
+            if (k >= kmax) break;
             // MN-major: tf32 uses SWIZZLE_128B_BASE32B (atoms of 4 k-rows, 512 B), bf16 plain SWIZZLE_128B (atoms of
             // 8 k-rows, 1024 B); one MMA consumes 8 resp. 16 k-rows = 1024 resp. 2048 bytes
             const uint64_t da = A_MN ? (DT ? make_desc(sa + k * 2048, SLAB_BYTES, 1024, 2) : make_desc(sa + k * 1024, SLAB_BYTES, 512, 1))
