@@ -735,10 +735,22 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
-    elif args.workload in ("c2a", "c3", "c4", "c5"):
-        run_secondary(args)
-    else:
-        run_ours(args)
+        return
+    try:
+        if args.workload in ("c2a", "c3", "c4", "c5"):
+            run_secondary(args)
+        else:
+            run_ours(args)
+    except Exception:
+        # a bounded device-side wait that gave up says which one (host-mapped memory outlives the CUDA context)
+        try:
+            from gic_b200 import _lib
+            info = _lib.trap_info()
+            if info:
+                print("gic_b200: device-side wait expired: %r (sites: include/gic_b200.h, gic_trap_info)" % (info,), file=sys.stderr, flush=True)
+        except Exception:
+            pass
+        raise
 
 
 if __name__ == "__main__":

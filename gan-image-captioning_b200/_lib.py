@@ -135,6 +135,8 @@ def _declare(L):
     L.gic_encoder_bwd_apply.argtypes = [I, P, P, P, P, P, P, I, I, I, P, F, F, P, P, P, P, P, P]
     L.gic_set_vocab_grads_event.restype = None
     L.gic_set_vocab_grads_event.argtypes = [P]
+    L.gic_set_embed_grads_event.restype = None
+    L.gic_set_embed_grads_event.argtypes = [P]
     L.gic_disc_set_prepared.restype = None
     L.gic_disc_set_prepared.argtypes = [P]
     L.gic_comm_create.restype = P
@@ -157,6 +159,9 @@ def _declare(L):
     L.gic_ctx_set_current.argtypes = [P]
     L.gic_ctx_destroy.restype = None
     L.gic_ctx_destroy.argtypes = [P]
+    L.gic_trap_info.restype = None
+    L.gic_trap_info.argtypes = [C.POINTER(C.c_ulonglong)]
+    L.gic_trap_notes.argtypes = [C.POINTER(C.c_ulonglong), I]
     L.gic_ctx_set_option.argtypes = [C.c_char_p, I]
     L.gic_ctx_clear_option.restype = None
     L.gic_ctx_clear_option.argtypes = [C.c_char_p]
@@ -237,6 +242,21 @@ class Context:
                 self.handle = None
         except Exception:
             pass
+
+
+def trap_info():
+    """(site, word, blockIdx.x, threadIdx.x, globaltimer) of the bounded device-side wait that gave up, or None
+    (include/gic_b200.h, gic_trap_info); readable after the CUDA context has died."""
+    out = (C.c_ulonglong * 4)()
+    lib().gic_trap_info(out)
+    if out[0] == 0:
+        return None
+    notes = (C.c_ulonglong * 128)()
+    n = lib().gic_trap_notes(notes, 32)
+    waits = [dict(site=int(notes[4 * i]), word=hex(int(notes[4 * i + 1])), block=int(notes[4 * i + 2] >> 32),
+                  thread=int(notes[4 * i + 2] & 0xffffffff)) for i in range(n)]
+    return dict(site=int(out[0]), word=hex(int(out[1])), block=int(out[2] >> 32), thread=int(out[2] & 0xffffffff), globaltimer=int(out[3]),
+                waits=waits)
 
 
 def set_option(name: str, value: int):

@@ -24,8 +24,15 @@
 namespace gic {
 
 constexpr int AR_MAX_WORLD = 8;              // one NVSwitch box
-constexpr int AR_CTAS = 48;            // CTAs per rank and call: 48 x 512 threads x 4 x 16 B in flight covers NVLink's latency-bandwidth product
-constexpr int AR_THREADS = 512;
+// CTAs per rank and call.  Footprint matters more than width: the exchange of the early buckets runs UNDER the backward pass,
+// next to persistent one-CTA-per-SM kernels.  The first version (48 CTAs x 512 threads x 128 registers = a whole register
+// file per CTA) could only be scheduled on an EMPTY SM and kept everything else off it: a 20 MB bucket took 150 - 200 us
+// under the BPTT kernel (45 us alone) and the chains beside it lost ~100 us.  256 threads x <= 64 registers (16 K registers,
+// 1 KB shared memory) co-resides with every kernel of the step; 64 x 256 x 8 x 16 B = 2 MB of peer loads in flight still
+// cover NVLink's latency-bandwidth product (~2 us x 750 GB/s).
+constexpr int AR_CTAS = 64;
+constexpr int AR_THREADS = 256;
+constexpr int AR_CTAS_PER_SM = 4;
 constexpr int AR_CHANNELS = 4;         // independent flag sets: calls on different streams may overlap in time
 
 struct ArFlags {                       // lives behind the data in every rank's symmetric allocation
@@ -122,7 +129,7 @@ __device__ __forceinline__ float ar_body(const ArRank& me, int W, size_t i0, siz
   return sq;
 }
 
-__global__ void __launch_bounds__(AR_THREADS, 1) allreduce_p2p_kernel(const __grid_constant__ ArArgs a) {
+__global__ void __launch_bounds__(AR_THREADS, AR_CTAS_PER_SM) allreduce_p2p_kernel(const __grid_constant__ ArArgs a) {
   const int W = a.world, ch = a.channel, c = blockIdx.x, tid = threadIdx.x;
   const int ly = blockIdx.y;                                   // 0 for a multi-process call
   const ArRank& me = a.r[ly];
@@ -147,11 +154,11 @@ __global__ void __launch_bounds__(AR_THREADS, 1) allreduce_p2p_kernel(const __gr
   const size_t stride = (size_t)AR_CTAS * AR_THREADS;
   const size_t i0 = s0 + (size_t)c * AR_THREADS + tid;
   // NVLink's latency-bandwidth product (~2 us x 750 GB/s) needs ~1.5 MB of loads in flight per rank, and a trip also has to
-  // hide its own W stores: every thread keeps 16 16-byte peer loads outstanding -- U elements x W ranks, all issued before
-  // the first one is consumed
-  if (W <= 2) sq = ar_body<8>(me, W, i0, s1, stride);
-  else if (W <= 4) sq = ar_body<4>(me, W, i0, s1, stride);
-  else sq = ar_body<2>(me, W, i0, s1, stride);
+  // hide its own W stores: every thread keeps 8 16-byte peer loads outstanding -- U elements x W ranks, all issued before
+  // the first one is consumed (8 x 4 data registers: the kernel stays within 64 registers per thread)
+  if (W <= 2) sq = ar_body<4>(me, W, i0, s1, stride);
+  else if (W <= 4) sq = ar_body<2>(me, W, i0, s1, stride);
+  else sq = ar_body<1>(me, W, i0, s1, stride);
   // partial square norm of this chunk: block reduction in a fixed order, pushed to every rank
   sq = warp_sum(sq);
   if ((tid & 31) == 0) s_red[tid >> 5] = sq;
@@ -311,7 +318,7 @@ int gic_allreduce(float* buf, size_t n, gic_comm_t* comm, int channel, float* sq
 int gic_allreduce_local_group(gic_comm_t* const* comms, float* const* bufs, float* const* sqnorms, size_t n, int world, int channel,
                               gic_stream_t stream) {
   GIC_REQUIRE(comms && bufs && world >= 1 && world <= AR_MAX_WORLD, GIC_ERR_SHAPE, "allreduce_local_group: bad group");
-  GIC_REQUIRE(world * AR_CTAS <= num_sms(), GIC_ERR_UNSUPPORTED, "allreduce_local_group: %d ranks x %d CTAs must be co-resident", world, AR_CTAS);
+  GIC_REQUIRE(world * AR_CTAS <= num_sms() * AR_CTAS_PER_SM, GIC_ERR_UNSUPPORTED, "allreduce_local_group: %d ranks x %d CTAs must be co-resident", world, AR_CTAS);
   ArArgs a;
   memset(&a, 0, sizeof(a));
   for (int r = 0; r < world; ++r) {

@@ -322,7 +322,7 @@ bptt_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           const unsigned int want = (unsigned int)st * gridDim.x;
           const long long t0 = clock64();
           while (ld_acquire_u32(a.counter) < want) {
-            if (clock64() - t0 > 4000000000ll) __trap();   // a protocol bug traps instead of hanging the GPU
+            if (clock64() - t0 > 4000000000ll) trap_report(6u, ((unsigned long long)ld_acquire_u32(a.counter) << 32) | want);   // a protocol bug traps instead of hanging the GPU
           }
           asm volatile("fence.proxy.async;" ::: "memory");
         }

@@ -308,6 +308,13 @@ static int record_vocab_grads_event(cudaStream_t s) {
   if (e != cudaSuccess) { set_error("cudaEventRecord(vocab grads): %s", cudaGetErrorString(e)); return GIC_ERR_CUDA; }
   return GIC_OK;
 }
+static int record_embed_grads_event(cudaStream_t s) {
+  cudaEvent_t ev = ctx().embed_grads_event;
+  if (!ev) return GIC_OK;
+  cudaError_t e = cudaEventRecord(ev, s);
+  if (e != cudaSuccess) { set_error("cudaEventRecord(embed grads): %s", cudaGetErrorString(e)); return GIC_ERR_CUDA; }
+  return GIC_OK;
+}
 static int decode_bwd(int mode, const float* dout, const float* demb, const float* emb, const float* W_e, int De,
                       const float* out, const int64_t* fed, const float* W_emb,
                       const float* const* W_ih, const float* const* W_hh, const float* W_out, float T, int pretrain,
@@ -467,7 +474,17 @@ static int decode_bwd(int mode, const float* dout, const float* demb, const floa
         GIC_TRY(gemm(mode, false, false, B, H, 4 * H, 1.f, dG_lt, 4 * H, W_ih[l], H, 0.f, ws + w.dxin, H, nullptr, s));
     }
   }
-  // 4. weight gradients, batched over all (t, b)
+  // 4. input gradients first (no attention): dX[L*B,E] = dG[0] W_ih[0]; t = 0 -> dfeatures, t >= 1 -> embedding rows.
+  // They need dG only, and dW_emb is 40 % of the generator's gradient bytes: formed BEFORE the weight-gradient GEMMs, its
+  // all-reduce (gic_set_embed_grads_event) runs underneath them instead of in the exposed tail of the step.
+  if (!at) {
+    if (rec_bf) GIC_TRY(gemm_bf16(false, false, L * B, E, 4 * H, 1.f, dG_bf, 4 * H, ws + w.wih_bf, E, 0.f, ws + w.dX, E, nullptr, s));
+    else GIC_TRY(gemm(mode, false, false, L * B, E, 4 * H, 1.f, ws + w.dG, 4 * H, W_ih[0], E, 0.f, ws + w.dX, E, nullptr, s));
+    if (!accumulate) cudaMemsetAsync(dW_emb, 0, (size_t)V * E * sizeof(float), s);
+    GIC_TRY(embed_scatter(ws + w.dX, fed, B, L, E, V, dW_emb, dfeat, s));
+    GIC_TRY(record_embed_grads_event(s));
+  }
+  // 5. weight gradients, batched over all (t, b)
   for (int l = 0; l < layers; ++l) {
     const float* dG_l = ws + w.dG + (size_t)l * dG_stride;           // [L*B, 4H]
     const int In = (l == 0) ? E : H;
@@ -484,11 +501,8 @@ static int decode_bwd(int mode, const float* dout, const float* demb, const floa
     if (!accumulate) cudaMemcpyAsync(db_hh[l], db_ih[l], (size_t)4 * H * sizeof(float), cudaMemcpyDeviceToDevice, s);
     else GIC_TRY(colsum_f32(dG_l, L * B, 4 * H, 4 * H, 1.f, true, db_hh[l], s));
   }
-  // 5. input gradients: dX[L*B,E] = dG[0] W_ih[0]; t = 0 -> dfeatures, t >= 1 -> embedding rows
-  if (!at) {
-    if (rec_bf) GIC_TRY(gemm_bf16(false, false, L * B, E, 4 * H, 1.f, dG_bf, 4 * H, ws + w.wih_bf, E, 0.f, ws + w.dX, E, nullptr, s));
-    else GIC_TRY(gemm(mode, false, false, L * B, E, 4 * H, 1.f, ws + w.dG, 4 * H, W_ih[0], E, 0.f, ws + w.dX, E, nullptr, s));
-  } else {
+  // 6. attention: the per-step dX is already there
+  if (at) {
     // dAk, dAv, dw_e: sums over the L steps, formed once (attn.cu)
     GIC_TRY(attn_bwd_accum(at->saved + al.alpha, at->ws + al.ds, at->saved + al.q, ws + w.dX, at->saved + al.Ak, at->w_e, B, L,
                            at->P, at->Da, E, at->ws + al.dAk, at->ws + al.dAv, at->dw_e, s));
@@ -499,9 +513,10 @@ static int decode_bwd(int mode, const float* dout, const float* demb, const floa
                  at->Cf, nullptr, s));
     GIC_TRY(gemm(mode, true, false, E, at->Cf, B * at->P, 1.f, at->ws + al.dAv, E, at->grid, at->Cf, 0.f, at->dW_v, at->Cf,
                  nullptr, s));
+    if (!accumulate) cudaMemsetAsync(dW_emb, 0, (size_t)V * E * sizeof(float), s);
+    GIC_TRY(embed_scatter(ws + w.dX, fed, B, L, E, V, dW_emb, dfeat, s));
+    GIC_TRY(record_embed_grads_event(s));
   }
-  if (!accumulate) cudaMemsetAsync(dW_emb, 0, (size_t)V * E * sizeof(float), s);
-  GIC_TRY(embed_scatter(ws + w.dX, fed, B, L, E, V, dW_emb, dfeat, s));
   (void)BE;
   return GIC_OK;
 }
@@ -922,6 +937,7 @@ int gic_philox_keep_mask(unsigned int tag, size_t n, float p, uint8_t* out, gic_
   return philox_keep_mask(tag, n, p, out, S(stream));
 }
 void gic_set_vocab_grads_event(void* cuda_event) { ctx().vocab_grads_event = reinterpret_cast<cudaEvent_t>(cuda_event); }
+void gic_set_embed_grads_event(void* cuda_event) { ctx().embed_grads_event = reinterpret_cast<cudaEvent_t>(cuda_event); }
 
 gic_ctx_t* gic_ctx_create(void) { return reinterpret_cast<gic_ctx_t*>(new (std::nothrow) Ctx()); }
 void gic_ctx_destroy(gic_ctx_t* c) {
@@ -930,6 +946,17 @@ void gic_ctx_destroy(gic_ctx_t* c) {
   delete p;
 }
 gic_ctx_t* gic_ctx_set_current(gic_ctx_t* c) { return reinterpret_cast<gic_ctx_t*>(ctx_set_current(reinterpret_cast<Ctx*>(c))); }
+void gic_trap_info(unsigned long long out[4]) {
+  const unsigned long long* p = trap_slot();
+  for (int i = 0; i < 4; ++i) out[i] = p ? p[i] : 0ull;
+}
+int gic_trap_notes(unsigned long long* out, int max_records) {
+  const unsigned long long* p = trap_slot();
+  int n = 0;
+  for (int r = 1; p && r < 32 && n < max_records; ++r)
+    if (p[4 * r] != 0ull) { for (int i = 0; i < 4; ++i) out[4 * n + i] = p[4 * r + i]; ++n; }
+  return n;
+}
 int gic_ctx_set_option(const char* name, int value) {
   GIC_REQUIRE(name && *name && strlen(name) < sizeof(Ctx::Opt().name), GIC_ERR_SHAPE, "gic_ctx_set_option: bad option name");
   option_set(name, value);

@@ -61,11 +61,19 @@ dz_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* a_free = bars + 1;             // [1]
   uint64_t* b_full = bars + 2;             // [3]
   uint64_t* b_empty = bars + 5;            // [3]
-  uint64_t* p_full = bars + 8;             // [3]
-  uint64_t* p_empty = bars + 11;           // [3]
-  uint64_t* t_full = bars + 14;            // [2]
-  uint64_t* t_empty = bars + 16;           // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  // p_full: one barrier per (stage, consuming group).  With three stages and two groups the tiles of a stage alternate
+  // between the groups; on a barrier shared by both, a group would see only every other phase, and a parity wait cannot tell
+  // "my phase k has completed" from "phase k - 1 has not completed yet" (same parity of the phase in progress).  That is
+  // what happened when the p load of tile it - 3 (HBM, the other group's) was still in flight while B / MMA / TMEM of tile
+  // it (L2-resident operands) were already through: the group consumed a stage that had not landed, arrived on p_empty a
+  // phase early, the producer's next expect_tx hit a barrier whose phase was still open -- an exception or a stalled
+  // pipeline once in ~30 000 training steps under the discriminator chain's HBM load (profiles/stress.py).  Per-group
+  // barriers make every waiter see every phase of the barrier it waits on.
+  uint64_t* p_full = bars + 8;             // [3][2]
+  uint64_t* p_empty = bars + 14;           // [3]
+  uint64_t* t_full = bars + 17;            // [2]
+  uint64_t* t_empty = bars + 19;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long lo = (long long)a.tiles * blockIdx.x / gridDim.x;
@@ -79,7 +87,7 @@ dz_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     mbar_init(a_full, 1); mbar_init(a_free, 1);
     for (int s = 0; s < DZ_STAGES; ++s) {
       mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1);
-      mbar_init(&p_full[s], 1); mbar_init(&p_empty[s], DZ_EPI_THREADS / 32);
+      mbar_init(&p_full[2 * s], 1); mbar_init(&p_full[2 * s + 1], 1); mbar_init(&p_empty[s], DZ_EPI_THREADS / 32);
     }
     for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], DZ_EPI_THREADS / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -119,10 +127,11 @@ dz_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int j = 0; j < DZ_BN / 32; ++j)
             tma_load_2d(sb + (kb * (DZ_BN / 32) + j) * 4096, &tmB, &b_full[s], n0 + 32 * j, kb * BK);
         mbar_wait(&p_empty[s], ph ^ 1);
-        mbar_expect_tx(&p_full[s], DZ_P_BYTES);
+        uint64_t* pf = &p_full[2 * s + (it & 1)];                       // the barrier of the group that takes this tile
+        mbar_expect_tx(pf, DZ_P_BYTES);
         uint8_t* sp = sP + s * DZ_P_BYTES;
-        tma_load_2d(sp, &tmP, &p_full[s], n0, m0);
-        tma_load_2d(sp + BM * 128, &tmP, &p_full[s], n0 + 32, m0);
+        tma_load_2d(sp, &tmP, pf, n0, m0);
+        tma_load_2d(sp + BM * 128, &tmP, pf, n0 + 32, m0);
       }
     }
   } else if (warp == 1) {
@@ -176,7 +185,6 @@ dz_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int m0 = mtile * BM, n0 = ntile * DZ_BN;
       if (mtile != cur_m) { cur_m = mtile; dotv = (m0 + row < a.M) ? __ldg(a.dot + m0 + row) : 0.f; }
       const int s = it % DZ_STAGES;
-      const uint32_t ph = (it / DZ_STAGES) & 1;
       const uint32_t acc = it & 1, accph = (it >> 1) & 1;                   // acc == grp
       uint8_t* prow = sP + s * DZ_P_BYTES + g * (BM * 128) + row * 128;      // this thread's 32 fp32 of the p tile
       uint8_t* orow = stage_o + row * 128;                                  // this row's 64 bf16 of the staging tile
@@ -187,7 +195,7 @@ dz_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cta(&t_empty[acc]);
-      mbar_wait(&p_full[s], ph);
+      mbar_wait(&p_full[2 * s + grp], (it / (2 * DZ_STAGES)) & 1);      // this group's uses of stage s are 6 tiles apart
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         float4* pp = reinterpret_cast<float4*>(prow + ((k ^ sw) << 4));

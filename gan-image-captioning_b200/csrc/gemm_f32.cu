@@ -109,6 +109,22 @@ void option_clear(const char* name) {
   if (Ctx::Opt* o = option_find(c, name)) { *o = c.opts[c.n_opts - 1]; --c.n_opts; }
 }
 
+unsigned long long* trap_slot() {
+  static unsigned long long* p = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* h = nullptr;
+    if (cudaHostAlloc(&h, 4096, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess) {
+      memset(h, 0, 4096);
+      p = static_cast<unsigned long long*>(h);
+    } else {
+      cudaGetLastError();
+    }
+  }
+  return p;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {

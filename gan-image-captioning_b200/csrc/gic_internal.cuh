@@ -41,6 +41,7 @@ struct Ctx {
   const float* prepared = nullptr;        // gic_disc_set_prepared
   RngStateHost rng = {0ull, 0ull, nullptr};   // gic_set_rng
   cudaEvent_t vocab_grads_event = nullptr;    // gic_set_vocab_grads_event
+  cudaEvent_t embed_grads_event = nullptr;    // gic_set_embed_grads_event
   // A/B and tuning switches (gic_ctx_set_option).  A name that was never set is looked up in the environment ONCE per
   // context (the first time a launch path asks) and remembered: no getenv on the launch paths after that.
   struct Opt { char name[28]; int value; bool has; };
@@ -49,6 +50,10 @@ struct Ctx {
   int n_opts = 0;
 };
 Ctx& ctx();                               // the calling thread's current context
+// Diagnostics of the bounded device-side waits: the site that gave up writes four words to this host-mapped buffer before
+// it traps (the context is dead afterwards, pinned host memory is not).  [0] site id (0 = none), [1] site-specific,
+// [2] blockIdx.x << 32 | threadIdx.x, [3] globaltimer.  gic_trap_info() reads it.
+unsigned long long* trap_slot();          // host-mapped; the same pointer is valid on the device (UVA); nullptr if unavailable
 int option(const char* name, int dflt);   // the current context's value of a switch (set_option > environment > dflt)
 bool option_is_set(const char* name);
 void option_set(const char* name, int value);

@@ -22,6 +22,45 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// One copy per translation unit (no relocatable device code): bound by trap_slot_bind(), which every make_map*() calls.
+static __device__ unsigned long long* s_trap_slot = nullptr;
+static inline void trap_slot_bind() {
+  static bool done = false;
+  if (done) return;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(cudaStreamPerThread, &st) != cudaSuccess) cudaGetLastError();
+  unsigned long long* p = trap_slot();
+  if (!p) { done = true; return; }
+  if (cudaMemcpyToSymbol(s_trap_slot, &p, sizeof(p)) == cudaSuccess) done = true;
+  else cudaGetLastError();                 // e.g. a capture in progress: the next eager launch binds it
+}
+// sites: 1 mbar_wait | 2 decode wait_token | 3 decode rec tiles | 4 decode row statistics | 5 decode rec flag | 6 BPTT grid barrier
+static __device__ __noinline__ void trap_report(unsigned int site, unsigned long long info) {
+  unsigned long long* p = s_trap_slot;
+  if (p != nullptr) {
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    p[1] = info;
+    p[2] = ((unsigned long long)blockIdx.x << 32) | threadIdx.x;
+    p[3] = now;
+    __threadfence_system();
+    p[0] = site;
+    __threadfence_system();
+  }
+  __trap();
+}
+// a wait that has lasted 2 s leaves a note (record 1 + warp index, 4 words each) and keeps waiting: when the first thread
+// traps at 4 s, every stuck role of the kernel has said what it was waiting for
+static __device__ __noinline__ void wait_note(unsigned int site, unsigned long long info) {
+  unsigned long long* p = s_trap_slot;
+  if (p == nullptr) return;
+  const unsigned int w = threadIdx.x >> 5;
+  unsigned long long* r = p + 4 * (1 + (w < 30u ? w : 30u));
+  r[1] = info;
+  r[2] = ((unsigned long long)blockIdx.x << 32) | threadIdx.x;
+  r[0] = site;
+  __threadfence_system();
+}
 // Bounded wait: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
@@ -38,7 +77,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       unsigned long long now;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
       if (t_start == 0ull) t_start = now;
-      else if (now - t_start > 4000000000ull) __trap();
+      else if (now - t_start > 4000000000ull) trap_report(1u, ((unsigned long long)addr << 32) | parity);
+      else if (now - t_start > 2000000000ull) wait_note(1u, ((unsigned long long)addr << 32) | parity);
     }
   }
 }
@@ -118,10 +158,11 @@ inline EncodeTiledFn encode_fn() {
 
 // 2-D fp32 tensor [rows, cols] (cols contiguous, leading dimension ld) with a box of box_cols x box_rows.
 // dtype TFLOAT32: the TMA unit rounds fp32 -> tf32 while staging (unbiased, unlike the MMA's own truncation).
-inline bool make_map(CUtensorMap* m, const float* base, int rows, int cols, int ld, int box_cols, int box_rows, bool rn,
+static inline bool make_map(CUtensorMap* m, const float* base, int rows, int cols, int ld, int box_cols, int box_rows, bool rn,
                      bool mn_major) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
+  trap_slot_bind();
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
@@ -134,7 +175,7 @@ inline bool make_map(CUtensorMap* m, const float* base, int rows, int cols, int 
 }
 
 // 2-D bf16 tensor [rows, cols] (cols contiguous, leading dimension ld elements), box box_cols x box_rows, 128B swizzle
-inline bool make_map_bf16(CUtensorMap* m, const void* base, int rows, int cols, int ld, int box_cols, int box_rows) {
+static inline bool make_map_bf16(CUtensorMap* m, const void* base, int rows, int cols, int ld, int box_cols, int box_rows) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};

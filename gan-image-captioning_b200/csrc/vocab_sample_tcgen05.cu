@@ -152,7 +152,7 @@ __device__ __forceinline__ int wait_token(const int2* tokpub, int m, int tag, in
       asm volatile("ld.relaxed.gpu.global.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(tokpub + m) : "memory");
       if (v.y == tag) { tok = v.x; break; }
       __nanosleep(20);
-      if (globaltimer_ns() - t0 > 4000000000ull) __trap();   // a protocol bug traps instead of hanging the GPU
+      if (globaltimer_ns() - t0 > 4000000000ull) tc::trap_report(2u, ((unsigned long long)(unsigned)m << 32) | (unsigned)tag);   // a protocol bug traps instead of hanging the GPU
     }
   }
   return __shfl_sync(0xffffffffu, tok, 0);
@@ -372,7 +372,7 @@ vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.rec_done + mtile) : "memory");
           if (v >= a.rec_expect) break;
           __nanosleep(100);
-          if (globaltimer_ns() - t0 > 4000000000ull) __trap();   // a protocol bug traps instead of hanging the GPU
+          if (globaltimer_ns() - t0 > 4000000000ull) trap_report(3u, ((unsigned long long)v << 32) | a.rec_expect);   // a protocol bug traps instead of hanging the GPU
         }
         asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(s_recflag)), "r"(1u) : "memory");
         VS_STAMP(13);
@@ -549,7 +549,7 @@ vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int i = 0; i < 8; ++i) ready = ready && (__float_as_uint(v[i].y) != 0u);
           if (ready) break;
           __nanosleep(20);
-          if (globaltimer_ns() - t0 > 4000000000ull) __trap();   // a protocol bug traps instead of hanging the GPU
+          if (globaltimer_ns() - t0 > 4000000000ull) trap_report(4u, ((unsigned long long)(unsigned)a.t << 32) | (unsigned)j0);   // a protocol bug traps instead of hanging the GPU
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -666,7 +666,7 @@ vocab_sample_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const unsigned long long t0 = globaltimer_ns();
           while (f == 0) {
             asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(f) : "r"(smem_u32(s_recflag)) : "memory");
-            if (globaltimer_ns() - t0 > 4000000000ull) __trap();
+            if (globaltimer_ns() - t0 > 4000000000ull) trap_report(5u, (unsigned long long)(unsigned)a.t);
           }
         }
         __syncwarp(am);

@@ -98,6 +98,7 @@ class GANInstructor:
         self._rng_offset = 0
         self._rng_dyn = None
         self._vocab_ev = None
+        self._embed_ev = None
         self.bucketed = os.environ.get("GIC_NO_BUCKET", "0") != "1"
         # data parallel: Encoder.bn over the GLOBAL batch (two [2, E] all-reduces per step) instead of per shard;
         # opt-in (args.sync_bn / GIC_SYNC_BN=1): the reference is single-GPU, per-shard statistics are the documented default
@@ -169,19 +170,31 @@ class GANInstructor:
         lib = _lib.lib()
         cur = torch.cuda.current_stream()
         if self._vocab_ev is None:
-            self._vocab_ev = torch.cuda.Event()
-            self._vocab_ev.record(cur)                  # materialises the cudaEvent_t handle
-        ev = self._vocab_ev
+            self._vocab_ev, self._embed_ev = torch.cuda.Event(), torch.cuda.Event()
+            self._vocab_ev.record(cur)                  # materialises the cudaEvent_t handles
+            self._embed_ev.record(cur)
+        ev, ev2 = self._vocab_ev, self._embed_ev
+        two = fg.n_early < fg.n_mid < fg.n              # second bucket: embed.weight, final before the weight-gradient GEMMs
         lib.gic_set_vocab_grads_event(ev.cuda_event)
+        if two:
+            lib.gic_set_embed_grads_event(ev2.cuda_event)
         try:
             run_backward()
         finally:
             lib.gic_set_vocab_grads_event(None)
+            lib.gic_set_embed_grads_event(None)
         comm = self._comm_stream()
         comm.wait_event(ev)
         with torch.cuda.stream(comm):
-            self._allreduce(fg.grad[:fg.n_early], 1, self._sq_g)
-        return True
+            self._mark("comm: early bucket (linear.weight) ready")
+            self._allreduce(fg.grad[:fg.n_early], 1, self._sq_g[0:1])
+            self._mark("comm: early bucket all-reduced")
+            if two:
+                comm.wait_event(ev2)
+                self._mark("comm: embed bucket ready")
+                self._allreduce(fg.grad[fg.n_early:fg.n_mid], 3, self._sq_g[1:2])
+                self._mark("comm: embed bucket all-reduced")
+        return 2 if two else 1
 
     def _gen_allreduce_rest(self, bucketed):
         """Phase 2 (issued after the discriminator's all-reduce so that NCCL's queue order is early bucket, D, rest)."""
@@ -189,10 +202,11 @@ class GANInstructor:
         if self.world <= 1:
             return
         if bucketed:
-            self._allreduce(fg.grad[fg.n_early:], 2, self._sq_g)
+            lo = fg.n_mid if bucketed == 2 else fg.n_early
+            self._allreduce(fg.grad[lo:], 2, self._sq_g[2:3])
             torch.cuda.current_stream().wait_stream(self._comm_stream())
         else:
-            self._allreduce(fg.grad, 2, self._sq_g)
+            self._allreduce(fg.grad, 2, self._sq_g[2:3])
 
     # ---- gradient exchange -------------------------------------------------------------------------------------------
     def _allreduce(self, t, channel, sq=None):
@@ -324,6 +338,7 @@ class GANInstructor:
         if need_g:
             self._flat_g = self._rehome(self._flat_g, gp, alloc)
             self._flat_g.n_early = self._flat_g.offsets[2]          # [linear.weight | linear.bias]
+            self._flat_g.n_mid = self._flat_g.offsets[3]            # ... | embed.weight]
         if need_d:
             self._flat_d = self._rehome(self._flat_d, dp, alloc)
 
@@ -590,7 +605,9 @@ class GANInstructor:
         # chain (D input gradient -> decoder BPTT).  The generator chain is latency-bound (L serial BPTT steps), so it
         # runs on a side stream under the D chain.  Q1: both read the PRE-update weights, so D's Adam waits for the
         # generator chain's last read of D weights.
-        self._sq_g = torch.zeros(1, device=dev)      # square norms of the reduced gradients (peer all-reduce accumulates them)
+        # square norms of the reduced gradients (the peer all-reduce accumulates them); one slot per generator bucket: two
+        # buckets may finish in either order, and a float sum must not depend on that (the replicas have to stay identical)
+        self._sq_g = torch.zeros(4, device=dev)
         self._sq_d = torch.zeros(1, device=dev)
         if side is not None and g_has_grad:
             bws2 = self._buf("disc_bws2", lib.gic_disc_bwd_workspace_floats(B, L, De, R, Fd))
@@ -620,10 +637,13 @@ class GANInstructor:
                 disc_bwd(seeds[1], k1, probs, None, saved_f, 1, 1, None, bws, ds)
                 self._mark("D chain: backward(fake) done")
                 d_sq = self._allreduce(fd.grad, 0, self._sq_d)
+                self._mark("D chain: gradients all-reduced")
             with torch.cuda.stream(side):
+                self._mark("G chain: backward done")
                 self._gen_allreduce_rest(g_bucketed)
+                self._mark("G chain: gradients all-reduced")
                 g_sq = self._peer is not None and self.world > 1 and not self.skip_allreduce and self._peer.owns(fg.grad)
-                out["g_sqnorm"] = self._clip_adam(fg, a.gen_lr, update, 3, self._sq_g if g_sq else None)
+                out["g_sqnorm"] = self._clip_adam(fg, a.gen_lr, update, 3, self._sq_g.sum().reshape(1) if g_sq else None)
                 self._mark("G chain: clip + Adam done")
             with torch.cuda.stream(dst):
                 dst.wait_event(gen_done)
@@ -640,10 +660,10 @@ class GANInstructor:
                 gen_chain(bws, stream)
             # -- data-parallel exchange: summed gradients, averaged inside the optimizer kernel
             d_sq = self._allreduce(fd.grad, 0, self._sq_d)
-            g_sq = self._allreduce(fg.grad, 2, self._sq_g) if g_has_grad else False
+            g_sq = self._allreduce(fg.grad, 2, self._sq_g[2:3]) if g_has_grad else False
             out["d_sqnorm"] = self._clip_adam(fd, a.disc_lr, update, 1, self._sq_d if d_sq else None)
             if g_has_grad:
-                out["g_sqnorm"] = self._clip_adam(fg, a.gen_lr, update, 3, self._sq_g if g_sq else None)
+                out["g_sqnorm"] = self._clip_adam(fg, a.gen_lr, update, 3, self._sq_g.sum().reshape(1) if g_sq else None)
         out["g_has_grad"] = g_has_grad
         return out
 

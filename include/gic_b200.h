@@ -310,6 +310,15 @@ void gic_ctx_destroy(gic_ctx_t* ctx);
  *   gic_ctx_clear_option  forget it: the next lookup consults the environment again, then the built-in default
  *   gic_ctx_get_option    the value a launch path would see (dflt when neither set nor in the environment) */
 int gic_ctx_set_option(const char* name, int value);
+/* The device-side waits of the library (mbarriers, the decode step's flags, the BPTT grid barrier) are bounded: a wait that
+ * lasts seconds traps instead of hanging the GPU, and the CUDA context is lost ("unspecified launch failure").  Before it
+ * traps the site writes who it was to host-mapped memory, which survives: out[0] = site (0: no trap happened; 1 mbarrier,
+ * 2 token wait, 3 recurrent tiles, 4 row statistics, 5 recurrent flag, 6 BPTT grid barrier), out[1] = site-specific word,
+ * out[2] = blockIdx.x << 32 | threadIdx.x, out[3] = %globaltimer. */
+void gic_trap_info(unsigned long long out[4]);
+/* Notes left by waits that had lasted 2 s when the trap came (one per warp of the stuck kernel: site, word, block/thread, -):
+ * up to max_records records of 4 words; returns how many. */
+int gic_trap_notes(unsigned long long* out, int max_records);
 void gic_ctx_clear_option(const char* name);
 int gic_ctx_get_option(const char* name, int dflt);
 
@@ -390,6 +399,10 @@ int gic_pack_captions(const int32_t* tokens, const int32_t* offsets, int B, int 
  * -- before the serial BPTT tail -- so the caller can all-reduce that bucket on another stream underneath the rest of
  * the backward (the reference is single-GPU). */
 void gic_set_vocab_grads_event(void* cuda_event);
+/* gic_set_embed_grads_event(ev): the same for dW_emb (embed.weight's gradient, another 40 % of the generator's gradient
+ * bytes at c2): recorded right after the embedding scatter, which the backward runs BEFORE its weight-gradient GEMMs so
+ * that this bucket's all-reduce overlaps them. */
+void gic_set_embed_grads_event(void* cuda_event);
 
 /* ---- data-parallel gradient exchange over NVLink / NVSwitch peer memory ("gic_allreduce") ----
  * The reference is single-GPU (--device-ids is parsed and ignored, src/args.py:213-216,276); data parallelism over the

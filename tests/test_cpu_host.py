@@ -292,3 +292,8 @@ def test_context_options_are_per_context_and_read_environment_once(monkeypatch):
     assert a.get_option("GIC_TEST_OPT_B", 1) == 1
     with pytest.raises(_lib.GicError):
         _lib.set_option("X" * 40, 1)
+
+
+def test_trap_info_is_empty_when_nothing_trapped():
+    from gic_b200 import _lib
+    assert _lib.trap_info() is None
