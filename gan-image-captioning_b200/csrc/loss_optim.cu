@@ -258,6 +258,50 @@ clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
   }
 }
 
+// The same update on 16-byte vectors, two vectors per thread and trip: eight 16-byte loads in flight per thread before the
+// first use (the scalar kernel kept four 4-byte loads in flight and reached 67 - 74 % of the HBM rate; this is the tail of
+// the step, nothing overlaps it).  Element-wise arithmetic is unchanged, so the result is bit-identical.
+__device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v, float coef, float lr_over_bc1, float inv_sqrt_bc2,
+                                          float b1, float b2, float eps) {
+  const float gi = g * coef;
+  const float mi = b1 * m + (1.f - b1) * gi;
+  const float vi = b2 * v + (1.f - b2) * gi * gi;
+  m = mi;
+  v = vi;
+  p -= lr_over_bc1 * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+}
+__global__ void __launch_bounds__(256)
+clip_adam_vec_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v, size_t n4,
+                     const float* __restrict__ sqnorm, float max_norm, float grad_scale, float lr_over_bc1, float inv_sqrt_bc2,
+                     const float* __restrict__ bc_dev, float b1, float b2, float eps) {
+  if (bc_dev) { lr_over_bc1 = __ldg(bc_dev); inv_sqrt_bc2 = __ldg(bc_dev + 1); }
+  float coef = grad_scale;
+  if (max_norm > 0.f && sqnorm) {
+    const float nrm = sqrtf(*sqnorm) * grad_scale;
+    coef *= fminf(1.f, max_norm / (nrm + 1e-6f));
+  }
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += 2 * stride) {
+    const size_t j = i + stride;
+    const bool two = j < n4;
+    float4 g0 = g[i], m0 = m[i], v0 = v[i], p0 = p[i];
+    float4 g1 = make_float4(0.f, 0.f, 0.f, 0.f), m1 = g1, v1 = g1, p1 = g1;
+    if (two) { g1 = g[j]; m1 = m[j]; v1 = v[j]; p1 = p[j]; }
+    adam_elem(p0.x, g0.x, m0.x, v0.x, coef, lr_over_bc1, inv_sqrt_bc2, b1, b2, eps);
+    adam_elem(p0.y, g0.y, m0.y, v0.y, coef, lr_over_bc1, inv_sqrt_bc2, b1, b2, eps);
+    adam_elem(p0.z, g0.z, m0.z, v0.z, coef, lr_over_bc1, inv_sqrt_bc2, b1, b2, eps);
+    adam_elem(p0.w, g0.w, m0.w, v0.w, coef, lr_over_bc1, inv_sqrt_bc2, b1, b2, eps);
+    m[i] = m0; v[i] = v0; p[i] = p0;
+    if (two) {
+      adam_elem(p1.x, g1.x, m1.x, v1.x, coef, lr_over_bc1, inv_sqrt_bc2, b1, b2, eps);
+      adam_elem(p1.y, g1.y, m1.y, v1.y, coef, lr_over_bc1, inv_sqrt_bc2, b1, b2, eps);
+      adam_elem(p1.z, g1.z, m1.z, v1.z, coef, lr_over_bc1, inv_sqrt_bc2, b1, b2, eps);
+      adam_elem(p1.w, g1.w, m1.w, v1.w, coef, lr_over_bc1, inv_sqrt_bc2, b1, b2, eps);
+      m[j] = m1; v[j] = v1; p[j] = p1;
+    }
+  }
+}
+
 int clip_adam(float* p, const float* g, float* m, float* v, size_t n, const float* sqnorm, float max_norm,
               float grad_scale, int step, float lr, float b1, float b2, float eps, const float* bc_dev, cudaStream_t s) {
   if (n == 0) return GIC_OK;
@@ -265,11 +309,24 @@ int clip_adam(float* p, const float* g, float* m, float* v, size_t n, const floa
   GIC_REQUIRE(step >= 1 || bc_dev, GIC_ERR_SHAPE, "clip_adam: step must be >= 1");
   if (step < 1) step = 1;
   const double bc1 = 1.0 - pow((double)b1, step), bc2 = 1.0 - pow((double)b2, step);
-  const int grid = min(cdiv((long long)n, 256), 8 * num_sms());
   ProfScope prof(PROF_ADAM, 28.0 * n, s);                              // read p,g,m,v; write p,m,v
-  clip_adam_kernel<<<grid, 256, 0, s>>>(p, g, m, v, n, sqnorm, max_norm, grad_scale, (float)(lr / bc1),
-                                        (float)(1.0 / sqrt(bc2)), bc_dev, b1, b2, eps);
-  return check_launch("clip_adam_kernel");
+  const size_t n4 = (aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v)) ? (n >> 2) : 0;
+  if (n4 > 0) {
+    const int grid = (int)min((long long)cdiv((long long)n4, 512), (long long)8 * num_sms());
+    clip_adam_vec_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g),
+                                              reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), n4, sqnorm, max_norm,
+                                              grad_scale, (float)(lr / bc1), (float)(1.0 / sqrt(bc2)), bc_dev, b1, b2, eps);
+    GIC_TRY(check_launch("clip_adam_kernel"));
+  }
+  const size_t done = n4 << 2;
+  if (done < n) {                                                      // unaligned buffers, or the last n % 4 elements
+    const int grid = min(cdiv((long long)(n - done), 256), 8 * num_sms());
+    clip_adam_kernel<<<grid, 256, 0, s>>>(p + done, g + done, m + done, v + done, n - done, sqnorm, max_norm, grad_scale,
+                                          (float)(lr / bc1), (float)(1.0 / sqrt(bc2)), bc_dev, b1, b2, eps);
+    if (n4 == 0) return check_launch("clip_adam_kernel");
+    return check_launch("clip_adam_tail_kernel");
+  }
+  return GIC_OK;
 }
 
 }  // namespace gic
