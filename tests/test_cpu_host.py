@@ -297,3 +297,24 @@ def test_context_options_are_per_context_and_read_environment_once(monkeypatch):
 def test_trap_info_is_empty_when_nothing_trapped():
     from gic_b200 import _lib
     assert _lib.trap_info() is None
+
+
+def test_generator_gradient_buckets_follow_the_order_the_backward_finishes_them():
+    """Data parallel: the flat generator gradient leaves in three contiguous buckets -- [linear.weight |
+    linear.bias] (final before the BPTT tail), [embed.weight] (formed before the weight-gradient GEMMs), the rest -- so the
+    flat layout has to start with exactly those tensors, each bucket 16-byte aligned."""
+    from gic_b200.args import default_args
+    from gic_b200.training import GANInstructor
+    a = default_args(vocab_size=30, gen_embed_dim=8, gen_hidden_dim=16, disc_num_filters=[4, 4, 4], device="cpu", conditional_gan=1,
+                     feature_dim=12)
+    inst = GANInstructor(a, device="cpu")
+    inst._ensure_flat()
+    fg, dec = inst._flat_g, inst.gen.decoder
+    assert fg.params[0] is dec.linear.weight and fg.params[1] is dec.linear.bias and fg.params[2] is dec.embed.weight
+    assert fg.n_early == fg.offsets[2] and fg.n_mid == fg.offsets[3]
+    assert 0 < fg.n_early < fg.n_mid < fg.n
+    assert fg.n_early % 4 == 0 and fg.n_mid % 4 == 0 and fg.n % 4 == 0
+    assert fg.n_mid - fg.n_early >= dec.embed.weight.numel()
+    # the views the backward writes into are the slices the buckets cover
+    assert fg.g(dec.embed.weight).data_ptr() == fg.grad.data_ptr() + 4 * fg.n_early
+    assert fg.g(dec.lstm_params()[0]).data_ptr() == fg.grad.data_ptr() + 4 * fg.n_mid
